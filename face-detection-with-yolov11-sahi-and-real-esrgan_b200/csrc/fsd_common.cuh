@@ -1,0 +1,119 @@
+// Shared host/device helpers for the sm_100a kernels behind include/fsd_b200.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/fsd_b200.h"
+
+namespace fsd {
+
+void set_error(const char* fmt, ...);
+
+#define FSD_CHECK_ARG(cond, ...)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            ::fsd::set_error(__VA_ARGS__);  \
+            return FSD_ERR_ARG;             \
+        }                                   \
+    } while (0)
+
+#define FSD_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ::fsd::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                             __LINE__);                                                         \
+            return FSD_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// Device-side table cached per (src,dst) resize pair (Kernel 1).
+struct ResizeTable {
+    int32_t* dev = nullptr;  // [dst] x int2-packed entries
+    int n = 0;
+};
+
+}  // namespace fsd
+
+// Handle: owns small device-side lookup tables and the TMA tensor-map cache.  No global state.
+struct fsd_context {
+    int device = 0;
+    int sm_count = 0;
+    int64_t launches = 0;
+    std::mutex mu;
+    // Kernel 1 coefficient tables keyed by (src, dst, axis)
+    std::map<std::tuple<int, int, int>, fsd::ResizeTable> resize_tables;
+    // Kernel 1 tensor maps keyed by (base, n, H, pitch/image_pitch, box_w, box_h)
+    std::map<std::tuple<uintptr_t, int, int, int64_t, int64_t, int, int>, CUtensorMap> tensor_maps;
+    void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
+};
+
+namespace fsd {
+
+// ---- PTX wrappers (sm_100a): mbarrier + TMA bulk tensor loads ------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// one lane of a fully converged warp (SASS: ELECT); use under a warp-uniform branch only
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 3-D tiled TMA load global -> shared, completion signalled on an mbarrier (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x,
+                                            int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+#endif
+
+}  // namespace fsd

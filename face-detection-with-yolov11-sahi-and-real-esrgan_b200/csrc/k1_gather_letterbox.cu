@@ -1,0 +1,372 @@
+// Kernel 1 — fused slice gather + letterbox + uint8 -> fp16/fp32 normalise.
+//
+// One CTA produces one [TR x TC] tile of one network input [3, out_h, out_w]:
+//   1. one thread issues a TMA box load (image pool viewed as a 3-D u32 tensor [N][H][pitch/4]) of the
+//      source rows/bytes the tile needs into shared memory and everybody waits on the mbarrier;
+//   2. horizontal pass: cv2's fixed-point row interpolation  (S[sx]*a0 + S[sx1]*a1) >> 4  is evaluated
+//      ONCE per needed source row into a planar u16 buffer (up-scales reuse each row for ~1/scale outputs);
+//   3. vertical pass + epilogue: ((b0*h0)>>16 + (b1*h1)>>16 + 2) >> 2, /255, channel reverse folded into
+//      the plane index, 8 outputs per thread -> one 128-bit (fp16) or two 128-bit (fp32) stores per plane.
+// The arithmetic is integer-exact w.r.t. cv2.resize(INTER_LINEAR) on uint8 (incl. the exact-2x area path);
+// the /255 matches torch's `im.half()/255` resp. `im.float()/255` (exhaustively checked over 0..255 in tests).
+#include "fsd_common.cuh"
+
+namespace fsd {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_MODE_LINEAR = 1;
+constexpr int K1_MODE_AREA2 = 2;
+
+struct K1Params {
+    const int32_t* entries;  // [B,3] image_index, x0, y0
+    const int2* xtab;        // [new_w] {sx, a0 | a1 << 16}
+    const int4* ytab;        // [new_h] {sy0, sy1, b0, b1}
+    void* out;
+    int src_w, src_h, new_w, new_h, pad_left, pad_top, out_w, out_h;
+    int tile_cols, tile_rows;  // TC (multiple of 8, divides 256 or equals it), TR
+    int box_w_elems, box_rows; // TMA box (u32 elements x rows)
+    int reverse;
+};
+
+template <typename T> struct OutVec;
+
+// exact float(v)/255 for integer v in [0,255]: one multiply + one Newton correction (verified == IEEE
+// division for all 256 inputs by tests/test_letterbox_math.py through the exported self-test).
+template <typename OutT>
+__device__ __forceinline__ float norm255(int v) {
+    const float rcp = 1.0f / 255.0f;
+    float fv = (float)v;
+    float q = fv * rcp;
+    // fp16 output: half(v * (1/255)) == half(v / 255) for all 256 inputs, the correction is not needed
+    if (sizeof(OutT) == 2) return q;
+    float r = fmaf(-q, 255.0f, fv);
+    return fmaf(r, rcp, q);
+}
+
+__device__ __forceinline__ void store8(__half* dst, const float (&f)[8]) {
+    __half2 h0 = __floats2half2_rn(f[0], f[1]);
+    __half2 h1 = __floats2half2_rn(f[2], f[3]);
+    __half2 h2 = __floats2half2_rn(f[4], f[5]);
+    __half2 h3 = __floats2half2_rn(f[6], f[7]);
+    uint4 v;
+    v.x = *reinterpret_cast<uint32_t*>(&h0);
+    v.y = *reinterpret_cast<uint32_t*>(&h1);
+    v.z = *reinterpret_cast<uint32_t*>(&h2);
+    v.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(dst) = v;
+}
+__device__ __forceinline__ void store8(float* dst, const float (&f)[8]) {
+    *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <int MODE, typename OutT>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
+    // dynamic smem, manually aligned to 128 B (TMA destination rule): [raw box | hbuf | ytab | mbarrier]
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+
+    const int tid = threadIdx.x;
+    const int TC = p.tile_cols, TR = p.tile_rows;
+    const int X0 = blockIdx.x * TC, Y0 = blockIdx.y * TR;
+    const int b = blockIdx.z;
+
+    const int raw_pitch = p.box_w_elems * 4;
+    const int raw_bytes = (raw_pitch * p.box_rows + 127) & ~127;
+    const int hbuf_bytes = (p.box_rows * 3 * TC * 2 + 127) & ~127;
+    uint8_t* raw = smem;                                                // [box_rows][raw_pitch]
+    uint16_t* hbuf = reinterpret_cast<uint16_t*>(smem + raw_bytes);     // [box_rows][3][TC]
+    int4* s_ytab = reinterpret_cast<int4*>(smem + raw_bytes + hbuf_bytes);  // [TR]
+    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem + raw_bytes + hbuf_bytes + 32 * 16);
+
+    // destination-pixel window of this tile (may be empty when the tile lies in the 114 border)
+    const int dx_lo = max(X0 - p.pad_left, 0), dx_hi = min(X0 + TC - p.pad_left, p.new_w) - 1;
+    const int dy_lo = max(Y0 - p.pad_top, 0), dy_hi = min(Y0 + TR - p.pad_top, p.new_h) - 1;
+    const bool has = dx_lo <= dx_hi && dy_lo <= dy_hi;
+
+    int sx_lo = 0, sy_lo = 0, nrows = 0, boff = 0;
+    if (has) {
+        const int img = __ldg(p.entries + 3 * b + 0);
+        const int x0 = __ldg(p.entries + 3 * b + 1);
+        const int y0 = __ldg(p.entries + 3 * b + 2);
+        sx_lo = __ldg(&p.xtab[dx_lo]).x;
+        sy_lo = __ldg(&p.ytab[dy_lo]).x;
+        nrows = __ldg(&p.ytab[dy_hi]).y - sy_lo + 1;
+        const int byte0 = (x0 + sx_lo) * 3;
+        boff = byte0 & 15;  // the TMA box must start on a 16-byte boundary of the row (unaligned starts fault)
+        // CUTLASS idiom: a warp-uniform branch + elect.sync, so the TMA operands stay in uniform registers
+        if (tid < 32) {
+            const int cx = (byte0 >> 4) << 2, cy = y0 + sy_lo;
+            if (elect_one_sync()) {
+                mbar_init(&bar, 1);
+                fence_barrier_init();
+                mbar_expect_tx(&bar, (uint32_t)(raw_pitch * p.box_rows));
+                tma_load_3d(raw, &tmap, &bar, cx, cy, img);
+            }
+        }
+        // stage this tile's vertical coefficients while the TMA is in flight
+        if (tid < TR) {
+            int dy = Y0 + tid - p.pad_top;
+            int4 ye = make_int4(0, 0, 0, 0);
+            if (dy >= 0 && dy < p.new_h) {
+                ye = __ldg(&p.ytab[dy]);
+                ye.x -= sy_lo;
+                ye.y -= sy_lo;
+            }
+            s_ytab[tid] = ye;
+        }
+    }
+    __syncthreads();  // barrier init + s_ytab visible
+
+    if (has) {
+        mbar_wait(&bar, 0);
+        // ---- horizontal pass: thread <-> (column j, row group) --------------------------------------
+        const int ncols = dx_hi - dx_lo + 1;
+        const int j = tid % TC, rg = tid / TC, rgs = K1_THREADS / TC;
+        if (j < ncols) {
+            const int2 xe = __ldg(&p.xtab[dx_lo + j]);
+            const int s1 = min(xe.x + 1, p.src_w - 1);
+            const int o0 = (xe.x - sx_lo) * 3 + boff, o1 = (s1 - sx_lo) * 3 + boff;
+            const int a0 = xe.y & 0xffff, a1 = (xe.y >> 16) & 0xffff;
+            const int col = dx_lo + j + p.pad_left - X0;
+            const int c0 = p.reverse ? 2 : 0, c2 = p.reverse ? 0 : 2;
+            for (int r = rg; r < nrows; r += rgs) {
+                const uint8_t* row = raw + r * raw_pitch;
+                uint16_t* hrow = hbuf + (size_t)r * 3 * TC + col;
+                int v0 = row[o0 + 0] * a0 + row[o1 + 0] * a1;
+                int v1 = row[o0 + 1] * a0 + row[o1 + 1] * a1;
+                int v2 = row[o0 + 2] * a0 + row[o1 + 2] * a1;
+                if (MODE == K1_MODE_LINEAR) { v0 >>= 4; v1 >>= 4; v2 >>= 4; }
+                hrow[c0 * TC] = (uint16_t)v0;
+                hrow[1 * TC] = (uint16_t)v1;
+                hrow[c2 * TC] = (uint16_t)v2;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- vertical pass + normalise + planar vector stores -------------------------------------------
+    const int vecs = TC / 8;
+    const int items = TR * 3 * vecs;
+    const float pad_val = norm255<OutT>(114);
+    OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * 3 * p.out_h * p.out_w;
+    for (int it = tid; it < items; it += K1_THREADS) {
+        const int v = it % vecs;
+        const int line = it / vecs;
+        const int c = line % 3, yl = line / 3;
+        const int Y = Y0 + yl, X = X0 + v * 8;
+        if (Y >= p.out_h || X >= p.out_w) continue;
+        const int dy = Y - p.pad_top;
+        float f[8];
+        if (!has || dy < 0 || dy >= p.new_h) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = pad_val;
+        } else {
+            const int4 ye = s_ytab[yl];
+            const uint4 ha = *reinterpret_cast<const uint4*>(hbuf + ((size_t)ye.x * 3 + c) * TC + v * 8);
+            const uint4 hb = *reinterpret_cast<const uint4*>(hbuf + ((size_t)ye.y * 3 + c) * TC + v * 8);
+            const uint32_t wa[4] = {ha.x, ha.y, ha.z, ha.w}, wb[4] = {hb.x, hb.y, hb.z, hb.w};
+            const int xl = X - p.pad_left;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int h0 = (wa[e >> 1] >> ((e & 1) * 16)) & 0xffff;
+                const int h1 = (wb[e >> 1] >> ((e & 1) * 16)) & 0xffff;
+                int val;
+                if (MODE == K1_MODE_LINEAR) val = (((ye.z * h0) >> 16) + ((ye.w * h1) >> 16) + 2) >> 2;
+                else val = (h0 + h1 + 2) >> 2;
+                const bool inside = (unsigned)(xl + e) < (unsigned)p.new_w;
+                f[e] = inside ? norm255<OutT>(val) : pad_val;
+            }
+        }
+        store8(out + ((size_t)c * p.out_h + Y) * p.out_w + X, f);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+// cv2 resize coefficient tables (resize.cpp, resizeGeneric_ / HResizeLinear / VResizeLinear, uint8 path).
+static void build_tables(int src, int dst, int mode, bool is_x, std::vector<int32_t>& tab) {
+    tab.resize((size_t)dst * (is_x ? 2 : 4));
+    const double inv_scale = (double)dst / (double)src;
+    const double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dst; ++d) {
+        int s, s1, w0, w1;
+        if (mode == K1_MODE_AREA2) {
+            s = 2 * d; s1 = 2 * d + 1; w0 = 1; w1 = 1;
+        } else {
+            float f = (float)((d + 0.5) * scale - 0.5);
+            s = (int)floorf(f);
+            f -= (float)s;
+            if (is_x) {
+                if (s < 0) { s = 0; f = 0.f; }
+                if (s >= src - 1) { s = src - 1; f = 0.f; }
+                s1 = s + 1 < src ? s + 1 : src - 1;
+            } else {
+                s1 = s + 1;
+                s = s < 0 ? 0 : (s > src - 1 ? src - 1 : s);
+                s1 = s1 < 0 ? 0 : (s1 > src - 1 ? src - 1 : s1);
+            }
+            w0 = (int)lrintf((1.f - f) * 2048.f);
+            w1 = (int)lrintf(f * 2048.f);
+        }
+        if (is_x) {
+            tab[2 * d + 0] = s;
+            tab[2 * d + 1] = (w0 & 0xffff) | (w1 << 16);
+        } else {
+            tab[4 * d + 0] = s; tab[4 * d + 1] = s1; tab[4 * d + 2] = w0; tab[4 * d + 3] = w1;
+        }
+    }
+}
+
+static int get_table(fsd_context* h, int src, int dst, int mode, bool is_x, const int32_t** dev,
+                     std::vector<int32_t>* host_copy) {
+    auto key = std::make_tuple(src, dst, (mode << 1) | (is_x ? 1 : 0));
+    std::vector<int32_t> tab;
+    build_tables(src, dst, mode, is_x, tab);
+    auto it = h->resize_tables.find(key);
+    if (it == h->resize_tables.end()) {
+        ResizeTable t;
+        t.n = (int)tab.size();
+        FSD_CUDA(cudaMalloc(&t.dev, tab.size() * sizeof(int32_t)));
+        FSD_CUDA(cudaMemcpy(t.dev, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        it = h->resize_tables.emplace(key, t).first;
+    }
+    *dev = it->second.dev;
+    if (host_copy) host_copy->swap(tab);
+    return FSD_OK;
+}
+
+template <int MODE, typename OutT>
+static int launch(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, int B, size_t smem,
+                  cudaStream_t stream) {
+    auto kern = k1_gather_letterbox_kernel<MODE, OutT>;
+    FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.out_w + p.tile_cols - 1) / p.tile_cols, (p.out_h + p.tile_rows - 1) / p.tile_rows, B);
+    kern<<<grid, K1_THREADS, smem, stream>>>(tmap, p);
+    FSD_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return FSD_OK;
+}
+
+}  // namespace fsd
+
+using namespace fsd;
+
+extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n_images, int H, int W,
+                                    int64_t row_pitch, int64_t image_pitch, const int32_t* entries, int B,
+                                    int src_w, int src_h, int imgsz, int stride, int reverse_channels,
+                                    int dtype, void* out, void* stream_) {
+    FSD_CHECK_ARG(h && images && entries && out, "fsd_gather_letterbox: null argument");
+    FSD_CHECK_ARG(n_images > 0 && H > 0 && W > 0 && B >= 0, "fsd_gather_letterbox: bad sizes");
+    FSD_CHECK_ARG(src_w > 0 && src_h > 0 && src_w <= W && src_h <= H, "fsd_gather_letterbox: source box %dx%d does not fit image %dx%d", src_w, src_h, W, H);
+    FSD_CHECK_ARG(dtype == FSD_F16 || dtype == FSD_F32, "fsd_gather_letterbox: dtype must be FSD_F16 or FSD_F32");
+    FSD_CHECK_ARG(B <= 65535, "fsd_gather_letterbox: at most 65535 entries per call");
+    if (((uintptr_t)images & 15) || (row_pitch & 15) || (image_pitch & 15) || row_pitch < (int64_t)W * 3 ||
+        (n_images > 1 && image_pitch < row_pitch * H)) {
+        set_error("fsd_gather_letterbox: image base/row_pitch/image_pitch must be 16-byte multiples and cover the image");
+        return FSD_ERR_ALIGN;
+    }
+    if (B == 0) return FSD_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::lock_guard<std::mutex> lock(h->mu);
+    FSD_CUDA(cudaSetDevice(h->device));
+
+    int32_t geom[8];
+    double gain;
+    int rc = fsd_letterbox_geometry(src_h, src_w, imgsz, stride, geom, &gain);
+    if (rc) return rc;
+    K1Params p;
+    p.entries = entries;
+    p.out = out;
+    p.src_w = src_w; p.src_h = src_h;
+    p.new_w = geom[0]; p.new_h = geom[1]; p.pad_left = geom[2]; p.pad_top = geom[3];
+    p.out_w = geom[4]; p.out_h = geom[5];
+    p.reverse = reverse_channels ? 1 : 0;
+    const int mode = geom[6] == 2 ? K1_MODE_AREA2 : K1_MODE_LINEAR;  // copy == linear with identity tables
+    FSD_CHECK_ARG(p.out_w % 8 == 0, "fsd_gather_letterbox: network input width %d must be a multiple of 8", p.out_w);
+
+    std::vector<int32_t> xt, yt;
+    const int32_t *xdev, *ydev;
+    rc = get_table(h, src_w, p.new_w, mode, true, &xdev, &xt);
+    if (rc) return rc;
+    rc = get_table(h, src_h, p.new_h, mode, false, &ydev, &yt);
+    if (rc) return rc;
+    p.xtab = reinterpret_cast<const int2*>(xdev);
+    p.ytab = reinterpret_cast<const int4*>(ydev);
+
+    // tile shape: widest TC whose source strip fits one 1024-byte TMA box row, tallest TR within the smem budget
+    const int tcs[] = {256, 128, 64, 32, 16, 8};
+    const int trs[] = {32, 16, 8, 4, 2, 1};
+    const size_t smem_budget = 56 * 1024;
+    int TC = 0, TR = 0, box_w = 0, box_rows = 0;
+    size_t smem = 0;
+    for (int tc : tcs) {
+        int need = 0;  // bytes of one source row needed by any tile of width tc (+15: the box starts 16-byte aligned)
+        for (int X0 = 0; X0 < p.out_w; X0 += tc) {
+            int lo = X0 - p.pad_left > 0 ? X0 - p.pad_left : 0;
+            int hi = (X0 + tc - p.pad_left < p.new_w ? X0 + tc - p.pad_left : p.new_w) - 1;
+            if (lo > hi) continue;
+            int s_lo = xt[2 * lo], s_hi = xt[2 * hi] + 1 < src_w ? xt[2 * hi] + 1 : src_w - 1;
+            int bytes = (s_hi - s_lo + 1) * 3 + 15;
+            if (bytes > need) need = bytes;
+        }
+        if (need > 1024) continue;
+        int bw = ((need + 15) / 16) * 4;  // u32 elements, inner box bytes multiple of 16
+        if (bw < 4) bw = 4;
+        for (int tr : trs) {
+            int rows = 1;
+            for (int Y0 = 0; Y0 < p.out_h; Y0 += tr) {
+                int lo = Y0 - p.pad_top > 0 ? Y0 - p.pad_top : 0;
+                int hi = (Y0 + tr - p.pad_top < p.new_h ? Y0 + tr - p.pad_top : p.new_h) - 1;
+                if (lo > hi) continue;
+                int r = yt[4 * hi + 1] - yt[4 * lo + 0] + 1;
+                if (r > rows) rows = r;
+            }
+            if (rows > 256) continue;
+            size_t s = (((size_t)bw * 4 * rows + 127) & ~(size_t)127) + (((size_t)rows * 3 * tc * 2 + 127) & ~(size_t)127) + 32 * 16 + 16 + 128;
+            if (s <= smem_budget) { TC = tc; TR = tr; box_w = bw; box_rows = rows; smem = s; break; }
+        }
+        if (TC) break;
+    }
+    if (!TC) {
+        set_error("fsd_gather_letterbox: resize %dx%d -> %dx%d exceeds the tile limits", src_w, src_h, p.new_w, p.new_h);
+        return FSD_ERR_CAPACITY;
+    }
+    p.tile_cols = TC; p.tile_rows = TR; p.box_w_elems = box_w; p.box_rows = box_rows;
+
+    // TMA tensor map over the image pool: u32 elements, dims {pitch/4, H, N}
+    if (n_images == 1) image_pitch = row_pitch * H;
+    auto key = std::make_tuple((uintptr_t)images, n_images, H, row_pitch, image_pitch, box_w, box_rows);
+    auto it = h->tensor_maps.find(key);
+    if (it == h->tensor_maps.end()) {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+        CUtensorMap m;
+        cuuint64_t gdim[3] = {(cuuint64_t)(row_pitch / 4), (cuuint64_t)H, (cuuint64_t)n_images};
+        cuuint64_t gstr[2] = {(cuuint64_t)row_pitch, (cuuint64_t)image_pitch};
+        cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = ((encode_fn)h->encode_tiled)(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)images, gdim,
+                                                  gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("fsd_gather_letterbox: cuTensorMapEncodeTiled failed with CUresult %d (pitch %lld, H %d, box %dx%d)",
+                      (int)r, (long long)row_pitch, H, box_w, box_rows);
+            return FSD_ERR_CUDA;
+        }
+        if (h->tensor_maps.size() > 256) h->tensor_maps.clear();
+        it = h->tensor_maps.emplace(key, m).first;
+    }
+    const CUtensorMap& tmap = it->second;
+
+    if (mode == K1_MODE_AREA2) {
+        return dtype == FSD_F16 ? launch<K1_MODE_AREA2, __half>(h, tmap, p, B, smem, stream)
+                                : launch<K1_MODE_AREA2, float>(h, tmap, p, B, smem, stream);
+    }
+    return dtype == FSD_F16 ? launch<K1_MODE_LINEAR, __half>(h, tmap, p, B, smem, stream)
+                            : launch<K1_MODE_LINEAR, float>(h, tmap, p, B, smem, stream);
+}

@@ -1,0 +1,160 @@
+/*
+ * fsd_b200.h — C ABI of the B200-native sliced face-detection hot path.
+ *
+ * The reference (ihsanhadi57/Face-Detection-With-YOLOv11-SAHI-and-Real-ESRGAN) is pure Python and has
+ * no FFI of its own: its plug-in boundary is the SAHI `DetectionModel` class protocol
+ * (docs sahi/base.py:12-196) and `get_sliced_prediction` (docs sahi/predict.py:142-345).
+ * This header is the boundary that sits UNDER that Python surface.  Each entry point names the
+ * reference code it replaces (file:line relative to the reference root; "[EXT …]" marks arithmetic that
+ * lives in an un-vendored dependency and is restated in SURVEY.md Appendix A).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative fsd_status; fsd_last_error() gives a
+ *     thread-local message for the last failure on the calling thread;
+ *   - all `dev` pointers are caller-allocated device memory, never retained or freed by the library;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and are asynchronous w.r.t. the host;
+ *   - no torch types, no global state beyond the handle.
+ */
+#ifndef FSD_B200_H
+#define FSD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fsd_context* fsd_handle_t;
+
+enum fsd_status {
+    FSD_OK = 0,
+    FSD_ERR_ARG = -1,      /* bad argument (null pointer, negative size, unsupported enum) */
+    FSD_ERR_ALIGN = -2,    /* pointer / pitch alignment not met (TMA needs 16-byte pitches) */
+    FSD_ERR_CUDA = -3,     /* a CUDA runtime/driver call failed */
+    FSD_ERR_CAPACITY = -4, /* problem larger than the compiled limits (see the function's doc) */
+    FSD_ERR_NO_DEVICE = -5 /* no sm_100 device visible: there is NO CPU fallback */
+};
+
+enum fsd_dtype { FSD_F16 = 0, FSD_F32 = 1 };
+enum fsd_merge_type { FSD_NMS = 0, FSD_GREEDYNMM = 1, FSD_NMM = 2 };
+enum fsd_metric { FSD_IOU = 0, FSD_IOS = 1 };
+enum fsd_layout { FSD_PLANAR = 0 /* [B,C,A] (NCHW) */, FSD_CHANNELS_LAST = 1 /* [B,A,C] (NHWC) */ };
+
+/* ---- library / handle -------------------------------------------------------------------------- */
+const char* fsd_version(void);
+const char* fsd_last_error(void);
+int fsd_create(int device, fsd_handle_t* out);
+int fsd_destroy(fsd_handle_t h);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches claim) */
+int64_t fsd_launch_count(fsd_handle_t h);
+
+/* ---- (a2) slice plan — replaces sahi.slicing.get_slice_bboxes [EXT sahi 0.11.34], called at
+ *      docs sahi/predict.py:229-238.  Host-side, integer exact.  boxes_xyxy holds up to `cap` rows of
+ *      [x0,y0,x1,y1]; *n receives the number of slices (also when it exceeds cap -> FSD_ERR_CAPACITY). */
+int fsd_slice_plan(int image_h, int image_w, int slice_h, int slice_w, double overlap_h_ratio,
+                   double overlap_w_ratio, int32_t* boxes_xyxy, int cap, int* n);
+
+/* ---- (a4) letterbox geometry — replaces ultralytics LetterBox(auto=True, scaleup=True, center=True)
+ *      [EXT ultralytics], reached from utils/yolo_wrapper.py:74-80.  Host-side.  geom[0..7] =
+ *      new_w, new_h (resized, un-padded), pad_left, pad_top, out_w, out_h, mode, reserved;
+ *      mode: 0 copy (no resize), 1 cv2 INTER_LINEAR fixed point, 2 cv2 exact-2x area average.
+ *      *gain = min(out_h/src_h, out_w/src_w) as ultralytics scale_boxes recomputes it. */
+int fsd_letterbox_geometry(int src_h, int src_w, int imgsz, int stride, int32_t geom[8], double* gain);
+
+/* ---- Kernel 1 (a4) fused slice gather + letterbox + u8 -> fp16/fp32 normalise.
+ *      Replaces numpy slice views (docs sahi/predict.py:270-276), np.ascontiguousarray (:106) and
+ *      ultralytics preprocess (cv2.resize INTER_LINEAR, copyMakeBorder 114, [..., ::-1], HWC->CHW, /255).
+ *      images: dev, n_images x [H, row_pitch] bytes of HWC uint8 (3 channels), image i at i*image_pitch;
+ *              base pointer, row_pitch and image_pitch must be multiples of 16 (TMA tensor-map rule).
+ *      entries: dev int32 [B,3] = (image_index, x0, y0) of each source box; all boxes are src_w x src_h.
+ *      out: dev [B,3,out_h,out_w] of dtype, with out_h/out_w from fsd_letterbox_geometry. */
+int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n_images, int H, int W,
+                         int64_t row_pitch, int64_t image_pitch, const int32_t* entries, int B, int src_w,
+                         int src_h, int imgsz, int stride, int reverse_channels, int dtype, void* out,
+                         void* stream);
+
+/* ---- Kernel 2a (a6,a7) fused pose-head decode + confidence gate + compaction.
+ *      Replaces ultralytics Detect/Pose._inference, DFL, dist2bbox, kpts_decode and the `xc` candidate
+ *      filter of non_max_suppression [EXT ultralytics], reached from utils/yolo_wrapper.py:74-80.
+ *      Per level l (strides 8,16,32): box[l] [B,64,h_l*w_l], cls[l] [B,1,...], kpt[l] [B,15,...] in
+ *      `layout`/`dtype`.  A candidate row is 24 floats:
+ *        [x1,y1,x2,y2 (letterboxed px), score, anchor_index, 15 kpt values (x,y,conf)x5, 3 pad].
+ *      Candidates of batch entry b are written to cand[b*cap_per_entry ...] in anchor order is NOT
+ *      guaranteed; `anchor_index` makes any later ordering deterministic.  count[b] receives the number of
+ *      candidates found (may exceed cap_per_entry: the excess is dropped and reported by the caller). */
+int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const void* const cls[3],
+                    const void* const kpt[3], const int32_t level_hw[6], int B, int layout, int dtype,
+                    float conf, float* cand, int cap_per_entry, int32_t* count, void* stream);
+
+/* ---- Kernel 3 (a7,a12) batched segment NMS / GREEDYNMM / NMM.
+ *      Replaces torchvision.ops.nms inside ultralytics non_max_suppression (stage 1: per slice, IOU,
+ *      thr 0.7, strict >, fp32, max_keep 300) and sahi.postprocess.combine.{NMS,GreedyNMM,NMM}Postprocess
+ *      with has_match + merge_object_prediction_pair [EXT sahi 0.11.34] (stage 2: per image), selected at
+ *      docs sahi/predict.py:44-49,250-259 and run at :297,:319.
+ *      boxes [N,4] f32 with row stride box_stride floats, scores [N] with stride score_stride, cats [N]
+ *      int32 or NULL; tie [N] int32 tie-break keys or NULL (then the index inside the segment is used);
+ *      segment s covers rows seg_offsets[s] .. seg_offsets[s]+seg_counts[s]-1.
+ *      cmp_strict: 0 -> match if metric >= thr (sahi), 1 -> metric > thr (torchvision).
+ *      precision:  0 -> fp64 metric (sahi 0.11.34), 1 -> fp32 metric (torchvision / old sahi).
+ *      Outputs (all dev): keep [N] global row ids in score-descending order per segment (written from
+ *      seg_offsets[s]); keep_count [S]; parent [N] = global row id of the keep a row was merged into, its
+ *      own id for keeps, -1 for rows dropped without merge; merged_boxes [N,4] and merged_scores [N]
+ *      (indexed like keep, union box after the has_match replay; for NMS a copy of the kept row).
+ *      workspace: dev scratch of at least fsd_merge_workspace_bytes(N, S, max_segment) bytes. */
+int64_t fsd_merge_workspace_bytes(int64_t N, int S, int max_segment);
+int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, const float* scores, int score_stride,
+              const int32_t* cats, const int32_t* tie, const int32_t* seg_offsets,
+              const int32_t* seg_counts, int S, int max_segment, int64_t N, int type, int metric,
+              double thr, int cmp_strict, int precision, int class_agnostic, int pre_cap, int max_keep,
+              int32_t* keep, int32_t* keep_count, int32_t* parent, float* merged_boxes,
+              float* merged_scores, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- Kernel 2b (a8-a11) finalize kept detections: un-letterbox (scale_boxes / scale_coords / clip),
+ *      int() truncation, + slice shift.  Replaces ultralytics scale_boxes/scale_coords/clip_boxes [EXT],
+ *      utils/yolo_wrapper.py:137-159 (astype(int), +shift, keypoints +shift), sahi ObjectAnnotation clamp
+ *      [EXT] and ObjectPrediction.get_shifted_object_prediction (docs sahi/prediction.py:94-120).
+ *      cand: Kernel 2a rows; keep/keep_count: Kernel 3 stage-1 output with one segment per batch entry
+ *      (segment b starts at b*cap_per_entry); entry_geom [B,8] int32 = (shift_x, shift_y, src_w, src_h,
+ *      pad_left, pad_top, full_w, full_h); entry_gain [B] f32.
+ *      Output rows are packed per group: group_of_entry [B] int32 (e.g. image id), group_offsets [G] int32 =
+ *      first output row of each group; out_count [G] must be zero on entry and receives rows per group.
+ *      det rows are 24 floats: [x1,y1,x2,y2 (full-image ints as float), score, entry, 15 kpts, order key,
+ *      2 pad]; rows of a group are written in (entry, stage-1 rank) order. */
+int fsd_finalize_dets(fsd_handle_t h, const float* cand, int cap_per_entry, const int32_t* keep,
+                      const int32_t* keep_count, int B, const int32_t* entry_geom, const float* entry_gain,
+                      const int32_t* group_of_entry, const int32_t* group_offsets, int G, int truncate,
+                      float* det, int32_t* out_count, void* stream);
+
+/* ---- Kernel 4 (a15) Real-ESRGAN tile crop / stitch.  Replaces RealESRGANer.enhance/pre_process/
+ *      tile_process/post_process [EXT realesrgan 0.3.0], reached from utils/enhancer.py:214.
+ *      fsd_esrgan_tile_table: host-side tile table; each row = 12 int32:
+ *        [px0,py0,pw,ph (padded input rect), in_x0,in_y0,in_w,in_h (interior), tile_elem_offset_lo,
+ *         tile_elem_offset_hi, out_elem_offset_lo, out_elem_offset_hi]
+ *      (offsets in elements into the packed tile buffers: input tiles 3*ph*pw each, output tiles
+ *       3*(ph*scale)*(pw*scale) each).  padded_hw receives the mod-padded H,W. */
+int fsd_esrgan_tile_table(int H, int W, int scale, int tile, int tile_pad, int pre_pad, int32_t* table,
+                          int cap, int* n_tiles, int32_t padded_hw[2]);
+/* crop: u8 HWC BGR image -> packed [3,ph,pw] RGB tiles of dtype, value/255, reflect pre-/mod-pad folded in */
+int fsd_esrgan_crop(fsd_handle_t h, const uint8_t* bgr, int H, int W, int64_t row_pitch, int pad_h,
+                    int pad_w, const int32_t* table_dev, int T, int dtype, void* tiles, void* stream);
+/* stitch: packed [3,ph*s,pw*s] RGB network outputs -> u8 HWC BGR [H*s, W*s]; clamp(0,1)*255 round-half-even */
+int fsd_esrgan_stitch(fsd_handle_t h, const void* tiles_out, const int32_t* table_dev, int T, int scale,
+                      int dtype, uint8_t* out_bgr, int out_h, int out_w, int64_t out_pitch, void* stream);
+
+/* ---- (f1) WIDER-FACE evaluation IoU — replaces the Cython bbox_overlaps of WiderFace-Evaluation,
+ *      imported at eval/eval_official_widerface.py:20-33 and called at :330.  boxes [N,4], query [K,4]
+ *      xyxy f64 (dev); overlaps [N,K] f64 (dev), "+1" pixel convention. */
+int fsd_bbox_overlaps_p1(fsd_handle_t h, const double* boxes, int N, const double* query, int K,
+                         double* overlaps, void* stream);
+
+/* ---- (f2) keypoint attach — replaces YOLOv11PoseDetectionModel.attach_keypoints_to_predictions
+ *      (utils/yolo_wrapper.py:168-217) for ONE image: for each merged box pick the LAST stage-1 detection
+ *      with the identical int box, else the FIRST detection with the largest IoU if that IoU > 0.5.
+ *      merged [M,4] f32, dets [D,4] f32 (row strides given in floats), src_index [M] int32 (-1: none). */
+int fsd_attach_keypoints(fsd_handle_t h, const float* merged, int merged_stride, int M, const float* dets,
+                         int det_stride, int D, int32_t* src_index, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSD_B200_H */

@@ -1,0 +1,78 @@
+"""Kernel 1 parity: fused slice gather + letterbox + normalise vs the cv2/torch oracle (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import letterbox as olb
+from oracle import slicing as osl
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_batch(images, entries, src_w, src_h, imgsz, half, reverse):
+    outs = []
+    for (i, x0, y0) in entries:
+        crop = np.ascontiguousarray(images[i][y0:y0 + src_h, x0:x0 + src_w])
+        if not reverse:  # ultralytics always flips; feed pre-flipped data to model "no flip"
+            crop = np.ascontiguousarray(crop[..., ::-1])
+        outs.append(olb.preprocess(crop, imgsz=imgsz, half=half))
+    return torch.cat(outs, 0)
+
+
+CASES = [
+    # (H, W, slice_h, slice_w, overlap, imgsz)                      what it exercises
+    (768, 1024, 512, 512, 0.2, 1024),     # C2: exact 2x up-scale
+    (1080, 1920, 640, 640, 0.2, 1024),    # C1: 1.6x up-scale
+    (480, 750, 640, 640, 0.2, 1024),      # image smaller than slice, odd pitch (2250 B rows)
+    (1366, 2048, 640, 640, 0.25, 1024),   # real WIDER size
+    (333, 517, 200, 300, 0.1, 640),       # odd everything, non-square slices, letterbox padding
+    (600, 800, 512, 512, 0.2, 512),       # imgsz == slice: pure copy
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_slices_match_oracle(cuda_device, case, dtype):
+    import fsd_b200.ops as ops
+
+    H, W, sh, sw, ov, imgsz = case
+    rng = np.random.default_rng(1234)
+    images = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(2)]
+    boxes = osl.get_slice_bboxes(H, W, sh, sw, overlap_height_ratio=ov, overlap_width_ratio=ov)
+    bw, bh = boxes[0][2] - boxes[0][0], boxes[0][3] - boxes[0][1]
+    entries = [(i, b[0], b[1]) for i in range(2) for b in boxes]
+    pool = ops.ImagePool.from_numpy(images, cuda_device)
+    out = ops.gather_letterbox(pool, torch.tensor(entries, dtype=torch.int32), bw, bh, imgsz=imgsz, dtype=dtype)
+    ref = _oracle_batch(images, entries, bw, bh, imgsz, dtype == torch.float16, True)
+    assert out.shape == ref.shape
+    assert torch.equal(out.cpu(), ref), f"max diff {(out.cpu().float() - ref.float()).abs().max()}"
+
+
+@pytest.mark.parametrize("shape", [(1080, 1920), (768, 1024), (2160, 3840), (1366, 2048), (2340, 4160), (37, 53)])
+def test_full_image_pass_matches_oracle(cuda_device, shape):
+    """The perform_standard_pred pass: down-scale (r<1), copy (r==1), exact-2x area path, tiny up-scale."""
+    import fsd_b200.ops as ops
+
+    H, W = shape
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    pool = ops.ImagePool.from_numpy([img], cuda_device)
+    for dtype in (torch.float16, torch.float32):
+        for reverse in (True, False):
+            out = ops.gather_letterbox(pool, torch.tensor([[0, 0, 0]], dtype=torch.int32), W, H, imgsz=1024,
+                                       dtype=dtype, reverse_channels=reverse)
+            ref = _oracle_batch([img], [(0, 0, 0)], W, H, 1024, dtype == torch.float16, reverse)
+            assert torch.equal(out.cpu(), ref)
+
+
+def test_bad_pitch_is_rejected(cuda_device):
+    import fsd_b200._cabi as cabi
+    import fsd_b200.ops as ops
+
+    pool = ops.ImagePool(1, 64, 64, cuda_device)
+    h = cabi.get_handle(0)
+    out = torch.empty((1, 3, 64, 64), dtype=torch.float16, device=cuda_device)
+    ent = torch.zeros((1, 3), dtype=torch.int32, device=cuda_device)
+    rc = h.lib.fsd_gather_letterbox(h.h, pool.buf.data_ptr(), 1, 64, 64, 64 * 3 + 2, 0, ent.data_ptr(), 1, 64, 64,
+                                    64, 32, 1, 0, out.data_ptr(), 0)
+    assert rc == -2 and b"16-byte" in h.lib.fsd_last_error()
