@@ -30,19 +30,19 @@ SIGNATURES = {
     "fsd_pose_decode": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), c_i32p, C.c_int, C.c_int,
                                   C.c_int, C.c_float, vp, C.c_int, vp, vp]),
     "fsd_merge_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
-    "fsd_merge": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int,
-                            C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp,
-                            vp, vp, C.c_int64, vp]),
-    "fsd_finalize_dets": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp,
-                                    vp]),
+    "fsd_merge": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int,
+                            C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
+                            vp, vp, vp, vp, C.c_int64, vp]),
+    "fsd_finalize_dets": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp,
+                                    C.c_int, vp, vp]),
     "fsd_esrgan_tile_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int,
                                         C.POINTER(C.c_int), c_i32p]),
-    "fsd_esrgan_crop": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, C.c_int, C.c_int,
+    "fsd_esrgan_crop": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
                                   vp, vp]),
-    "fsd_esrgan_stitch": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int64,
+    "fsd_esrgan_stitch": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int64,
                                     vp]),
     "fsd_bbox_overlaps_p1": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp]),
-    "fsd_attach_keypoints": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp]),
+    "fsd_attach_keypoints": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
 }
 
 FSD_F16, FSD_F32 = 0, 1

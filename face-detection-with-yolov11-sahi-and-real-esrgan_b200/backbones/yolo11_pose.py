@@ -1,0 +1,245 @@
+"""YOLO11-pose in plain PyTorch (random-init; there is no network for checkpoints).
+
+Architecture follows ultralytics' `yolo11-pose.yaml` as recorded in SURVEY.md App. A.4.1 — the model the
+reference loads through `ultralytics.YOLO(model_path)` at utils/yolo_wrapper.py:55 ([EXT ultralytics]).
+Conv+BN pairs are built already fused (ultralytics fuses them before inference), so `Conv` = Conv2d(bias) + SiLU.
+
+The module stops at the raw per-level head convolutions: `forward` returns
+    [(box [B,64,h,w], cls [B,nc,h,w], kpt [B,15,h,w]) for stride in (8,16,32)]
+and the decode (DFL, anchors, sigmoid, key-points, NMS) is Kernel 2/3's job (or oracle/yolo_head.py on the CPU).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _make_divisible(x, divisor=8):
+    return int(math.ceil(x / divisor) * divisor)
+
+
+class Conv(nn.Module):
+    def __init__(self, c1, c2, k=1, s=1, g=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, k // 2, groups=g, bias=True)
+        self.act = nn.SiLU(inplace=True) if act else nn.Identity()
+
+    def forward(self, x):
+        return self.act(self.conv(x))
+
+
+class DWConv(Conv):
+    def __init__(self, c1, c2, k=1, s=1, act=True):
+        super().__init__(c1, c2, k, s, g=math.gcd(c1, c2), act=act)
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, c1, c2, shortcut=True, k=(3, 3), e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, k[0], 1)
+        self.cv2 = Conv(c_, c2, k[1], 1)
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x):
+        return x + self.cv2(self.cv1(x)) if self.add else self.cv2(self.cv1(x))
+
+
+class C3k(nn.Module):
+    def __init__(self, c1, c2, n=2, shortcut=True, e=0.5, k=3):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1, self.cv2, self.cv3 = Conv(c1, c_, 1, 1), Conv(c1, c_, 1, 1), Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, k=(k, k), e=1.0) for _ in range(n)))
+
+    def forward(self, x):
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+
+
+class C3k2(nn.Module):
+    def __init__(self, c1, c2, n=1, c3k=False, e=0.5, shortcut=True):
+        super().__init__()
+        self.c = int(c2 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
+        self.cv2 = Conv((2 + n) * self.c, c2, 1)
+        self.m = nn.ModuleList(C3k(self.c, self.c, 2, shortcut) if c3k else Bottleneck(self.c, self.c, shortcut)
+                               for _ in range(n))
+
+    def forward(self, x):
+        y = list(self.cv1(x).chunk(2, 1))
+        y.extend(m(y[-1]) for m in self.m)
+        return self.cv2(torch.cat(y, 1))
+
+
+class SPPF(nn.Module):
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1, self.cv2 = Conv(c1, c_, 1, 1), Conv(c_ * 4, c2, 1, 1)
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+
+    def forward(self, x):
+        y = [self.cv1(x)]
+        y.extend(self.m(y[-1]) for _ in range(3))
+        return self.cv2(torch.cat(y, 1))
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, num_heads=8, attn_ratio=0.5):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.key_dim = int(self.head_dim * attn_ratio)
+        self.scale = self.key_dim ** -0.5
+        h = dim + self.key_dim * num_heads * 2
+        self.qkv = Conv(dim, h, 1, act=False)
+        self.proj = Conv(dim, dim, 1, act=False)
+        self.pe = Conv(dim, dim, 3, 1, g=dim, act=False)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        N = H * W
+        qkv = self.qkv(x)
+        q, k, v = qkv.reshape(B, self.num_heads, self.key_dim * 2 + self.head_dim, N).split(
+            [self.key_dim, self.key_dim, self.head_dim], dim=2)
+        attn = (q.transpose(-2, -1) @ k) * self.scale
+        attn = attn.softmax(dim=-1)
+        x = (v @ attn.transpose(-2, -1)).reshape(B, C, H, W) + self.pe(v.reshape(B, C, H, W))
+        return self.proj(x)
+
+
+class PSABlock(nn.Module):
+    def __init__(self, c, attn_ratio=0.5, num_heads=4):
+        super().__init__()
+        self.attn = Attention(c, num_heads=num_heads, attn_ratio=attn_ratio)
+        self.ffn = nn.Sequential(Conv(c, c * 2, 1), Conv(c * 2, c, 1, act=False))
+
+    def forward(self, x):
+        x = x + self.attn(x)
+        return x + self.ffn(x)
+
+
+class C2PSA(nn.Module):
+    def __init__(self, c1, c2, n=1, e=0.5):
+        super().__init__()
+        assert c1 == c2
+        self.c = int(c1 * e)
+        self.cv1, self.cv2 = Conv(c1, 2 * self.c, 1, 1), Conv(2 * self.c, c1, 1)
+        self.m = nn.Sequential(*(PSABlock(self.c, attn_ratio=0.5, num_heads=max(1, self.c // 64)) for _ in range(n)))
+
+    def forward(self, x):
+        a, b = self.cv1(x).split((self.c, self.c), dim=1)
+        return self.cv2(torch.cat((a, self.m(b)), 1))
+
+
+class PoseHead(nn.Module):
+    """ultralytics Pose(Detect) head up to (and including) the last 1x1 convolutions of cv2/cv3/cv4."""
+
+    def __init__(self, nc, kpt_shape, ch):
+        super().__init__()
+        self.nc, self.kpt_shape, self.reg_max = nc, tuple(kpt_shape), 16
+        self.nk = kpt_shape[0] * kpt_shape[1]
+        c2, c3 = max(16, ch[0] // 4, self.reg_max * 4), max(ch[0], min(nc, 100))
+        c4 = max(ch[0] // 4, self.nk)
+        self.cv2 = nn.ModuleList(nn.Sequential(Conv(x, c2, 3), Conv(c2, c2, 3), nn.Conv2d(c2, 4 * self.reg_max, 1))
+                                 for x in ch)
+        self.cv3 = nn.ModuleList(nn.Sequential(nn.Sequential(DWConv(x, x, 3), Conv(x, c3, 1)),
+                                               nn.Sequential(DWConv(c3, c3, 3), Conv(c3, c3, 1)),
+                                               nn.Conv2d(c3, nc, 1)) for x in ch)
+        self.cv4 = nn.ModuleList(nn.Sequential(Conv(x, c4, 3), Conv(c4, c4, 3), nn.Conv2d(c4, self.nk, 1)) for x in ch)
+
+    def forward(self, feats):
+        return [(self.cv2[i](x), self.cv3[i](x), self.cv4[i](x)) for i, x in enumerate(feats)]
+
+
+class YOLO11Pose(nn.Module):
+    strides = (8, 16, 32)
+
+    def __init__(self, nc=1, kpt_shape=(5, 3), depth=0.50, width=0.25, max_channels=1024):
+        super().__init__()
+        ch = lambda c: _make_divisible(min(c, max_channels) * width, 8)  # noqa: E731
+        rep = lambda n: max(round(n * depth), 1)  # noqa: E731
+        c64, c128, c256, c512, c1024 = ch(64), ch(128), ch(256), ch(512), ch(1024)
+        self.nc, self.kpt_shape = nc, tuple(kpt_shape)
+        # backbone
+        self.b0 = Conv(3, c64, 3, 2)
+        self.b1 = Conv(c64, c128, 3, 2)
+        self.b2 = C3k2(c128, c256, rep(2), False, 0.25)
+        self.b3 = Conv(c256, c256, 3, 2)
+        self.b4 = C3k2(c256, c512, rep(2), False, 0.25)
+        self.b5 = Conv(c512, c512, 3, 2)
+        self.b6 = C3k2(c512, c512, rep(2), True)
+        self.b7 = Conv(c512, c1024, 3, 2)
+        self.b8 = C3k2(c1024, c1024, rep(2), True)
+        self.b9 = SPPF(c1024, c1024, 5)
+        self.b10 = C2PSA(c1024, c1024, rep(2))
+        # neck
+        self.h13 = C3k2(c1024 + c512, c512, rep(2), False)
+        self.h16 = C3k2(c512 + c512, c256, rep(2), False)
+        self.h17 = Conv(c256, c256, 3, 2)
+        self.h19 = C3k2(c256 + c512, c512, rep(2), False)
+        self.h20 = Conv(c512, c512, 3, 2)
+        self.h22 = C3k2(c512 + c1024, c1024, rep(2), True)
+        self.head = PoseHead(nc, kpt_shape, (c256, c512, c1024))
+
+    def forward(self, x):
+        x = self.b1(self.b0(x))
+        p3 = self.b4(self.b3(self.b2(x)))
+        p4 = self.b6(self.b5(p3))
+        p5 = self.b10(self.b9(self.b8(self.b7(p4))))
+        n4 = self.h13(torch.cat((F.interpolate(p5, scale_factor=2.0, mode="nearest"), p4), 1))
+        n3 = self.h16(torch.cat((F.interpolate(n4, scale_factor=2.0, mode="nearest"), p3), 1))
+        m4 = self.h19(torch.cat((self.h17(n3), n4), 1))
+        m5 = self.h22(torch.cat((self.h20(m4), p5), 1))
+        return self.head([n3, m4, m5])
+
+    @staticmethod
+    def anchors_for(h, w):
+        """number of anchors for a network input of h x w"""
+        return sum((h // s) * (w // s) for s in YOLO11Pose.strides)
+
+
+def _init_variance_preserving(model: nn.Module, gen: torch.Generator):
+    """Random init that keeps activations O(1) through ~100 SiLU convs so fp16 inference does not flush to zero."""
+    for m in model.modules():
+        if isinstance(m, nn.Conv2d):
+            fan_in = m.in_channels // m.groups * m.kernel_size[0] * m.kernel_size[1]
+            std = 1.6 / math.sqrt(fan_in)
+            with torch.no_grad():
+                m.weight.copy_(torch.randn(m.weight.shape, generator=gen) * std)
+                m.bias.zero_()
+
+
+@torch.no_grad()
+def calibrate_head(model: YOLO11Pose, sample: torch.Tensor, cls_logit_mean=-6.0, cls_logit_std=2.0,
+                   box_logit_std=1.5, kpt_std=1.0):
+    """Rescale the last 1x1 head convolutions so that random-init outputs look like a trained detector's:
+    a fraction of a percent of anchors pass conf=0.5, DFL bins are peaked, key-points are O(1) offsets.
+    Deterministic given the weights and `sample` (a fixed seeded image batch)."""
+    model.eval()
+    outs = model(sample)
+    for lvl, (box, cls, kpt) in enumerate(outs):
+        for branch, t, tgt_mean, tgt_std in ((model.head.cv2, box, 1.0, box_logit_std),
+                                             (model.head.cv3, cls, cls_logit_mean, cls_logit_std),
+                                             (model.head.cv4, kpt, 0.0, kpt_std)):
+            conv = branch[lvl][-1]
+            std = float(t.float().std())
+            mean = float(t.float().mean())
+            scale = tgt_std / max(std, 1e-6)
+            conv.weight.mul_(scale)
+            conv.bias.copy_((conv.bias - mean) * scale + tgt_mean)
+    return model
+
+
+def build_yolo11n_pose(seed: int = 0, calibrate: bool = True, nc: int = 1, kpt_shape=(5, 3)) -> YOLO11Pose:
+    """YOLO11n-pose (depth 0.50, width 0.25), nc=1 'face', 5 key-points x (x, y, conf); deterministic random init."""
+    gen = torch.Generator().manual_seed(seed)
+    model = YOLO11Pose(nc=nc, kpt_shape=kpt_shape)
+    _init_variance_preserving(model, gen)
+    if calibrate:
+        sample = torch.rand((1, 3, 256, 256), generator=gen)
+        calibrate_head(model, sample)
+    return model.eval()

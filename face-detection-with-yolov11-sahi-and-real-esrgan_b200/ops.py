@@ -89,3 +89,191 @@ def gather_letterbox(pool: ImagePool, entries: torch.Tensor, src_w: int, src_h: 
                                      1 if reverse_channels else 0, _TORCH_DTYPE[out.dtype], out.data_ptr(),
                                      _stream_ptr(pool.device)), "fsd_gather_letterbox")
     return out
+
+
+# ---- Kernel 2a ------------------------------------------------------------------------------------------
+ROW = 24  # floats per candidate / detection row (see include/fsd_b200.h)
+
+
+def _level_layout(levels):
+    """(layout, dtype) of the head tensors; all nine must agree and be dense in NCHW or channels-last order."""
+    t0 = levels[0][0]
+    layout = None
+    for lvl in levels:
+        for t in lvl:
+            _require_cuda(t, "head tensor")
+            if t.dtype != t0.dtype:
+                raise ValueError("head tensors must share one dtype")
+            if t.is_contiguous():
+                lay = _cabi.FSD_PLANAR
+            elif t.is_contiguous(memory_format=torch.channels_last):
+                lay = _cabi.FSD_CHANNELS_LAST
+            else:
+                raise ValueError("head tensors must be contiguous (NCHW) or channels_last")
+            if t.shape[1] == 1 or t.shape[2] * t.shape[3] == 1:
+                continue  # ambiguous strides: a 1-channel tensor is both layouts at once
+            if layout is None:
+                layout = lay
+            elif layout != lay:
+                raise ValueError("head tensors mix NCHW and channels_last")
+    return (layout if layout is not None else _cabi.FSD_PLANAR), _TORCH_DTYPE[t0.dtype]
+
+
+def pose_decode(levels, conf: float, cap_per_entry: int = 1024, cand: torch.Tensor | None = None,
+                count: torch.Tensor | None = None):
+    """Kernel 2a.  levels = [(box [B,64,h,w], cls [B,1,h,w], kpt [B,15,h,w])] for strides 8/16/32.
+    Returns (cand [B, cap, 24] f32, count [B] i32)."""
+    layout, dt = _level_layout(levels)
+    B = int(levels[0][0].shape[0])
+    dev = levels[0][0].device
+    if levels[0][1].shape[1] != 1 or levels[0][2].shape[1] != 15 or levels[0][0].shape[1] != 64:
+        raise ValueError("pose_decode expects nc=1, kpt_shape=(5,3), reg_max=16 head tensors")
+    if cand is None:
+        cand = torch.empty((B, cap_per_entry, ROW), dtype=torch.float32, device=dev)
+    if count is None:
+        count = torch.empty((B,), dtype=torch.int32, device=dev)
+    arr = lambda k: (C.c_void_p * 3)(*[lvl[k].data_ptr() for lvl in levels])  # noqa: E731
+    hw = (C.c_int32 * 6)(*[int(v) for lvl in levels for v in lvl[0].shape[2:]])
+    h = _handle_for(cand)
+    check(h.lib.fsd_pose_decode(h.h, arr(0), arr(1), arr(2), hw, B, layout, dt, float(conf), cand.data_ptr(),
+                                int(cand.shape[1]), count.data_ptr(), _stream_ptr(dev)), "fsd_pose_decode")
+    return cand, count
+
+
+# ---- Kernel 3 -------------------------------------------------------------------------------------------
+_MERGE_TYPE = {"NMS": _cabi.FSD_NMS, "GREEDYNMM": _cabi.FSD_GREEDYNMM, "NMM": _cabi.FSD_NMM}
+_METRIC = {"IOU": _cabi.FSD_IOU, "IOS": _cabi.FSD_IOS}
+
+
+def merge_segments(rows: torch.Tensor, seg_offsets: torch.Tensor, seg_counts: torch.Tensor | None, max_segment: int,
+                   merge_type="NMS", metric="IOU", thr=0.5, cmp_strict=False, precision="fp64", class_agnostic=True,
+                   pre_cap=0, max_keep=0, box_col=0, score_col=4, tie_col=None, cats: torch.Tensor | None = None,
+                   want_parent=True):
+    """Kernel 3 over a [N, R] float32 row matrix (boxes at box_col..+3, score at score_col, optional int-bits
+    tie-break key at tie_col).  Returns dict(keep, keep_count, parent, boxes, scores, cats)."""
+    _require_cuda(rows, "rows")
+    assert rows.dtype == torch.float32 and rows.dim() == 2 and rows.is_contiguous()
+    N, R = rows.shape
+    dev = rows.device
+    S = int(seg_offsets.shape[0])
+    keep = torch.empty((N,), dtype=torch.int32, device=dev)
+    keep_count = torch.empty((S,), dtype=torch.int32, device=dev)
+    parent = torch.full((N,), -1, dtype=torch.int32, device=dev) if want_parent else None
+    mboxes = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    mscores = torch.empty((N,), dtype=torch.float32, device=dev)
+    mcats = torch.empty((N,), dtype=torch.int32, device=dev) if cats is not None else None
+    h = _handle_for(rows)
+    ws_bytes = int(h.lib.fsd_merge_workspace_bytes(N, S, int(max_segment)))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    base = rows.data_ptr()
+    check(h.lib.fsd_merge(h.h, base + 4 * box_col, R, base + 4 * score_col, R,
+                          _ptr(cats), 1, (base + 4 * tie_col) if tie_col is not None else 0, R,
+                          seg_offsets.data_ptr(), _ptr(seg_counts), S, int(max_segment),
+                          _MERGE_TYPE[merge_type], _METRIC[metric], float(thr), 1 if cmp_strict else 0,
+                          0 if precision == "fp64" else 1, 1 if class_agnostic else 0, int(pre_cap), int(max_keep),
+                          keep.data_ptr(), keep_count.data_ptr(), _ptr(parent), mboxes.data_ptr(),
+                          mscores.data_ptr(), _ptr(mcats), ws.data_ptr(), ws_bytes, _stream_ptr(dev)), "fsd_merge")
+    return dict(keep=keep, keep_count=keep_count, parent=parent, boxes=mboxes, scores=mscores, cats=mcats)
+
+
+# ---- Kernel 2b ------------------------------------------------------------------------------------------
+def finalize_dets(cand, keep, keep_count, entry_geom, entry_fgeom, group_range, group_offsets, det, out_count,
+                  det_cap_per_group: int, truncate: bool = True):
+    """Kernel 2b: append the kept rows of every entry to its image's detection list (see the header)."""
+    B, cap = int(cand.shape[0]), int(cand.shape[1])
+    G = int(group_range.shape[0])
+    h = _handle_for(cand)
+    check(h.lib.fsd_finalize_dets(h.h, cand.data_ptr(), cap, keep.data_ptr(), keep_count.data_ptr(), B,
+                                  entry_geom.data_ptr(), entry_fgeom.data_ptr(), group_range.data_ptr(),
+                                  group_offsets.data_ptr(), G, 1 if truncate else 0, det.data_ptr(),
+                                  int(det_cap_per_group), out_count.data_ptr(), _stream_ptr(cand.device)),
+          "fsd_finalize_dets")
+    return det, out_count
+
+
+# ---- Kernel 4 -------------------------------------------------------------------------------------------
+def esrgan_tile_table(H: int, W: int, scale: int, tile: int, tile_pad: int = 10, pre_pad: int = 0):
+    """Host tile table [T,12] int32 + (padded_h, padded_w)."""
+    lib = _cabi.load_library()
+    n = C.c_int(0)
+    hw = (C.c_int32 * 2)()
+    check(lib.fsd_esrgan_tile_table(H, W, scale, tile, tile_pad, pre_pad, None, 0, C.byref(n), hw), "fsd_esrgan_tile_table")
+    tab = np.zeros((max(1, n.value), 12), dtype=np.int32)
+    check(lib.fsd_esrgan_tile_table(H, W, scale, tile, tile_pad, pre_pad, tab.ctypes.data_as(_cabi.c_i32p),
+                                    n.value, C.byref(n), hw), "fsd_esrgan_tile_table")
+    return tab[: n.value], (int(hw[0]), int(hw[1]))
+
+
+def _off64(row, k):
+    return int(np.uint32(row[k])) | (int(row[k + 1]) << 32)
+
+
+def esrgan_crop(img: torch.Tensor, table: np.ndarray, scale: int, pre_pad: int = 0, dtype=torch.float16):
+    """Kernel 4a: img [H,W,3] uint8 BGR (CUDA, row-contiguous) -> (packed tile buffer, table on device)."""
+    _require_cuda(img, "image")
+    H, W = int(img.shape[0]), int(img.shape[1])
+    assert img.dtype == torch.uint8 and img.stride(2) == 1 and img.stride(1) == 3
+    last = table[-1]
+    total = _off64(last, 8) + (3 * int(last[2]) * int(last[3]) + 7) // 8 * 8
+    tiles = torch.empty((total,), dtype=dtype, device=img.device)
+    tab_host = np.ascontiguousarray(table, dtype=np.int32)
+    tab_dev = torch.from_numpy(tab_host).to(img.device)
+    h = _handle_for(img)
+    check(h.lib.fsd_esrgan_crop(h.h, img.data_ptr(), H, W, img.stride(0), H + pre_pad, W + pre_pad,
+                                tab_dev.data_ptr(), tab_host.ctypes.data, len(tab_host), _TORCH_DTYPE[dtype],
+                                tiles.data_ptr(), _stream_ptr(img.device)), "fsd_esrgan_crop")
+    return tiles, tab_dev
+
+
+def tile_view(buf: torch.Tensor, row, scale: int = 1, out: bool = False) -> torch.Tensor:
+    """[1,3,h,w] view of one tile inside a packed buffer (input tiles: out=False; network outputs: out=True)."""
+    off = _off64(row, 10 if out else 8)
+    h, w = int(row[3]) * scale, int(row[2]) * scale
+    return buf[off: off + 3 * h * w].view(1, 3, h, w)
+
+
+def esrgan_out_buffer(table: np.ndarray, scale: int, dtype, device) -> torch.Tensor:
+    last = table[-1]
+    total = _off64(last, 10) + (3 * int(last[2]) * int(last[3]) * scale * scale + 7) // 8 * 8
+    return torch.empty((total,), dtype=dtype, device=device)
+
+
+def esrgan_stitch(tiles_out: torch.Tensor, table: np.ndarray, tab_dev: torch.Tensor, scale: int, H: int, W: int,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """Kernel 4b: packed network outputs -> [H*scale, W*scale, 3] uint8 BGR."""
+    _require_cuda(tiles_out, "tile outputs")
+    oh, ow = H * scale, W * scale
+    if out is None:
+        out = torch.empty((oh, ow, 3), dtype=torch.uint8, device=tiles_out.device)
+    tab_host = np.ascontiguousarray(table, dtype=np.int32)
+    h = _handle_for(tiles_out)
+    check(h.lib.fsd_esrgan_stitch(h.h, tiles_out.data_ptr(), tab_dev.data_ptr(), tab_host.ctypes.data, len(tab_host),
+                                  scale, _TORCH_DTYPE[tiles_out.dtype], out.data_ptr(), oh, ow, out.stride(0),
+                                  _stream_ptr(tiles_out.device)), "fsd_esrgan_stitch")
+    return out
+
+
+# ---- evaluation helpers (f1, f2) -------------------------------------------------------------------------
+def bbox_overlaps_p1(boxes: torch.Tensor, query: torch.Tensor) -> torch.Tensor:
+    """WIDER-FACE bbox_overlaps ('+1' convention): boxes [N,4], query [K,4] float64 CUDA -> [N,K] float64."""
+    _require_cuda(boxes, "boxes")
+    boxes = boxes.to(torch.float64).contiguous()
+    query = query.to(device=boxes.device, dtype=torch.float64).contiguous()
+    out = torch.zeros((boxes.shape[0], query.shape[0]), dtype=torch.float64, device=boxes.device)
+    h = _handle_for(boxes)
+    check(h.lib.fsd_bbox_overlaps_p1(h.h, boxes.data_ptr(), int(boxes.shape[0]), query.data_ptr(),
+                                     int(query.shape[0]), out.data_ptr(), _stream_ptr(boxes.device)),
+          "fsd_bbox_overlaps_p1")
+    return out
+
+
+def attach_keypoints(merged: torch.Tensor, m_off, m_cnt, dets: torch.Tensor, d_off, d_cnt) -> torch.Tensor:
+    """(f2) per merged box -> global detection row whose key-points the reference would attach (-1: none)."""
+    _require_cuda(merged, "merged boxes")
+    src = torch.full((merged.shape[0],), -1, dtype=torch.int32, device=merged.device)
+    h = _handle_for(merged)
+    check(h.lib.fsd_attach_keypoints(h.h, merged.data_ptr(), merged.stride(0), m_off.data_ptr(), m_cnt.data_ptr(),
+                                     dets.data_ptr(), dets.stride(0), d_off.data_ptr(), d_cnt.data_ptr(),
+                                     int(m_off.shape[0]), src.data_ptr(), _stream_ptr(merged.device)),
+          "fsd_attach_keypoints")
+    return src

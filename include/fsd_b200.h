@@ -88,58 +88,65 @@ int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const void* const 
 
 /* ---- Kernel 3 (a7,a12) batched segment NMS / GREEDYNMM / NMM.
  *      Replaces torchvision.ops.nms inside ultralytics non_max_suppression (stage 1: per slice, IOU,
- *      thr 0.7, strict >, fp32, max_keep 300) and sahi.postprocess.combine.{NMS,GreedyNMM,NMM}Postprocess
- *      with has_match + merge_object_prediction_pair [EXT sahi 0.11.34] (stage 2: per image), selected at
- *      docs sahi/predict.py:44-49,250-259 and run at :297,:319.
- *      boxes [N,4] f32 with row stride box_stride floats, scores [N] with stride score_stride, cats [N]
- *      int32 or NULL; tie [N] int32 tie-break keys or NULL (then the index inside the segment is used);
- *      segment s covers rows seg_offsets[s] .. seg_offsets[s]+seg_counts[s]-1.
+ *      thr 0.7, strict >, fp32, max_keep 300, pre_cap 30000) and sahi.postprocess.combine.{NMS,GreedyNMM,NMM}
+ *      Postprocess with has_match + merge_object_prediction_pair [EXT sahi 0.11.34] (stage 2: per image),
+ *      selected at docs sahi/predict.py:44-49,250-259 and run at :297,:319.
+ *      boxes [.,4] f32 at row stride box_stride floats, scores at stride score_stride, cats int32 at stride
+ *      cat_stride (NULL: one class), tie int32 tie-break keys at stride tie_stride (NULL: index in segment);
+ *      segment s covers rows seg_offsets[s] .. +min(seg_counts[s], max_segment)-1 (seg_counts NULL: all full).
  *      cmp_strict: 0 -> match if metric >= thr (sahi), 1 -> metric > thr (torchvision).
- *      precision:  0 -> fp64 metric (sahi 0.11.34), 1 -> fp32 metric (torchvision / old sahi).
- *      Outputs (all dev): keep [N] global row ids in score-descending order per segment (written from
- *      seg_offsets[s]); keep_count [S]; parent [N] = global row id of the keep a row was merged into, its
- *      own id for keeps, -1 for rows dropped without merge; merged_boxes [N,4] and merged_scores [N]
- *      (indexed like keep, union box after the has_match replay; for NMS a copy of the kept row).
- *      workspace: dev scratch of at least fsd_merge_workspace_bytes(N, S, max_segment) bytes. */
+ *      precision:  0 -> fp64 metric (sahi 0.11.34), 1 -> fp32 metric (torchvision).
+ *      Rank order inside a segment: score descending, ties by ascending tie key.
+ *      Outputs (dev): keep [.] global row ids in rank order, written from seg_offsets[s]; keep_count [S];
+ *      parent [.] (may be NULL) = global row id of the keep that claimed a row (its own id for keeps, -1 for
+ *      rows cut by pre_cap/max_keep); merged_boxes [.,4], merged_scores [.], merged_cats [.] (may be NULL) are
+ *      indexed like keep: the union box after the has_match replay (NMS: the kept row itself).
+ *      workspace: dev scratch of fsd_merge_workspace_bytes() bytes (only touched when max_segment > 4096).
+ *      Limit: max_segment <= 32768 (FSD_ERR_CAPACITY beyond). */
 int64_t fsd_merge_workspace_bytes(int64_t N, int S, int max_segment);
 int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, const float* scores, int score_stride,
-              const int32_t* cats, const int32_t* tie, const int32_t* seg_offsets,
-              const int32_t* seg_counts, int S, int max_segment, int64_t N, int type, int metric,
+              const int32_t* cats, int cat_stride, const int32_t* tie, int tie_stride,
+              const int32_t* seg_offsets, const int32_t* seg_counts, int S, int max_segment, int type, int metric,
               double thr, int cmp_strict, int precision, int class_agnostic, int pre_cap, int max_keep,
-              int32_t* keep, int32_t* keep_count, int32_t* parent, float* merged_boxes,
-              float* merged_scores, void* workspace, int64_t workspace_bytes, void* stream);
+              int32_t* keep, int32_t* keep_count, int32_t* parent, float* merged_boxes, float* merged_scores,
+              int32_t* merged_cats, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- Kernel 2b (a8-a11) finalize kept detections: un-letterbox (scale_boxes / scale_coords / clip),
  *      int() truncation, + slice shift.  Replaces ultralytics scale_boxes/scale_coords/clip_boxes [EXT],
- *      utils/yolo_wrapper.py:137-159 (astype(int), +shift, keypoints +shift), sahi ObjectAnnotation clamp
+ *      utils/yolo_wrapper.py:137-159 (astype(int), +shift, keypoints +shift), the sahi ObjectAnnotation clamp
  *      [EXT] and ObjectPrediction.get_shifted_object_prediction (docs sahi/prediction.py:94-120).
- *      cand: Kernel 2a rows; keep/keep_count: Kernel 3 stage-1 output with one segment per batch entry
- *      (segment b starts at b*cap_per_entry); entry_geom [B,8] int32 = (shift_x, shift_y, src_w, src_h,
- *      pad_left, pad_top, full_w, full_h); entry_gain [B] f32.
- *      Output rows are packed per group: group_of_entry [B] int32 (e.g. image id), group_offsets [G] int32 =
- *      first output row of each group; out_count [G] must be zero on entry and receives rows per group.
- *      det rows are 24 floats: [x1,y1,x2,y2 (full-image ints as float), score, entry, 15 kpts, order key,
- *      2 pad]; rows of a group are written in (entry, stage-1 rank) order. */
+ *      cand: Kernel 2a rows; keep/keep_count: Kernel 3 stage-1 output, one segment per batch entry (segment b
+ *      starts at row b*cap_per_entry); entry_geom [B,8] int32 = (shift_x, shift_y, src_w, src_h, box_pad_x,
+ *      box_pad_y, full_w, full_h); entry_fgeom [B,4] f32 = (gain, kpt_pad_x, kpt_pad_y, 0).
+ *      Rows are packed per group (image): group_range [G,2] = first / one-past-last entry of the group (entries
+ *      of a group are contiguous), group_offsets [G] = first det row of the group; out_count [G] is IN/OUT: rows
+ *      already present (so a second call can append the full-image pass) -> rows after this call.
+ *      det rows are 24 floats: [x1,y1,x2,y2 (full-image ints as float), score, entry (int bits), 15 kpts,
+ *      source cand row (int bits), 2 pad]; rows of a group are in (entry, stage-1 rank) order — the order the
+ *      reference appends ObjectPredictions in. */
 int fsd_finalize_dets(fsd_handle_t h, const float* cand, int cap_per_entry, const int32_t* keep,
-                      const int32_t* keep_count, int B, const int32_t* entry_geom, const float* entry_gain,
-                      const int32_t* group_of_entry, const int32_t* group_offsets, int G, int truncate,
-                      float* det, int32_t* out_count, void* stream);
+                      const int32_t* keep_count, int B, const int32_t* entry_geom, const float* entry_fgeom,
+                      const int32_t* group_range, const int32_t* group_offsets, int G, int truncate, float* det,
+                      int det_cap_per_group, int32_t* out_count, void* stream);
 
 /* ---- Kernel 4 (a15) Real-ESRGAN tile crop / stitch.  Replaces RealESRGANer.enhance/pre_process/
  *      tile_process/post_process [EXT realesrgan 0.3.0], reached from utils/enhancer.py:214.
  *      fsd_esrgan_tile_table: host-side tile table; each row = 12 int32:
- *        [px0,py0,pw,ph (padded input rect), in_x0,in_y0,in_w,in_h (interior), tile_elem_offset_lo,
- *         tile_elem_offset_hi, out_elem_offset_lo, out_elem_offset_hi]
- *      (offsets in elements into the packed tile buffers: input tiles 3*ph*pw each, output tiles
- *       3*(ph*scale)*(pw*scale) each).  padded_hw receives the mod-padded H,W. */
+ *        [px0,py0,pw,ph (padded input rect), in_x0,in_y0,in_w,in_h (interior), tile_elem_offset lo,hi,
+ *         out_elem_offset lo,hi]  (offsets in elements into the packed buffers: input tiles 3*ph*pw each, output
+ *        tiles 3*(ph*scale)*(pw*scale) each, both rounded up to 8 elements).  padded_hw = H,W after pre-/mod-pad. */
 int fsd_esrgan_tile_table(int H, int W, int scale, int tile, int tile_pad, int pre_pad, int32_t* table,
                           int cap, int* n_tiles, int32_t padded_hw[2]);
-/* crop: u8 HWC BGR image -> packed [3,ph,pw] RGB tiles of dtype, value/255, reflect pre-/mod-pad folded in */
-int fsd_esrgan_crop(fsd_handle_t h, const uint8_t* bgr, int H, int W, int64_t row_pitch, int pad_h,
-                    int pad_w, const int32_t* table_dev, int T, int dtype, void* tiles, void* stream);
-/* stitch: packed [3,ph*s,pw*s] RGB network outputs -> u8 HWC BGR [H*s, W*s]; clamp(0,1)*255 round-half-even */
-int fsd_esrgan_stitch(fsd_handle_t h, const void* tiles_out, const int32_t* table_dev, int T, int scale,
-                      int dtype, uint8_t* out_bgr, int out_h, int out_w, int64_t out_pitch, void* stream);
+/* crop: u8 HWC BGR image -> packed [3,ph,pw] RGB tiles of dtype, value/255; pre_h/pre_w = H,W + pre_pad (the
+ *       right/bottom reflect pre-pad and mod-pad are folded into the index map); table given on device and host */
+int fsd_esrgan_crop(fsd_handle_t h, const uint8_t* bgr, int H, int W, int64_t row_pitch, int pre_h, int pre_w,
+                    const int32_t* table_dev, const int32_t* table_host, int T, int dtype, void* tiles,
+                    void* stream);
+/* stitch: packed [3,ph*s,pw*s] RGB network outputs -> u8 HWC BGR [out_h,out_w] (= H*s, W*s);
+ *         clamp(0,1)*255, round-half-even; halos, mod-pad and pre-pad are dropped */
+int fsd_esrgan_stitch(fsd_handle_t h, const void* tiles_out, const int32_t* table_dev,
+                      const int32_t* table_host, int T, int scale, int dtype, uint8_t* out_bgr, int out_h,
+                      int out_w, int64_t out_pitch, void* stream);
 
 /* ---- (f1) WIDER-FACE evaluation IoU — replaces the Cython bbox_overlaps of WiderFace-Evaluation,
  *      imported at eval/eval_official_widerface.py:20-33 and called at :330.  boxes [N,4], query [K,4]
@@ -148,11 +155,14 @@ int fsd_bbox_overlaps_p1(fsd_handle_t h, const double* boxes, int N, const doubl
                          double* overlaps, void* stream);
 
 /* ---- (f2) keypoint attach — replaces YOLOv11PoseDetectionModel.attach_keypoints_to_predictions
- *      (utils/yolo_wrapper.py:168-217) for ONE image: for each merged box pick the LAST stage-1 detection
- *      with the identical int box, else the FIRST detection with the largest IoU if that IoU > 0.5.
- *      merged [M,4] f32, dets [D,4] f32 (row strides given in floats), src_index [M] int32 (-1: none). */
-int fsd_attach_keypoints(fsd_handle_t h, const float* merged, int merged_stride, int M, const float* dets,
-                         int det_stride, int D, int32_t* src_index, void* stream);
+ *      (utils/yolo_wrapper.py:168-217), batched over S images: for each merged box pick the LAST stage-1
+ *      detection of the same image with the identical box, else the detection whose box has the largest IoU
+ *      (first maximum, then the last detection sharing that box) if that IoU > 0.5.
+ *      merged rows of image s: m_off[s] .. +m_cnt[s]; detections: d_off[s] .. +d_cnt[s] (strides in floats);
+ *      src_index [.] (indexed like merged) receives the global detection row or -1. */
+int fsd_attach_keypoints(fsd_handle_t h, const float* merged, int merged_stride, const int32_t* m_off,
+                         const int32_t* m_cnt, const float* dets, int det_stride, const int32_t* d_off,
+                         const int32_t* d_cnt, int S, int32_t* src_index, void* stream);
 
 #ifdef __cplusplus
 }
