@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — sliced face-detect images/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+Workload (config.workload): BASELINE.json configs[1] — YOLOv11n-face SAHI on synthetic WIDER-FACE-shaped 1024x768
+images, 512x512 slices (0.2 overlap -> 6 slices) + the full-image pass, imgsz 1024 (the reference plug-in default),
+GREEDYNMM / IOS / 0.5 merge, conf 0.5, fp16 network input.  A "step" is one batch of `--batch` images through the whole
+hot path (Kernel 1 -> backbone -> Kernel 2a -> Kernel 3 -> Kernel 2b -> Kernel 3 -> attach/pack -> D2H of the results).
+
+  value     images/sec with the step's images already resident in HBM
+  e2e       images/sec through the public API (fsd_b200.api.get_sliced_prediction_batch) from PINNED HOST images,
+            H2D copies and result D2H + Python result objects inside the timed region
+  roofline  Kernel 1 (slice launch): algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference: the CPU oracle (reference-equivalent restatement: sequential batch-1 slices,
+            per-box Python objects, CPU merge) on a bounded sample of the same images, all host threads.
+
+Multi-GPU: launched by torchrun with one rank per GPU; images are sharded by index (weak scaling: every rank runs
+`steps` batches of its own shard), no collective on the hot path, one all-gather of detections after the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, SLICE, OVERLAP, IMGSZ, CONF = 768, 1024, 512, 0.2, 1024, 0.5
+WORKLOAD = "C2: YOLOv11n-face SAHI, synthetic 1024x768 images, 512x512 slices (0.2 overlap, 6 slices) + full-image pass, imgsz 1024, GREEDYNMM/IOS/0.5"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="images per step and per GPU")
+    ap.add_argument("--images", type=int, default=4096, help="size of the synthetic data set (all GPUs together)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=6, help="images of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_arm_setup():
+    import torch
+
+    import fsd_b200  # noqa: F401
+    from fsd_b200.backbones.yolo11_pose import build_yolo11n_pose
+    from oracle.yolo_head import OracleYOLO
+    from oracle.yolo_wrapper import YOLOv11PoseDetectionModel
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = YOLOv11PoseDetectionModel(model=OracleYOLO(build_yolo11n_pose(), half=False), confidence_threshold=CONF,
+                                      device="cpu", image_size=IMGSZ)
+    return model
+
+
+def cpu_arm_image(model, img):
+    from oracle.predict import get_sliced_prediction
+
+    model.keypoints_cache = {}
+    res = get_sliced_prediction(img, model, slice_height=SLICE, slice_width=SLICE, overlap_height_ratio=OVERLAP,
+                                overlap_width_ratio=OVERLAP, postprocess_type="GREEDYNMM", postprocess_match_metric="IOS",
+                                postprocess_match_threshold=0.5, verbose=0)
+    return model.attach_keypoints_to_predictions(res.object_prediction_list)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference-equivalent CPU restatement, one image per step, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    from fsd_b200.synthetic import make_image
+
+    model = cpu_arm_setup()
+    imgs = [make_image(i, H, W)[0] for i in range(min(args.steps + args.warmup, 8))]
+    for i in range(args.warmup):
+        cpu_arm_image(model, imgs[i % len(imgs)])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu_arm_image(model, imgs[(args.warmup + i) % len(imgs)])
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "sliced face-detect images/sec", "value": v, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} images (1 per step) of the C2 workload, oracle port of the reference CPU path "
+                                       f"(sahi/ultralytics/realesrgan are not installable here); os.cpu_count()={os.cpu_count()}"},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for s in self.samples for k in range(4) if len(s) > 2 + k and s[2 + k].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import fsd_b200  # noqa: F401
+    from fsd_b200 import _cabi, ops
+    from fsd_b200.api import get_sliced_prediction_batch
+    from fsd_b200.plugins import YOLOv11PoseDetectionModel
+    from fsd_b200.synthetic import make_image, make_pool_on_device
+    from fsd_b200.yolo import YOLO
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    n_local = max(B, (args.images // world) // B * B)   # images this rank owns (index i*world + rank)
+    n_resident = min(n_local, max(B, (args.steps + args.warmup) * B))
+    # ---- synthetic data: generated in HBM (device RNG), mirrored into pinned host memory for the e2e leg
+    pool = make_pool_on_device(n_resident, H, W, dev, seed=1234 + rank * 100003)
+    model = YOLOv11PoseDetectionModel(model=YOLO("random-init"), confidence_threshold=CONF, device=str(dev), image_size=IMGSZ)
+    eng = model.engine()
+    h = _cabi.get_handle(local)
+    kw = dict(postprocess_type="GREEDYNMM", match_metric="IOS", match_threshold=0.5)
+
+    def step_resident(i):
+        a = (i % (n_resident // B)) * B
+        return eng.detect(pool.subpool(a, a + B), SLICE, SLICE, OVERLAP, OVERLAP, True, **kw)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- leg 1: inputs resident in HBM -------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    # Kernel 1 timing hooks (CUDA events on the launching stream = torch's current stream)
+    k1_events = []
+    orig_gather = ops.gather_letterbox
+
+    def timed_gather(pool_, entries, src_w, src_h, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_gather(pool_, entries, src_w, src_h, *a, **k)
+        e1.record()
+        k1_events.append((src_w, int(entries.shape[0]), e0, e1))
+        return out
+
+    ops.gather_letterbox = timed_gather
+    sampler = ClockSampler(local)
+    sync_all()
+    sampler.start()
+    launches0 = h.launches
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    n_dets = 0
+    for i in range(args.steps):
+        n_dets += int(step_resident(args.warmup + i).offsets[-1])
+    t1.record()
+    sync_all()
+    launches = h.launches - launches0
+    clocks = sampler.stop()
+    ops.gather_letterbox = orig_gather
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = world * args.steps * B / (ms / 1000.0)
+
+    # roofline of the dominant kernel: Kernel 1 slice launch
+    sl = [(n, e0.elapsed_time(e1)) for (sw, n, e0, e1) in k1_events if sw == SLICE]
+    k1_ms = sum(t for _, t in sl) / max(len(sl), 1)
+    n_entries = sl[0][0] if sl else 0
+    k1_bytes = n_entries * 3 * IMGSZ * IMGSZ * 2 + (n_entries // 6) * H * W * 3  # every network input once + the source once
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k1_gather_letterbox_kernel (slice launch)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "bytes_per_launch": k1_bytes, "launch_ms": k1_ms, "launches_timed": len(sl)}
+
+    # ---- leg 2: end to end through the public API from pinned host memory ---------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        n_host = min(n_resident, 4 * B)
+        host = torch.empty((n_host, H, W, 3), dtype=torch.uint8).pin_memory()
+        for i in range(n_host):
+            host[i].copy_(pool.view(i))
+        torch.cuda.synchronize(dev)
+        hpool = ops.ImagePool(B, H, W, dev)
+
+        def step_e2e(i):
+            a = (i * B) % n_host // B * B
+            return get_sliced_prediction_batch([host[a + j] for j in range(B)], model, SLICE, SLICE, OVERLAP, OVERLAP, True,
+                                               "GREEDYNMM", "IOS", 0.5, False, as_objects=True, pool=hpool)
+
+        for i in range(max(1, args.warmup // 2)):
+            step_e2e(i)
+        sync_all()
+        e_steps = max(2, args.steps // 2)
+        w0 = time.perf_counter()
+        d2h = 0
+        for i in range(e_steps):
+            res = step_e2e(i)
+            d2h += sum(len(r.object_prediction_list) for r in res) * ops.ROW * 4 + (B + 1) * 4
+        sync_all()
+        dt = time.perf_counter() - w0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": world * e_steps * B / dt, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3,
+               "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps,
+               "api": "fsd_b200.api.get_sliced_prediction_batch (pinned host images in, PredictionResult objects out)"}
+
+    # ---- the one collective: all-gather of detections for evaluation (after the timed region) -------------
+    gathered = None
+    if world > 1:
+        from fsd_b200.shard import gather_detections
+
+        last = step_resident(0)
+        ids = torch.repeat_interleave(torch.arange(B, device=dev) * world + rank,
+                                      torch.from_numpy(np.diff(last.offsets)).to(dev))
+        rows = torch.from_numpy(np.concatenate([last.boxes, last.scores[:, None]], 1)).to(dev)
+        gi, gr = gather_detections(ids.long(), rows)
+        gathered = int(gi.shape[0])
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        model_cpu = cpu_arm_setup()
+        imgs = [pool.view(i).cpu().numpy().copy() for i in range(args.cpu_sample)]
+        cpu_arm_image(model_cpu, imgs[0])
+        c0 = time.perf_counter()
+        for im in imgs:
+            cpu_arm_image(model_cpu, im)
+        cdt = time.perf_counter() - c0
+        cpu_base = {"value": len(imgs) / cdt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": f"first {len(imgs)} images of this run's data set through the oracle port of the reference CPU path "
+                              f"(sequential batch-1 slices at imgsz {IMGSZ}, fp32, per-box Python objects, CPU GREEDYNMM); "
+                              f"os.cpu_count()={os.cpu_count()}"}
+
+    if rank == 0:
+        line = {"metric": "sliced face-detect images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "images_per_step_per_gpu": B, "data_set_images": args.images,
+                           "resident_images_per_gpu": n_resident, "slices_per_image": 6, "network_inputs_per_image": 7,
+                           "conf": CONF, "weights": "random-init YOLO11n-pose (calibrated head), seed 0",
+                           "l2": "inputs larger than L2: each step gathers %.0f MB of source pixels into %.1f GB of network input"
+                                 % (B * H * W * 3 / 1e6, B * (6 * 3 * IMGSZ * IMGSZ + 3 * H * W) * 2 / 1e9),
+                           "parallelism": f"image-index sharding x{world}, no hot-path collective"},
+                "detections_per_image": n_dets / (args.steps * B), "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base}
+        if gathered is not None:
+            line["allgather_detections"] = gathered
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

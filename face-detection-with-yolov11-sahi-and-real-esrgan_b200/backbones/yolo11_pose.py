@@ -240,6 +240,13 @@ def build_yolo11n_pose(seed: int = 0, calibrate: bool = True, nc: int = 1, kpt_s
     model = YOLO11Pose(nc=nc, kpt_shape=kpt_shape)
     _init_variance_preserving(model, gen)
     if calibrate:
-        sample = torch.rand((1, 3, 256, 256), generator=gen)
+        # calibrate on one synthetic WIDER-like image, up-scaled 2x like a SAHI slice at imgsz 1024
+        from ..synthetic import make_image
+
+        img, _ = make_image(10_000, 320, 320, seed=seed)
+        sample = torch.from_numpy(img).permute(2, 0, 1)[None].float() / 255.0
+        sample = torch.nn.functional.interpolate(sample, scale_factor=2.0, mode="bilinear", align_corners=False)
         calibrate_head(model, sample)
+    for p in model.parameters():
+        p.requires_grad_(False)
     return model.eval()

@@ -200,9 +200,62 @@ __global__ void __launch_bounds__(K2_THREADS) k2_finalize_kernel(const K2bParams
     if (threadIdx.x == 0) p.out_count[g] = min(base, p.det_cap);
 }
 
+// ---- result packing: merged boxes + attached key-points of all images into one contiguous row list ---------
+__global__ void __launch_bounds__(K2_THREADS)
+k2_pack_kernel(const float* __restrict__ det, const int32_t* __restrict__ group_offsets,
+               const int32_t* __restrict__ keep, const int32_t* __restrict__ keep_count,
+               const float* __restrict__ mboxes, const float* __restrict__ mscores,
+               const int32_t* __restrict__ src_index, int G, float* __restrict__ out, int32_t* __restrict__ out_offsets) {
+    __shared__ int s_base;
+    const int g = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int base = 0;
+        for (int i = 0; i < g; ++i) base += keep_count[i];
+        s_base = base;
+        out_offsets[g] = base;
+        if (g == G - 1) out_offsets[G] = base + keep_count[g];
+    }
+    __syncthreads();
+    const int base = s_base, n = keep_count[g], off = group_offsets[g];
+    for (int i = threadIdx.x; i < n; i += K2_THREADS) {
+        float* o = out + (size_t)(base + i) * ROW;
+        const float* mb = mboxes + (size_t)(off + i) * 4;
+        o[0] = mb[0]; o[1] = mb[1]; o[2] = mb[2]; o[3] = mb[3];
+        o[4] = mscores[off + i];
+        const int src = src_index ? src_index[off + i] : -1;
+        o[5] = __int_as_float(src);
+        if (src >= 0) {
+            const float* d = det + (size_t)src * ROW;
+#pragma unroll
+            for (int k = 0; k < 15; ++k) o[6 + k] = d[6 + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 15; ++k) o[6 + k] = 0.f;
+        }
+        o[21] = __int_as_float(keep[off + i]);
+        o[22] = __int_as_float(g);
+        o[23] = 0.f;
+    }
+}
+
 }  // namespace fsd
 
 using namespace fsd;
+
+extern "C" int fsd_pack_results(fsd_handle_t h, const float* det, const int32_t* group_offsets, const int32_t* keep,
+                                const int32_t* keep_count, const float* merged_boxes, const float* merged_scores,
+                                const int32_t* src_index, int G, float* out, int32_t* out_offsets, void* stream_) {
+    FSD_CHECK_ARG(h && det && group_offsets && keep && keep_count && merged_boxes && merged_scores && out && out_offsets,
+                  "fsd_pack_results: null argument");
+    FSD_CHECK_ARG(G >= 0, "fsd_pack_results: bad G");
+    if (G == 0) return FSD_OK;
+    FSD_CUDA(cudaSetDevice(h->device));
+    k2_pack_kernel<<<G, K2_THREADS, 0, (cudaStream_t)stream_>>>(det, group_offsets, keep, keep_count, merged_boxes,
+                                                               merged_scores, src_index, G, out, out_offsets);
+    FSD_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return FSD_OK;
+}
 
 extern "C" int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const void* const cls[3],
                                const void* const kpt[3], const int32_t level_hw[6], int B, int layout, int dtype,

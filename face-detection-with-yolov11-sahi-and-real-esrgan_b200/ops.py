@@ -63,6 +63,13 @@ class ImagePool:
         """[H, W, 3] view of slot `index` (strided when the pitch is padded)."""
         return self.buf[index, :, : self.w * 3].unflatten(1, (self.w, 3))
 
+    def subpool(self, start: int, stop: int) -> "ImagePool":
+        """View of images [start, stop) sharing this pool's memory."""
+        sub = object.__new__(ImagePool)
+        sub.n, sub.h, sub.w, sub.pitch = stop - start, self.h, self.w, self.pitch
+        sub.buf = self.buf[start:stop]
+        return sub
+
     @classmethod
     def from_numpy(cls, images, device="cuda") -> "ImagePool":
         h, w = images[0].shape[:2]
@@ -189,6 +196,21 @@ def finalize_dets(cand, keep, keep_count, entry_geom, entry_fgeom, group_range, 
                                   int(det_cap_per_group), out_count.data_ptr(), _stream_ptr(cand.device)),
           "fsd_finalize_dets")
     return det, out_count
+
+
+def pack_results(det, group_offsets, s2, src_index, out: torch.Tensor | None = None):
+    """(a1) pack stage-2 results of all images into contiguous rows; returns (rows [cap,24], offsets [G+1] i32)."""
+    G = int(group_offsets.shape[0])
+    dev = det.device
+    if out is None:
+        out = torch.empty((det.shape[0], ROW), dtype=torch.float32, device=dev)
+    offsets = torch.empty((G + 1,), dtype=torch.int32, device=dev)
+    h = _handle_for(det)
+    check(h.lib.fsd_pack_results(h.h, det.data_ptr(), group_offsets.data_ptr(), s2["keep"].data_ptr(),
+                                 s2["keep_count"].data_ptr(), s2["boxes"].data_ptr(), s2["scores"].data_ptr(),
+                                 _ptr(src_index), G, out.data_ptr(), offsets.data_ptr(), _stream_ptr(dev)),
+          "fsd_pack_results")
+    return out, offsets
 
 
 # ---- Kernel 4 -------------------------------------------------------------------------------------------

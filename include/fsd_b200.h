@@ -129,6 +129,15 @@ int fsd_finalize_dets(fsd_handle_t h, const float* cand, int cap_per_entry, cons
                       const int32_t* group_range, const int32_t* group_offsets, int G, int truncate, float* det,
                       int det_cap_per_group, int32_t* out_count, void* stream);
 
+/* ---- (a1) result packing — the tail of get_sliced_prediction (docs sahi/predict.py:317-345): the merged boxes of
+ *      all G images (Kernel 3 stage-2 outputs, indexed from group_offsets[g]) plus the key-points picked by
+ *      fsd_attach_keypoints are packed into ONE contiguous list of 24-float rows so a single D2H copy returns a
+ *      whole batch: [x1,y1,x2,y2, score, source det row (int bits, -1: no key-points), 15 kpts, stage-2 keep id
+ *      (int bits), image index (int bits), pad].  out_offsets [G+1] receives the first row of each image. */
+int fsd_pack_results(fsd_handle_t h, const float* det, const int32_t* group_offsets, const int32_t* keep,
+                     const int32_t* keep_count, const float* merged_boxes, const float* merged_scores,
+                     const int32_t* src_index, int G, float* out, int32_t* out_offsets, void* stream);
+
 /* ---- Kernel 4 (a15) Real-ESRGAN tile crop / stitch.  Replaces RealESRGANer.enhance/pre_process/
  *      tile_process/post_process [EXT realesrgan 0.3.0], reached from utils/enhancer.py:214.
  *      fsd_esrgan_tile_table: host-side tile table; each row = 12 int32:
