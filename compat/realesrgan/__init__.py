@@ -1,0 +1,8 @@
+"""`realesrgan` import shim (utils/enhancer.py:12)."""
+import os as _os
+import sys as _sys
+
+_root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+if _root not in _sys.path:
+    _sys.path.insert(0, _root)
+from fsd_b200.enhancer import RealESRGANer  # noqa: E402,F401

@@ -11,3 +11,15 @@ Sub-modules:
   shard      image-index data parallelism + the one all-gather of detections
 """
 __version__ = "0.1.0"
+
+
+def install_compat() -> str:
+    """Put compat/ (the `sahi` / `ultralytics` / `realesrgan` / `basicsr` / `bbox` import shims) first on sys.path so the
+    reference's scripts run unmodified on top of this package.  Returns the directory."""
+    import os
+    import sys
+
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compat")
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    return d

@@ -25,7 +25,10 @@ def _first(lst, default):
 
 
 class YOLOv11PoseDetectionModel(DetectionModel):
-    supports_batched_slices = True  # get_sliced_prediction takes the fused device path for this plug-in
+    @property
+    def supports_batched_slices(self):
+        """get_sliced_prediction takes the fused device path when `.model` is the B200 YOLO front end."""
+        return isinstance(self.model, YOLO)
 
     def __init__(self, model_path: str = None, confidence_threshold: float = 0.3, device: str = "cpu",
                  image_size: int = 1024, **kwargs):
@@ -47,7 +50,11 @@ class YOLOv11PoseDetectionModel(DetectionModel):
         self.category_mapping = {"0": "face"}
 
     def set_model(self, model, **kwargs):
-        self.model = model if isinstance(model, YOLO) else YOLO(model)
+        # an fsd_b200.YOLO, a torch backbone to wrap, or any object with ultralytics' `.predict` surface
+        if isinstance(model, YOLO) or hasattr(model, "predict"):
+            self.model = model
+        else:
+            self.model = YOLO(model)
         self.category_mapping = {"0": "face"}
 
     def unload_model(self):
@@ -71,9 +78,10 @@ class YOLOv11PoseDetectionModel(DetectionModel):
     def perform_inference(self, image: np.ndarray):
         if image.dtype != np.uint8:
             image = (image * 255).astype(np.uint8)
+        extra = {"half": self.half} if isinstance(self.model, YOLO) else {}
         self._original_predictions = self.model.predict(source=image, conf=self.confidence_threshold,
                                                         device=self._cuda_device(), imgsz=self.image_size,
-                                                        verbose=False, half=self.half)
+                                                        verbose=False, **extra)
 
     def _create_object_prediction_list_from_original_predictions(self, shift_amount_list=[[0, 0]], full_shape_list=None):
         preds = self._original_predictions
