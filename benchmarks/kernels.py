@@ -1,0 +1,159 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmarks: achieved GB/s against the algorithmic bytes of SURVEY §8(d), CUDA-event timed,
+inputs larger than L2 (126 MB) so every launch streams from HBM.  One JSON line per measurement.
+
+    python benchmarks/kernels.py [k1|k2|k3|k4|ref|all]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import fsd_b200  # noqa: E402,F401
+from fsd_b200 import _cabi, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(min(ts))
+
+
+def report(name, nbytes, fn, **extra):
+    med, best = timeit(fn)
+    print(json.dumps({"kernel": name, "ms_median": round(med, 4), "ms_best": round(best, 4), "algorithmic_MB": round(nbytes / 1e6, 2),
+                      "GBps_median": round(nbytes / med / 1e6, 1), "frac_of_measured_peak": round(nbytes / med / 1e6 / PEAK, 3),
+                      "peak_GBps": PEAK, **extra}), flush=True)
+
+
+def bench_ref():
+    n = 1 << 30
+    a = torch.empty(n, dtype=torch.uint8, device=dev)
+    b = torch.empty(n, dtype=torch.uint8, device=dev)
+    report("torch copy_ 1 GiB (read+write)", 2 * n, lambda: b.copy_(a))
+    report("torch fill_ 1 GiB (write only)", n, lambda: b.fill_(7))
+
+
+def bench_k1():
+    cases = [("C2 slices 512^2 -> 1024^2 (2x up)", 768, 1024, 512, 0.2, 32, False),
+             ("C2 full 768x1024 (copy)", 768, 1024, None, 0.2, 64, True),
+             ("C1 slices 640^2 -> 1024^2 (1.6x up)", 1080, 1920, 640, 0.2, 24, False),
+             ("C1 full 1080x1920 -> 576x1024 (down)", 1080, 1920, None, 0.2, 64, True),
+             ("C3 full 2160x3840 -> 576x1024 (down 3.75x)", 2160, 3840, None, 0.2, 16, True)]
+    for name, H, W, sl, ov, N, full in cases:
+        pool = ops.ImagePool(N, H, W, dev)
+        pool.buf.random_(0, 256)
+        if full:
+            ent = torch.tensor([[i, 0, 0] for i in range(N)], dtype=torch.int32, device=dev)
+            sw, sh = W, H
+        else:
+            boxes = _cabi.slice_plan(H, W, sl, sl, ov, ov)
+            ent = torch.tensor([[i, b[0], b[1]] for i in range(N) for b in boxes], dtype=torch.int32, device=dev)
+            sw = sh = sl
+        g = _cabi.letterbox_geometry(sh, sw, 1024, 32)
+        for dt in (torch.float16, torch.float32):
+            out = torch.empty((ent.shape[0], 3, g["out_h"], g["out_w"]), dtype=dt, device=dev)
+            nbytes = out.numel() * out.element_size() + N * H * W * 3
+            report(f"K1 {name} {str(dt)[6:]}", nbytes, lambda: ops.gather_letterbox(pool, ent, sw, sh, 1024, 32, True, dt, out=out),
+                   entries=int(ent.shape[0]))
+        del pool, out
+
+
+def bench_k2():
+    from fsd_b200.backbones.yolo11_pose import YOLO11Pose
+
+    for B, H, W, conf in ((96, 1024, 1024, 0.5), (96, 1024, 1024, 0.01)):
+        for cl in (True, False):
+            g = torch.Generator(device=dev).manual_seed(0)
+            levels = []
+            for s in (8, 16, 32):
+                h, w = H // s, W // s
+                ts = [torch.randn((B, c, h, w), generator=g, device=dev, dtype=torch.float16) * sc + m
+                      for c, sc, m in ((64, 1.5, 1.0), (1, 2.0, -6.0), (15, 1.0, 0.0))]
+                if cl:
+                    ts = [t.contiguous(memory_format=torch.channels_last) for t in ts]
+                levels.append(tuple(ts))
+            A = YOLO11Pose.anchors_for(H, W)
+            cand = torch.empty((B, 8192, ops.ROW), dtype=torch.float32, device=dev)
+            count = torch.empty((B,), dtype=torch.int32, device=dev)
+            ops.pose_decode(levels, conf, cand=cand, count=count)
+            n = int(count.sum())
+            full = B * 80 * A * 2 + n * ops.ROW * 4
+            gated = B * A * 2 + n * (79 * 2 + ops.ROW * 4)
+            report(f"K2a decode B={B} {H}x{W} conf={conf} {'NHWC' if cl else 'NCHW'}", full,
+                   lambda: ops.pose_decode(levels, conf, cand=cand, count=count), survivors=n, gated_MB=round(gated / 1e6, 2))
+
+
+def bench_k3():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_k3_merge_gpu import sahi_like_boxes
+
+    rng = np.random.default_rng(0)
+    for n_target, S in ((256, 148), (1024, 148), (4096, 32), (9900, 8)):
+        seg = sahi_like_boxes(rng, max(2, n_target // 3), dup=(1, 5), size=(10, 60), canvas=(3840, 2160))
+        while len(seg) < n_target:
+            seg = np.concatenate([seg, sahi_like_boxes(rng, 50, dup=(1, 5), size=(10, 60), canvas=(3840, 2160))])
+        seg = seg[:n_target]
+        rows = torch.from_numpy(np.tile(seg, (S, 1))).to(dev)
+        offs = torch.arange(S, dtype=torch.int32, device=dev) * n_target
+        for mtype, metric, kw in (("NMS", "IOU", dict(precision="fp64")), ("GREEDYNMM", "IOS", dict(precision="fp64")),
+                                  ("NMS", "IOU", dict(precision="fp32", cmp_strict=True, max_keep=300, thr=0.7))):
+            thr = kw.pop("thr", 0.5)
+            fn = lambda: ops.merge_segments(rows, offs, None, n_target, merge_type=mtype, metric=metric, thr=thr, want_parent=False, **kw)  # noqa: E731
+            r = fn()
+            med, best = timeit(fn, iters=5, warmup=2)
+            print(json.dumps({"kernel": f"K3 {mtype}/{metric} {kw['precision']} N={n_target} x{S} segments", "ms_median": round(med, 4),
+                              "us_per_launch": round(med * 1e3, 1), "us_per_segment_amortised": round(med * 1e3 / S, 2),
+                              "keeps_per_segment": int(r["keep_count"][0]), "mask_MB_if_materialised": round(n_target * ((n_target + 63) // 64) * 8 * 2 / 1e6, 3),
+                              "pair_MFLOP": round(n_target * n_target / 2 * 20 / 1e6, 1)}), flush=True)
+
+
+def bench_k4():
+    for H, W, scale, tile in ((1080, 1920, 2, 400), (1080, 1920, 4, 400)):
+        N = 8
+        imgs = [torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, device=dev) for _ in range(N)]
+        table, _ = ops.esrgan_tile_table(H, W, scale, tile, 10, 0)
+        tiles, tab_dev = ops.esrgan_crop(imgs[0], table, scale)
+        crop_bytes = H * W * 3 + sum(3 * int(r[2]) * int(r[3]) for r in table) * 2
+        k = [0]
+
+        def crop():
+            k[0] = (k[0] + 1) % N
+            ops.esrgan_crop(imgs[k[0]], table, scale)
+
+        report(f"K4 crop {W}x{H} x{scale} tile {tile} fp16", crop_bytes, crop, tiles=len(table))
+        outs = [torch.rand(ops.esrgan_out_buffer(table, scale, torch.float16, dev).shape, device=dev).half() for _ in range(4)]
+        dst = [torch.empty((H * scale, W * scale, 3), dtype=torch.uint8, device=dev) for _ in range(4)]
+        stitch_bytes = H * W * scale * scale * 3 * (2 + 1)
+
+        def stitch():
+            k[0] = (k[0] + 1) % 4
+            ops.esrgan_stitch(outs[k[0]], table, tab_dev, scale, H, W, out=dst[k[0]])
+
+        report(f"K4 stitch {W}x{H} x{scale} tile {tile} fp16", stitch_bytes, stitch, tiles=len(table))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4)):
+        if which in ("all", name):
+            fn()

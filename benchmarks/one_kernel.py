@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Run ONE kernel configuration a few times (the target of `ncu --set full -k regex:...`).
+    python benchmarks/one_kernel.py k1_c2 | k1_c2_f32 | k2 | k3 | k4"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import fsd_b200  # noqa: E402,F401
+from fsd_b200 import _cabi, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+which = sys.argv[1] if len(sys.argv) > 1 else "k1_c2"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+if which.startswith("k1"):
+    N = 32
+    pool = ops.ImagePool(N, 768, 1024, dev)
+    pool.buf.random_(0, 256)
+    boxes = _cabi.slice_plan(768, 1024, 512, 512, 0.2, 0.2)
+    ent = torch.tensor([[i, b[0], b[1]] for i in range(N) for b in boxes], dtype=torch.int32, device=dev)
+    dt = torch.float32 if which.endswith("f32") else torch.float16
+    out = torch.empty((ent.shape[0], 3, 1024, 1024), dtype=dt, device=dev)
+    for _ in range(iters):
+        ops.gather_letterbox(pool, ent, 512, 512, 1024, 32, True, dt, out=out)
+elif which == "k4":
+    H, W, scale, tile = 1080, 1920, 2, 400
+    img = torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, device=dev)
+    table, _ = ops.esrgan_tile_table(H, W, scale, tile, 10, 0)
+    for _ in range(iters):
+        tiles, tab_dev = ops.esrgan_crop(img, table, scale)
+        outb = torch.rand(ops.esrgan_out_buffer(table, scale, torch.float16, dev).shape, device=dev).half()
+        ops.esrgan_stitch(outb, table, tab_dev, scale, H, W)
+torch.cuda.synchronize()
+print("done", which)

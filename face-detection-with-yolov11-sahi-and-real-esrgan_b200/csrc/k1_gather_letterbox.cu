@@ -9,6 +9,8 @@
 //      the plane index, 8 outputs per thread -> one 128-bit (fp16) or two 128-bit (fp32) stores per plane.
 // The arithmetic is integer-exact w.r.t. cv2.resize(INTER_LINEAR) on uint8 (incl. the exact-2x area path);
 // the /255 matches torch's `im.half()/255` resp. `im.float()/255` (exhaustively checked over 0..255 in tests).
+#include <stdlib.h>
+
 #include "fsd_common.cuh"
 
 namespace fsd {
@@ -26,6 +28,7 @@ struct K1Params {
     int tile_cols, tile_rows;  // TC (multiple of 8, divides 256 or equals it), TR
     int box_w_elems, box_rows; // TMA box (u32 elements x rows)
     int reverse;
+    int tiles_per_cta;  // vertically consecutive tiles marched by one CTA (x-dependent set-up amortised, TMA prefetched)
 };
 
 template <typename T> struct OutVec;
@@ -60,126 +63,192 @@ __device__ __forceinline__ void store8(float* dst, const float (&f)[8]) {
     *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+// vertical pass for 8 consecutive pixels of one plane: cv2's ((b0*h0)>>16 + (b1*h1)>>16 + 2) >> 2 with the two
+// products as IMAD.HI against the pre-shifted coefficients, then /255
 template <int MODE, typename OutT>
+__device__ __forceinline__ void vertical8(const uint16_t* r0, const uint16_t* r1, const int4 ye, float (&f)[8]) {
+    const uint4 ha = *reinterpret_cast<const uint4*>(r0);
+    const uint4 hb = *reinterpret_cast<const uint4*>(r1);
+    const uint32_t wa[4] = {ha.x, ha.y, ha.z, ha.w}, wb[4] = {hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t h0 = (e & 1) ? (wa[e >> 1] >> 16) : (wa[e >> 1] & 0xffffu);
+        const uint32_t h1 = (e & 1) ? (wb[e >> 1] >> 16) : (wb[e >> 1] & 0xffffu);
+        int val;
+        if (MODE == K1_MODE_LINEAR) val = (int)((__umulhi((uint32_t)ye.z, h0) + __umulhi((uint32_t)ye.w, h1) + 2u) >> 2);
+        else val = (int)((h0 + h1 + 2u) >> 2);
+        f[e] = norm255<OutT>(val);
+    }
+}
+
+
+template <int MODE, typename OutT, int TC>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
-    // dynamic smem, manually aligned to 128 B (TMA destination rule): [raw box | hbuf | ytab | mbarrier]
+    // dynamic smem, manually aligned to 128 B (TMA destination rule): [raw box x2 | hbuf | ytab | 2 mbarriers]
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
 
+    constexpr int VECS = TC / 8;               // 8-pixel store vectors per tile row
+    constexpr int ROWS_PER_PASS = K1_THREADS / VECS;
+    constexpr int RGS = K1_THREADS / TC > 0 ? K1_THREADS / TC : 1;
     const int tid = threadIdx.x;
-    const int TC = p.tile_cols, TR = p.tile_rows;
-    const int X0 = blockIdx.x * TC, Y0 = blockIdx.y * TR;
+    const int TR = p.tile_rows;
+    const int X0 = blockIdx.x * TC;
     const int b = blockIdx.z;
 
     const int raw_pitch = p.box_w_elems * 4;
     const int raw_bytes = (raw_pitch * p.box_rows + 127) & ~127;
     const int hbuf_bytes = (p.box_rows * 3 * TC * 2 + 127) & ~127;
-    uint8_t* raw = smem;                                                // [box_rows][raw_pitch]
-    uint16_t* hbuf = reinterpret_cast<uint16_t*>(smem + raw_bytes);     // [box_rows][3][TC]
-    int4* s_ytab = reinterpret_cast<int4*>(smem + raw_bytes + hbuf_bytes);  // [TR]
-    uint64_t& bar = *reinterpret_cast<uint64_t*>(smem + raw_bytes + hbuf_bytes + 32 * 16);
+    uint8_t* raw0 = smem;                                                       // 2 x [box_rows][raw_pitch]
+    uint16_t* hbuf = reinterpret_cast<uint16_t*>(smem + 2 * raw_bytes);         // [box_rows][3][TC]
+    int4* s_ytab = reinterpret_cast<int4*>(smem + 2 * raw_bytes + hbuf_bytes);  // [TR]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * raw_bytes + hbuf_bytes + 32 * 16);
 
-    // destination-pixel window of this tile (may be empty when the tile lies in the 114 border)
+    // ---- x-dependent set-up, once per CTA ---------------------------------------------------------------
     const int dx_lo = max(X0 - p.pad_left, 0), dx_hi = min(X0 + TC - p.pad_left, p.new_w) - 1;
-    const int dy_lo = max(Y0 - p.pad_top, 0), dy_hi = min(Y0 + TR - p.pad_top, p.new_h) - 1;
-    const bool has = dx_lo <= dx_hi && dy_lo <= dy_hi;
-
-    int sx_lo = 0, sy_lo = 0, nrows = 0, boff = 0;
-    if (has) {
-        const int img = __ldg(p.entries + 3 * b + 0);
-        const int x0 = __ldg(p.entries + 3 * b + 1);
-        const int y0 = __ldg(p.entries + 3 * b + 2);
+    const bool has_x = dx_lo <= dx_hi;
+    const int img = __ldg(p.entries + 3 * b + 0);
+    const int x0 = __ldg(p.entries + 3 * b + 1);
+    const int y0 = __ldg(p.entries + 3 * b + 2);
+    int cx = 0, boff = 0, sx_lo = 0;
+    if (has_x) {
         sx_lo = __ldg(&p.xtab[dx_lo]).x;
-        sy_lo = __ldg(&p.ytab[dy_lo]).x;
-        nrows = __ldg(&p.ytab[dy_hi]).y - sy_lo + 1;
         const int byte0 = (x0 + sx_lo) * 3;
-        boff = byte0 & 15;  // the TMA box must start on a 16-byte boundary of the row (unaligned starts fault)
-        // CUTLASS idiom: a warp-uniform branch + elect.sync, so the TMA operands stay in uniform registers
-        if (tid < 32) {
-            const int cx = (byte0 >> 4) << 2, cy = y0 + sy_lo;
-            if (elect_one_sync()) {
-                mbar_init(&bar, 1);
-                fence_barrier_init();
-                mbar_expect_tx(&bar, (uint32_t)(raw_pitch * p.box_rows));
-                tma_load_3d(raw, &tmap, &bar, cx, cy, img);
-            }
-        }
-        // stage this tile's vertical coefficients while the TMA is in flight
-        if (tid < TR) {
-            int dy = Y0 + tid - p.pad_top;
-            int4 ye = make_int4(0, 0, 0, 0);
-            if (dy >= 0 && dy < p.new_h) {
-                ye = __ldg(&p.ytab[dy]);
-                ye.x -= sy_lo;
-                ye.y -= sy_lo;
-            }
-            s_ytab[tid] = ye;
-        }
+        boff = byte0 & 15;       // the TMA box must start on a 16-byte boundary of the row (unaligned starts fault)
+        cx = (byte0 >> 4) << 2;  // u32 element coordinate of that boundary
     }
-    __syncthreads();  // barrier init + s_ytab visible
+    // horizontal pass role: thread <-> (column j, row group rg)
+    const int j = tid % TC, rg = tid / TC;
+    const bool hp = has_x && j <= dx_hi - dx_lo && rg < RGS;
+    int o0 = 0, o1 = 0, a0 = 0, a1 = 0, hcol = 0;
+    if (hp) {
+        const int2 xe = __ldg(&p.xtab[dx_lo + j]);
+        const int s1 = min(xe.x + 1, p.src_w - 1);
+        o0 = (xe.x - sx_lo) * 3 + boff;
+        o1 = (s1 - sx_lo) * 3 + boff;
+        a0 = xe.y & 0xffff;
+        a1 = (xe.y >> 16) & 0xffff;
+        hcol = dx_lo + j + p.pad_left - X0;
+    }
+    const int c0 = p.reverse ? 2 * TC : 0, c2 = p.reverse ? 0 : 2 * TC;
+    // vertical pass role: thread <-> (8-pixel vector v, rows vrow, vrow + ROWS_PER_PASS, ..)
+    const int v = tid % VECS, vrow = tid / VECS;
+    const int X = X0 + v * 8;
+    unsigned inside = 0;  // columns of this vector inside the resized image (the rest is 114 border)
+    {
+        const int lo = min(max(p.pad_left - X, 0), 8), hi = min(max(p.pad_left + p.new_w - X, 0), 8);
+        if (has_x && hi > lo) inside = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+    }
+    const float pad_val = norm255<OutT>(114);
+    const size_t plane = (size_t)p.out_h * p.out_w;
+    OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * 3 * plane + X;
+    const uint16_t* hv = hbuf + v * 8;
 
-    if (has) {
-        mbar_wait(&bar, 0);
-        // ---- horizontal pass: thread <-> (column j, row group) --------------------------------------
-        const int ncols = dx_hi - dx_lo + 1;
-        const int j = tid % TC, rg = tid / TC, rgs = K1_THREADS / TC;
-        if (j < ncols) {
-            const int2 xe = __ldg(&p.xtab[dx_lo + j]);
-            const int s1 = min(xe.x + 1, p.src_w - 1);
-            const int o0 = (xe.x - sx_lo) * 3 + boff, o1 = (s1 - sx_lo) * 3 + boff;
-            const int a0 = xe.y & 0xffff, a1 = (xe.y >> 16) & 0xffff;
-            const int col = dx_lo + j + p.pad_left - X0;
-            const int c0 = p.reverse ? 2 : 0, c2 = p.reverse ? 0 : 2;
-            for (int r = rg; r < nrows; r += rgs) {
-                const uint8_t* row = raw + r * raw_pitch;
-                uint16_t* hrow = hbuf + (size_t)r * 3 * TC + col;
-                int v0 = row[o0 + 0] * a0 + row[o1 + 0] * a1;
-                int v1 = row[o0 + 1] * a0 + row[o1 + 1] * a1;
-                int v2 = row[o0 + 2] * a0 + row[o1 + 2] * a1;
-                if (MODE == K1_MODE_LINEAR) { v0 >>= 4; v1 >>= 4; v2 >>= 4; }
-                hrow[c0 * TC] = (uint16_t)v0;
-                hrow[1 * TC] = (uint16_t)v1;
-                hrow[c2 * TC] = (uint16_t)v2;
-            }
-        }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
     }
     __syncthreads();
 
-    // ---- vertical pass + normalise + planar vector stores -------------------------------------------
-    const int vecs = TC / 8;
-    const int items = TR * 3 * vecs;
-    const float pad_val = norm255<OutT>(114);
-    OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * 3 * p.out_h * p.out_w;
-    for (int it = tid; it < items; it += K1_THREADS) {
-        const int v = it % vecs;
-        const int line = it / vecs;
-        const int c = line % 3, yl = line / 3;
-        const int Y = Y0 + yl, X = X0 + v * 8;
-        if (Y >= p.out_h || X >= p.out_w) continue;
-        const int dy = Y - p.pad_top;
-        float f[8];
-        if (!has || dy < 0 || dy >= p.new_h) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = pad_val;
-        } else {
-            const int4 ye = s_ytab[yl];
-            const uint4 ha = *reinterpret_cast<const uint4*>(hbuf + ((size_t)ye.x * 3 + c) * TC + v * 8);
-            const uint4 hb = *reinterpret_cast<const uint4*>(hbuf + ((size_t)ye.y * 3 + c) * TC + v * 8);
-            const uint32_t wa[4] = {ha.x, ha.y, ha.z, ha.w}, wb[4] = {hb.x, hb.y, hb.z, hb.w};
-            const int xl = X - p.pad_left;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int h0 = (wa[e >> 1] >> ((e & 1) * 16)) & 0xffff;
-                const int h1 = (wb[e >> 1] >> ((e & 1) * 16)) & 0xffff;
-                int val;
-                if (MODE == K1_MODE_LINEAR) val = (((ye.z * h0) >> 16) + ((ye.w * h1) >> 16) + 2) >> 2;
-                else val = (h0 + h1 + 2) >> 2;
-                const bool inside = (unsigned)(xl + e) < (unsigned)p.new_w;
-                f[e] = inside ? norm255<OutT>(val) : pad_val;
+    const int tile0 = blockIdx.y * p.tiles_per_cta;
+    const int n_tiles = min(p.tiles_per_cta, (p.out_h + TR - 1) / TR - tile0);
+    // source-row window of tile t: rows [sy_lo, sy_lo + nrows) of the box; nrows == 0 -> the tile is all border
+    auto tile_rows = [&](int t, int& sy_lo, int& nrows) {
+        const int Y0 = (tile0 + t) * TR;
+        const int dy_lo = max(Y0 - p.pad_top, 0), dy_hi = min(Y0 + TR - p.pad_top, p.new_h) - 1;
+        sy_lo = 0; nrows = 0;
+        if (has_x && dy_lo <= dy_hi) {
+            sy_lo = __ldg(&p.ytab[dy_lo]).x;
+            nrows = __ldg(&p.ytab[dy_hi]).y - sy_lo + 1;
+        }
+    };
+    auto issue = [&](int t) {  // warp 0 only (warp-uniform branch + elect.sync keeps the TMA operands uniform)
+        int sy_lo, nrows;
+        tile_rows(t, sy_lo, nrows);
+        if (nrows > 0 && elect_one_sync()) {
+            uint64_t* bar = &bars[t & 1];
+            mbar_expect_tx(bar, (uint32_t)(raw_pitch * p.box_rows));
+            tma_load_3d(raw0 + (t & 1) * raw_bytes, &tmap, bar, cx, y0 + sy_lo, img);
+        }
+    };
+    if (tid < 32) issue(0);
+    uint32_t phase0 = 0, phase1 = 0;  // a buffer's mbarrier flips phase only when a TMA was issued for it
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int Y0 = (tile0 + t) * TR;
+        int sy_lo, nrows;
+        tile_rows(t, sy_lo, nrows);
+        // stage this tile's vertical coefficients: {row0*3*TC, row1*3*TC, b0<<16, b1<<16}; x < 0 marks a border row
+        if (tid < TR) {
+            const int dy = Y0 + tid - p.pad_top;
+            int4 ye = make_int4(-1, 0, 0, 0);
+            if (nrows > 0 && dy >= 0 && dy < p.new_h) {
+                ye = __ldg(&p.ytab[dy]);
+                ye.x = (ye.x - sy_lo) * 3 * TC;
+                ye.y = (ye.y - sy_lo) * 3 * TC;
+                if (MODE == K1_MODE_LINEAR) { ye.z <<= 16; ye.w <<= 16; }
+            }
+            s_ytab[tid] = ye;
+        }
+        __syncthreads();  // ytab visible; everybody is done with hbuf and with the raw buffer of tile t-1
+        if (tid < 32 && t + 1 < n_tiles) issue(t + 1);  // prefetch the next tile's source rows under this tile's math
+
+        if (nrows > 0) {
+            if (t & 1) { mbar_wait(&bars[1], phase1); phase1 ^= 1u; } else { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
+            if (hp) {
+                // ---- horizontal pass: cv2's (S[sx]*a0 + S[sx1]*a1) >> 4, once per needed source row
+                const uint8_t* row = raw0 + (t & 1) * raw_bytes + rg * raw_pitch;
+                uint16_t* hrow = hbuf + rg * 3 * TC + hcol;
+#pragma unroll 2
+                for (int r = rg; r < nrows; r += RGS) {
+                    int v0 = row[o0 + 0] * a0 + row[o1 + 0] * a1;
+                    int v1 = row[o0 + 1] * a0 + row[o1 + 1] * a1;
+                    int v2 = row[o0 + 2] * a0 + row[o1 + 2] * a1;
+                    if (MODE == K1_MODE_LINEAR) { v0 >>= 4; v1 >>= 4; v2 >>= 4; }
+                    hrow[c0] = (uint16_t)v0;
+                    hrow[TC] = (uint16_t)v1;
+                    hrow[c2] = (uint16_t)v2;
+                    row += RGS * raw_pitch;
+                    hrow += RGS * 3 * TC;
+                }
             }
         }
-        store8(out + ((size_t)c * p.out_h + Y) * p.out_w + X, f);
+        __syncthreads();
+
+        // ---- vertical pass + normalise + planar vector stores
+        if (X < p.out_w) {
+            for (int yl = vrow; yl < TR; yl += ROWS_PER_PASS) {
+                const int Y = Y0 + yl;
+                if (Y >= p.out_h) break;
+                const int4 ye = s_ytab[yl];
+                OutT* orow = out + (size_t)Y * p.out_w;
+                if (ye.x < 0 || inside == 0) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = pad_val;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) store8(orow + c * plane, f);
+                } else if (inside == 0xffu) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float f[8];
+                        vertical8<MODE, OutT>(hv + ye.x + c * TC, hv + ye.y + c * TC, ye, f);
+                        store8(orow + c * plane, f);
+                    }
+                } else {  // vector straddling the left/right 114 border (at most two vectors per tile row)
+#pragma unroll 1
+                    for (int c = 0; c < 3; ++c) {
+                        float f[8];
+                        vertical8<MODE, OutT>(hv + ye.x + c * TC, hv + ye.y + c * TC, ye, f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) if (!((inside >> e) & 1u)) f[e] = pad_val;
+                        store8(orow + c * plane, f);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -237,16 +306,28 @@ static int get_table(fsd_context* h, int src, int dst, int mode, bool is_x, cons
     return FSD_OK;
 }
 
-template <int MODE, typename OutT>
-static int launch(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, int B, size_t smem,
-                  cudaStream_t stream) {
-    auto kern = k1_gather_letterbox_kernel<MODE, OutT>;
+template <int MODE, typename OutT, int TC>
+static int launch_tc(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, int B, size_t smem, cudaStream_t stream) {
+    auto kern = k1_gather_letterbox_kernel<MODE, OutT, TC>;
     FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((p.out_w + p.tile_cols - 1) / p.tile_cols, (p.out_h + p.tile_rows - 1) / p.tile_rows, B);
+    const int tiles_y = (p.out_h + p.tile_rows - 1) / p.tile_rows;
+    dim3 grid((p.out_w + TC - 1) / TC, (tiles_y + p.tiles_per_cta - 1) / p.tiles_per_cta, B);
     kern<<<grid, K1_THREADS, smem, stream>>>(tmap, p);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;
+}
+
+template <int MODE, typename OutT>
+static int launch(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, int B, size_t smem, cudaStream_t stream) {
+    switch (p.tile_cols) {
+        case 256: return launch_tc<MODE, OutT, 256>(h, tmap, p, B, smem, stream);
+        case 128: return launch_tc<MODE, OutT, 128>(h, tmap, p, B, smem, stream);
+        case 64: return launch_tc<MODE, OutT, 64>(h, tmap, p, B, smem, stream);
+        case 32: return launch_tc<MODE, OutT, 32>(h, tmap, p, B, smem, stream);
+        case 16: return launch_tc<MODE, OutT, 16>(h, tmap, p, B, smem, stream);
+        default: return launch_tc<MODE, OutT, 8>(h, tmap, p, B, smem, stream);
+    }
 }
 
 }  // namespace fsd
@@ -324,7 +405,7 @@ extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n
                 if (r > rows) rows = r;
             }
             if (rows > 256) continue;
-            size_t s = (((size_t)bw * 4 * rows + 127) & ~(size_t)127) + (((size_t)rows * 3 * tc * 2 + 127) & ~(size_t)127) + 32 * 16 + 16 + 128;
+            size_t s = 2 * (((size_t)bw * 4 * rows + 127) & ~(size_t)127) + (((size_t)rows * 3 * tc * 2 + 127) & ~(size_t)127) + 32 * 16 + 16 + 128;
             if (s <= smem_budget) { TC = tc; TR = tr; box_w = bw; box_rows = rows; smem = s; break; }
         }
         if (TC) break;
@@ -334,6 +415,8 @@ extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n
         return FSD_ERR_CAPACITY;
     }
     p.tile_cols = TC; p.tile_rows = TR; p.box_w_elems = box_w; p.box_rows = box_rows;
+    p.tiles_per_cta = getenv("FSD_K1_TPC") ? atoi(getenv("FSD_K1_TPC")) : 2;
+    if (p.tiles_per_cta < 1) p.tiles_per_cta = 1;
 
     // TMA tensor map over the image pool: u32 elements, dims {pitch/4, H, N}
     if (n_images == 1) image_pitch = row_pitch * H;
