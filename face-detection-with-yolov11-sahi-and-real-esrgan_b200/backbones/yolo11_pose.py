@@ -28,7 +28,17 @@ class Conv(nn.Module):
         self.act = nn.SiLU(inplace=True) if act else nn.Identity()
 
     def forward(self, x):
-        return self.act(self.conv(x))
+        c = self.conv
+        if (x.is_cuda and x.dtype == torch.float16 and c.out_channels % 8 == 0 and isinstance(self.act, nn.SiLU)
+                and not torch.is_grad_enabled()):
+            # cuDNN convolution without bias, then ONE hand-written pass for + bias and SiLU (fsd_bias_act_inplace)
+            y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
+            if y.is_contiguous(memory_format=torch.channels_last):
+                from ..ops import bias_act_
+
+                return bias_act_(y, c.bias, "silu")
+            return self.act(y + c.bias.view(1, -1, 1, 1))
+        return self.act(c(x))
 
 
 class DWConv(Conv):

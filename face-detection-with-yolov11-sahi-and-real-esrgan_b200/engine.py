@@ -79,6 +79,7 @@ class SlicedFaceDetector:
         if channels_last:
             bb = bb.to(memory_format=torch.channels_last)
         self.backbone = bb
+        torch.backends.cudnn.benchmark = True  # per-shape algorithm search: the batched shapes repeat for every step
         self._plans: Dict = {}
         self._dev_cache: Dict = {}
         self.handle = _cabi.get_handle(self.device.index or 0)

@@ -213,6 +213,21 @@ def pack_results(det, group_offsets, s2, src_index, out: torch.Tensor | None = N
     return out, offsets
 
 
+_ACT = {None: 0, "none": 0, "silu": 1, "lrelu": 2}
+
+
+def bias_act_(x: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: float = 0.2) -> torch.Tensor:
+    """(a5) in-place conv epilogue x = act(x + bias[c]) for a channels-last CUDA tensor [N,C,H,W] (one HBM pass)."""
+    _require_cuda(x, "x")
+    n, c, hh, ww = x.shape
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("bias_act_ needs a dense channels_last tensor")
+    h = _handle_for(x)
+    check(h.lib.fsd_bias_act_inplace(h.h, x.data_ptr(), bias.data_ptr(), n * hh * ww, c, _ACT[act], float(slope),
+                                     _TORCH_DTYPE[x.dtype], _stream_ptr(x.device)), "fsd_bias_act_inplace")
+    return x
+
+
 # ---- Kernel 4 -------------------------------------------------------------------------------------------
 def esrgan_tile_table(H: int, W: int, scale: int, tile: int, tile_pad: int = 10, pre_pad: int = 0):
     """Host tile table [T,12] int32 + (padded_h, padded_w)."""

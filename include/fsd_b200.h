@@ -138,6 +138,13 @@ int fsd_pack_results(fsd_handle_t h, const float* det, const int32_t* group_offs
                      const int32_t* keep_count, const float* merged_boxes, const float* merged_scores,
                      const int32_t* src_index, int G, float* out, int32_t* out_offsets, void* stream);
 
+/* ---- (a5) backbone conv epilogue: x = act(x + bias[c]) in place over a dense channels-last tensor [n_pixels, channels]
+ *      (act: 0 none, 1 SiLU, 2 LeakyReLU(slope)).  The conv backbones stay PyTorch/cuDNN (BASELINE.json north_star);
+ *      this replaces the two eager elementwise passes torch runs after every convolution of ultralytics' Conv
+ *      (conv -> +bias -> SiLU) and basicsr's RRDB blocks (conv -> +bias -> LeakyReLU 0.2) with one read+write. */
+int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, int64_t n_pixels, int channels, int act,
+                         float slope, int dtype, void* stream);
+
 /* ---- Kernel 4 (a15) Real-ESRGAN tile crop / stitch.  Replaces RealESRGANer.enhance/pre_process/
  *      tile_process/post_process [EXT realesrgan 0.3.0], reached from utils/enhancer.py:214.
  *      fsd_esrgan_tile_table: host-side tile table; each row = 12 int32:

@@ -85,3 +85,21 @@ def test_round_half_even_and_clamp(cuda_device):
     ref = out.cpu().clamp_(0, 1).numpy()
     ref = (np.transpose(ref[[2, 1, 0]], (1, 2, 0)) * 255.0).round().astype(np.uint8)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("act", ["silu", "lrelu", "none"])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_bias_act_epilogue(cuda_device, act, dtype):
+    """(a5) fused conv epilogue vs torch: x + bias then SiLU / LeakyReLU(0.2), channels-last, in place."""
+    import fsd_b200.ops as ops
+
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn((3, 32, 17, 23), generator=g) * 3).to(dtype).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    b = torch.randn((32,), generator=g).to(dtype).to(cuda_device)
+    ref = (x.float() + b.float().view(1, -1, 1, 1))
+    ref = {"silu": torch.nn.functional.silu, "lrelu": lambda t: torch.nn.functional.leaky_relu(t, 0.2), "none": lambda t: t}[act](ref)
+    got = ops.bias_act_(x.clone(memory_format=torch.channels_last), b, act, 0.2)
+    tol = 2e-3 if dtype == torch.float16 else 1e-5
+    assert torch.allclose(got.float(), ref, atol=tol, rtol=tol)
+    with pytest.raises(Exception):
+        ops.bias_act_(x.contiguous(), b, act)
