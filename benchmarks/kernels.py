@@ -70,11 +70,12 @@ def bench_k1():
             ent = torch.tensor([[i, b[0], b[1]] for i in range(N) for b in boxes], dtype=torch.int32, device=dev)
             sw = sh = sl
         g = _cabi.letterbox_geometry(sh, sw, 1024, 32)
-        for dt in (torch.float16, torch.float32):
-            out = torch.empty((ent.shape[0], 3, g["out_h"], g["out_w"]), dtype=dt, device=dev)
+        for dt, cl in ((torch.float16, False), (torch.float16, True), (torch.float32, False)):
+            out = torch.empty((ent.shape[0], 3, g["out_h"], g["out_w"]), dtype=dt, device=dev,
+                              memory_format=torch.channels_last if cl else torch.contiguous_format)
             nbytes = out.numel() * out.element_size() + N * H * W * 3
-            report(f"K1 {name} {str(dt)[6:]}", nbytes, lambda: ops.gather_letterbox(pool, ent, sw, sh, 1024, 32, True, dt, out=out),
-                   entries=int(ent.shape[0]))
+            report(f"K1 {name} {str(dt)[6:]} {'NHWC' if cl else 'NCHW'}", nbytes,
+                   lambda: ops.gather_letterbox(pool, ent, sw, sh, 1024, 32, True, dt, out=out), entries=int(ent.shape[0]))
         del pool, out
 
 

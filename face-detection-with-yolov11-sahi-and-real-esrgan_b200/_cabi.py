@@ -26,7 +26,7 @@ SIGNATURES = {
                                  C.POINTER(C.c_int)]),
     "fsd_letterbox_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, C.POINTER(C.c_double)]),
     "fsd_gather_letterbox": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, vp, C.c_int,
-                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "fsd_pose_decode": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), c_i32p, C.c_int, C.c_int,
                                   C.c_int, C.c_float, vp, C.c_int, vp, vp]),
     "fsd_merge_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),

@@ -59,6 +59,7 @@ int fsd_destroy(fsd_handle_t h) {
     cudaSetDevice(h->device);
     for (auto& kv : h->resize_tables)
         if (kv.second.dev) cudaFree(kv.second.dev);
+    for (void* d : h->dev_allocs) cudaFree(d);
     delete h;
     return FSD_OK;
 }

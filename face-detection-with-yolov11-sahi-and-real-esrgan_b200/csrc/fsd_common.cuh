@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <tuple>
@@ -53,6 +54,8 @@ struct fsd_context {
     std::map<std::tuple<int, int, int>, fsd::ResizeTable> resize_tables;
     // Kernel 1 tensor maps keyed by (base, n, H, pitch/image_pitch, box_w, box_h)
     std::map<std::tuple<uintptr_t, int, int, int64_t, int64_t, int, int>, CUtensorMap> tensor_maps;
+    std::map<std::tuple<int, int, int, int>, std::shared_ptr<void>> k1_plans;  // Kernel 1 geometry plans
+    std::vector<void*> dev_allocs;  // device buffers owned by the handle (freed in fsd_destroy)
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
 };
 

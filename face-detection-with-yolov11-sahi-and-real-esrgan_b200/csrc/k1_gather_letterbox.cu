@@ -63,6 +63,51 @@ __device__ __forceinline__ void store8(float* dst, const float (&f)[8]) {
     *reinterpret_cast<float4*>(dst + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+// 8 pixels of one plane in store precision (fp16: 4 packed words, fp32: 8 floats)
+template <typename OutT> struct Packed8;
+template <> struct Packed8<__half> {
+    uint32_t w[4];
+    __device__ __forceinline__ void set(const float (&f)[8]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+            w[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+    }
+};
+template <> struct Packed8<float> {
+    float f[8];
+    __device__ __forceinline__ void set(const float (&g)[8]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = g[e];
+    }
+};
+
+// channels-last store of 8 pixels x 3 channels (48 B fp16 / 96 B fp32, contiguous)
+__device__ __forceinline__ void store_nhwc(__half* dst, const Packed8<__half>& c0, const Packed8<__half>& c1, const Packed8<__half>& c2) {
+    uint32_t o[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // word k of a plane holds pixels (2k, 2k+1)
+        o[3 * k + 0] = __byte_perm(c0.w[k], c1.w[k], 0x5410);  // p(2k).c0, p(2k).c1
+        o[3 * k + 1] = __byte_perm(c2.w[k], c0.w[k], 0x7610);  // p(2k).c2, p(2k+1).c0
+        o[3 * k + 2] = __byte_perm(c1.w[k], c2.w[k], 0x7632);  // p(2k+1).c1, p(2k+1).c2
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    d[2] = make_uint4(o[8], o[9], o[10], o[11]);
+}
+__device__ __forceinline__ void store_nhwc(float* dst, const Packed8<float>& c0, const Packed8<float>& c1, const Packed8<float>& c2) {
+    float4* d = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {  // 4 pixels = 12 floats = 3 float4
+        const int e = 4 * k;
+        d[3 * k + 0] = make_float4(c0.f[e], c1.f[e], c2.f[e], c0.f[e + 1]);
+        d[3 * k + 1] = make_float4(c1.f[e + 1], c2.f[e + 1], c0.f[e + 2], c1.f[e + 2]);
+        d[3 * k + 2] = make_float4(c2.f[e + 2], c0.f[e + 3], c1.f[e + 3], c2.f[e + 3]);
+    }
+}
+
 // vertical pass for 8 consecutive pixels of one plane: cv2's ((b0*h0)>>16 + (b1*h1)>>16 + 2) >> 2 with the two
 // products as IMAD.HI against the pre-shifted coefficients, then /255
 template <int MODE, typename OutT>
@@ -82,7 +127,7 @@ __device__ __forceinline__ void vertical8(const uint16_t* r0, const uint16_t* r1
 }
 
 
-template <int MODE, typename OutT, int TC>
+template <int MODE, typename OutT, int TC, bool NHWC>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Params p) {
     // dynamic smem, manually aligned to 128 B (TMA destination rule): [raw box x2 | hbuf | ytab | 2 mbarriers]
@@ -102,8 +147,8 @@ k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Par
     const int hbuf_bytes = (p.box_rows * 3 * TC * 2 + 127) & ~127;
     uint8_t* raw0 = smem;                                                       // 2 x [box_rows][raw_pitch]
     uint16_t* hbuf = reinterpret_cast<uint16_t*>(smem + 2 * raw_bytes);         // [box_rows][3][TC]
-    int4* s_ytab = reinterpret_cast<int4*>(smem + 2 * raw_bytes + hbuf_bytes);  // [TR]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * raw_bytes + hbuf_bytes + 32 * 16);
+    int4* s_ytab2 = reinterpret_cast<int4*>(smem + 2 * raw_bytes + hbuf_bytes);  // 2 x [32], double-buffered by tile parity
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * raw_bytes + hbuf_bytes + 64 * 16);
 
     // ---- x-dependent set-up, once per CTA ---------------------------------------------------------------
     const int dx_lo = max(X0 - p.pad_left, 0), dx_hi = min(X0 + TC - p.pad_left, p.new_w) - 1;
@@ -142,7 +187,7 @@ k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Par
     }
     const float pad_val = norm255<OutT>(114);
     const size_t plane = (size_t)p.out_h * p.out_w;
-    OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * 3 * plane + X;
+    OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * 3 * plane + (NHWC ? (size_t)X * 3 : (size_t)X);
     const uint16_t* hv = hbuf + v * 8;
 
     if (tid == 0) {
@@ -181,6 +226,7 @@ k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Par
         int sy_lo, nrows;
         tile_rows(t, sy_lo, nrows);
         // stage this tile's vertical coefficients: {row0*3*TC, row1*3*TC, b0<<16, b1<<16}; x < 0 marks a border row
+        int4* s_ytab = s_ytab2 + (t & 1) * 32;  // tile t+1 stages while slower warps still read tile t's table
         if (tid < TR) {
             const int dy = Y0 + tid - p.pad_top;
             int4 ye = make_int4(-1, 0, 0, 0);
@@ -223,29 +269,52 @@ k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Par
                 const int Y = Y0 + yl;
                 if (Y >= p.out_h) break;
                 const int4 ye = s_ytab[yl];
-                OutT* orow = out + (size_t)Y * p.out_w;
-                if (ye.x < 0 || inside == 0) {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = pad_val;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) store8(orow + c * plane, f);
-                } else if (inside == 0xffu) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
+                OutT* orow = out + (size_t)Y * p.out_w * (NHWC ? 3 : 1);
+                const bool border = ye.x < 0 || inside == 0;
+                if (!NHWC) {
+                    // planar NCHW: one plane at a time keeps the register footprint at one 8-pixel vector
+                    if (border) {
                         float f[8];
-                        vertical8<MODE, OutT>(hv + ye.x + c * TC, hv + ye.y + c * TC, ye, f);
-                        store8(orow + c * plane, f);
-                    }
-                } else {  // vector straddling the left/right 114 border (at most two vectors per tile row)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = pad_val;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) store8(orow + c * plane, f);
+                    } else if (inside == 0xffu) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float f[8];
+                            vertical8<MODE, OutT>(hv + ye.x + c * TC, hv + ye.y + c * TC, ye, f);
+                            store8(orow + c * plane, f);
+                        }
+                    } else {  // vector straddling the left/right 114 border (at most two vectors per tile row)
 #pragma unroll 1
+                        for (int c = 0; c < 3; ++c) {
+                            float f[8];
+                            vertical8<MODE, OutT>(hv + ye.x + c * TC, hv + ye.y + c * TC, ye, f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) if (!((inside >> e) & 1u)) f[e] = pad_val;
+                            store8(orow + c * plane, f);
+                        }
+                    }
+                } else {
+                    // channels-last: the three planes of 8 pixels are packed first, then interleaved into 48 (96) bytes
+                    Packed8<OutT> pk[3];
+#pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         float f[8];
-                        vertical8<MODE, OutT>(hv + ye.x + c * TC, hv + ye.y + c * TC, ye, f);
+                        if (border) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) if (!((inside >> e) & 1u)) f[e] = pad_val;
-                        store8(orow + c * plane, f);
+                            for (int e = 0; e < 8; ++e) f[e] = pad_val;
+                        } else {
+                            vertical8<MODE, OutT>(hv + ye.x + c * TC, hv + ye.y + c * TC, ye, f);
+                            if (inside != 0xffu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) if (!((inside >> e) & 1u)) f[e] = pad_val;
+                            }
+                        }
+                        pk[c].set(f);
                     }
+                    store_nhwc(orow, pk[0], pk[1], pk[2]);
                 }
             }
         }
@@ -306,9 +375,9 @@ static int get_table(fsd_context* h, int src, int dst, int mode, bool is_x, cons
     return FSD_OK;
 }
 
-template <int MODE, typename OutT, int TC>
+template <int MODE, typename OutT, int TC, bool NHWC>
 static int launch_tc(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, int B, size_t smem, cudaStream_t stream) {
-    auto kern = k1_gather_letterbox_kernel<MODE, OutT, TC>;
+    auto kern = k1_gather_letterbox_kernel<MODE, OutT, TC, NHWC>;
     FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_y = (p.out_h + p.tile_rows - 1) / p.tile_rows;
     dim3 grid((p.out_w + TC - 1) / TC, (tiles_y + p.tiles_per_cta - 1) / p.tiles_per_cta, B);
@@ -318,16 +387,21 @@ static int launch_tc(fsd_context* h, const CUtensorMap& tmap, const K1Params& p,
     return FSD_OK;
 }
 
-template <int MODE, typename OutT>
-static int launch(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, int B, size_t smem, cudaStream_t stream) {
+template <int MODE, typename OutT, bool NHWC>
+static int launch_l(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, int B, size_t smem, cudaStream_t stream) {
     switch (p.tile_cols) {
-        case 256: return launch_tc<MODE, OutT, 256>(h, tmap, p, B, smem, stream);
-        case 128: return launch_tc<MODE, OutT, 128>(h, tmap, p, B, smem, stream);
-        case 64: return launch_tc<MODE, OutT, 64>(h, tmap, p, B, smem, stream);
-        case 32: return launch_tc<MODE, OutT, 32>(h, tmap, p, B, smem, stream);
-        case 16: return launch_tc<MODE, OutT, 16>(h, tmap, p, B, smem, stream);
-        default: return launch_tc<MODE, OutT, 8>(h, tmap, p, B, smem, stream);
+        case 256: return launch_tc<MODE, OutT, 256, NHWC>(h, tmap, p, B, smem, stream);
+        case 128: return launch_tc<MODE, OutT, 128, NHWC>(h, tmap, p, B, smem, stream);
+        case 64: return launch_tc<MODE, OutT, 64, NHWC>(h, tmap, p, B, smem, stream);
+        case 32: return launch_tc<MODE, OutT, 32, NHWC>(h, tmap, p, B, smem, stream);
+        case 16: return launch_tc<MODE, OutT, 16, NHWC>(h, tmap, p, B, smem, stream);
+        default: return launch_tc<MODE, OutT, 8, NHWC>(h, tmap, p, B, smem, stream);
     }
+}
+
+template <int MODE, typename OutT>
+static int launch(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, int B, size_t smem, int nhwc, cudaStream_t stream) {
+    return nhwc ? launch_l<MODE, OutT, true>(h, tmap, p, B, smem, stream) : launch_l<MODE, OutT, false>(h, tmap, p, B, smem, stream);
 }
 
 }  // namespace fsd
@@ -337,11 +411,12 @@ using namespace fsd;
 extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n_images, int H, int W,
                                     int64_t row_pitch, int64_t image_pitch, const int32_t* entries, int B,
                                     int src_w, int src_h, int imgsz, int stride, int reverse_channels,
-                                    int dtype, void* out, void* stream_) {
+                                    int dtype, int out_layout, void* out, void* stream_) {
     FSD_CHECK_ARG(h && images && entries && out, "fsd_gather_letterbox: null argument");
     FSD_CHECK_ARG(n_images > 0 && H > 0 && W > 0 && B >= 0, "fsd_gather_letterbox: bad sizes");
     FSD_CHECK_ARG(src_w > 0 && src_h > 0 && src_w <= W && src_h <= H, "fsd_gather_letterbox: source box %dx%d does not fit image %dx%d", src_w, src_h, W, H);
     FSD_CHECK_ARG(dtype == FSD_F16 || dtype == FSD_F32, "fsd_gather_letterbox: dtype must be FSD_F16 or FSD_F32");
+    FSD_CHECK_ARG(out_layout == FSD_PLANAR || out_layout == FSD_CHANNELS_LAST, "fsd_gather_letterbox: bad output layout");
     FSD_CHECK_ARG(B <= 65535, "fsd_gather_letterbox: at most 65535 entries per call");
     if (((uintptr_t)images & 15) || (row_pitch & 15) || (image_pitch & 15) || row_pitch < (int64_t)W * 3 ||
         (n_images > 1 && image_pitch < row_pitch * H)) {
@@ -405,7 +480,7 @@ extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n
                 if (r > rows) rows = r;
             }
             if (rows > 256) continue;
-            size_t s = 2 * (((size_t)bw * 4 * rows + 127) & ~(size_t)127) + (((size_t)rows * 3 * tc * 2 + 127) & ~(size_t)127) + 32 * 16 + 16 + 128;
+            size_t s = 2 * (((size_t)bw * 4 * rows + 127) & ~(size_t)127) + (((size_t)rows * 3 * tc * 2 + 127) & ~(size_t)127) + 64 * 16 + 16 + 128;
             if (s <= smem_budget) { TC = tc; TR = tr; box_w = bw; box_rows = rows; smem = s; break; }
         }
         if (TC) break;
@@ -445,11 +520,12 @@ extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n
         it = h->tensor_maps.emplace(key, m).first;
     }
     const CUtensorMap& tmap = it->second;
+    const int nhwc = out_layout == FSD_CHANNELS_LAST;
 
     if (mode == K1_MODE_AREA2) {
-        return dtype == FSD_F16 ? launch<K1_MODE_AREA2, __half>(h, tmap, p, B, smem, stream)
-                                : launch<K1_MODE_AREA2, float>(h, tmap, p, B, smem, stream);
+        return dtype == FSD_F16 ? launch<K1_MODE_AREA2, __half>(h, tmap, p, B, smem, nhwc, stream)
+                                : launch<K1_MODE_AREA2, float>(h, tmap, p, B, smem, nhwc, stream);
     }
-    return dtype == FSD_F16 ? launch<K1_MODE_LINEAR, __half>(h, tmap, p, B, smem, stream)
-                            : launch<K1_MODE_LINEAR, float>(h, tmap, p, B, smem, stream);
+    return dtype == FSD_F16 ? launch<K1_MODE_LINEAR, __half>(h, tmap, p, B, smem, nhwc, stream)
+                            : launch<K1_MODE_LINEAR, float>(h, tmap, p, B, smem, nhwc, stream);
 }

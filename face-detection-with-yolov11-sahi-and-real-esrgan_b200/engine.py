@@ -131,9 +131,7 @@ class SlicedFaceDetector:
         """backbone + Kernel 2a over a batch of network inputs, in chunks that bound activation memory."""
         E = x.shape[0]
         for a in range(0, E, self.chunk):
-            xb = x[a:a + self.chunk]
-            if self.channels_last:
-                xb = xb.contiguous(memory_format=torch.channels_last)
+            xb = x[a:a + self.chunk]  # Kernel 1 already wrote the layout the backbone wants: no conversion pass
             levels = self.backbone(xb)
             if self.head_hook is not None:
                 levels = self.head_hook(kind, a, xb, levels)
@@ -159,7 +157,8 @@ class SlicedFaceDetector:
         while True:  # retried with a larger candidate capacity if a slice overflowed it
             cand_s = torch.empty((E, self.cap, ROW), dtype=torch.float32, device=dev)
             count_s = torch.empty((E,), dtype=torch.int32, device=dev)
-            x_s = ops.gather_letterbox(pool, t["ent_s"], plan.box_w, plan.box_h, self.imgsz, self.stride, self.reverse, self.dtype)
+            x_s = ops.gather_letterbox(pool, t["ent_s"], plan.box_w, plan.box_h, self.imgsz, self.stride, self.reverse, self.dtype,
+                                       channels_last=self.channels_last)
             self._forward_entries("slices", x_s, cand_s, count_s)
             del x_s
             s1 = self._stage1(cand_s, count_s, t["seg_s"])
@@ -171,7 +170,8 @@ class SlicedFaceDetector:
             if plan.g_full is not None:
                 cand_f = torch.empty((N, self.cap, ROW), dtype=torch.float32, device=dev)
                 count_f = torch.empty((N,), dtype=torch.int32, device=dev)
-                x_f = ops.gather_letterbox(pool, t["ent_f"], plan.W, plan.H, self.imgsz, self.stride, self.reverse, self.dtype)
+                x_f = ops.gather_letterbox(pool, t["ent_f"], plan.W, plan.H, self.imgsz, self.stride, self.reverse, self.dtype,
+                                           channels_last=self.channels_last)
                 self._forward_entries("full", x_f, cand_f, count_f)
                 del x_f
                 s1f = self._stage1(cand_f, count_f, t["seg_f"])
@@ -227,7 +227,8 @@ class SlicedFaceDetector:
             while True:
                 cand = torch.empty((1, self.cap, ROW), dtype=torch.float32, device=dev)
                 count = torch.empty((1,), dtype=torch.int32, device=dev)
-                x = ops.gather_letterbox(pool, torch.zeros((1, 3), **i32), W, H, self.imgsz, self.stride, self.reverse, self.dtype)
+                x = ops.gather_letterbox(pool, torch.zeros((1, 3), **i32), W, H, self.imgsz, self.stride, self.reverse, self.dtype,
+                                         channels_last=self.channels_last)
                 self._forward_entries("single", x, cand, count)
                 if int(count[0]) > self.cap:
                     self.cap = 1 << (int(count[0]) - 1).bit_length()

@@ -81,19 +81,26 @@ class ImagePool:
 
 def gather_letterbox(pool: ImagePool, entries: torch.Tensor, src_w: int, src_h: int, imgsz: int = 1024,
                      stride: int = 32, reverse_channels: bool = True, dtype=torch.float16,
-                     out: torch.Tensor | None = None) -> torch.Tensor:
-    """Kernel 1: entries int32 [B,3] (image_index, x0, y0) -> [B,3,out_h,out_w] network input."""
+                     out: torch.Tensor | None = None, channels_last: bool = False) -> torch.Tensor:
+    """Kernel 1: entries int32 [B,3] (image_index, x0, y0) -> [B,3,out_h,out_w] network input (NCHW or channels-last)."""
     _require_cuda(pool.buf, "image pool")
     g = _cabi.letterbox_geometry(src_h, src_w, imgsz, stride)
     B = int(entries.shape[0])
     if out is None:
-        out = torch.empty((B, 3, g["out_h"], g["out_w"]), dtype=dtype, device=pool.device)
+        out = torch.empty((B, 3, g["out_h"], g["out_w"]), dtype=dtype, device=pool.device,
+                          memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    if out.is_contiguous():
+        layout = _cabi.FSD_PLANAR
+    elif out.is_contiguous(memory_format=torch.channels_last):
+        layout = _cabi.FSD_CHANNELS_LAST
+    else:
+        raise ValueError("gather_letterbox output must be dense NCHW or channels_last")
     if entries.dtype != torch.int32 or not entries.is_cuda or not entries.is_contiguous():
         entries = entries.to(device=pool.device, dtype=torch.int32).contiguous()
     h = _handle_for(pool.buf)
     check(h.lib.fsd_gather_letterbox(h.h, pool.buf.data_ptr(), pool.n, pool.h, pool.w, pool.pitch,
                                      pool.image_pitch, entries.data_ptr(), B, src_w, src_h, imgsz, stride,
-                                     1 if reverse_channels else 0, _TORCH_DTYPE[out.dtype], out.data_ptr(),
+                                     1 if reverse_channels else 0, _TORCH_DTYPE[out.dtype], layout, out.data_ptr(),
                                      _stream_ptr(pool.device)), "fsd_gather_letterbox")
     return out
 

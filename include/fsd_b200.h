@@ -67,11 +67,12 @@ int fsd_letterbox_geometry(int src_h, int src_w, int imgsz, int stride, int32_t 
  *      images: dev, n_images x [H, row_pitch] bytes of HWC uint8 (3 channels), image i at i*image_pitch;
  *              base pointer, row_pitch and image_pitch must be multiples of 16 (TMA tensor-map rule).
  *      entries: dev int32 [B,3] = (image_index, x0, y0) of each source box; all boxes are src_w x src_h.
- *      out: dev [B,3,out_h,out_w] of dtype, with out_h/out_w from fsd_letterbox_geometry. */
+ *      out: dev [B,3,out_h,out_w] of dtype (out_h/out_w from fsd_letterbox_geometry), stored planar
+ *           (FSD_PLANAR, NCHW) or channels-last (FSD_CHANNELS_LAST, [B,out_h,out_w,3]) per out_layout. */
 int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n_images, int H, int W,
                          int64_t row_pitch, int64_t image_pitch, const int32_t* entries, int B, int src_w,
-                         int src_h, int imgsz, int stride, int reverse_channels, int dtype, void* out,
-                         void* stream);
+                         int src_h, int imgsz, int stride, int reverse_channels, int dtype, int out_layout,
+                         void* out, void* stream);
 
 /* ---- Kernel 2a (a6,a7) fused pose-head decode + confidence gate + compaction.
  *      Replaces ultralytics Detect/Pose._inference, DFL, dist2bbox, kpts_decode and the `xc` candidate

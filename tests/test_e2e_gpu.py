@@ -106,8 +106,11 @@ def test_batch_api_equals_single_image_api(cuda_device):
     batch = get_sliced_prediction_batch(imgs, model, 256, 256, 0.2, 0.2)
     # a different batch size changes cuDNN's algorithm choice, hence (slightly) the head tensors: compare loosely here,
     # the exact comparison is test_fused_path_equals_oracle_flow
+    n_kp = n_all = 0
     for img, res in zip(imgs, batch):
         one = get_sliced_prediction(img, model, slice_height=256, slice_width=256, verbose=0)
         assert abs(len(one.object_prediction_list) - len(res.object_prediction_list)) <= max(5, len(one.object_prediction_list) // 3)
         assert (res.image_width, res.image_height) == (512, 384)
-        assert any(hasattr(p, "keypoints") for p in res.object_prediction_list)  # union boxes may match no detection
+        n_kp += sum(hasattr(p, "keypoints") for p in res.object_prediction_list)  # union boxes may match no detection
+        n_all += len(res.object_prediction_list)
+    assert n_all > 0 and n_kp >= n_all // 2

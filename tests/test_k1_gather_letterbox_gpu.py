@@ -74,5 +74,24 @@ def test_bad_pitch_is_rejected(cuda_device):
     out = torch.empty((1, 3, 64, 64), dtype=torch.float16, device=cuda_device)
     ent = torch.zeros((1, 3), dtype=torch.int32, device=cuda_device)
     rc = h.lib.fsd_gather_letterbox(h.h, pool.buf.data_ptr(), 1, 64, 64, 64 * 3 + 2, 0, ent.data_ptr(), 1, 64, 64,
-                                    64, 32, 1, 0, out.data_ptr(), 0)
+                                    64, 32, 1, 0, 0, out.data_ptr(), 0)
     assert rc == -2 and b"16-byte" in h.lib.fsd_last_error()
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[4]])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_channels_last_output(cuda_device, case, dtype):
+    """Kernel 1 can emit the network input channels-last (what the cuDNN backbone consumes without a layout copy)."""
+    import fsd_b200.ops as ops
+
+    H, W, sh, sw, ov, imgsz = case
+    rng = np.random.default_rng(99)
+    images = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8)]
+    boxes = osl.get_slice_bboxes(H, W, sh, sw, overlap_height_ratio=ov, overlap_width_ratio=ov)
+    bw, bh = boxes[0][2] - boxes[0][0], boxes[0][3] - boxes[0][1]
+    entries = [(0, b[0], b[1]) for b in boxes]
+    pool = ops.ImagePool.from_numpy(images, cuda_device)
+    out = ops.gather_letterbox(pool, torch.tensor(entries, dtype=torch.int32), bw, bh, imgsz=imgsz, dtype=dtype, channels_last=True)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    ref = _oracle_batch(images, entries, bw, bh, imgsz, dtype == torch.float16, True)
+    assert torch.equal(out.cpu(), ref)
