@@ -139,7 +139,7 @@ def bench_k4():
 
         def crop():
             k[0] = (k[0] + 1) % N
-            ops.esrgan_crop(imgs[k[0]], table, scale)
+            ops.esrgan_crop(imgs[k[0]], table, scale, tab_dev=tab_dev, tiles=tiles)
 
         report(f"K4 crop {W}x{H} x{scale} tile {tile} fp16", crop_bytes, crop, tiles=len(table))
         outs = [torch.rand(ops.esrgan_out_buffer(table, scale, torch.float16, dev).shape, device=dev).half() for _ in range(4)]

@@ -40,6 +40,26 @@ class Conv(nn.Module):
             return self.act(y + c.bias.view(1, -1, 1, 1))
         return self.act(c(x))
 
+    def forward_split(self, x, sizes):
+        """The same convolution evaluated as one conv per output-channel group (weight views, no copies): every
+        group comes out dense, so consumers of `chunk`/`split` need no strided-slice copy and residual adds vectorise."""
+        c, outs, a = self.conv, [], 0
+        fused = (x.is_cuda and x.dtype == torch.float16 and isinstance(self.act, nn.SiLU) and not torch.is_grad_enabled()
+                 and all(n % 8 == 0 for n in sizes))
+        if not fused:
+            return list(self.forward(x).split(sizes, 1))
+        from ..ops import bias_act_
+
+        for n in sizes:
+            y = F.conv2d(x, c.weight[a:a + n], None, c.stride, c.padding, c.dilation, c.groups)
+            if y.is_contiguous(memory_format=torch.channels_last):
+                y = bias_act_(y, c.bias[a:a + n], "silu")
+            else:
+                y = self.act(y + c.bias[a:a + n].view(1, -1, 1, 1))
+            outs.append(y)
+            a += n
+        return outs
+
 
 class DWConv(Conv):
     def __init__(self, c1, c2, k=1, s=1, act=True):
@@ -79,7 +99,7 @@ class C3k2(nn.Module):
                                for _ in range(n))
 
     def forward(self, x):
-        y = list(self.cv1(x).chunk(2, 1))
+        y = self.cv1.forward_split(x, [self.c, self.c])
         y.extend(m(y[-1]) for m in self.m)
         return self.cv2(torch.cat(y, 1))
 
@@ -141,8 +161,19 @@ class C2PSA(nn.Module):
         self.m = nn.Sequential(*(PSABlock(self.c, attn_ratio=0.5, num_heads=max(1, self.c // 64)) for _ in range(n)))
 
     def forward(self, x):
-        a, b = self.cv1(x).split((self.c, self.c), dim=1)
+        a, b = self.cv1.forward_split(x, [self.c, self.c])
         return self.cv2(torch.cat((a, self.m(b)), 1))
+
+
+def _up_cat(a, b):
+    """cat(nearest-2x(a), b): one fused pass on the GPU (fsd_upsample2x_concat), plain torch elsewhere."""
+    if (a.is_cuda and a.dtype == torch.float16 and a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0
+            and a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last)
+            and not torch.is_grad_enabled()):
+        from ..ops import upsample2x_concat
+
+        return upsample2x_concat(a, b)
+    return torch.cat((F.interpolate(a, scale_factor=2.0, mode="nearest"), b), 1)
 
 
 class PoseHead(nn.Module):
@@ -200,8 +231,8 @@ class YOLO11Pose(nn.Module):
         p3 = self.b4(self.b3(self.b2(x)))
         p4 = self.b6(self.b5(p3))
         p5 = self.b10(self.b9(self.b8(self.b7(p4))))
-        n4 = self.h13(torch.cat((F.interpolate(p5, scale_factor=2.0, mode="nearest"), p4), 1))
-        n3 = self.h16(torch.cat((F.interpolate(n4, scale_factor=2.0, mode="nearest"), p3), 1))
+        n4 = self.h13(_up_cat(p5, p4))
+        n3 = self.h16(_up_cat(n4, p3))
         m4 = self.h19(torch.cat((self.h17(n3), n4), 1))
         m5 = self.h22(torch.cat((self.h20(m4), p5), 1))
         return self.head([n3, m4, m5])

@@ -48,6 +48,9 @@ struct MatchCfg {
 
 __device__ __forceinline__ bool match_pair(const float4 a, const float4 b, int ca, int cb, const MatchCfg& m) {
     if (!m.class_agnostic && ca != cb) return false;
+    // disjoint boxes have intersection 0 -> metric 0 -> no match for any positive threshold: decided with four fp32
+    // min/max and two compares (exact: comparisons only), so the fp64 path below runs for overlapping pairs only
+    if (m.thr > 0.0 && (fminf(a.z, b.z) <= fmaxf(a.x, b.x) || fminf(a.w, b.w) <= fmaxf(a.y, b.y))) return false;
     if (m.precision == 1) {
         // torchvision nms_kernel: fp32 areas / intersection, quotient compared against the double threshold
         const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);

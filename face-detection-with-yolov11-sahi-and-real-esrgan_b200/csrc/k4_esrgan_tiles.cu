@@ -28,6 +28,37 @@ template <typename OutT> __device__ __forceinline__ OutT to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
 
+// v/255 in the precision the reference produces: fp32 IEEE division (astype(float32)/255), then .half() for fp16
+// tiles.  half(v * (1/255)) == half(v / 255) for all 256 inputs; fp32 needs the Newton-corrected quotient.
+template <typename OutT> __device__ __forceinline__ float unit255(uint32_t v) {
+    const float rcp = 1.0f / 255.0f;
+    const float fv = (float)v;
+    const float q = fv * rcp;
+    if (sizeof(OutT) == 2) return q;
+    const float r = fmaf(-q, 255.0f, fv);
+    return fmaf(r, rcp, q);
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store_vec8(OutT* o, const float (&v)[8], int nx) {
+    if (nx == 8 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        if (sizeof(OutT) == 2) {
+            __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+            __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(o) = pk;
+        } else {
+            float* f = reinterpret_cast<float*>(o);
+            *reinterpret_cast<float4*>(f) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(f + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    } else {
+        for (int e = 0; e < nx; ++e) o[e] = to_out<OutT>(v[e]);
+    }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(K4_THREADS)
 k4_crop_kernel(const uint8_t* __restrict__ img, int H, int W, int64_t pitch, int H_pre, int W_pre,
@@ -43,39 +74,86 @@ k4_crop_kernel(const uint8_t* __restrict__ img, int H, int W, int64_t pitch, int
         const uint8_t* row = img + (size_t)sy * pitch;
         const int nx = min(8, pw - x);
         float v[3][8];
+        const int gx = px0 + x;
+        if (nx == 8 && gx + 8 <= W && sy + 1 < H) {
+            // fast path: the 24 source bytes are contiguous and an aligned 28-byte window stays inside the image buffer
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(row + (size_t)gx * 3);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+            const int sh = (int)(addr & 3) * 8;
+            uint32_t w[7];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            if (e < nx) {
-                const int sx = reflect_index(px0 + x + e, W_pre, W);
-                const uint8_t* px = row + (size_t)sx * 3;
-                // astype(float32) / 255 (IEEE divide), BGR -> RGB
-                v[0][e] = __fdiv_rn((float)__ldg(px + 2), 255.0f);
-                v[1][e] = __fdiv_rn((float)__ldg(px + 1), 255.0f);
-                v[2][e] = __fdiv_rn((float)__ldg(px + 0), 255.0f);
-            } else {
-                v[0][e] = v[1][e] = v[2][e] = 0.f;
+            for (int k = 0; k < 7; ++k) w[k] = __ldg(wp + k);
+            uint32_t s[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s[k] = __funnelshift_r(w[k], w[k + 1], sh);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int i = 3 * e + c;  // byte i of the stream = pixel e, BGR channel c
+                    v[2 - c][e] = unit255<OutT>((s[i >> 2] >> (8 * (i & 3))) & 0xffu);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (e < nx) {
+                    const int sx = reflect_index(gx + e, W_pre, W);
+                    const uint8_t* px = row + (size_t)sx * 3;
+                    v[0][e] = unit255<OutT>(__ldg(px + 2));
+                    v[1][e] = unit255<OutT>(__ldg(px + 1));
+                    v[2][e] = unit255<OutT>(__ldg(px + 0));
+                } else {
+                    v[0][e] = v[1][e] = v[2][e] = 0.f;
+                }
             }
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            OutT* o = dst + ((size_t)c * ph + y) * pw + x;
-            if (nx == 8 && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && sizeof(OutT) == 2) {
-                __half2 h0 = __floats2half2_rn(v[c][0], v[c][1]), h1 = __floats2half2_rn(v[c][2], v[c][3]);
-                __half2 h2 = __floats2half2_rn(v[c][4], v[c][5]), h3 = __floats2half2_rn(v[c][6], v[c][7]);
-                uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(o) = pk;
-            } else {
-                for (int e = 0; e < nx; ++e) o[e] = to_out<OutT>(v[c][e]);
-            }
-        }
+        for (int c = 0; c < 3; ++c) store_vec8<OutT>(dst + ((size_t)c * ph + y) * pw + x, v[c], nx);
     }
 }
 
 template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
 template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(__ldg(p)); }
+
+// 16 consecutive plane values as floats: 128-/64-bit loads when the address allows, scalar otherwise
+template <typename T> __device__ __forceinline__ void load16(const T* p, float (&f)[16]);
+template <> __device__ __forceinline__ void load16<__half>(const __half* p, float (&f)[16]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((a & 15) == 0) {
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(p)), v1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+            f[2 * k] = t.x; f[2 * k + 1] = t.y;
+        }
+    } else if ((a & 7) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + q);
+            const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+            const float2 t1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+            f[4 * q] = t0.x; f[4 * q + 1] = t0.y; f[4 * q + 2] = t1.x; f[4 * q + 3] = t1.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __half2float(__ldg(p + e));
+    }
+}
+template <> __device__ __forceinline__ void load16<float>(const float* p, float (&f)[16]) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+            f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __ldg(p + e);
+    }
+}
 
 // clamp_(0,1) -> *255.0 -> numpy round (half-even) -> uint8
 __device__ __forceinline__ uint32_t quant255(float v) {
@@ -104,16 +182,21 @@ k4_stitch_kernel(const InT* __restrict__ tiles_out, const int32_t* __restrict__ 
         const InT* r = src + (size_t)(ty0 + y) * tw + tx0 + x;  // R plane; G at +plane, B at +2*plane
         uint8_t* o = out + (size_t)(oy0 + y) * out_pitch + (size_t)(ox0 + x) * 3;
         if (nx == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-            uint32_t q[48];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                q[3 * e + 0] = quant255(ld_as_float<InT>(r + 2 * plane + e));  // B
-                q[3 * e + 1] = quant255(ld_as_float<InT>(r + plane + e));      // G
-                q[3 * e + 2] = quant255(ld_as_float<InT>(r + e));              // R
-            }
+            float f[3][16];
+            load16<InT>(r, f[2]);               // R plane -> byte 2 of each BGR pixel
+            load16<InT>(r + plane, f[1]);       // G
+            load16<InT>(r + 2 * plane, f[0]);   // B
             uint32_t w[12];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) w[k] = q[4 * k] | (q[4 * k + 1] << 8) | (q[4 * k + 2] << 16) | (q[4 * k + 3] << 24);
+            for (int k = 0; k < 12; ++k) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = 4 * k + j;    // output byte i = pixel i/3, BGR channel i%3
+                    word |= quant255(f[i % 3][i / 3]) << (8 * j);
+                }
+                w[k] = word;
+            }
             uint4* o4 = reinterpret_cast<uint4*>(o);
             o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
             o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -149,44 +232,57 @@ __global__ void bbox_overlaps_p1_kernel(const double* __restrict__ boxes, int N,
     out[i] = v;
 }
 
-// ---- (f2) key-point attach (utils/yolo_wrapper.py:168-217), one CTA per image ---------------------------
-__global__ void attach_keypoints_kernel(const float* __restrict__ merged, int merged_stride,
-                                        const int32_t* __restrict__ m_off, const int32_t* __restrict__ m_cnt,
-                                        const float* __restrict__ dets, int det_stride,
-                                        const int32_t* __restrict__ d_off, const int32_t* __restrict__ d_cnt,
-                                        int32_t* __restrict__ src_index) {
+// ---- (f2) key-point attach (utils/yolo_wrapper.py:168-217): one CTA per image, one WARP per merged box ----
+// lanes stride over the image's detections; the reference's sequential rule (exact key -> LAST detection with that box;
+// else the FIRST detection reaching the maximum IoU, if > 0.5, then the LAST detection sharing that box) is recovered
+// by warp reductions on (iou, -index) / max(index).
+__global__ void __launch_bounds__(256)
+attach_keypoints_kernel(const float* __restrict__ merged, int merged_stride,
+                        const int32_t* __restrict__ m_off, const int32_t* __restrict__ m_cnt,
+                        const float* __restrict__ dets, int det_stride,
+                        const int32_t* __restrict__ d_off, const int32_t* __restrict__ d_cnt,
+                        int32_t* __restrict__ src_index) {
     const int s = blockIdx.x;
     const int mo = m_off[s], mn = m_cnt[s], dof = d_off[s], dn = d_cnt[s];
-    for (int i = threadIdx.x; i < mn; i += blockDim.x) {
-        const float* mb = merged + (size_t)(mo + i) * merged_stride;
-        const double bx1 = mb[0], by1 = mb[1], bx2 = mb[2], by2 = mb[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < mn; i += nwarps) {
+        const float4 mb = *reinterpret_cast<const float4*>(merged + (size_t)(mo + i) * merged_stride);
+        const double bx1 = mb.x, by1 = mb.y, bx2 = mb.z, by2 = mb.w;
         int exact = -1, best = -1;
         double best_iou = 0.0;
-        for (int j = 0; j < dn; ++j) {
-            const float* d = dets + (size_t)(dof + j) * det_stride;
-            const double dx1 = d[0], dy1 = d[1], dx2 = d[2], dy2 = d[3];
-            if (dx1 == bx1 && dy1 == by1 && dx2 == bx2 && dy2 == by2) { exact = j; continue; }
-            const double ix1 = fmax(bx1, dx1), iy1 = fmax(by1, dy1), ix2 = fmin(bx2, dx2), iy2 = fmin(by2, dy2);
-            double iou = 0.0;
-            if (!(ix2 < ix1 || iy2 < iy1)) {
-                const double inter = (ix2 - ix1) * (iy2 - iy1);
-                const double uni = (bx2 - bx1) * (by2 - by1) + (dx2 - dx1) * (dy2 - dy1) - inter;
-                iou = uni > 0 ? inter / uni : 0.0;
-            }
-            if (iou > best_iou) { best_iou = iou; best = j; }
+        for (int j = lane; j < dn; j += 32) {
+            const float4 d = *reinterpret_cast<const float4*>(dets + (size_t)(dof + j) * det_stride);
+            if (d.x == mb.x && d.y == mb.y && d.z == mb.z && d.w == mb.w) { exact = j; continue; }
+            if (fminf(mb.z, d.z) < fmaxf(mb.x, d.x) || fminf(mb.w, d.w) < fmaxf(mb.y, d.y)) continue;  // IoU 0 never wins
+            const double ix1 = fmax(bx1, (double)d.x), iy1 = fmax(by1, (double)d.y);
+            const double ix2 = fmin(bx2, (double)d.z), iy2 = fmin(by2, (double)d.w);
+            const double inter = (ix2 - ix1) * (iy2 - iy1);
+            const double uni = (bx2 - bx1) * (by2 - by1) + ((double)d.z - (double)d.x) * ((double)d.w - (double)d.y) - inter;
+            const double iou = uni > 0 ? inter / uni : 0.0;
+            if (iou > best_iou) { best_iou = iou; best = j; }  // ascending j per lane: keeps the lane's first maximum
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            exact = max(exact, __shfl_xor_sync(0xffffffffu, exact, o));
+            const double oi = __shfl_xor_sync(0xffffffffu, best_iou, o);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+            if (oi > best_iou || (oi == best_iou && ob >= 0 && (best < 0 || ob < best))) { best_iou = oi; best = ob; }
         }
         int res = -1;
         if (exact >= 0) res = exact;
         else if (best >= 0 && best_iou > 0.5) {
             // the cache is a dict keyed by the box: the value is the LAST detection inserted with that box
-            const float* d = dets + (size_t)(dof + best) * det_stride;
-            res = best;
-            for (int j = best + 1; j < dn; ++j) {
-                const float* e = dets + (size_t)(dof + j) * det_stride;
-                if (e[0] == d[0] && e[1] == d[1] && e[2] == d[2] && e[3] == d[3]) res = j;
+            const float4 d = *reinterpret_cast<const float4*>(dets + (size_t)(dof + best) * det_stride);
+            int last = best;
+            for (int j = best + 1 + lane; j < dn; j += 32) {
+                const float4 e = *reinterpret_cast<const float4*>(dets + (size_t)(dof + j) * det_stride);
+                if (e.x == d.x && e.y == d.y && e.z == d.z && e.w == d.w) last = j;
             }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+            res = last;
         }
-        src_index[mo + i] = res < 0 ? -1 : dof + res;
+        if (lane == 0) src_index[mo + i] = res < 0 ? -1 : dof + res;
     }
 }
 
@@ -292,10 +388,11 @@ extern "C" int fsd_attach_keypoints(fsd_handle_t h, const float* merged, int mer
                                     const int32_t* m_cnt, const float* dets, int det_stride, const int32_t* d_off,
                                     const int32_t* d_cnt, int S, int32_t* src_index, void* stream_) {
     FSD_CHECK_ARG(h && merged && m_off && m_cnt && dets && d_off && d_cnt && src_index, "fsd_attach_keypoints: null argument");
-    FSD_CHECK_ARG(S >= 0 && merged_stride >= 4 && det_stride >= 4, "fsd_attach_keypoints: bad sizes");
+    FSD_CHECK_ARG(S >= 0 && merged_stride >= 4 && det_stride >= 4 && merged_stride % 4 == 0 && det_stride % 4 == 0,
+                  "fsd_attach_keypoints: row strides must be multiples of 4 floats (16-byte rows)");
     if (S == 0) return FSD_OK;
     FSD_CUDA(cudaSetDevice(h->device));
-    attach_keypoints_kernel<<<S, 128, 0, (cudaStream_t)stream_>>>(merged, merged_stride, m_off, m_cnt, dets, det_stride, d_off, d_cnt, src_index);
+    attach_keypoints_kernel<<<S, 256, 0, (cudaStream_t)stream_>>>(merged, merged_stride, m_off, m_cnt, dets, det_stride, d_off, d_cnt, src_index);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

@@ -45,9 +45,50 @@ k5_bias_act_float_kernel(float4* __restrict__ x, const float4* __restrict__ bias
     }
 }
 
+// out[n,y,x,:] = concat(a[n,y/2,x/2,:], b[n,y,x,:]) — the FPN "nearest 2x up-sample, then concat" of the YOLO neck in ONE
+// pass (torch runs an up-sample kernel, then a concat kernel: the up-sampled tensor is written and read once more).
+__global__ void __launch_bounds__(K5_THREADS)
+k5_upsample2x_concat_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                            int N, int h, int w, int ca_vec, int cb_vec) {
+    const int H = 2 * h, W = 2 * w, cv = ca_vec + cb_vec;
+    const size_t total = (size_t)N * H * W * cv;
+    for (size_t i = (size_t)blockIdx.x * K5_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * K5_THREADS) {
+        const int c = (int)(i % cv);
+        const size_t pix = i / cv;
+        if (c < ca_vec) {
+            const int x = (int)(pix % W), y = (int)((pix / W) % H);
+            const size_t n = pix / ((size_t)W * H);
+            out[i] = __ldg(a + ((n * h + (y >> 1)) * w + (x >> 1)) * ca_vec + c);
+        } else {
+            out[i] = __ldg(b + pix * cb_vec + (c - ca_vec));
+        }
+    }
+}
+
 }  // namespace fsd
 
 using namespace fsd;
+
+extern "C" int fsd_upsample2x_concat(fsd_handle_t h, const void* a, const void* b, void* out, int N, int ah, int aw,
+                                     int ca, int cb, int dtype, void* stream_) {
+    FSD_CHECK_ARG(h && a && b && out, "fsd_upsample2x_concat: null argument");
+    FSD_CHECK_ARG(dtype == FSD_F16 || dtype == FSD_F32, "fsd_upsample2x_concat: bad dtype");
+    const int per_vec = dtype == FSD_F16 ? 8 : 4;
+    FSD_CHECK_ARG(N >= 0 && ah > 0 && aw > 0 && ca > 0 && cb > 0 && ca % per_vec == 0 && cb % per_vec == 0,
+                  "fsd_upsample2x_concat: channel counts must be positive multiples of %d", per_vec);
+    if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)out & 15)) { set_error("fsd_upsample2x_concat: pointers must be 16-byte aligned"); return FSD_ERR_ALIGN; }
+    if (N == 0) return FSD_OK;
+    const size_t total = (size_t)N * 4 * ah * aw * ((ca + cb) / per_vec);
+    const size_t want = (total + K5_THREADS - 1) / K5_THREADS;
+    const int grid = (int)(want < (size_t)h->sm_count * 32 ? want : (size_t)h->sm_count * 32);
+    FSD_CUDA(cudaSetDevice(h->device));
+    k5_upsample2x_concat_kernel<<<grid, K5_THREADS, 0, (cudaStream_t)stream_>>>((const uint4*)a, (const uint4*)b, (uint4*)out, N, ah, aw,
+                                                                               ca / per_vec, cb / per_vec);
+    FSD_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return FSD_OK;
+}
+
 
 extern "C" int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, int64_t n_pixels, int channels, int act,
                                     float slope, int dtype, void* stream_) {

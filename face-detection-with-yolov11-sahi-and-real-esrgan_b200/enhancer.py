@@ -35,6 +35,7 @@ class RealESRGANer:
             p.requires_grad_(False)
         self.model = model.half() if half else model.float()
         self.max_tile_batch = max_tile_batch
+        self._tab_cache = {}
 
     @torch.no_grad()
     def enhance_device(self, img_dev: torch.Tensor) -> torch.Tensor:
@@ -44,7 +45,10 @@ class RealESRGANer:
         tile = self.tile_size if self.tile_size > 0 else max(H, W) + self.pre_pad + 4  # tile 0: one tile, no halo
         table, _ = ops.esrgan_tile_table(H, W, s, tile, self.tile_pad if self.tile_size > 0 else 0, self.pre_pad)
         dtype = torch.float16 if self.half else torch.float32
-        tiles, tab_dev = ops.esrgan_crop(img_dev, table, s, self.pre_pad, dtype)
+        key = (H, W)
+        cached = self._tab_cache.get(key)
+        tiles, tab_dev = ops.esrgan_crop(img_dev, table, s, self.pre_pad, dtype, tab_dev=cached)
+        self._tab_cache[key] = tab_dev
         outbuf = ops.esrgan_out_buffer(table, s, dtype, img_dev.device)
         groups = defaultdict(list)
         for i, row in enumerate(table):

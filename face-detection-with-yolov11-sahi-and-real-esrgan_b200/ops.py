@@ -235,6 +235,22 @@ def bias_act_(x: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: flo
     return x
 
 
+def upsample2x_concat(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """(a5) cat(interpolate(a, 2x nearest), b, dim=1) for channels-last CUDA tensors, one pass."""
+    _require_cuda(a, "a")
+    n, ca, ah, aw = a.shape
+    nb, cb, bh, bw = b.shape
+    if (nb, bh, bw) != (n, 2 * ah, 2 * aw) or a.dtype != b.dtype:
+        raise ValueError("upsample2x_concat: b must be [N, Cb, 2h, 2w] of a's dtype")
+    if not (a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last)):
+        raise ValueError("upsample2x_concat needs dense channels_last tensors")
+    out = torch.empty((n, ca + cb, bh, bw), dtype=a.dtype, device=a.device, memory_format=torch.channels_last)
+    h = _handle_for(a)
+    check(h.lib.fsd_upsample2x_concat(h.h, a.data_ptr(), b.data_ptr(), out.data_ptr(), n, ah, aw, ca, cb,
+                                      _TORCH_DTYPE[a.dtype], _stream_ptr(a.device)), "fsd_upsample2x_concat")
+    return out
+
+
 # ---- Kernel 4 -------------------------------------------------------------------------------------------
 def esrgan_tile_table(H: int, W: int, scale: int, tile: int, tile_pad: int = 10, pre_pad: int = 0):
     """Host tile table [T,12] int32 + (padded_h, padded_w)."""
@@ -252,16 +268,20 @@ def _off64(row, k):
     return int(np.uint32(row[k])) | (int(row[k + 1]) << 32)
 
 
-def esrgan_crop(img: torch.Tensor, table: np.ndarray, scale: int, pre_pad: int = 0, dtype=torch.float16):
-    """Kernel 4a: img [H,W,3] uint8 BGR (CUDA, row-contiguous) -> (packed tile buffer, table on device)."""
+def esrgan_crop(img: torch.Tensor, table: np.ndarray, scale: int, pre_pad: int = 0, dtype=torch.float16,
+                tab_dev: torch.Tensor | None = None, tiles: torch.Tensor | None = None):
+    """Kernel 4a: img [H,W,3] uint8 BGR (CUDA, row-contiguous) -> (packed tile buffer, table on device).
+    Pass `tab_dev` / `tiles` from a previous call to reuse the uploaded table and the tile buffer."""
     _require_cuda(img, "image")
     H, W = int(img.shape[0]), int(img.shape[1])
     assert img.dtype == torch.uint8 and img.stride(2) == 1 and img.stride(1) == 3
     last = table[-1]
     total = _off64(last, 8) + (3 * int(last[2]) * int(last[3]) + 7) // 8 * 8
-    tiles = torch.empty((total,), dtype=dtype, device=img.device)
+    if tiles is None:
+        tiles = torch.empty((total,), dtype=dtype, device=img.device)
     tab_host = np.ascontiguousarray(table, dtype=np.int32)
-    tab_dev = torch.from_numpy(tab_host).to(img.device)
+    if tab_dev is None:
+        tab_dev = torch.from_numpy(tab_host).to(img.device)
     h = _handle_for(img)
     check(h.lib.fsd_esrgan_crop(h.h, img.data_ptr(), H, W, img.stride(0), H + pre_pad, W + pre_pad,
                                 tab_dev.data_ptr(), tab_host.ctypes.data, len(tab_host), _TORCH_DTYPE[dtype],

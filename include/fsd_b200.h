@@ -146,6 +146,11 @@ int fsd_pack_results(fsd_handle_t h, const float* det, const int32_t* group_offs
 int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, int64_t n_pixels, int channels, int act,
                          float slope, int dtype, void* stream);
 
+/* ---- (a5) YOLO neck: out = concat(nearest_upsample_2x(a), b) along channels, channels-last, in ONE pass.
+ *      a [N,ah,aw,ca], b [N,2ah,2aw,cb], out [N,2ah,2aw,ca+cb]; replaces torch's upsample kernel + concat kernel. */
+int fsd_upsample2x_concat(fsd_handle_t h, const void* a, const void* b, void* out, int N, int ah, int aw, int ca,
+                          int cb, int dtype, void* stream);
+
 /* ---- Kernel 4 (a15) Real-ESRGAN tile crop / stitch.  Replaces RealESRGANer.enhance/pre_process/
  *      tile_process/post_process [EXT realesrgan 0.3.0], reached from utils/enhancer.py:214.
  *      fsd_esrgan_tile_table: host-side tile table; each row = 12 int32:

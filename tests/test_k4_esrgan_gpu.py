@@ -103,3 +103,27 @@ def test_bias_act_epilogue(cuda_device, act, dtype):
     assert torch.allclose(got.float(), ref, atol=tol, rtol=tol)
     with pytest.raises(Exception):
         ops.bias_act_(x.contiguous(), b, act)
+
+
+def test_upsample_concat_and_split_conv_equal_torch(cuda_device):
+    """(a5) the fused neck op and the split-weight convolution are exact re-arrangements of the PyTorch backbone."""
+    import fsd_b200.ops as ops
+    from fsd_b200.backbones.yolo11_pose import build_yolo11n_pose
+
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn((2, 16, 5, 7), generator=g).half().to(cuda_device).contiguous(memory_format=torch.channels_last)
+    b = torch.randn((2, 24, 10, 14), generator=g).half().to(cuda_device).contiguous(memory_format=torch.channels_last)
+    ref = torch.cat((torch.nn.functional.interpolate(a, scale_factor=2.0, mode="nearest"), b), 1)
+    assert torch.equal(ops.upsample2x_concat(a, b), ref)
+    # whole backbone: GPU fp16 (fused epilogue, split convs, fused neck) vs the same weights in plain torch fp32 on the CPU
+    model = build_yolo11n_pose()
+    x = torch.rand((1, 3, 128, 160), generator=g)
+    want = model(x)
+    gpu = build_yolo11n_pose().half().to(cuda_device).to(memory_format=torch.channels_last)
+    with torch.no_grad():
+        got = gpu(x.half().to(cuda_device).contiguous(memory_format=torch.channels_last))
+    for lw, lg in zip(want, got):
+        for tw, tg in zip(lw, lg):
+            assert tw.shape == tg.shape
+            err = (tg.float().cpu() - tw).abs().max().item()
+            assert err < 0.08 * max(1.0, tw.abs().max().item()), err  # fp16 network vs fp32 network
