@@ -23,18 +23,38 @@ except Exception:
     PEAK = 6650.0
 
 
-def timeit(fn, iters=10, warmup=3):
+def timeit(fn, iters=10, warmup=3, reps=5):
+    """Median / best device time of ONE call of fn in ms.  `reps` calls are captured into a CUDA graph and replayed so the
+    figure is the kernel's device time, not the Python/ctypes launch path (which dominates for 20-us kernels)."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(reps):
+                fn()
+    except Exception:
+        graph = None
+        torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        if graph is not None:
+            graph.replay()
+        else:
+            for _ in range(reps):
+                fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / reps)
     return float(np.median(ts)), float(min(ts))
 
 

@@ -25,6 +25,38 @@ if which.startswith("k1"):
     out = torch.empty((ent.shape[0], 3, 1024, 1024), dtype=dt, device=dev)
     for _ in range(iters):
         ops.gather_letterbox(pool, ent, 512, 512, 1024, 32, True, dt, out=out)
+elif which == "k1_nhwc":
+    N = 32
+    pool = ops.ImagePool(N, 768, 1024, dev)
+    pool.buf.random_(0, 256)
+    boxes = _cabi.slice_plan(768, 1024, 512, 512, 0.2, 0.2)
+    ent = torch.tensor([[i, b[0], b[1]] for i in range(N) for b in boxes], dtype=torch.int32, device=dev)
+    out = torch.empty((ent.shape[0], 3, 1024, 1024), dtype=torch.float16, device=dev, memory_format=torch.channels_last)
+    for _ in range(iters):
+        ops.gather_letterbox(pool, ent, 512, 512, 1024, 32, True, torch.float16, out=out)
+elif which == "k2":
+    B, H, W = 96, 1024, 1024
+    g = torch.Generator(device=dev).manual_seed(0)
+    levels = []
+    for s_ in (8, 16, 32):
+        h, w = H // s_, W // s_
+        levels.append(tuple((torch.randn((B, c, h, w), generator=g, device=dev, dtype=torch.float16) * sc + m).contiguous(memory_format=torch.channels_last)
+                            for c, sc, m in ((64, 1.5, 1.0), (1, 2.0, -6.0), (15, 1.0, 0.0))))
+    cand = torch.empty((B, 4096, ops.ROW), dtype=torch.float32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    for _ in range(iters):
+        ops.pose_decode(levels, 0.5, cand=cand, count=count)
+elif which == "k3":
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_k3_merge_gpu import sahi_like_boxes
+
+    rng = np.random.default_rng(0)
+    seg = sahi_like_boxes(rng, 400, dup=(1, 5), size=(10, 60), canvas=(3840, 2160))[:1024]
+    S = 148
+    rows = torch.from_numpy(np.tile(seg, (S, 1))).to(dev)
+    offs = torch.arange(S, dtype=torch.int32, device=dev) * len(seg)
+    for _ in range(iters):
+        ops.merge_segments(rows, offs, None, len(seg), merge_type="GREEDYNMM", metric="IOS", thr=0.5, want_parent=False)
 elif which == "k4":
     H, W, scale, tile = 1080, 1920, 2, 400
     img = torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, device=dev)

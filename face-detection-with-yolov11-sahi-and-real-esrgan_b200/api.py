@@ -8,7 +8,10 @@ import numpy as np
 import torch
 
 from . import ops
+from .sahi_api.annotation import Category
 from .sahi_api.prediction import ObjectPrediction, PredictionResult
+
+_FACE = Category(id=0, name="face")
 
 
 def get_sliced_prediction_batch(images: Sequence, detection_model, slice_height: int, slice_width: int,
@@ -33,13 +36,95 @@ def get_sliced_prediction_batch(images: Sequence, detection_model, slice_height:
     out: List[PredictionResult] = []
     for i in range(len(images)):
         boxes, scores, kpts, has_k = batch.image(i)
-        preds = []
-        for j in range(len(boxes)):
-            op = ObjectPrediction(bbox=[int(v) for v in boxes[j]], category_id=0, category_name="face",
-                                  score=float(scores[j]), shift_amount=[0, 0], full_shape=None)
-            if has_k[j]:
-                op.keypoints = kpts[j]
-            preds.append(op)
+        ib, sc, hk = boxes.astype(np.int64).tolist(), scores.tolist(), has_k.tolist()
+        preds = [ObjectPrediction.from_merged_row(b[0], b[1], b[2], b[3], sc[j], _FACE, kpts[j] if hk[j] else None)
+                 for j, b in enumerate(ib)]
         out.append(PredictionResult(object_prediction_list=preds, image=images[i], durations_in_seconds={},
                                     image_size=(w, h)))
     return out
+
+
+class _Slot:
+    def __init__(self, n, h, w, device, rows_cap):
+        self.pool = ops.ImagePool(n, h, w, device)
+        self.stream = torch.cuda.Stream(device=device)
+        self.event = torch.cuda.Event()
+        self.h_off = torch.empty((n + 1,), dtype=torch.int32).pin_memory()
+        self.h_rows = torch.empty((rows_cap, ops.ROW), dtype=torch.float32).pin_memory()
+        self.h_cmax = torch.empty((1,), dtype=torch.int32).pin_memory()
+        self.dev = None
+        self.images = None
+
+
+def predict_stream(batches, detection_model, slice_height: int, slice_width: int, overlap_height_ratio: float = 0.2,
+                   overlap_width_ratio: float = 0.2, perform_standard_pred: bool = True,
+                   postprocess_type: str = "GREEDYNMM", postprocess_match_metric: str = "IOS",
+                   postprocess_match_threshold: float = 0.5, postprocess_class_agnostic: bool = False, depth: int = 2,
+                   rows_per_image_hint: int = 256):
+    """Pipelined batch prediction: yields one list[PredictionResult] per batch of `batches` (an iterable of equal-length
+    lists of same-sized HWC uint8 images, ideally pinned CPU tensors), in order.
+
+    `depth` batches are in flight: the H2D upload of batch i+1 and the D2H + result-object construction of batch i-1
+    overlap with the device pipeline of batch i (each batch on its own CUDA stream and image pool)."""
+    eng = detection_model.engine()
+    eng.truncate = True
+    slots, pending, k = None, [], 0
+
+    def finish(slot):
+        slot.event.synchronize()
+        n = slot.pool.n
+        off = slot.h_off.numpy().copy()
+        total = int(off[-1])
+        if int(slot.h_cmax[0]) > eng.cap:  # a slice overflowed the candidate capacity: redo this batch synchronously
+            batch = eng.detect(slot.pool, slice_height, slice_width, overlap_height_ratio, overlap_width_ratio,
+                               perform_standard_pred, postprocess_type, postprocess_match_metric, postprocess_match_threshold)
+            off, total = batch.offsets, int(batch.offsets[-1])
+            host = np.concatenate([batch.boxes, batch.scores[:, None], (batch.has_keypoints.astype(np.float32) - 1)[:, None].view(np.float32),
+                                   batch.keypoints.reshape(-1, 15)], 1) if total else np.zeros((0, 21), np.float32)
+            srcs = np.where(batch.has_keypoints, 0, -1)
+        else:
+            if total <= slot.h_rows.shape[0]:
+                host = slot.h_rows[:total].numpy()
+            else:  # more detections than the pinned window: fetch the rest
+                host = slot.dev["rows"][:total].cpu().numpy()
+            srcs = host[:, 5].copy().view(np.int32) if total else np.zeros((0,), np.int32)
+        w, h = slot.pool.w, slot.pool.h
+        out = []
+        boxes_all = host[:, :4].astype(np.int64).tolist()
+        scores_all = host[:, 4].tolist()
+        kp_all = host[:, 6:21].reshape(-1, 5, 3).copy()
+        for i in range(n):
+            a, b = int(off[i]), int(off[i + 1])
+            preds = [ObjectPrediction.from_merged_row(bx[0], bx[1], bx[2], bx[3], scores_all[j], _FACE,
+                                                      kp_all[j] if srcs[j] >= 0 else None)
+                     for j, bx in zip(range(a, b), boxes_all[a:b])]
+            out.append(PredictionResult(object_prediction_list=preds, image=slot.images[i], durations_in_seconds={}, image_size=(w, h)))
+        slot.dev, slot.images = None, None
+        return out
+
+    for images in batches:
+        n, (h, w) = len(images), images[0].shape[:2]
+        if slots is None:
+            slots = [_Slot(n, h, w, eng.device, n * rows_per_image_hint) for _ in range(depth)]
+        slot = slots[k % depth]
+        k += 1
+        if slot.dev is not None:
+            yield finish(pending.pop(0))
+        if (slot.pool.n, slot.pool.h, slot.pool.w) != (n, h, w):
+            raise ValueError("predict_stream needs batches of one common size")
+        slot.images = images
+        with torch.cuda.stream(slot.stream):
+            for i, im in enumerate(images):
+                slot.pool.upload(i, im, non_blocking=True)
+            dev = eng.detect(slot.pool, slice_height, slice_width, overlap_height_ratio, overlap_width_ratio,
+                             perform_standard_pred, postprocess_type, postprocess_match_metric,
+                             postprocess_match_threshold, postprocess_class_agnostic, to_host=False)
+            slot.h_off.copy_(dev["offsets"], non_blocking=True)
+            slot.h_rows.copy_(dev["rows"][: slot.h_rows.shape[0]], non_blocking=True)
+            cmax = dev["count_s"].max() if dev["count_f"] is None else torch.maximum(dev["count_s"].max(), dev["count_f"].max())
+            slot.h_cmax.copy_(cmax.reshape(1), non_blocking=True)
+            slot.event.record(slot.stream)
+        slot.dev = dev
+        pending.append(slot)
+    while pending:
+        yield finish(pending.pop(0))

@@ -84,13 +84,12 @@ def _fused_sliced_prediction(image_as_pil, detection_model, slice_height, slice_
     batch = eng.detect(pool, slice_height, slice_width, ov_h, ov_w, perform_standard_pred, postprocess_type,
                        match_metric, match_threshold, want_stage1=hasattr(detection_model, "keypoints_cache"))
     boxes, scores, kpts, has_k = batch.image(0)
-    preds = []
-    for i in range(len(boxes)):
-        op = ObjectPrediction(bbox=[int(v) for v in boxes[i]], category_id=0, category_name="face",
-                              score=float(scores[i]), shift_amount=[0, 0], full_shape=None)
-        if has_k[i]:
-            op.keypoints = kpts[i]
-        preds.append(op)
+    from .annotation import Category
+
+    face = Category(id=0, name="face")
+    ib, sc, hk = boxes.astype(np.int64).tolist(), scores.tolist(), has_k.tolist()
+    preds = [ObjectPrediction.from_merged_row(b[0], b[1], b[2], b[3], sc[j], face, kpts[j] if hk[j] else None)
+             for j, b in enumerate(ib)]
     if batch.stage1 is not None:  # same side channel the reference fills slice by slice (utils/yolo_wrapper.py:155-162)
         cache = detection_model.keypoints_cache
         for r in batch.stage1["rows"][0]:

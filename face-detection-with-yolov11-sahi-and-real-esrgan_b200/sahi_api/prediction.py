@@ -8,7 +8,7 @@ from typing import Any, Dict, List, Optional
 
 import numpy as np
 
-from .annotation import ObjectAnnotation
+from .annotation import BoundingBox, Category, ObjectAnnotation
 from .slicing import read_image_as_pil
 
 
@@ -39,6 +39,22 @@ class ObjectPrediction(ObjectAnnotation):
         self.score = PredictionScore(score)
         super().__init__(bbox=bbox, category_id=category_id, segmentation=segmentation, category_name=category_name,
                          shift_amount=shift_amount, full_shape=full_shape)
+
+    @classmethod
+    def from_merged_row(cls, x1: int, y1: int, x2: int, y2: int, score: float, category: Category, keypoints=None):
+        """Fast construction for rows coming back from the device pipeline: the values already satisfy every rule the
+        regular constructor enforces (non-negative ints in full-image coordinates, shift (0, 0), no full_shape clamp),
+        so the per-object validation is skipped — a batch returns thousands of these."""
+        self = object.__new__(cls)
+        box = object.__new__(BoundingBox)
+        object.__setattr__(box, "box", [x1, y1, x2, y2])
+        object.__setattr__(box, "shift_amount", (0, 0))
+        score_obj = object.__new__(PredictionScore)
+        score_obj.value = score
+        self.score, self.mask, self.bbox, self.category, self.merged = score_obj, None, box, category, None
+        if keypoints is not None:
+            self.keypoints = keypoints
+        return self
 
     def get_shifted_object_prediction(self):
         """Copy mapped into full-image coordinates (shift applied, shift_amount reset, no upper clamp)."""

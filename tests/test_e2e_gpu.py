@@ -114,3 +114,23 @@ def test_batch_api_equals_single_image_api(cuda_device):
         n_kp += sum(hasattr(p, "keypoints") for p in res.object_prediction_list)  # union boxes may match no detection
         n_all += len(res.object_prediction_list)
     assert n_all > 0 and n_kp >= n_all // 2
+
+
+def test_predict_stream_equals_batch_api(cuda_device):
+    """The pipelined API (2 batches in flight on separate streams) returns exactly what the synchronous batch call returns."""
+    from fsd_b200.api import get_sliced_prediction_batch, predict_stream
+    from fsd_b200.plugins import YOLOv11PoseDetectionModel
+    from fsd_b200.synthetic import make_image
+    from fsd_b200.yolo import YOLO
+
+    model = YOLOv11PoseDetectionModel(model=YOLO("random-init"), confidence_threshold=0.4, device="cuda:0", image_size=512)
+    imgs = [torch.from_numpy(make_image(300 + i, 384, 512)[0]).pin_memory() for i in range(12)]
+    groups = [imgs[0:4], imgs[4:8], imgs[8:12], imgs[0:4]]
+    want = [get_sliced_prediction_batch(g, model, 256, 256, 0.2, 0.2) for g in groups]
+    got = list(predict_stream(iter(groups), model, 256, 256, 0.2, 0.2, depth=2, rows_per_image_hint=8))  # tiny window: exercises the refetch
+    assert len(got) == len(want)
+    for gb, wb in zip(got, want):
+        for gr, wr in zip(gb, wb):
+            a = [(p.bbox.to_xyxy(), round(p.score.value, 6), hasattr(p, "keypoints")) for p in gr.object_prediction_list]
+            b = [(p.bbox.to_xyxy(), round(p.score.value, 6), hasattr(p, "keypoints")) for p in wr.object_prediction_list]
+            assert a == b
