@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr",
+    "-fmad=false",  # parity: no implicit FMA contraction (kernels use explicit fmaf where a fused op is intended)
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
 ]
 

@@ -178,7 +178,12 @@ k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Par
     }
     const int c0 = p.reverse ? 2 * TC : 0, c2 = p.reverse ? 0 : 2 * TC;
     // vertical pass role: thread <-> (8-pixel vector v, rows vrow, vrow + ROWS_PER_PASS, ..)
-    const int v = tid % VECS, vrow = tid / VECS;
+    // With one thread per column (TC == 256) and no left border shift, a warp's 32 columns are exactly the four 8-pixel
+    // vectors 4w..4w+3: the warp then consumes only what it produced itself, so the pass boundary needs __syncwarp()
+    // instead of a CTA barrier and warps drift freely between the LSU-heavy horizontal and the ALU-heavy vertical pass.
+    const bool warp_private = (TC == K1_THREADS) && has_x && (dx_lo + p.pad_left - X0 == 0);
+    const int v = warp_private ? 4 * (tid >> 5) + (tid & 3) : tid % VECS;
+    const int vrow = warp_private ? (tid & 31) >> 2 : tid / VECS;
     const int X = X0 + v * 8;
     unsigned inside = 0;  // columns of this vector inside the resized image (the rest is 114 border)
     {
@@ -261,7 +266,7 @@ k1_gather_letterbox_kernel(const __grid_constant__ CUtensorMap tmap, const K1Par
                 }
             }
         }
-        __syncthreads();
+        if (warp_private) __syncwarp(); else __syncthreads();
 
         // ---- vertical pass + normalise + planar vector stores
         if (X < p.out_w) {

@@ -219,14 +219,17 @@ __global__ void bbox_overlaps_p1_kernel(const double* __restrict__ boxes, int N,
     const int n = (int)(i / K), k = (int)(i % K);
     const double* b = boxes + 4 * (size_t)n;
     const double* q = query + 4 * (size_t)k;
-    const double qa = (q[2] - q[0] + 1) * (q[3] - q[1] + 1);
-    const double iw = fmin(b[2], q[2]) - fmax(b[0], q[0]) + 1;
+    // explicitly rounded operations in the Cython source's order (no FMA contraction: bit-identical to the CPU result)
+    const double qa = __dmul_rn(__dadd_rn(__dsub_rn(q[2], q[0]), 1.0), __dadd_rn(__dsub_rn(q[3], q[1]), 1.0));
+    const double iw = __dadd_rn(__dsub_rn(fmin(b[2], q[2]), fmax(b[0], q[0])), 1.0);
     double v = 0.0;
     if (iw > 0) {
-        const double ih = fmin(b[3], q[3]) - fmax(b[1], q[1]) + 1;
+        const double ih = __dadd_rn(__dsub_rn(fmin(b[3], q[3]), fmax(b[1], q[1])), 1.0);
         if (ih > 0) {
-            const double ua = (b[2] - b[0] + 1) * (b[3] - b[1] + 1) + qa - iw * ih;
-            v = iw * ih / ua;
+            const double ba = __dmul_rn(__dadd_rn(__dsub_rn(b[2], b[0]), 1.0), __dadd_rn(__dsub_rn(b[3], b[1]), 1.0));
+            const double inter = __dmul_rn(iw, ih);
+            const double ua = __dsub_rn(__dadd_rn(ba, qa), inter);
+            v = __ddiv_rn(inter, ua);
         }
     }
     out[i] = v;

@@ -22,9 +22,9 @@ def make_image(index: int, height: int = 768, width: int = 1024, seed: int = 123
     for _ in range(k):
         w = float(np.exp(rng.uniform(np.log(face_px[0]), np.log(face_px[1]))))
         h = w * rng.uniform(1.1, 1.4)
-        cx, cy = rng.uniform(w / 2, width - w / 2), rng.uniform(h / 2, height - h / 2)
         if h >= height or w >= width:
             continue
+        cx, cy = rng.uniform(w / 2, width - w / 2), rng.uniform(h / 2, height - h / 2)
         x0, x1 = max(int(cx - w / 2) - 1, 0), min(int(cx + w / 2) + 2, width)
         y0, y1 = max(int(cy - h / 2) - 1, 0), min(int(cy + h / 2) + 2, height)
         m = ((xx[y0:y1, x0:x1] - cx) / (w / 2)) ** 2 + ((yy[y0:y1, x0:x1] - cy) / (h / 2)) ** 2 <= 1.0

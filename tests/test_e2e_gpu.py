@@ -134,3 +134,34 @@ def test_predict_stream_equals_batch_api(cuda_device):
             a = [(p.bbox.to_xyxy(), round(p.score.value, 6), hasattr(p, "keypoints")) for p in gr.object_prediction_list]
             b = [(p.bbox.to_xyxy(), round(p.score.value, 6), hasattr(p, "keypoints")) for p in wr.object_prediction_list]
             assert a == b
+
+
+def test_fused_path_edge_cases(cuda_device):
+    """No detections at all; an image smaller than the slice (one slice, no full-image pass); image with an odd row pitch."""
+    from fsd_b200.plugins import YOLOv11PoseDetectionModel
+    from fsd_b200.sahi_api import get_sliced_prediction
+    from fsd_b200.synthetic import make_image
+    from fsd_b200.yolo import YOLO
+    from oracle import predict as opred
+    from oracle.yolo_head import OracleYOLO
+    from oracle.yolo_wrapper import YOLOv11PoseDetectionModel as OracleModel
+
+    yolo = YOLO("random-init")
+    # (1) confidence so high that nothing survives: empty list, no error, image size still reported
+    model = YOLOv11PoseDetectionModel(model=yolo, confidence_threshold=1.0, device="cuda:0", image_size=512)
+    img, _ = make_image(7, 300, 401)  # 401*3 = 1203 bytes per row: not a multiple of 16 -> pitched pool
+    res = get_sliced_prediction(img, model, slice_height=256, slice_width=256, verbose=0)
+    assert res.object_prediction_list == [] and (res.image_width, res.image_height) == (401, 300)
+    assert model.attach_keypoints_to_predictions(res.object_prediction_list) == []
+    # (2) image smaller than the slice: exactly one slice and no standard pass, compared with the oracle flow
+    model = YOLOv11PoseDetectionModel(model=yolo, confidence_threshold=0.3, device="cuda:0", image_size=512)
+    eng = model.engine()
+    rec = Recorder()
+    eng.head_hook = rec.hook
+    got = get_sliced_prediction(img, model, slice_height=512, slice_width=512, verbose=0)
+    eng.head_hook = None
+    assert len(rec.items) == 1
+    omodel = OracleModel(model=OracleYOLO(None, half=True, head_hook=rec.lookup), confidence_threshold=0.3, device="cpu", image_size=512)
+    want = opred.get_sliced_prediction(img, omodel, slice_height=512, slice_width=512, verbose=0)
+    assert [r[0] for r in as_rows(got.object_prediction_list)] == [r[0] for r in as_rows(want.object_prediction_list)]
+    assert len(got.object_prediction_list) > 0
