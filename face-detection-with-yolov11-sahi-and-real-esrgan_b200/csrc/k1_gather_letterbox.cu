@@ -409,6 +409,9 @@ static int launch(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, in
     return nhwc ? launch_l<MODE, OutT, true>(h, tmap, p, B, smem, stream) : launch_l<MODE, OutT, false>(h, tmap, p, B, smem, stream);
 }
 
+int launch_upscale2x(fsd_context* h, const uint8_t* images, int64_t row_pitch, int64_t image_pitch, const int32_t* entries,
+                     int B, int src_w, int src_h, int reverse, int nhwc, void* out, cudaStream_t stream);  // k1_upscale2x.cu
+
 }  // namespace fsd
 
 using namespace fsd;
@@ -446,6 +449,14 @@ extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n
     p.reverse = reverse_channels ? 1 : 0;
     const int mode = geom[6] == 2 ? K1_MODE_AREA2 : K1_MODE_LINEAR;  // copy == linear with identity tables
     FSD_CHECK_ARG(p.out_w % 8 == 0, "fsd_gather_letterbox: network input width %d must be a multiple of 8", p.out_w);
+    // exact 2x up-scale without letterbox border, fp16 output: the small-integer fast path (k1_upscale2x.cu), unless
+    // FSD_K1_GENERIC=1 forces the general TMA kernel (used by the parity tests to cover both)
+    if (mode == K1_MODE_LINEAR && dtype == FSD_F16 && p.new_w == 2 * src_w && p.new_h == 2 * src_h && p.pad_left == 0 &&
+        p.pad_top == 0 && p.out_w == p.new_w && p.out_h == p.new_h && src_w >= 2 && src_h >= 2 && !getenv("FSD_K1_GENERIC")) {
+        if (n_images == 1) image_pitch = row_pitch * H;
+        return launch_upscale2x(h, images, row_pitch, image_pitch, entries, B, src_w, src_h, p.reverse,
+                                out_layout == FSD_CHANNELS_LAST, out, stream);
+    }
 
     std::vector<int32_t> xt, yt;
     const int32_t *xdev, *ydev;

@@ -1,0 +1,161 @@
+// Kernel 1, exact-2x fast path: slice gather + cv2 INTER_LINEAR 2x up-scale + uint8 -> fp16 normalise.
+//
+// SAHI slices whose side is half the network size (BASELINE config 2: 512x512 slices at imgsz 1024) resize by exactly
+// 2.  cv2's fixed-point weights are then the constants 0.75/0.25 (1536/512 of 2048) on both axes, and the two passes
+// collapse to small-integer arithmetic (all exact, derived from the general formula):
+//     s      = 3*p[j] + p[j+1]   (odd output column)   |   p[j] + 3*p[j+1]   (even output column)      <= 1020
+//     h      = (1536*p0 + 512*p1) >> 4 = 32*s
+//     (1536*h) >> 16 = (3*s) >> 2 =: A        (512*h) >> 16 = s >> 2 =: B
+//     out(2k+1) = (A[k] + B[k+1] + 2) >> 2      out(2k+2) = (B[k] + A[k+1] + 2) >> 2
+// with source indices clamped at the borders (which reproduces cv2's border rules: x weights collapse to (2048, 0),
+// y indices clip).  Everything fits 16-bit lanes, so one 32-bit register carries two output columns through every step:
+// about 6 instructions per output element instead of 17 in the general kernel, which makes this path HBM-bound.
+// One thread produces 8 output columns x 3 channels and marches down the source rows, keeping A/B of the previous row
+// in registers; source bytes come straight from L1/L2 (they are 6 % of the traffic), stores are 128-bit.
+#include "fsd_common.cuh"
+
+namespace fsd {
+
+constexpr int UP2_THREADS = 128;
+constexpr int UP2_ROWS = 16;  // source rows marched by one thread (32 output rows)
+
+struct Up2Params {
+    const uint8_t* images;
+    int64_t row_pitch, image_pitch;
+    const int32_t* entries;  // [B,3] image_index, x0, y0
+    __half* out;
+    int src_w, src_h, reverse;
+};
+
+__device__ __forceinline__ uint32_t norm255_pair(uint32_t w) {  // (vB << 16 | vA), 8-bit values -> half2(vA/255, vB/255)
+    const __half2 magic = __halves2half2(__ushort_as_half(0x6400), __ushort_as_half(0x6400));
+    uint32_t m = w | 0x64006400u;
+    const __half2 v = __hsub2(*reinterpret_cast<__half2*>(&m), magic);
+    const __half2 c_hi = __halves2half2(__ushort_as_half(0x1C04), __ushort_as_half(0x1C04));  // fp16(1/255)
+    const __half2 c_lo = __halves2half2(__ushort_as_half(0x0001), __ushort_as_half(0x0001));  // 2^-24
+    const __half2 r = __hfma2(v, c_hi, __hmul2(v, c_lo));  // == half(float(v)/255) for all 256 inputs (exhaustive search)
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// A/B words of one source row for one channel: 4 words = output columns (2j..2j+7), two columns per word
+struct RowAB { uint32_t a[4], b[4]; };
+
+__device__ __forceinline__ void row_ab(const uint32_t (&p)[6], RowAB& r) {
+    // p[i] = source pixel j-1+i (one channel).  word i = (se_i, so_{i+1}) = (p[i] + 3 p[i+1], 3 p[i+1] + p[i+2])
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t s = p[i] + p[i + 1] * 0x00030003u + (p[i + 2] << 16);
+        r.a[i] = ((s * 3u) >> 2) & 0x0fff0fffu;
+        r.b[i] = (s >> 2) & 0x03ff03ffu;
+    }
+}
+
+__device__ __forceinline__ void out_row(const uint32_t (&x)[4], const uint32_t (&y)[4], uint32_t (&o)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = norm255_pair(((x[i] + y[i] + 0x00020002u) >> 2) & 0x00ff00ffu);
+}
+
+template <bool NHWC>
+__global__ void __launch_bounds__(UP2_THREADS)
+k1_upscale2x_kernel(const Up2Params p) {
+    const int b = blockIdx.z;
+    const int v = blockIdx.x * UP2_THREADS + threadIdx.x;  // 8-column output vector index
+    const int out_w = 2 * p.src_w, out_h = 2 * p.src_h;
+    if ((v & ~31) * 8 >= out_w) return;  // whole warp beyond the row (warp-uniform)
+    const bool active = v * 8 < out_w;   // a partially filled warp keeps its idle lanes for the warp-level store transpose
+    const int img = __ldg(p.entries + 3 * b + 0), x0 = __ldg(p.entries + 3 * b + 1), y0 = __ldg(p.entries + 3 * b + 2);
+    const uint8_t* base = p.images + (size_t)img * p.image_pitch + (size_t)y0 * p.row_pitch + (size_t)x0 * 3;
+    const int j = v * 4;  // first source column of this vector (output columns 2j .. 2j+7 use source j-1 .. j+4)
+    int off[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) off[i] = min(max(j - 1 + i, 0), p.src_w - 1) * 3;
+    const int c0 = p.reverse ? 2 : 0, c2 = p.reverse ? 0 : 2;  // plane <- source channel
+    const size_t plane = (size_t)out_h * out_w;
+    __half* out = p.out + (size_t)b * 3 * plane + (NHWC ? (size_t)v * 24 : (size_t)v * 8);
+    // channels-last: first byte (within an output row) and base pointer of this WARP's 32 vectors
+    const int warp_byte0 = (v & ~31) * 48;
+    __half* out_warp = p.out + (size_t)b * 3 * plane + (size_t)(v & ~31) * 24;
+    __shared__ uint4 s_stage[NHWC ? UP2_THREADS * 3 : 1];
+
+    auto load_row = [&](int k, RowAB (&r)[3]) {
+        const uint8_t* row = base + (size_t)min(max(k, 0), p.src_h - 1) * p.row_pitch;
+        uint32_t px[3][6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            px[0][i] = __ldg(row + off[i] + c0);
+            px[1][i] = __ldg(row + off[i] + 1);
+            px[2][i] = __ldg(row + off[i] + c2);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) row_ab(px[c], r[c]);
+    };
+    auto store_row = [&](int Y, const uint32_t (&o)[3][4]) {
+        if (NHWC) {
+            uint32_t w[12];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // word k of a plane holds pixels (2k, 2k+1)
+                w[3 * k + 0] = __byte_perm(o[0][k], o[1][k], 0x5410);
+                w[3 * k + 1] = __byte_perm(o[2][k], o[0][k], 0x7610);
+                w[3 * k + 2] = __byte_perm(o[1][k], o[2][k], 0x7632);
+            }
+            // each thread owns 48 contiguous bytes; a direct store would make every STG.128 of the warp hit 32 chunks
+            // 48 B apart (half-filled sectors).  Transpose through the warp's smem slab so that every store instruction
+            // writes one contiguous 512-byte run (conflict-free: 48-byte stride -> distinct banks per quarter-warp).
+            uint4* slab = s_stage + (threadIdx.x & ~31) * 3;
+            const int lane = threadIdx.x & 31;
+            slab[lane * 3 + 0] = make_uint4(w[0], w[1], w[2], w[3]);
+            slab[lane * 3 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+            slab[lane * 3 + 2] = make_uint4(w[8], w[9], w[10], w[11]);
+            __syncwarp();
+            uint4* d = reinterpret_cast<uint4*>(out_warp + (size_t)Y * out_w * 3);
+            const int nchunk = min(96, (out_w * 3 * 2 - warp_byte0) / 16);  // the last warp of a row may be partial
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k * 32 + lane < nchunk) d[k * 32 + lane] = slab[k * 32 + lane];
+            __syncwarp();
+        } else if (active) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                *reinterpret_cast<uint4*>(out + c * plane + (size_t)Y * out_w) = make_uint4(o[c][0], o[c][1], o[c][2], o[c][3]);
+        }
+    };
+
+    // march k = k_lo .. k_hi-1: source rows (k, k+1) -> output rows 2k+1 and 2k+2 (k = -1 and k = src_h-1 are half steps)
+    const int k_lo = -1 + (int)blockIdx.y * UP2_ROWS;
+    const int k_hi = min(k_lo + UP2_ROWS, p.src_h);
+    RowAB prev[3], cur[3];
+    load_row(k_lo, prev);
+    for (int k = k_lo; k < k_hi; ++k) {
+        load_row(k + 1, cur);
+        uint32_t o[3][4];
+        if (2 * k + 1 >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out_row(prev[c].a, cur[c].b, o[c]);
+            store_row(2 * k + 1, o);
+        }
+        if (2 * k + 2 < out_h) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) out_row(prev[c].b, cur[c].a, o[c]);
+            store_row(2 * k + 2, o);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) prev[c] = cur[c];
+    }
+}
+
+// called by fsd_gather_letterbox when the geometry is an exact 2x up-scale without letterbox border and fp16 output
+int launch_upscale2x(fsd_context* h, const uint8_t* images, int64_t row_pitch, int64_t image_pitch, const int32_t* entries,
+                     int B, int src_w, int src_h, int reverse, int nhwc, void* out, cudaStream_t stream) {
+    Up2Params p;
+    p.images = images; p.row_pitch = row_pitch; p.image_pitch = image_pitch; p.entries = entries;
+    p.out = reinterpret_cast<__half*>(out); p.src_w = src_w; p.src_h = src_h; p.reverse = reverse;
+    const int vecs = (2 * src_w + 7) / 8;
+    dim3 grid((vecs + UP2_THREADS - 1) / UP2_THREADS, (src_h + 1 + UP2_ROWS - 1) / UP2_ROWS, B);
+    if (nhwc) k1_upscale2x_kernel<true><<<grid, UP2_THREADS, 0, stream>>>(p);
+    else k1_upscale2x_kernel<false><<<grid, UP2_THREADS, 0, stream>>>(p);
+    FSD_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return FSD_OK;
+}
+
+}  // namespace fsd

@@ -95,3 +95,27 @@ def test_channels_last_output(cuda_device, case, dtype):
     assert out.is_contiguous(memory_format=torch.channels_last)
     ref = _oracle_batch(images, entries, bw, bh, imgsz, dtype == torch.float16, True)
     assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("size", [(512, 512), (64, 96), (8, 12), (36, 516), (300, 500)])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_exact_2x_fast_path_equals_general_kernel_and_oracle(cuda_device, size, channels_last, monkeypatch):
+    """imgsz == 2 x slice takes the small-integer fast path (k1_upscale2x.cu); it must equal cv2 AND the general TMA kernel."""
+    import fsd_b200.ops as ops
+
+    sh, sw = size
+    H, W = sh + 37, sw + 21
+    imgsz = 2 * max(sh, sw)
+    g = olb.letterbox_geometry(sh, sw, imgsz)
+    rng = np.random.default_rng(5)
+    images = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(2)]
+    entries = [(0, 0, 0), (1, 21, 37), (0, 7, 3), (1, 0, 37)]
+    pool = ops.ImagePool.from_numpy(images, cuda_device)
+    ent = torch.tensor(entries, dtype=torch.int32)
+    fast = ops.gather_letterbox(pool, ent, sw, sh, imgsz=imgsz, dtype=torch.float16, channels_last=channels_last)
+    ref = _oracle_batch(images, entries, sw, sh, imgsz, True, True)
+    assert torch.equal(fast.cpu(), ref)
+    if (g["new_w"], g["new_h"], g["left"], g["top"]) == (2 * sw, 2 * sh, 0, 0):  # the fast path was eligible: cross-check
+        monkeypatch.setenv("FSD_K1_GENERIC", "1")
+        general = ops.gather_letterbox(pool, ent, sw, sh, imgsz=imgsz, dtype=torch.float16, channels_last=channels_last)
+        assert torch.equal(general, fast)
