@@ -235,8 +235,15 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k1_gather_letterbox_kernel (slice launch)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of the same launch (ncu --set full capture under profiles/)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))
+        if tj.get("entries") == n_entries:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k1_upscale2x_kernel<channels_last> via fsd_gather_letterbox (slice launch: 6 slices x B images, exact-2x path)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "bytes_per_launch": k1_bytes, "launch_ms": k1_ms, "launches_timed": len(sl)}
 

@@ -15,7 +15,7 @@ from fsd_b200 import _cabi, ops  # noqa: E402
 dev = torch.device("cuda:0")
 which = sys.argv[1] if len(sys.argv) > 1 else "k1_c2"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-if which.startswith("k1"):
+if which in ("k1_c2", "k1_c2_f32"):
     N = 32
     pool = ops.ImagePool(N, 768, 1024, dev)
     pool.buf.random_(0, 256)
@@ -26,7 +26,7 @@ if which.startswith("k1"):
     for _ in range(iters):
         ops.gather_letterbox(pool, ent, 512, 512, 1024, 32, True, dt, out=out)
 elif which == "k1_nhwc":
-    N = 32
+    N = int(os.environ.get("FSD_N", "32"))
     pool = ops.ImagePool(N, 768, 1024, dev)
     pool.buf.random_(0, 256)
     boxes = _cabi.slice_plan(768, 1024, 512, 512, 0.2, 0.2)
