@@ -2,7 +2,7 @@
 """Per-kernel micro-benchmarks: achieved GB/s against the algorithmic bytes of SURVEY §8(d), CUDA-event timed,
 inputs larger than L2 (126 MB) so every launch streams from HBM.  One JSON line per measurement.
 
-    python benchmarks/kernels.py [k1|k2|k3|k4|ref|all]
+    python benchmarks/kernels.py [k1|k2|k3|k4|k5|ref|all]
 """
 import json
 import os
@@ -149,32 +149,58 @@ def bench_k3():
 
 
 def bench_k4():
+    """C5 shapes.  frames = 1 is the reference's per-image call (a 1080p frame is a 20 / 75 MB launch: latency-bound);
+    frames = 8 is the batch mode (one launch over 8 frames of a stream)."""
     for H, W, scale, tile in ((1080, 1920, 2, 400), (1080, 1920, 4, 400)):
-        N = 8
-        imgs = [torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, device=dev) for _ in range(N)]
-        table, _ = ops.esrgan_tile_table(H, W, scale, tile, 10, 0)
-        tiles, tab_dev = ops.esrgan_crop(imgs[0], table, scale)
-        crop_bytes = H * W * 3 + sum(3 * int(r[2]) * int(r[3]) for r in table) * 2
-        k = [0]
+        for frames in (1, 8):
+            R = 3  # rotate buffers so consecutive replays do not hit L2
+            imgs = [torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(R)]
+            table, _ = ops.esrgan_tile_table(H, W, scale, tile, 10, 0)
+            tiles, tab_dev = ops.esrgan_crop(imgs[0], table, scale)
+            crop_bytes = frames * (H * W * 3 + sum(3 * int(r[2]) * int(r[3]) for r in table) * 2)
+            k = [0]
 
-        def crop():
-            k[0] = (k[0] + 1) % N
-            ops.esrgan_crop(imgs[k[0]], table, scale, tab_dev=tab_dev, tiles=tiles)
+            def crop():
+                k[0] = (k[0] + 1) % R
+                ops.esrgan_crop(imgs[k[0]], table, scale, tab_dev=tab_dev, tiles=tiles)
 
-        report(f"K4 crop {W}x{H} x{scale} tile {tile} fp16", crop_bytes, crop, tiles=len(table))
-        outs = [torch.rand(ops.esrgan_out_buffer(table, scale, torch.float16, dev).shape, device=dev).half() for _ in range(4)]
-        dst = [torch.empty((H * scale, W * scale, 3), dtype=torch.uint8, device=dev) for _ in range(4)]
-        stitch_bytes = H * W * scale * scale * 3 * (2 + 1)
+            report(f"K4 crop {W}x{H} x{scale} tile {tile} fp16 frames={frames}", crop_bytes, crop, tiles=len(table))
+            del imgs, tiles
+            outs = [torch.rand(ops.esrgan_out_buffer(table, scale, torch.float16, dev, n_images=frames).shape, device=dev).half() for _ in range(R)]
+            dst = [torch.empty((frames, H * scale, W * scale, 3), dtype=torch.uint8, device=dev) for _ in range(R)]
+            stitch_bytes = frames * H * W * scale * scale * 3 * (2 + 1)
 
-        def stitch():
-            k[0] = (k[0] + 1) % 4
-            ops.esrgan_stitch(outs[k[0]], table, tab_dev, scale, H, W, out=dst[k[0]])
+            def stitch():
+                k[0] = (k[0] + 1) % R
+                ops.esrgan_stitch(outs[k[0]], table, tab_dev, scale, H, W, out=dst[k[0]])
 
-        report(f"K4 stitch {W}x{H} x{scale} tile {tile} fp16", stitch_bytes, stitch, tiles=len(table))
+            report(f"K4 stitch {W}x{H} x{scale} tile {tile} fp16 frames={frames}", stitch_bytes, stitch, tiles=len(table))
+            del outs, dst
+
+
+def bench_k5():
+    """conv epilogue passes of the backbone at the shapes of the C2 step (96 network inputs of 1024^2 per chunk)."""
+    cl = lambda *shape: torch.randn(shape, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    for name, n, c, hw in (("b0 out 16ch 512^2", 96, 16, 512), ("b2.cv2 out 64ch 256^2", 96, 64, 256), ("b4.cv2 out 128ch 128^2", 96, 128, 128)):
+        x = cl(n, c, hw, hw)
+        bias = torch.randn((c,), device=dev, dtype=torch.float16)
+        nbytes = 2 * x.numel() * 2
+        report(f"K5 bias+SiLU in place {name}", nbytes, lambda: ops.bias_act_(x, bias, "silu"))
+        report(f"K5 bias+SiLU general (dense out) {name}", nbytes, lambda: ops.bias_act(x, bias, "silu"))
+        buf = cl(n, 2 * c, hw, hw)
+        res = cl(n, c, hw, hw)
+        report(f"K5 bias+SiLU+residual -> concat slot {name}", nbytes + x.numel() * 2,
+               lambda: ops.bias_act(x, bias, "silu", out=buf[:, c:], residual=res))
+        del x, buf, res
+    buf = cl(96, 512, 32, 32)
+    report("K5 SPPF pool 96 x 128ch 32x32 (read slot 0, write slots 1-3)", buf.numel() * 2, lambda: ops.sppf_pool_(buf))
+    a, b = cl(96, 128, 64, 64), cl(96, 64, 128, 128)
+    report("K5 upsample2x+concat 96 x (128ch 64^2 , 64ch 128^2)", (a.numel() + b.numel() + 96 * 192 * 128 * 128) * 2,
+           lambda: ops.upsample2x_concat(a, b))
 
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4)):
+    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4), ("k5", bench_k5)):
         if which in ("all", name):
             fn()

@@ -59,11 +59,12 @@ elif which == "k3":
         ops.merge_segments(rows, offs, None, len(seg), merge_type="GREEDYNMM", metric="IOS", thr=0.5, want_parent=False)
 elif which == "k4":
     H, W, scale, tile = 1080, 1920, 2, 400
-    img = torch.randint(0, 256, (H, W, 3), dtype=torch.uint8, device=dev)
+    frames = int(os.environ.get("FSD_FRAMES", "1"))
+    img = torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, device=dev)
     table, _ = ops.esrgan_tile_table(H, W, scale, tile, 10, 0)
     for _ in range(iters):
         tiles, tab_dev = ops.esrgan_crop(img, table, scale)
-        outb = torch.rand(ops.esrgan_out_buffer(table, scale, torch.float16, dev).shape, device=dev).half()
+        outb = torch.rand(ops.esrgan_out_buffer(table, scale, torch.float16, dev, n_images=frames).shape, device=dev).half()
         ops.esrgan_stitch(outb, table, tab_dev, scale, H, W)
 torch.cuda.synchronize()
 print("done", which)

@@ -37,13 +37,16 @@ SIGNATURES = {
                                     C.c_int, vp, vp]),
     "fsd_pack_results": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]),
     "fsd_bias_act_inplace": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
+    "fsd_bias_act": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int64, C.c_int,
+                               C.c_int, C.c_float, C.c_int, vp]),
+    "fsd_sppf_pool": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fsd_upsample2x_concat": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fsd_esrgan_tile_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int,
                                         C.POINTER(C.c_int), c_i32p]),
     "fsd_esrgan_crop": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int,
-                                  vp, vp]),
+                                  vp, C.c_int, C.c_int64, C.c_int64, vp]),
     "fsd_esrgan_stitch": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int64,
-                                    vp]),
+                                    C.c_int, C.c_int64, C.c_int64, vp]),
     "fsd_bbox_overlaps_p1": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp]),
     "fsd_attach_keypoints": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
 }

@@ -21,44 +21,41 @@ def _make_divisible(x, divisor=8):
     return int(math.ceil(x / divisor) * divisor)
 
 
+def _cat_buffer(x, channels, h=None, w=None):
+    """Empty channels-last [N, channels, H, W] buffer whose channel slots the conv epilogues fill (no torch.cat pass)."""
+    return torch.empty((x.shape[0], channels, x.shape[2] if h is None else h, x.shape[3] if w is None else w),
+                       dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+
+
 class Conv(nn.Module):
     def __init__(self, c1, c2, k=1, s=1, g=1, act=True):
         super().__init__()
         self.conv = nn.Conv2d(c1, c2, k, s, k // 2, groups=g, bias=True)
         self.act = nn.SiLU(inplace=True) if act else nn.Identity()
 
-    def forward(self, x):
+    def forward(self, x, out=None, residual=None, out2=None):
+        """act(conv(x) + bias) (+ residual).  On the GPU in fp16 the convolution runs in cuDNN without bias and ONE
+        hand-written pass (fsd_bias_act) applies bias, activation and the residual and stores the result into `out` —
+        which may be a channel slot of a concat buffer — and the trailing channels into `out2` as well."""
         c = self.conv
-        if (x.is_cuda and x.dtype == torch.float16 and c.out_channels % 8 == 0 and isinstance(self.act, nn.SiLU)
-                and not torch.is_grad_enabled()):
-            # cuDNN convolution without bias, then ONE hand-written pass for + bias and SiLU (fsd_bias_act_inplace)
+        if (x.is_cuda and x.dtype == torch.float16 and c.out_channels % 8 == 0 and not torch.is_grad_enabled()):
             y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
             if y.is_contiguous(memory_format=torch.channels_last):
-                from ..ops import bias_act_
+                from ..ops import bias_act
 
-                return bias_act_(y, c.bias, "silu")
-            return self.act(y + c.bias.view(1, -1, 1, 1))
-        return self.act(c(x))
-
-    def forward_split(self, x, sizes):
-        """The same convolution evaluated as one conv per output-channel group (weight views, no copies): every
-        group comes out dense, so consumers of `chunk`/`split` need no strided-slice copy and residual adds vectorise."""
-        c, outs, a = self.conv, [], 0
-        fused = (x.is_cuda and x.dtype == torch.float16 and isinstance(self.act, nn.SiLU) and not torch.is_grad_enabled()
-                 and all(n % 8 == 0 for n in sizes))
-        if not fused:
-            return list(self.forward(x).split(sizes, 1))
-        from ..ops import bias_act_
-
-        for n in sizes:
-            y = F.conv2d(x, c.weight[a:a + n], None, c.stride, c.padding, c.dilation, c.groups)
-            if y.is_contiguous(memory_format=torch.channels_last):
-                y = bias_act_(y, c.bias[a:a + n], "silu")
-            else:
-                y = self.act(y + c.bias[a:a + n].view(1, -1, 1, 1))
-            outs.append(y)
-            a += n
-        return outs
+                return bias_act(y, c.bias, "silu" if isinstance(self.act, nn.SiLU) else "none", out=out,
+                                residual=residual, out2=out2)
+            y = self.act(y + c.bias.view(1, -1, 1, 1))
+        else:
+            y = self.act(c(x))
+        if residual is not None:
+            y = residual + y
+        if out2 is not None:
+            out2.copy_(y[:, y.shape[1] - out2.shape[1]:])
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
 
 
 class DWConv(Conv):
@@ -74,19 +71,27 @@ class Bottleneck(nn.Module):
         self.cv2 = Conv(c_, c2, k[1], 1)
         self.add = shortcut and c1 == c2
 
-    def forward(self, x):
-        return x + self.cv2(self.cv1(x)) if self.add else self.cv2(self.cv1(x))
+    def forward(self, x, out=None):
+        return self.cv2(self.cv1(x), out=out, residual=x if self.add else None)
 
 
 class C3k(nn.Module):
     def __init__(self, c1, c2, n=2, shortcut=True, e=0.5, k=3):
         super().__init__()
         c_ = int(c2 * e)
+        self.c_ = c_
         self.cv1, self.cv2, self.cv3 = Conv(c1, c_, 1, 1), Conv(c1, c_, 1, 1), Conv(2 * c_, c2, 1)
-        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, k=(k, k), e=1.0) for _ in range(n)))
+        self.m = nn.ModuleList(Bottleneck(c_, c_, shortcut, k=(k, k), e=1.0) for _ in range(n))
 
-    def forward(self, x):
-        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+    def forward(self, x, out=None):
+        buf = _cat_buffer(x, 2 * self.c_)
+        y = self.cv1(x)
+        for i, m in enumerate(self.m):
+            y = m(y, out=buf[:, :self.c_] if i == len(self.m) - 1 else None)
+        if len(self.m) == 0:
+            buf[:, :self.c_].copy_(y)
+        self.cv2(x, out=buf[:, self.c_:])
+        return self.cv3(buf, out=out)
 
 
 class C3k2(nn.Module):
@@ -98,23 +103,44 @@ class C3k2(nn.Module):
         self.m = nn.ModuleList(C3k(self.c, self.c, 2, shortcut) if c3k else Bottleneck(self.c, self.c, shortcut)
                                for _ in range(n))
 
-    def forward(self, x):
-        y = self.cv1.forward_split(x, [self.c, self.c])
-        y.extend(m(y[-1]) for m in self.m)
-        return self.cv2(torch.cat(y, 1))
+    def forward(self, x, out=None, out2=None):
+        c, n = self.c, len(self.m)
+        buf = _cat_buffer(x, (2 + n) * c)
+        y = torch.empty((x.shape[0], c, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                        memory_format=torch.channels_last)
+        # cv1 fills slots 0-1 of the concat buffer; its second half is also stored densely as the input of m[0]
+        self.cv1(x, out=buf[:, :2 * c], out2=y)
+        for i, m in enumerate(self.m):
+            y = m(y, out=buf[:, (2 + i) * c:(3 + i) * c])
+            if i + 1 < n:
+                y = y.contiguous(memory_format=torch.channels_last)
+        return self.cv2(buf, out=out, out2=out2)
 
 
 class SPPF(nn.Module):
     def __init__(self, c1, c2, k=5):
         super().__init__()
         c_ = c1 // 2
+        self.c_ = c_
         self.cv1, self.cv2 = Conv(c1, c_, 1, 1), Conv(c_ * 4, c2, 1, 1)
         self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
 
     def forward(self, x):
-        y = [self.cv1(x)]
-        y.extend(self.m(y[-1]) for _ in range(3))
-        return self.cv2(torch.cat(y, 1))
+        buf = _cat_buffer(x, 4 * self.c_)
+        h, w = x.shape[2:]
+        if (x.is_cuda and x.dtype == torch.float16 and self.c_ % 8 == 0 and self.m.kernel_size == 5
+                and 2 * h * w * 16 <= 200 * 1024 and not torch.is_grad_enabled()):
+            from ..ops import sppf_pool_
+
+            self.cv1(x, out=buf[:, :self.c_])
+            sppf_pool_(buf)  # slots 1..3 = m(y), m(m(y)), m(m(m(y))) in one launch
+        else:
+            y = self.cv1(x)
+            buf[:, :self.c_].copy_(y)
+            for i in range(1, 4):
+                y = self.m(y)
+                buf[:, i * self.c_:(i + 1) * self.c_].copy_(y)
+        return self.cv2(buf)
 
 
 class Attention(nn.Module):
@@ -129,7 +155,7 @@ class Attention(nn.Module):
         self.proj = Conv(dim, dim, 1, act=False)
         self.pe = Conv(dim, dim, 3, 1, g=dim, act=False)
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
         B, C, H, W = x.shape
         N = H * W
         qkv = self.qkv(x)
@@ -138,7 +164,7 @@ class Attention(nn.Module):
         attn = (q.transpose(-2, -1) @ k) * self.scale
         attn = attn.softmax(dim=-1)
         x = (v @ attn.transpose(-2, -1)).reshape(B, C, H, W) + self.pe(v.reshape(B, C, H, W))
-        return self.proj(x)
+        return self.proj(x, residual=residual)
 
 
 class PSABlock(nn.Module):
@@ -147,9 +173,9 @@ class PSABlock(nn.Module):
         self.attn = Attention(c, num_heads=num_heads, attn_ratio=attn_ratio)
         self.ffn = nn.Sequential(Conv(c, c * 2, 1), Conv(c * 2, c, 1, act=False))
 
-    def forward(self, x):
-        x = x + self.attn(x)
-        return x + self.ffn(x)
+    def forward(self, x, out=None):
+        x = self.attn(x, residual=x)
+        return self.ffn[1](self.ffn[0](x), out=out, residual=x)
 
 
 class C2PSA(nn.Module):
@@ -158,11 +184,17 @@ class C2PSA(nn.Module):
         assert c1 == c2
         self.c = int(c1 * e)
         self.cv1, self.cv2 = Conv(c1, 2 * self.c, 1, 1), Conv(2 * self.c, c1, 1)
-        self.m = nn.Sequential(*(PSABlock(self.c, attn_ratio=0.5, num_heads=max(1, self.c // 64)) for _ in range(n)))
+        self.m = nn.ModuleList(PSABlock(self.c, attn_ratio=0.5, num_heads=max(1, self.c // 64)) for _ in range(n))
 
-    def forward(self, x):
-        a, b = self.cv1.forward_split(x, [self.c, self.c])
-        return self.cv2(torch.cat((a, self.m(b)), 1))
+    def forward(self, x, out2=None):
+        c = self.c
+        buf = _cat_buffer(x, 2 * c)
+        b = torch.empty((x.shape[0], c, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                        memory_format=torch.channels_last)
+        self.cv1(x, out=buf, out2=b)  # slot 0 = a, slot 1 is overwritten by m(b) below
+        for i, m in enumerate(self.m):
+            b = m(b, out=buf[:, c:] if i == len(self.m) - 1 else None)
+        return self.cv2(buf, out2=out2)
 
 
 def _up_cat(a, b):
@@ -230,11 +262,18 @@ class YOLO11Pose(nn.Module):
         x = self.b1(self.b0(x))
         p3 = self.b4(self.b3(self.b2(x)))
         p4 = self.b6(self.b5(p3))
-        p5 = self.b10(self.b9(self.b8(self.b7(p4))))
-        n4 = self.h13(_up_cat(p5, p4))
+        c5 = self.b7.conv.out_channels
+        h5, w5 = (p4.shape[2] - 1) // 2 + 1, (p4.shape[3] - 1) // 2 + 1
+        cat22 = _cat_buffer(x, self.h20.conv.out_channels + c5, h5, w5)  # cat(h20(m4), p5): p5 stored by its producer
+        p5 = self.b10(self.b9(self.b8(self.b7(p4))), out2=cat22[:, self.h20.conv.out_channels:])
+        c17 = self.h17.conv.out_channels
+        cat19 = _cat_buffer(x, c17 + self.h13.cv2.conv.out_channels, p4.shape[2], p4.shape[3])  # cat(h17(n3), n4)
+        n4 = self.h13(_up_cat(p5, p4), out2=cat19[:, c17:])
         n3 = self.h16(_up_cat(n4, p3))
-        m4 = self.h19(torch.cat((self.h17(n3), n4), 1))
-        m5 = self.h22(torch.cat((self.h20(m4), p5), 1))
+        self.h17(n3, out=cat19[:, :c17])
+        m4 = self.h19(cat19)
+        self.h20(m4, out=cat22[:, :self.h20.conv.out_channels])
+        m5 = self.h22(cat22)
         return self.head([n3, m4, m5])
 
     @staticmethod

@@ -59,11 +59,44 @@ __device__ __forceinline__ void store_vec8(OutT* o, const float (&v)[8], int nx)
     }
 }
 
+// (vB << 16 | vA), two 8-bit values -> half2(vA/255, vB/255): 0x6400|v is the half 1024+v; the two-term product equals
+// half(float(v)/255) — what `img.astype(float32)/255 -> .half()` yields — for all 256 inputs (exhaustive search, K1).
+__device__ __forceinline__ uint32_t k4_norm255_pair(uint32_t w) {
+    const __half2 magic = __halves2half2(__ushort_as_half(0x6400), __ushort_as_half(0x6400));
+    uint32_t m = w | 0x64006400u;
+    const __half2 v = __hsub2(*reinterpret_cast<__half2*>(&m), magic);
+    const __half2 c_hi = __halves2half2(__ushort_as_half(0x1C04), __ushort_as_half(0x1C04));  // fp16(1/255)
+    const __half2 c_lo = __halves2half2(__ushort_as_half(0x0001), __ushort_as_half(0x0001));  // 2^-24
+    const __half2 r = __hfma2(v, c_hi, __hmul2(v, c_lo));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// 8 halfs to a 2-byte-aligned address with the widest stores its alignment allows (tile rows are pw halfs long, so a row
+// start is 16-byte aligned only when pw % 8 == 0; the scalar fallback used to cost 8 stores per plane)
+__device__ __forceinline__ void store8h(__half* o, const uint32_t (&w)[4]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(o);
+    if ((a & 15) == 0) {
+        *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if ((a & 7) == 0) {
+        reinterpret_cast<uint2*>(o)[0] = make_uint2(w[0], w[1]);
+        reinterpret_cast<uint2*>(o)[1] = make_uint2(w[2], w[3]);
+    } else if ((a & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) reinterpret_cast<uint32_t*>(o)[k] = w[k];
+    } else {
+        unsigned short* u = reinterpret_cast<unsigned short*>(o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { u[2 * k] = (unsigned short)(w[k] & 0xffffu); u[2 * k + 1] = (unsigned short)(w[k] >> 16); }
+    }
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(K4_THREADS)
 k4_crop_kernel(const uint8_t* __restrict__ img, int H, int W, int64_t pitch, int H_pre, int W_pre,
-               const int32_t* __restrict__ table, OutT* __restrict__ tiles) {
+               const int32_t* __restrict__ table, OutT* __restrict__ tiles, int64_t image_pitch, int64_t tiles_image_stride) {
     const int32_t* t = table + (size_t)blockIdx.y * TT;
+    img += (size_t)blockIdx.z * image_pitch;        // blockIdx.z = image of the batch
+    tiles += (size_t)blockIdx.z * tiles_image_stride;
     const int px0 = t[0], py0 = t[1], pw = t[2], ph = t[3];
     OutT* dst = tiles + off64(t, 8);
     const int vecs = (pw + 7) >> 3;
@@ -73,19 +106,39 @@ k4_crop_kernel(const uint8_t* __restrict__ img, int H, int W, int64_t pitch, int
         const int sy = reflect_index(py0 + y, H_pre, H);
         const uint8_t* row = img + (size_t)sy * pitch;
         const int nx = min(8, pw - x);
-        float v[3][8];
         const int gx = px0 + x;
-        if (nx == 8 && gx + 8 <= W && sy + 1 < H) {
-            // fast path: the 24 source bytes are contiguous and an aligned 28-byte window stays inside the image buffer
+        const bool fast = nx == 8 && gx + 8 <= W && sy + 1 < H;
+        uint32_t s[6];
+        if (fast) {
+            // the 24 source bytes are contiguous and an aligned 28-byte window stays inside the image buffer
             const uintptr_t addr = reinterpret_cast<uintptr_t>(row + (size_t)gx * 3);
             const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
             const int sh = (int)(addr & 3) * 8;
             uint32_t w[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) w[k] = __ldg(wp + k);
-            uint32_t s[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) s[k] = __funnelshift_r(w[k], w[k + 1], sh);
+        }
+        if (fast && sizeof(OutT) == 2) {
+            // packed path: pixel pair (2k, 2k+1) of BGR channel c = stream bytes 6k+c and 6k+3+c -> one half2
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ia = 6 * k + c, ib = ia + 3;
+                    const uint32_t sel = (uint32_t)(ia & 3) | ((uint32_t)(4 * ((ib >> 2) - (ia >> 2)) + (ib & 3)) << 8);
+                    // selector nibble 0 -> stream byte ia, nibble 2 -> stream byte ib (bytes 1 and 3 are masked off)
+                    const uint32_t pr = __byte_perm(s[ia >> 2], s[ib >> 2], sel);
+                    o[k] = k4_norm255_pair(pr & 0x00ff00ffu);
+                }
+                store8h(reinterpret_cast<__half*>(dst) + ((size_t)(2 - c) * ph + y) * pw + x, o);
+            }
+            continue;
+        }
+        float v[3][8];
+        if (fast) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
 #pragma unroll
@@ -164,8 +217,11 @@ __device__ __forceinline__ uint32_t quant255(float v) {
 template <typename InT>
 __global__ void __launch_bounds__(K4_THREADS)
 k4_stitch_kernel(const InT* __restrict__ tiles_out, const int32_t* __restrict__ table, int scale,
-                 uint8_t* __restrict__ out, int out_h, int out_w, int64_t out_pitch) {
+                 uint8_t* __restrict__ out, int out_h, int out_w, int64_t out_pitch, int64_t tiles_image_stride,
+                 int64_t out_image_pitch) {
     const int32_t* t = table + (size_t)blockIdx.y * TT;
+    tiles_out += (size_t)blockIdx.z * tiles_image_stride;  // blockIdx.z = image of the batch
+    out += (size_t)blockIdx.z * out_image_pitch;
     const int px0 = t[0], py0 = t[1], pw = t[2], ph = t[3], ix0 = t[4], iy0 = t[5], iw = t[6], ih = t[7];
     const InT* src = tiles_out + off64(t, 10);
     const int tw = pw * scale, th = ph * scale;
@@ -181,7 +237,52 @@ k4_stitch_kernel(const InT* __restrict__ tiles_out, const int32_t* __restrict__ 
         const int nx = min(16, ow - x);
         const InT* r = src + (size_t)(ty0 + y) * tw + tx0 + x;  // R plane; G at +plane, B at +2*plane
         uint8_t* o = out + (size_t)(oy0 + y) * out_pitch + (size_t)(ox0 + x) * 3;
-        if (nx == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+        if (sizeof(InT) == 2 && nx == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && (reinterpret_cast<uintptr_t>(r) & 3) == 0 && (plane & 1) == 0) {
+            // packed-half path: clamp in half2 (exact), then ONE fp16 FMA v*255 + 1024 — the product is exact inside the FMA
+            // and the sum is rounded once at ulp 1 (round-half-even), i.e. exactly numpy's (clamp(v)*255.0).round(); the
+            // integer is the low byte of the result (0x6400 + n).  Bytes are gathered into BGR order with PRMT.
+            uint32_t hw[3][8];  // hw[ch][m] = quantised pixels (2m, 2m+1) of BGR channel ch
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const __half* pp = reinterpret_cast<const __half*>(r) + (size_t)(2 - ch) * plane;
+                const uintptr_t a = reinterpret_cast<uintptr_t>(pp);
+                uint32_t raw[8];
+                if ((a & 15) == 0) {
+                    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(pp)), v1 = __ldg(reinterpret_cast<const uint4*>(pp) + 1);
+                    raw[0] = v0.x; raw[1] = v0.y; raw[2] = v0.z; raw[3] = v0.w; raw[4] = v1.x; raw[5] = v1.y; raw[6] = v1.z; raw[7] = v1.w;
+                } else if ((a & 7) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(pp) + q); raw[2 * q] = v.x; raw[2 * q + 1] = v.y; }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) raw[q] = __ldg(reinterpret_cast<const uint32_t*>(pp) + q);
+                }
+                const __half2 zero = __float2half2_rn(0.f), one = __float2half2_rn(1.f);
+                const __half2 k255 = __float2half2_rn(255.f), k1024 = __float2half2_rn(1024.f);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    __half2 v = *reinterpret_cast<const __half2*>(&raw[m]);
+                    v = __hmin2(__hmax2(v, zero), one);
+                    v = __hfma2(v, k255, k1024);
+                    hw[ch][m] = *reinterpret_cast<const uint32_t*>(&v);
+                }
+            }
+            uint32_t w[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                // output byte i = 4k+j: pixel i/3, BGR channel i%3 -> byte (px&1)*2 of hw[ch][px>>1]
+                const int i0 = 4 * k, i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3;
+                const uint32_t lo = __byte_perm(hw[i0 % 3][(i0 / 3) >> 1], hw[i1 % 3][(i1 / 3) >> 1],
+                                                (uint32_t)(((i0 / 3) & 1) * 2) | ((uint32_t)(4 + ((i1 / 3) & 1) * 2) << 4));
+                const uint32_t hi = __byte_perm(hw[i2 % 3][(i2 / 3) >> 1], hw[i3 % 3][(i3 / 3) >> 1],
+                                                (uint32_t)(((i2 / 3) & 1) * 2) | ((uint32_t)(4 + ((i3 / 3) & 1) * 2) << 4));
+                w[k] = __byte_perm(lo, hi, 0x5410);
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+            o4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            o4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            o4[2] = make_uint4(w[8], w[9], w[10], w[11]);
+        } else if (nx == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
             float f[3][16];
             load16<InT>(r, f[2]);               // R plane -> byte 2 of each BGR pixel
             load16<InT>(r + plane, f[1]);       // G
@@ -334,20 +435,23 @@ extern "C" int fsd_esrgan_tile_table(int H, int W, int scale, int tile, int tile
 
 extern "C" int fsd_esrgan_crop(fsd_handle_t h, const uint8_t* bgr, int H, int W, int64_t row_pitch, int pre_h,
                                int pre_w, const int32_t* table_dev, const int32_t* table_host, int T, int dtype,
-                               void* tiles, void* stream_) {
+                               void* tiles, int n_images, int64_t image_pitch, int64_t tiles_image_stride,
+                               void* stream_) {
     FSD_CHECK_ARG(h && bgr && table_dev && table_host && tiles, "fsd_esrgan_crop: null argument");
     FSD_CHECK_ARG(H > 0 && W > 0 && T >= 0 && row_pitch >= (int64_t)W * 3 && pre_h >= H && pre_w >= W, "fsd_esrgan_crop: bad sizes");
     FSD_CHECK_ARG(dtype == FSD_F16 || dtype == FSD_F32, "fsd_esrgan_crop: bad dtype");
-    if (T == 0) return FSD_OK;
+    FSD_CHECK_ARG(n_images >= 0 && n_images <= 65535 && (n_images <= 1 || (image_pitch >= row_pitch * H && tiles_image_stride > 0 && tiles_image_stride % 8 == 0)),
+                  "fsd_esrgan_crop: bad batch strides (tile stride must be a positive multiple of 8 elements)");
+    if (T == 0 || n_images == 0) return FSD_OK;
     int max_items = 1;
     for (int i = 0; i < T; ++i) {
         const int items = table_host[i * TT + 3] * ((table_host[i * TT + 2] + 7) / 8);
         if (items > max_items) max_items = items;
     }
-    dim3 grid((max_items + K4_THREADS - 1) / K4_THREADS, T);
+    dim3 grid((max_items + K4_THREADS - 1) / K4_THREADS, T, n_images);
     FSD_CUDA(cudaSetDevice(h->device));
-    if (dtype == FSD_F16) k4_crop_kernel<__half><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>(bgr, H, W, row_pitch, pre_h, pre_w, table_dev, (__half*)tiles);
-    else k4_crop_kernel<float><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>(bgr, H, W, row_pitch, pre_h, pre_w, table_dev, (float*)tiles);
+    if (dtype == FSD_F16) k4_crop_kernel<__half><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>(bgr, H, W, row_pitch, pre_h, pre_w, table_dev, (__half*)tiles, image_pitch, tiles_image_stride);
+    else k4_crop_kernel<float><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>(bgr, H, W, row_pitch, pre_h, pre_w, table_dev, (float*)tiles, image_pitch, tiles_image_stride);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;
@@ -355,20 +459,23 @@ extern "C" int fsd_esrgan_crop(fsd_handle_t h, const uint8_t* bgr, int H, int W,
 
 extern "C" int fsd_esrgan_stitch(fsd_handle_t h, const void* tiles_out, const int32_t* table_dev,
                                  const int32_t* table_host, int T, int scale, int dtype, uint8_t* out_bgr, int out_h,
-                                 int out_w, int64_t out_pitch, void* stream_) {
+                                 int out_w, int64_t out_pitch, int n_images, int64_t tiles_image_stride,
+                                 int64_t out_image_pitch, void* stream_) {
     FSD_CHECK_ARG(h && tiles_out && table_dev && table_host && out_bgr, "fsd_esrgan_stitch: null argument");
     FSD_CHECK_ARG(T >= 0 && scale > 0 && out_h > 0 && out_w > 0 && out_pitch >= (int64_t)out_w * 3, "fsd_esrgan_stitch: bad sizes");
     FSD_CHECK_ARG(dtype == FSD_F16 || dtype == FSD_F32, "fsd_esrgan_stitch: bad dtype");
-    if (T == 0) return FSD_OK;
+    FSD_CHECK_ARG(n_images >= 0 && n_images <= 65535 && (n_images <= 1 || (out_image_pitch >= out_pitch * out_h && tiles_image_stride > 0 && tiles_image_stride % 8 == 0)),
+                  "fsd_esrgan_stitch: bad batch strides (tile stride must be a positive multiple of 8 elements)");
+    if (T == 0 || n_images == 0) return FSD_OK;
     int max_items = 1;
     for (int i = 0; i < T; ++i) {
         const int items = table_host[i * TT + 7] * scale * ((table_host[i * TT + 6] * scale + 15) / 16);
         if (items > max_items) max_items = items;
     }
-    dim3 grid((max_items + K4_THREADS - 1) / K4_THREADS, T);
+    dim3 grid((max_items + K4_THREADS - 1) / K4_THREADS, T, n_images);
     FSD_CUDA(cudaSetDevice(h->device));
-    if (dtype == FSD_F16) k4_stitch_kernel<__half><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>((const __half*)tiles_out, table_dev, scale, out_bgr, out_h, out_w, out_pitch);
-    else k4_stitch_kernel<float><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>((const float*)tiles_out, table_dev, scale, out_bgr, out_h, out_w, out_pitch);
+    if (dtype == FSD_F16) k4_stitch_kernel<__half><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>((const __half*)tiles_out, table_dev, scale, out_bgr, out_h, out_w, out_pitch, tiles_image_stride, out_image_pitch);
+    else k4_stitch_kernel<float><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>((const float*)tiles_out, table_dev, scale, out_bgr, out_h, out_w, out_pitch, tiles_image_stride, out_image_pitch);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

@@ -45,6 +45,89 @@ k5_bias_act_float_kernel(float4* __restrict__ x, const float4* __restrict__ bias
     }
 }
 
+// General epilogue: out[pix, c] = act(x[pix, c] + bias[c]) (+ res[pix, c]), where `out` and `res` may be channel slots of
+// wider channels-last buffers (own pixel stride), and channels >= out2_c0 are additionally copied to a second
+// destination.  This lets the conv epilogue write straight into the concat buffer of C3k2 / SPPF / C2PSA (torch.cat was
+// 14.5 % of the step in profiles/r1_launches_bench_b32_final.txt) and folds the bottleneck's residual add.
+struct K5GenArgs {
+    const uint4* x; const uint4* bias; uint4* out; const uint4* res; uint4* out2;
+    unsigned n_vec; int c_vec; int out_stride; int res_stride; int out2_stride; int out2_c0; float slope;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(K5_THREADS) k5_bias_act_general_half_kernel(const K5GenArgs a) {
+    for (unsigned i = blockIdx.x * K5_THREADS + threadIdx.x; i < a.n_vec; i += gridDim.x * K5_THREADS) {
+        const unsigned pix = i / (unsigned)a.c_vec;
+        const int c = (int)(i - pix * (unsigned)a.c_vec);
+        uint4 v = __ldcs(a.x + i);
+        const uint4 b = __ldg(a.bias + c);
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (a.res) r = __ldg(a.res + (size_t)pix * a.res_stride + c);
+        __half2* hv = reinterpret_cast<__half2*>(&v);
+        const __half2* hb = reinterpret_cast<const __half2*>(&b);
+        const __half2* hr = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(hv[k]);
+            const float2 g = __half22float2(hb[k]);
+            __half2 o = __floats2half2_rn(activate<ACT>(f.x + g.x, a.slope), activate<ACT>(f.y + g.y, a.slope));
+            // the residual is added in fp16 after the activation is rounded, exactly as torch's `x + act(conv)` does
+            if (a.res) o = __hadd2(o, hr[k]);
+            hv[k] = o;
+        }
+        a.out[(size_t)pix * a.out_stride + c] = v;
+        if (a.out2 && c >= a.out2_c0) a.out2[(size_t)pix * a.out2_stride + (c - a.out2_c0)] = v;
+    }
+}
+
+// SPPF pooling: ultralytics SPPF = cat(y, m(y), m(m(y)), m(m(m(y)))) with m = MaxPool2d(5, 1, 2).  The input is channel
+// slot 0 of the [N,H,W,4c] concat buffer; this kernel fills slots 1..3.  One CTA owns one image x one 8-channel vector:
+// the H*W map lives in shared memory and each 5x5 max is done separably (row pass, column pass); borders clip exactly
+// like -inf padding.  torch ran 3 max_pool launches + a concat (5.4 % + part of 14.5 % of the step).
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+    __half2* x = reinterpret_cast<__half2*>(&a);
+    const __half2* y = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = __hmax2_nan(x[k], y[k]);
+    return a;
+}
+
+__global__ void __launch_bounds__(K5_THREADS) k5_sppf_pool_kernel(uint4* __restrict__ buf, int H, int W, int c_vec) {
+    extern __shared__ uint4 k5_smem[];
+    const int P = H * W;
+    uint4* A = k5_smem;      // current map
+    uint4* T = k5_smem + P;  // row-max of A
+    const int cv = blockIdx.x % c_vec;
+    const size_t n = blockIdx.x / c_vec;
+    const int ct = 4 * c_vec;  // pixel stride of the concat buffer in vectors
+    uint4* base = buf + n * (size_t)P * ct + cv;
+    for (int p = threadIdx.x; p < P; p += K5_THREADS) A[p] = base[(size_t)p * ct];
+    __syncthreads();
+    for (int rep = 1; rep <= 3; ++rep) {
+        for (int p = threadIdx.x; p < P; p += K5_THREADS) {
+            const int x = p % W;
+            uint4 m = A[p];
+            if (x >= 1) m = hmax8(m, A[p - 1]);
+            if (x >= 2) m = hmax8(m, A[p - 2]);
+            if (x + 1 < W) m = hmax8(m, A[p + 1]);
+            if (x + 2 < W) m = hmax8(m, A[p + 2]);
+            T[p] = m;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < P; p += K5_THREADS) {
+            const int y = p / W;
+            uint4 m = T[p];
+            if (y >= 1) m = hmax8(m, T[p - W]);
+            if (y >= 2) m = hmax8(m, T[p - 2 * W]);
+            if (y + 1 < H) m = hmax8(m, T[p + W]);
+            if (y + 2 < H) m = hmax8(m, T[p + 2 * W]);
+            A[p] = m;  // safe: the column pass reads T only
+            base[(size_t)p * ct + rep * c_vec] = m;
+        }
+        __syncthreads();
+    }
+}
+
 // out[n,y,x,:] = concat(a[n,y/2,x/2,:], b[n,y,x,:]) — the FPN "nearest 2x up-sample, then concat" of the YOLO neck in ONE
 // pass (torch runs an up-sample kernel, then a concat kernel: the up-sampled tensor is written and read once more).
 __global__ void __launch_bounds__(K5_THREADS)
@@ -111,6 +194,58 @@ extern "C" int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, i
     else K<2><<<grid, K5_THREADS, 0, s>>>((T*)x, (const T*)bias, n_vec, c_vec, slope);
     if (dtype == FSD_F16) { LAUNCH(k5_bias_act_half_kernel, uint4) } else { LAUNCH(k5_bias_act_float_kernel, float4) }
 #undef LAUNCH
+    FSD_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return FSD_OK;
+}
+
+extern "C" int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, void* out, int64_t out_pixel_stride,
+                            const void* residual, int64_t residual_pixel_stride, void* out2, int64_t out2_pixel_stride,
+                            int out2_first_channel, int64_t n_pixels, int channels, int act, float slope, int dtype,
+                            void* stream_) {
+    FSD_CHECK_ARG(h && x && bias && out, "fsd_bias_act: null argument");
+    FSD_CHECK_ARG(dtype == FSD_F16, "fsd_bias_act: only fp16 is implemented (use fsd_bias_act_inplace for fp32)");
+    FSD_CHECK_ARG(n_pixels >= 0 && channels > 0 && channels % 8 == 0 && act >= 0 && act <= 2, "fsd_bias_act: bad sizes / activation");
+    FSD_CHECK_ARG(out_pixel_stride >= channels && out_pixel_stride % 8 == 0, "fsd_bias_act: out pixel stride must be >= channels and a multiple of 8");
+    FSD_CHECK_ARG(!residual || (residual_pixel_stride >= channels && residual_pixel_stride % 8 == 0), "fsd_bias_act: bad residual stride");
+    FSD_CHECK_ARG(!out2 || (out2_first_channel >= 0 && out2_first_channel < channels && out2_first_channel % 8 == 0 &&
+                            out2_pixel_stride >= channels - out2_first_channel && out2_pixel_stride % 8 == 0),
+                  "fsd_bias_act: bad second destination");
+    if (((uintptr_t)x & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)out & 15) || ((uintptr_t)residual & 15) || ((uintptr_t)out2 & 15)) {
+        set_error("fsd_bias_act: pointers must be 16-byte aligned");
+        return FSD_ERR_ALIGN;
+    }
+    if (n_pixels == 0) return FSD_OK;
+    const size_t n_vec = (size_t)n_pixels * channels / 8;
+    FSD_CHECK_ARG(n_vec < 0xffffffffull, "fsd_bias_act: tensor too large for one launch (%zu vectors)", n_vec);
+    K5GenArgs a;
+    a.x = (const uint4*)x; a.bias = (const uint4*)bias; a.out = (uint4*)out; a.res = (const uint4*)residual; a.out2 = (uint4*)out2;
+    a.n_vec = (unsigned)n_vec; a.c_vec = channels / 8; a.out_stride = (int)(out_pixel_stride / 8);
+    a.res_stride = (int)(residual_pixel_stride / 8); a.out2_stride = (int)(out2_pixel_stride / 8);
+    a.out2_c0 = out2_first_channel / 8; a.slope = slope;
+    const size_t want = (n_vec + K5_THREADS - 1) / K5_THREADS;
+    const int grid = (int)(want < (size_t)h->sm_count * 16 ? want : (size_t)h->sm_count * 16);
+    cudaStream_t s = (cudaStream_t)stream_;
+    FSD_CUDA(cudaSetDevice(h->device));
+    if (act == 0) k5_bias_act_general_half_kernel<0><<<grid, K5_THREADS, 0, s>>>(a);
+    else if (act == 1) k5_bias_act_general_half_kernel<1><<<grid, K5_THREADS, 0, s>>>(a);
+    else k5_bias_act_general_half_kernel<2><<<grid, K5_THREADS, 0, s>>>(a);
+    FSD_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return FSD_OK;
+}
+
+extern "C" int fsd_sppf_pool(fsd_handle_t h, void* buf, int N, int H, int W, int c, int dtype, void* stream_) {
+    FSD_CHECK_ARG(h && buf, "fsd_sppf_pool: null argument");
+    FSD_CHECK_ARG(dtype == FSD_F16, "fsd_sppf_pool: only fp16 is implemented");
+    FSD_CHECK_ARG(N >= 0 && H > 0 && W > 0 && c > 0 && c % 8 == 0, "fsd_sppf_pool: bad sizes (c must be a multiple of 8)");
+    if ((uintptr_t)buf & 15) { set_error("fsd_sppf_pool: pointer must be 16-byte aligned"); return FSD_ERR_ALIGN; }
+    const size_t smem = (size_t)2 * H * W * sizeof(uint4);
+    FSD_CHECK_ARG(smem <= 200 * 1024, "fsd_sppf_pool: map of %d x %d does not fit shared memory", H, W);
+    if (N == 0) return FSD_OK;
+    FSD_CUDA(cudaSetDevice(h->device));
+    if (smem > 48 * 1024) FSD_CUDA(cudaFuncSetAttribute(k5_sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_sppf_pool_kernel<<<N * (c / 8), K5_THREADS, smem, (cudaStream_t)stream_>>>((uint4*)buf, H, W, c / 8);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

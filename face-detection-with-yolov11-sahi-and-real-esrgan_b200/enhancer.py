@@ -39,28 +39,35 @@ class RealESRGANer:
 
     @torch.no_grad()
     def enhance_device(self, img_dev: torch.Tensor) -> torch.Tensor:
-        """[H,W,3] uint8 BGR on the device -> [H*s,W*s,3] uint8 BGR on the device (no host round trip)."""
-        H, W = int(img_dev.shape[0]), int(img_dev.shape[1])
+        """[H,W,3] uint8 BGR on the device -> [H*s,W*s,3] uint8 BGR on the device (no host round trip).
+        A batch [N,H,W,3] of same-sized frames is cropped and stitched by ONE launch each and its same-shaped tiles share
+        RRDBNet batches across frames (the reference enhances frame by frame, tile by tile)."""
+        batched = img_dev.dim() == 4
+        frames = img_dev if batched else img_dev[None]
+        N, H, W = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
         s = self.scale
         tile = self.tile_size if self.tile_size > 0 else max(H, W) + self.pre_pad + 4  # tile 0: one tile, no halo
         table, _ = ops.esrgan_tile_table(H, W, s, tile, self.tile_pad if self.tile_size > 0 else 0, self.pre_pad)
         dtype = torch.float16 if self.half else torch.float32
         key = (H, W)
         cached = self._tab_cache.get(key)
-        tiles, tab_dev = ops.esrgan_crop(img_dev, table, s, self.pre_pad, dtype, tab_dev=cached)
+        tiles, tab_dev = ops.esrgan_crop(frames, table, s, self.pre_pad, dtype, tab_dev=cached)
         self._tab_cache[key] = tab_dev
-        outbuf = ops.esrgan_out_buffer(table, s, dtype, img_dev.device)
+        outbuf = ops.esrgan_out_buffer(table, s, dtype, img_dev.device, n_images=N)
         groups = defaultdict(list)
-        for i, row in enumerate(table):
-            groups[(int(row[3]), int(row[2]))].append(i)
+        for n in range(N):
+            for i, row in enumerate(table):
+                groups[(int(row[3]), int(row[2]))].append((n, i))
         for (_, _), idxs in groups.items():  # same-shaped tiles go through RRDBNet as one batch
             for a in range(0, len(idxs), self.max_tile_batch):
                 part = idxs[a:a + self.max_tile_batch]
-                x = torch.cat([ops.tile_view(tiles, table[i]) for i in part], 0) if len(part) > 1 else ops.tile_view(tiles, table[part[0]])
+                views = [ops.tile_view(tiles[n], table[i]) for n, i in part]
+                x = torch.cat(views, 0) if len(part) > 1 else views[0]
                 y = self.model(x)
-                for j, i in enumerate(part):
-                    ops.tile_view(outbuf, table[i], s, out=True).copy_(y[j:j + 1])
-        return ops.esrgan_stitch(outbuf, table, tab_dev, s, H, W)
+                for j, (n, i) in enumerate(part):
+                    ops.tile_view(outbuf[n], table[i], s, out=True).copy_(y[j:j + 1])
+        out = ops.esrgan_stitch(outbuf, table, tab_dev, s, H, W)
+        return out if batched else out[0]
 
     def enhance(self, img, outscale=None, alpha_upsampler="realesrgan"):
         if not isinstance(img, np.ndarray) or img.ndim != 3 or img.shape[2] != 3 or img.dtype != np.uint8:

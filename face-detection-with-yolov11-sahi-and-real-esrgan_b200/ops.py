@@ -235,6 +235,55 @@ def bias_act_(x: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: flo
     return x
 
 
+def _slot_stride(t: torch.Tensor, n: int, c: int, hh: int, ww: int, name: str) -> int:
+    """Pixel stride (elements) of `t`, a [N,C,H,W] channel slot of a dense channels-last buffer."""
+    if tuple(t.shape) != (n, c, hh, ww):
+        raise ValueError(f"{name}: expected shape {(n, c, hh, ww)}, got {tuple(t.shape)}")
+    ct = t.stride(3) if ww > 1 else (t.stride(2) if hh > 1 else t.stride(0))
+    ok = (c == 1 or t.stride(1) == 1) and (ww == 1 or t.stride(3) == ct) and (hh == 1 or t.stride(2) == ww * ct) \
+        and (n == 1 or t.stride(0) == hh * ww * ct) and ct >= c
+    if not ok:
+        raise ValueError(f"{name} must be a channel slot of a dense channels_last tensor (strides {t.stride()})")
+    return int(ct)
+
+
+def bias_act(x: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: float = 0.2, out: torch.Tensor | None = None,
+             residual: torch.Tensor | None = None, out2: torch.Tensor | None = None) -> torch.Tensor:
+    """(a5) general fp16 conv epilogue: out = act(x + bias[c]) (+ residual).  `x` is the dense channels-last raw
+    convolution [N,C,H,W]; `out` (default: x itself), `residual` and `out2` may be channel slots (views `buf[:, a:b]`) of
+    wider channels-last buffers.  `out2` [N,C2,H,W] additionally receives the LAST C2 channels.  Returns `out`."""
+    _require_cuda(x, "x")
+    n, c, hh, ww = x.shape
+    if x.dtype != torch.float16 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("bias_act needs a dense channels_last fp16 tensor")
+    if out is None:
+        out = x
+    so = _slot_stride(out, n, c, hh, ww, "out")
+    sr = _slot_stride(residual, n, c, hh, ww, "residual") if residual is not None else 0
+    c2 = int(out2.shape[1]) if out2 is not None else 0
+    s2 = _slot_stride(out2, n, c2, hh, ww, "out2") if out2 is not None else 0
+    h = _handle_for(x)
+    check(h.lib.fsd_bias_act(h.h, x.data_ptr(), bias.data_ptr(), out.data_ptr(), so,
+                             residual.data_ptr() if residual is not None else None, sr,
+                             out2.data_ptr() if out2 is not None else None, s2, c - c2 if out2 is not None else 0,
+                             n * hh * ww, c, _ACT[act], float(slope), _TORCH_DTYPE[x.dtype], _stream_ptr(x.device)),
+          "fsd_bias_act")
+    return out
+
+
+def sppf_pool_(buf: torch.Tensor) -> torch.Tensor:
+    """(a5) fills channel slots 1..3 of the dense channels-last [N,4c,H,W] fp16 buffer with the cascaded 5x5 max pools of
+    slot 0 (ultralytics SPPF), one launch."""
+    _require_cuda(buf, "buf")
+    n, c4, hh, ww = buf.shape
+    if buf.dtype != torch.float16 or not buf.is_contiguous(memory_format=torch.channels_last) or c4 % 32:
+        raise ValueError("sppf_pool_ needs a dense channels_last fp16 [N,4c,H,W] buffer with c % 8 == 0")
+    h = _handle_for(buf)
+    check(h.lib.fsd_sppf_pool(h.h, buf.data_ptr(), n, hh, ww, c4 // 4, _TORCH_DTYPE[buf.dtype], _stream_ptr(buf.device)),
+          "fsd_sppf_pool")
+    return buf
+
+
 def upsample2x_concat(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """(a5) cat(interpolate(a, 2x nearest), b, dim=1) for channels-last CUDA tensors, one pass."""
     _require_cuda(a, "a")
@@ -268,24 +317,36 @@ def _off64(row, k):
     return int(np.uint32(row[k])) | (int(row[k + 1]) << 32)
 
 
+def esrgan_tile_elems(table: np.ndarray, scale: int = 1, out: bool = False) -> int:
+    """Elements of one image's packed tile buffer (input tiles, or network outputs when out=True)."""
+    last = table[-1]
+    n = 3 * int(last[2]) * int(last[3]) * (scale * scale if out else 1)
+    return _off64(last, 10 if out else 8) + (n + 7) // 8 * 8
+
+
 def esrgan_crop(img: torch.Tensor, table: np.ndarray, scale: int, pre_pad: int = 0, dtype=torch.float16,
                 tab_dev: torch.Tensor | None = None, tiles: torch.Tensor | None = None):
-    """Kernel 4a: img [H,W,3] uint8 BGR (CUDA, row-contiguous) -> (packed tile buffer, table on device).
+    """Kernel 4a: img [H,W,3] — or a batch [N,H,W,3] — uint8 BGR (CUDA, rows contiguous) -> (packed tile buffer
+    [elems] or [N, elems], table on device).  One launch crops the whole batch with the same tile table.
     Pass `tab_dev` / `tiles` from a previous call to reuse the uploaded table and the tile buffer."""
     _require_cuda(img, "image")
-    H, W = int(img.shape[0]), int(img.shape[1])
-    assert img.dtype == torch.uint8 and img.stride(2) == 1 and img.stride(1) == 3
-    last = table[-1]
-    total = _off64(last, 8) + (3 * int(last[2]) * int(last[3]) + 7) // 8 * 8
+    batched = img.dim() == 4
+    im = img if batched else img[None]
+    N, H, W = int(im.shape[0]), int(im.shape[1]), int(im.shape[2])
+    assert im.dtype == torch.uint8 and im.stride(3) == 1 and im.stride(2) == 3
+    total = esrgan_tile_elems(table)
     if tiles is None:
-        tiles = torch.empty((total,), dtype=dtype, device=img.device)
+        tiles = torch.empty((N, total) if batched else (total,), dtype=dtype, device=img.device)
+    tl = tiles if tiles.dim() == 2 else tiles[None]
+    assert tl.shape[0] == N and tl.stride(1) == 1 and tl.shape[1] >= total
     tab_host = np.ascontiguousarray(table, dtype=np.int32)
     if tab_dev is None:
         tab_dev = torch.from_numpy(tab_host).to(img.device)
     h = _handle_for(img)
-    check(h.lib.fsd_esrgan_crop(h.h, img.data_ptr(), H, W, img.stride(0), H + pre_pad, W + pre_pad,
-                                tab_dev.data_ptr(), tab_host.ctypes.data, len(tab_host), _TORCH_DTYPE[dtype],
-                                tiles.data_ptr(), _stream_ptr(img.device)), "fsd_esrgan_crop")
+    check(h.lib.fsd_esrgan_crop(h.h, im.data_ptr(), H, W, im.stride(1), H + pre_pad, W + pre_pad,
+                                tab_dev.data_ptr(), tab_host.ctypes.data, len(tab_host), _TORCH_DTYPE[tl.dtype],
+                                tl.data_ptr(), N, im.stride(0) if N > 1 else 0, tl.stride(0) if N > 1 else 0,
+                                _stream_ptr(img.device)), "fsd_esrgan_crop")
     return tiles, tab_dev
 
 
@@ -296,23 +357,29 @@ def tile_view(buf: torch.Tensor, row, scale: int = 1, out: bool = False) -> torc
     return buf[off: off + 3 * h * w].view(1, 3, h, w)
 
 
-def esrgan_out_buffer(table: np.ndarray, scale: int, dtype, device) -> torch.Tensor:
-    last = table[-1]
-    total = _off64(last, 10) + (3 * int(last[2]) * int(last[3]) * scale * scale + 7) // 8 * 8
-    return torch.empty((total,), dtype=dtype, device=device)
+def esrgan_out_buffer(table: np.ndarray, scale: int, dtype, device, n_images: int | None = None) -> torch.Tensor:
+    total = esrgan_tile_elems(table, scale, out=True)
+    return torch.empty((total,) if n_images is None else (n_images, total), dtype=dtype, device=device)
 
 
 def esrgan_stitch(tiles_out: torch.Tensor, table: np.ndarray, tab_dev: torch.Tensor, scale: int, H: int, W: int,
                   out: torch.Tensor | None = None) -> torch.Tensor:
-    """Kernel 4b: packed network outputs -> [H*scale, W*scale, 3] uint8 BGR."""
+    """Kernel 4b: packed network outputs [elems] -> [H*scale, W*scale, 3] uint8 BGR, or a batch [N, elems] ->
+    [N, H*scale, W*scale, 3] in one launch."""
     _require_cuda(tiles_out, "tile outputs")
     oh, ow = H * scale, W * scale
+    batched = tiles_out.dim() == 2
+    tl = tiles_out if batched else tiles_out[None]
+    N = int(tl.shape[0])
     if out is None:
-        out = torch.empty((oh, ow, 3), dtype=torch.uint8, device=tiles_out.device)
+        out = torch.empty((N, oh, ow, 3) if batched else (oh, ow, 3), dtype=torch.uint8, device=tiles_out.device)
+    o = out if out.dim() == 4 else out[None]
+    assert o.shape[0] == N and o.stride(3) == 1 and o.stride(2) == 3 and tl.stride(1) == 1
     tab_host = np.ascontiguousarray(table, dtype=np.int32)
     h = _handle_for(tiles_out)
-    check(h.lib.fsd_esrgan_stitch(h.h, tiles_out.data_ptr(), tab_dev.data_ptr(), tab_host.ctypes.data, len(tab_host),
-                                  scale, _TORCH_DTYPE[tiles_out.dtype], out.data_ptr(), oh, ow, out.stride(0),
+    check(h.lib.fsd_esrgan_stitch(h.h, tl.data_ptr(), tab_dev.data_ptr(), tab_host.ctypes.data, len(tab_host),
+                                  scale, _TORCH_DTYPE[tl.dtype], o.data_ptr(), oh, ow, o.stride(1), N,
+                                  tl.stride(0) if N > 1 else 0, o.stride(0) if N > 1 else 0,
                                   _stream_ptr(tiles_out.device)), "fsd_esrgan_stitch")
     return out
 

@@ -146,6 +146,19 @@ int fsd_pack_results(fsd_handle_t h, const float* det, const int32_t* group_offs
 int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, int64_t n_pixels, int channels, int act,
                          float slope, int dtype, void* stream);
 
+/* ---- (a5) general conv epilogue (fp16, channels-last): out[pix,c] = act(x[pix,c] + bias[c]) (+ residual[pix,c]).
+ *      `out` / `residual` / `out2` may be channel slots of wider channels-last buffers: each has its own pixel stride
+ *      (elements).  Channels >= out2_first_channel are also stored to out2 (NULL = none).  With it the epilogue of
+ *      ultralytics' Conv writes straight into the concat buffer of C3k2 / SPPF / C2PSA (`torch.cat((...), 1)` in
+ *      ultralytics/nn/modules/block.py, reached from utils/yolo_wrapper.py:72) and folds Bottleneck's `x + cv2(cv1(x))`. */
+int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, void* out, int64_t out_pixel_stride,
+                 const void* residual, int64_t residual_pixel_stride, void* out2, int64_t out2_pixel_stride,
+                 int out2_first_channel, int64_t n_pixels, int channels, int act, float slope, int dtype, void* stream);
+
+/* ---- (a5) SPPF pooling: buf is the [N,H,W,4c] fp16 channels-last concat buffer whose channel slot 0 holds y; fills
+ *      slots 1..3 with m(y), m(m(y)), m(m(m(y))), m = MaxPool2d(kernel 5, stride 1, padding 2) (ultralytics SPPF). */
+int fsd_sppf_pool(fsd_handle_t h, void* buf, int N, int H, int W, int c, int dtype, void* stream);
+
 /* ---- (a5) YOLO neck: out = concat(nearest_upsample_2x(a), b) along channels, channels-last, in ONE pass.
  *      a [N,ah,aw,ca], b [N,2ah,2aw,cb], out [N,2ah,2aw,ca+cb]; replaces torch's upsample kernel + concat kernel. */
 int fsd_upsample2x_concat(fsd_handle_t h, const void* a, const void* b, void* out, int N, int ah, int aw, int ca,
@@ -160,15 +173,20 @@ int fsd_upsample2x_concat(fsd_handle_t h, const void* a, const void* b, void* ou
 int fsd_esrgan_tile_table(int H, int W, int scale, int tile, int tile_pad, int pre_pad, int32_t* table,
                           int cap, int* n_tiles, int32_t padded_hw[2]);
 /* crop: u8 HWC BGR image -> packed [3,ph,pw] RGB tiles of dtype, value/255; pre_h/pre_w = H,W + pre_pad (the
- *       right/bottom reflect pre-pad and mod-pad are folded into the index map); table given on device and host */
+ *       right/bottom reflect pre-pad and mod-pad are folded into the index map); table given on device and host.
+ *       n_images same-sized images (image_pitch bytes apart) are cropped by ONE launch with the same table; image i's
+ *       tiles start tiles_image_stride ELEMENTS after image i-1's (a 1080p frame is only ~20 MB: batching frames is
+ *       what lets the launch reach HBM speed).  n_images = 1 reproduces the reference's per-image call. */
 int fsd_esrgan_crop(fsd_handle_t h, const uint8_t* bgr, int H, int W, int64_t row_pitch, int pre_h, int pre_w,
                     const int32_t* table_dev, const int32_t* table_host, int T, int dtype, void* tiles,
-                    void* stream);
+                    int n_images, int64_t image_pitch, int64_t tiles_image_stride, void* stream);
 /* stitch: packed [3,ph*s,pw*s] RGB network outputs -> u8 HWC BGR [out_h,out_w] (= H*s, W*s);
- *         clamp(0,1)*255, round-half-even; halos, mod-pad and pre-pad are dropped */
+ *         clamp(0,1)*255, round-half-even; halos, mod-pad and pre-pad are dropped.  n_images outputs
+ *         (out_image_pitch bytes apart) are stitched by one launch from tile sets tiles_image_stride elements apart. */
 int fsd_esrgan_stitch(fsd_handle_t h, const void* tiles_out, const int32_t* table_dev,
                       const int32_t* table_host, int T, int scale, int dtype, uint8_t* out_bgr, int out_h,
-                      int out_w, int64_t out_pitch, void* stream);
+                      int out_w, int64_t out_pitch, int n_images, int64_t tiles_image_stride, int64_t out_image_pitch,
+                      void* stream);
 
 /* ---- (f1) WIDER-FACE evaluation IoU — replaces the Cython bbox_overlaps of WiderFace-Evaluation,
  *      imported at eval/eval_official_widerface.py:20-33 and called at :330.  boxes [N,4], query [K,4]

@@ -127,3 +127,80 @@ def test_upsample_concat_and_split_conv_equal_torch(cuda_device):
             assert tw.shape == tg.shape
             err = (tg.float().cpu() - tw).abs().max().item()
             assert err < 0.08 * max(1.0, tw.abs().max().item()), err  # fp16 network vs fp32 network
+
+
+@pytest.mark.parametrize("act", ["silu", "none"])
+def test_bias_act_into_concat_slot_with_residual(cuda_device, act):
+    """(a5) general epilogue: writes act(x+bias)+residual into a channel slot of a wider channels-last buffer, copies the
+    trailing channels to a second destination; equals the torch sequence conv-bias-act, `x + y`, torch.cat exactly."""
+    import fsd_b200.ops as ops
+
+    g = torch.Generator().manual_seed(7)
+    cl = lambda t: t.half().to(cuda_device).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    x = cl(torch.randn((3, 32, 9, 13), generator=g) * 3)
+    bias = torch.randn((32,), generator=g).half().to(cuda_device)
+    left = cl(torch.randn((3, 16, 9, 13), generator=g))
+    resbuf = cl(torch.randn((3, 48, 9, 13), generator=g))
+    res = resbuf[:, 8:40]  # a strided slot as residual
+    f = torch.nn.functional.silu if act == "silu" else (lambda t: t)
+    y = f((x.float() + bias.float().view(1, -1, 1, 1))).half()  # what bias_act_ produces (rounded once)
+    assert torch.equal(ops.bias_act_(x.clone(memory_format=torch.channels_last), bias, act), y)
+    want = torch.cat((left, res + y), 1)
+    buf = torch.full((3, 48, 9, 13), float("nan"), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    buf[:, :16].copy_(left)
+    tail = torch.empty((3, 8, 9, 13), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    out = ops.bias_act(x, bias, act, out=buf[:, 16:], residual=res, out2=tail)
+    assert out.data_ptr() == buf[:, 16:].data_ptr()
+    assert torch.equal(buf, want)
+    assert torch.equal(tail, want[:, 40:])
+    # in place, no extras == the dedicated in-place kernel
+    assert torch.equal(ops.bias_act(x.clone(memory_format=torch.channels_last), bias, act), y)
+    with pytest.raises(Exception):
+        ops.bias_act(x, bias, act, out=buf[:, 16:].contiguous())  # NCHW-dense is not a channels-last slot
+    with pytest.raises(Exception):
+        ops.bias_act(x, bias, act, out=buf[:, 4:36])  # slot not 16-byte aligned
+
+
+@pytest.mark.parametrize("hw", [(32, 32), (24, 32), (3, 5), (1, 1), (40, 40)])
+def test_sppf_pool_equals_cascaded_maxpool(cuda_device, hw):
+    """(a5) one-launch SPPF pooling == three cascaded MaxPool2d(5,1,2) + torch.cat (bit-exact: max only selects)."""
+    import fsd_b200.ops as ops
+
+    g = torch.Generator().manual_seed(hw[0] * 100 + hw[1])
+    y = torch.randn((3, 16, *hw), generator=g).half().to(cuda_device)
+    m = torch.nn.MaxPool2d(5, 1, 2)
+    y1 = m(y); y2 = m(y1); y3 = m(y2)
+    want = torch.cat((y, y1, y2, y3), 1)
+    buf = torch.zeros((3, 64, *hw), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    buf[:, :16].copy_(y)
+    ops.sppf_pool_(buf)
+    assert torch.equal(buf, want)
+
+
+@pytest.mark.parametrize("size,tile,scale", [((61, 77), 32, 2), ((130, 203), 64, 4), ((97, 64), 200, 2)])
+def test_batched_crop_stitch_equals_per_image(cuda_device, size, tile, scale):
+    """K4 batch mode (n_images > 1, one launch) is bit-identical to the reference's frame-by-frame calls, including a
+    batch taken as a strided view (image pitch > H*W*3) and the product-level RealESRGANer.enhance_device."""
+    import fsd_b200.ops as ops
+    from fsd_b200.enhancer import RealESRGANer as GpuESRGANer
+
+    H, W = size
+    rng = np.random.default_rng(H + W + scale)
+    imgs = torch.from_numpy(rng.integers(0, 256, (5, H + 3, W, 3), dtype=np.uint8)).to(cuda_device)
+    batch = imgs[:, :H]  # image pitch (H+3)*W*3 != H*W*3
+    table, _ = ops.esrgan_tile_table(H, W, scale, tile, 10, 0)
+    tiles, tab_dev = ops.esrgan_crop(batch, table, scale, 0, torch.float16)
+    assert tiles.shape[0] == 5
+    outs = ops.esrgan_out_buffer(table, scale, torch.float16, cuda_device, n_images=5)
+    outs.copy_(torch.rand(outs.shape, device=cuda_device) * 1.2 - 0.1)
+    got = ops.esrgan_stitch(outs, table, tab_dev, scale, H, W)
+    assert got.shape == (5, H * scale, W * scale, 3)
+    for n in range(5):
+        t1, _ = ops.esrgan_crop(batch[n].contiguous(), table, scale, 0, torch.float16, tab_dev=tab_dev)
+        for row in table:  # (the 0-7 padding elements between packed tiles are never written: compare tile views)
+            assert torch.equal(ops.tile_view(t1, row), ops.tile_view(tiles[n], row)), f"image {n}: batched crop differs"
+        assert torch.equal(ops.esrgan_stitch(outs[n], table, tab_dev, scale, H, W), got[n]), f"image {n}: batched stitch differs"
+    up = GpuESRGANer(scale=scale, model=NearestUpsampler(scale), tile=tile, tile_pad=10, pre_pad=0, half=False, max_tile_batch=7)
+    whole = up.enhance_device(batch.contiguous())
+    assert torch.equal(whole, torch.repeat_interleave(torch.repeat_interleave(batch, scale, 1), scale, 2))
+    assert torch.equal(up.enhance_device(batch[2].contiguous()), whole[2])
