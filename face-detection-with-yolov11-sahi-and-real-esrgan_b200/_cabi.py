@@ -37,6 +37,8 @@ SIGNATURES = {
                                     C.c_int, vp, vp]),
     "fsd_pack_results": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]),
     "fsd_bias_act_inplace": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
+    "fsd_kernel_timing_enable": (C.c_int, [vp, C.c_uint]),
+    "fsd_kernel_timing_read": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]),
     "fsd_bias_act": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                C.c_int, C.c_float, C.c_int, vp]),
     "fsd_sppf_pool": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
@@ -54,6 +56,7 @@ SIGNATURES = {
 FSD_F16, FSD_F32 = 0, 1
 FSD_NMS, FSD_GREEDYNMM, FSD_NMM = 0, 1, 2
 FSD_IOU, FSD_IOS = 0, 1
+FSD_KERNEL_GATHER, FSD_KERNEL_BIAS_ACT = 1, 5
 FSD_PLANAR, FSD_CHANNELS_LAST = 0, 1
 
 _lib = None
@@ -122,6 +125,23 @@ class Handle:
     @property
     def launches(self) -> int:
         return int(self.lib.fsd_launch_count(self.h))
+
+    def timing_enable(self, kernels=(FSD_KERNEL_GATHER,)) -> None:
+        """Start (clearing earlier samples) the in-library CUDA-event timing of the given FSD_KERNEL_* ids; () stops it."""
+        mask = 0
+        for k in kernels or ():
+            mask |= 1 << int(k)
+        check(self.lib.fsd_kernel_timing_enable(self.h, mask), "fsd_kernel_timing_enable")
+
+    def timing_read(self):
+        """[(kernel id, units, tag, ms)] for every instrumented launch since timing_enable(True); waits for them."""
+        n = C.c_int(0)
+        check(self.lib.fsd_kernel_timing_read(self.h, None, 0, C.byref(n)), "fsd_kernel_timing_read")
+        if n.value == 0:
+            return []
+        buf = (C.c_double * (4 * n.value))()
+        check(self.lib.fsd_kernel_timing_read(self.h, buf, n.value, C.byref(n)), "fsd_kernel_timing_read")
+        return [(int(buf[4 * i]), int(buf[4 * i + 1]), int(buf[4 * i + 2]), float(buf[4 * i + 3])) for i in range(n.value)]
 
 
 _handles: dict[int, Handle] = {}

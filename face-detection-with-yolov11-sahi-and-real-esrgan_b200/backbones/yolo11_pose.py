@@ -156,14 +156,21 @@ class Attention(nn.Module):
         self.pe = Conv(dim, dim, 3, 1, g=dim, act=False)
 
     def forward(self, x, residual=None):
+        """ultralytics Attention.forward: softmax(q^T k * scale) applied to v, plus the depth-wise positional conv of v.
+        Evaluated with torch's fused scaled_dot_product_attention on the channels-last memory of the qkv convolution
+        ([B, N, heads, 2*key_dim + head_dim] is a free view of it), instead of matmul -> scale -> softmax -> matmul
+        (three [B, heads, N, N] round trips through HBM)."""
         B, C, H, W = x.shape
         N = H * W
-        qkv = self.qkv(x)
-        q, k, v = qkv.reshape(B, self.num_heads, self.key_dim * 2 + self.head_dim, N).split(
-            [self.key_dim, self.key_dim, self.head_dim], dim=2)
-        attn = (q.transpose(-2, -1) @ k) * self.scale
-        attn = attn.softmax(dim=-1)
-        x = (v @ attn.transpose(-2, -1)).reshape(B, C, H, W) + self.pe(v.reshape(B, C, H, W))
+        qkv = self.qkv(x)  # [B, heads * (2 kd + hd), H, W]; channel = head * (2 kd + hd) + d
+        t = qkv.permute(0, 2, 3, 1).reshape(B, N, self.num_heads, 2 * self.key_dim + self.head_dim)
+        q, k, v = t.split([self.key_dim, self.key_dim, self.head_dim], dim=3)  # [B, N, heads, d], unit last stride
+        o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), scale=self.scale)
+        o = o.transpose(1, 2).reshape(B, H, W, C).permute(0, 3, 1, 2)    # [B, C, H, W], channel = head * hd + d
+        vv = v.reshape(B, H, W, C).permute(0, 3, 1, 2)                    # same channel order, channels-last dense
+        if not o.is_contiguous(memory_format=torch.channels_last):
+            o = o.contiguous(memory_format=torch.channels_last)
+        x = self.pe(vv, residual=o)
         return self.proj(x, residual=residual)
 
 
@@ -224,8 +231,25 @@ class PoseHead(nn.Module):
                                                nn.Conv2d(c3, nc, 1)) for x in ch)
         self.cv4 = nn.ModuleList(nn.Sequential(Conv(x, c4, 3), Conv(c4, c4, 3), nn.Conv2d(c4, self.nk, 1)) for x in ch)
 
+    @staticmethod
+    def _branch(seq, x):
+        """Sequential(..., nn.Conv2d 1x1 with bias): the last convolution's bias goes through the one-pass epilogue when
+        its channel count allows (box: 64), instead of torch's separate broadcast add."""
+        last = seq[-1]
+        for m in seq[:-1]:
+            x = m(x)
+        if (x.is_cuda and x.dtype == torch.float16 and last.out_channels % 8 == 0 and not torch.is_grad_enabled()):
+            y = F.conv2d(x, last.weight, None, last.stride, last.padding, last.dilation, last.groups)
+            if y.is_contiguous(memory_format=torch.channels_last):
+                from ..ops import bias_act
+
+                return bias_act(y, last.bias, "none")
+            return y + last.bias.view(1, -1, 1, 1)
+        return last(x)
+
     def forward(self, feats):
-        return [(self.cv2[i](x), self.cv3[i](x), self.cv4[i](x)) for i, x in enumerate(feats)]
+        return [(self._branch(self.cv2[i], x), self._branch(self.cv3[i], x), self._branch(self.cv4[i], x))
+                for i, x in enumerate(feats)]
 
 
 class YOLO11Pose(nn.Module):

@@ -60,11 +60,40 @@ int fsd_destroy(fsd_handle_t h) {
     for (auto& kv : h->resize_tables)
         if (kv.second.dev) cudaFree(kv.second.dev);
     for (void* d : h->dev_allocs) cudaFree(d);
+    for (auto& t : h->timing_samples) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     delete h;
     return FSD_OK;
 }
 
 int64_t fsd_launch_count(fsd_handle_t h) { return h ? h->launches : 0; }
+
+int fsd_kernel_timing_enable(fsd_handle_t h, unsigned kernel_mask) {
+    FSD_CHECK_ARG(h != nullptr, "fsd_kernel_timing_enable: null handle");
+    FSD_CUDA(cudaSetDevice(h->device));
+    for (auto& t : h->timing_samples) { h->event_pool.push_back(t.e0); h->event_pool.push_back(t.e1); }
+    h->timing_samples.clear();
+    h->timing = kernel_mask;
+    return FSD_OK;
+}
+
+int fsd_kernel_timing_read(fsd_handle_t h, double* samples, int cap, int* n) {
+    FSD_CHECK_ARG(h != nullptr && n != nullptr, "fsd_kernel_timing_read: null argument");
+    FSD_CUDA(cudaSetDevice(h->device));
+    const int total = (int)h->timing_samples.size();
+    *n = total;
+    if (!samples) return FSD_OK;
+    for (int i = 0; i < total && i < cap; ++i) {
+        auto& t = h->timing_samples[i];
+        FSD_CUDA(cudaEventSynchronize(t.e1));
+        float ms = 0.f;
+        FSD_CUDA(cudaEventElapsedTime(&ms, t.e0, t.e1));
+        samples[4 * i + 0] = (double)t.kernel; samples[4 * i + 1] = (double)t.units;
+        samples[4 * i + 2] = (double)t.tag; samples[4 * i + 3] = (double)ms;
+    }
+    if (total > cap) { fsd::set_error("fsd_kernel_timing_read: %d samples exceed capacity %d", total, cap); return FSD_ERR_CAPACITY; }
+    return FSD_OK;
+}
 
 // (a2) sahi.slicing.get_slice_bboxes restated: overlap = int(ratio*slice) truncation,
 // row-major grid, border slices shifted back inside the image.

@@ -57,7 +57,32 @@ struct fsd_context {
     std::map<std::tuple<int, int, int, int>, std::shared_ptr<void>> k1_plans;  // Kernel 1 geometry plans
     std::vector<void*> dev_allocs;  // device buffers owned by the handle (freed in fsd_destroy)
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
+    // optional device timing (fsd_kernel_timing_enable): CUDA events recorded on the launching stream right around
+    // each kernel launch, inside the library, so no host-side preparation falls between the two records
+    struct TimingSample { int kernel; int64_t units; int64_t tag; cudaEvent_t e0, e1; };
+    unsigned timing = 0;  // bit mask of (1 << FSD_KERNEL_*)
+    std::vector<TimingSample> timing_samples;
+    std::vector<cudaEvent_t> event_pool;
 };
+
+namespace fsd {
+// RAII bracket around one kernel launch; a no-op unless timing is enabled on the handle.
+struct TimedLaunch {
+    fsd_context* h; cudaStream_t stream; cudaEvent_t e1 = nullptr;
+    TimedLaunch(fsd_context* h_, int kernel, int64_t units, int64_t tag, cudaStream_t s) : h(h_), stream(s) {
+        if (!(h->timing >> kernel & 1u) || h->timing_samples.size() >= (1u << 20)) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!h->event_pool.empty()) { ev[i] = h->event_pool.back(); h->event_pool.pop_back(); }
+            else if (cudaEventCreate(&ev[i]) != cudaSuccess) return;
+        }
+        e1 = ev[1];
+        h->timing_samples.push_back({kernel, units, tag, ev[0], ev[1]});
+        cudaEventRecord(ev[0], stream);
+    }
+    ~TimedLaunch() { if (e1) cudaEventRecord(e1, stream); }
+};
+}  // namespace fsd
 
 namespace fsd {
 

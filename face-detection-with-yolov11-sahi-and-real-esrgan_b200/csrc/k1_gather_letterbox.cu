@@ -386,7 +386,10 @@ static int launch_tc(fsd_context* h, const CUtensorMap& tmap, const K1Params& p,
     FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_y = (p.out_h + p.tile_rows - 1) / p.tile_rows;
     dim3 grid((p.out_w + TC - 1) / TC, (tiles_y + p.tiles_per_cta - 1) / p.tiles_per_cta, B);
-    kern<<<grid, K1_THREADS, smem, stream>>>(tmap, p);
+    {
+        TimedLaunch timed(h, FSD_KERNEL_GATHER, B, p.src_w, stream);
+        kern<<<grid, K1_THREADS, smem, stream>>>(tmap, p);
+    }
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

@@ -151,8 +151,11 @@ int launch_upscale2x(fsd_context* h, const uint8_t* images, int64_t row_pitch, i
     p.out = reinterpret_cast<__half*>(out); p.src_w = src_w; p.src_h = src_h; p.reverse = reverse;
     const int vecs = (2 * src_w + 7) / 8;
     dim3 grid((vecs + UP2_THREADS - 1) / UP2_THREADS, (src_h + 1 + UP2_ROWS - 1) / UP2_ROWS, B);
-    if (nhwc) k1_upscale2x_kernel<true><<<grid, UP2_THREADS, 0, stream>>>(p);
-    else k1_upscale2x_kernel<false><<<grid, UP2_THREADS, 0, stream>>>(p);
+    {
+        TimedLaunch timed(h, FSD_KERNEL_GATHER, B, src_w, stream);
+        if (nhwc) k1_upscale2x_kernel<true><<<grid, UP2_THREADS, 0, stream>>>(p);
+        else k1_upscale2x_kernel<false><<<grid, UP2_THREADS, 0, stream>>>(p);
+    }
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

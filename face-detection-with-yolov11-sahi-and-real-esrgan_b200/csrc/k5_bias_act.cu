@@ -227,9 +227,14 @@ extern "C" int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, voi
     const int grid = (int)(want < (size_t)h->sm_count * 16 ? want : (size_t)h->sm_count * 16);
     cudaStream_t s = (cudaStream_t)stream_;
     FSD_CUDA(cudaSetDevice(h->device));
-    if (act == 0) k5_bias_act_general_half_kernel<0><<<grid, K5_THREADS, 0, s>>>(a);
-    else if (act == 1) k5_bias_act_general_half_kernel<1><<<grid, K5_THREADS, 0, s>>>(a);
-    else k5_bias_act_general_half_kernel<2><<<grid, K5_THREADS, 0, s>>>(a);
+    {
+        // units = bytes this launch moves (read x [+ residual], write out [+ out2])
+        const int64_t bytes = (int64_t)n_pixels * 2 * ((residual ? 3 : 2) * channels + (out2 ? channels - out2_first_channel : 0));
+        TimedLaunch timed(h, FSD_KERNEL_BIAS_ACT, bytes, channels, s);
+        if (act == 0) k5_bias_act_general_half_kernel<0><<<grid, K5_THREADS, 0, s>>>(a);
+        else if (act == 1) k5_bias_act_general_half_kernel<1><<<grid, K5_THREADS, 0, s>>>(a);
+        else k5_bias_act_general_half_kernel<2><<<grid, K5_THREADS, 0, s>>>(a);
+    }
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

@@ -48,6 +48,17 @@ int fsd_destroy(fsd_handle_t h);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches claim) */
 int64_t fsd_launch_count(fsd_handle_t h);
 
+/* Optional device timing for measurement (bench.py's roofline): while enabled, the instrumented kernels are bracketed
+ * by CUDA events recorded on the launching stream INSIDE the library, right around the launch, so host-side preparation
+ * never falls inside a sample.  enable() clears earlier samples; read() waits for each sample's end event and
+ * returns rows [kernel id (FSD_KERNEL_*), units, tag, milliseconds]:
+ *   FSD_KERNEL_GATHER   units = entries of the launch, tag = src_w
+ *   FSD_KERNEL_BIAS_ACT units = bytes the launch moves, tag = channels
+ * (the reference has no counterpart; its timing is wall-clock around model.predict, utils/yolo_wrapper.py:67-80) */
+enum { FSD_KERNEL_GATHER = 1, FSD_KERNEL_BIAS_ACT = 5 };
+int fsd_kernel_timing_enable(fsd_handle_t h, unsigned kernel_mask /* OR of (1u << FSD_KERNEL_*); 0 = off */);
+int fsd_kernel_timing_read(fsd_handle_t h, double* samples /* [cap,4] or NULL */, int cap, int* n);
+
 /* ---- (a2) slice plan — replaces sahi.slicing.get_slice_bboxes [EXT sahi 0.11.34], called at
  *      docs sahi/predict.py:229-238.  Host-side, integer exact.  boxes_xyxy holds up to `cap` rows of
  *      [x0,y0,x1,y1]; *n receives the number of slices (also when it exceeds cap -> FSD_ERR_CAPACITY). */

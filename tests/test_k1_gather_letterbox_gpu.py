@@ -119,3 +119,31 @@ def test_exact_2x_fast_path_equals_general_kernel_and_oracle(cuda_device, size, 
         monkeypatch.setenv("FSD_K1_GENERIC", "1")
         general = ops.gather_letterbox(pool, ent, sw, sh, imgsz=imgsz, dtype=torch.float16, channels_last=channels_last)
         assert torch.equal(general, fast)
+
+
+def test_in_library_kernel_timing(cuda_device):
+    """fsd_kernel_timing_*: one sample per instrumented launch, tagged (kernel id, entries, src_w), positive device time;
+    kernels outside the mask are not sampled and re-enabling clears the list."""
+    import fsd_b200.ops as ops
+    from fsd_b200 import _cabi
+
+    pool = ops.ImagePool(2, 96, 128, cuda_device)
+    pool.buf.random_(0, 256)
+    ent = torch.tensor([[0, 0, 0], [1, 32, 16], [1, 64, 32]], dtype=torch.int32, device=cuda_device)
+    h = _cabi.get_handle(cuda_device.index or 0)
+    h.timing_enable((_cabi.FSD_KERNEL_GATHER,))
+    ops.gather_letterbox(pool, ent, 64, 64, 128, 32)              # exact-2x fast path
+    ops.gather_letterbox(pool, ent[:2], 48, 40, 128, 32)          # general TMA kernel
+    x = torch.randn((1, 16, 8, 8), device=cuda_device).half().contiguous(memory_format=torch.channels_last)
+    ops.bias_act(x, torch.zeros(16, device=cuda_device).half(), "silu")  # not in the mask
+    got = h.timing_read()
+    assert [(k, u, t) for k, u, t, _ in got] == [(_cabi.FSD_KERNEL_GATHER, 3, 64), (_cabi.FSD_KERNEL_GATHER, 2, 48)]
+    assert all(0.0 < ms < 50.0 for *_, ms in got)
+    h.timing_enable((_cabi.FSD_KERNEL_BIAS_ACT,))
+    assert h.timing_read() == []
+    ops.bias_act(x, torch.zeros(16, device=cuda_device).half(), "silu")
+    (k, units, tag, ms), = h.timing_read()
+    assert (k, units, tag) == (_cabi.FSD_KERNEL_BIAS_ACT, 2 * x.numel() * 2, 16) and ms > 0
+    h.timing_enable(())
+    ops.bias_act(x, torch.zeros(16, device=cuda_device).half(), "silu")
+    assert h.timing_read() == []
