@@ -39,6 +39,19 @@ class Conv(nn.Module):
         which may be a channel slot of a concat buffer — and the trailing channels into `out2` as well."""
         c = self.conv
         if (x.is_cuda and x.dtype == torch.float16 and c.out_channels % 8 == 0 and not torch.is_grad_enabled()):
+            if (c.in_channels == 3 and c.out_channels == 16 and c.kernel_size == (3, 3) and c.stride == (2, 2)
+                    and c.padding == (1, 1) and c.groups == 1 and isinstance(self.act, nn.SiLU) and out is None
+                    and residual is None and out2 is None and x.shape[3] % 2 == 0
+                    and x.is_contiguous(memory_format=torch.channels_last)):
+                # the stem: cuDNN has no good kernel for a 3-channel channels-last input; one hand-written tensor-core
+                # kernel does convolution + bias + SiLU (fsd_stem_conv)
+                from ..ops import stem_conv
+
+                cached = getattr(self, "_w_dense", None)  # (weight version, dense [o,c,ky,kx] copy of the channels-last weight)
+                if cached is None or cached[0] != (c.weight._version, c.weight.data_ptr()):
+                    cached = ((c.weight._version, c.weight.data_ptr()), c.weight.detach().contiguous().clone())
+                    self._w_dense = cached
+                return stem_conv(x, cached[1], c.bias)
             y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
             if y.is_contiguous(memory_format=torch.channels_last):
                 from ..ops import bias_act

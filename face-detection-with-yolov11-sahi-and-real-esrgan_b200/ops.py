@@ -271,6 +271,24 @@ def bias_act(x: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: floa
     return out
 
 
+def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(a5) SiLU(conv2d(x, weight, bias, stride=2, padding=1)) for the 3-channel fp16 channels-last network input, one kernel.
+    x [E,3,H,W] channels-last dense, weight [16,3,3,3] standard-contiguous, bias [16] -> [E,16,H/2,W/2] channels-last."""
+    _require_cuda(x, "x")
+    e, c, hh, ww = x.shape
+    if c != 3 or x.dtype != torch.float16 or not x.is_contiguous(memory_format=torch.channels_last) or ww % 2:
+        raise ValueError("stem_conv needs a dense channels_last fp16 [E,3,H,W] input with even W")
+    if tuple(weight.shape) != (16, 3, 3, 3) or not weight.is_contiguous() or weight.dtype != torch.float16:
+        raise ValueError("stem_conv needs a contiguous fp16 [16,3,3,3] weight")
+    oh, ow = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((e, 16, oh, ow), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    h = _handle_for(x)
+    check(h.lib.fsd_stem_conv(h.h, x.data_ptr(), e, hh, ww, weight.data_ptr(), bias.data_ptr(), 16, _TORCH_DTYPE[x.dtype],
+                              out.data_ptr(), _stream_ptr(x.device)), "fsd_stem_conv")
+    return out
+
+
 def sppf_pool_(buf: torch.Tensor) -> torch.Tensor:
     """(a5) fills channel slots 1..3 of the dense channels-last [N,4c,H,W] fp16 buffer with the cascaded 5x5 max pools of
     slot 0 (ultralytics SPPF), one launch."""

@@ -170,6 +170,13 @@ int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, void* out, int
  *      slots 1..3 with m(y), m(m(y)), m(m(m(y))), m = MaxPool2d(kernel 5, stride 1, padding 2) (ultralytics SPPF). */
 int fsd_sppf_pool(fsd_handle_t h, void* buf, int N, int H, int W, int c, int dtype, void* stream);
 
+/* ---- (a5) YOLO stem: out = SiLU(conv3x3_stride2_pad1(x) + bias) for the 3-channel network input, fp16 channels-last:
+ *      x [E,H,W,3] (Kernel 1's channels-last output), weight [16,3,3,3] (o,c,ky,kx dense), bias [16],
+ *      out [E,(H-1)/2+1,(W-1)/2+1,16].  Replaces layer 0 of yolo11-pose.yaml (ultralytics Conv(3,16,3,2), run inside
+ *      model.predict at utils/yolo_wrapper.py:72) as cuDNN convolution + epilogue pass; tensor cores via mma.sync. */
+int fsd_stem_conv(fsd_handle_t h, const void* x, int E, int H, int W, const void* weight, const void* bias,
+                  int out_channels, int dtype, void* out, void* stream);
+
 /* ---- (a5) YOLO neck: out = concat(nearest_upsample_2x(a), b) along channels, channels-last, in ONE pass.
  *      a [N,ah,aw,ca], b [N,2ah,2aw,cb], out [N,2ah,2aw,ca+cb]; replaces torch's upsample kernel + concat kernel. */
 int fsd_upsample2x_concat(fsd_handle_t h, const void* a, const void* b, void* out, int N, int ah, int aw, int ca,

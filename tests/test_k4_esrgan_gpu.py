@@ -204,3 +204,23 @@ def test_batched_crop_stitch_equals_per_image(cuda_device, size, tile, scale):
     whole = up.enhance_device(batch.contiguous())
     assert torch.equal(whole, torch.repeat_interleave(torch.repeat_interleave(batch, scale, 1), scale, 2))
     assert torch.equal(up.enhance_device(batch[2].contiguous()), whole[2])
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 128), (2, 96, 160), (1, 34, 70), (2, 768, 1024)])
+def test_stem_conv_matches_torch(cuda_device, shape):
+    """(a5) fsd_stem_conv == SiLU(conv2d(x, w, b, stride 2, pad 1)) evaluated in fp32 on the same fp16 inputs; the kernel
+    accumulates in fp32 on tensor cores and rounds once, so it must sit within one fp16 rounding of the fp32 result."""
+    import fsd_b200.ops as ops
+
+    E, H, W = shape
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.rand((E, 3, H, W), generator=g).half().to(cuda_device).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((16, 3, 3, 3), generator=g) * 0.4).half().to(cuda_device)
+    b = torch.randn((16,), generator=g).half().to(cuda_device)
+    got = ops.stem_conv(x, w, b)
+    ref = torch.nn.functional.silu(torch.nn.functional.conv2d(x.float(), w.float(), b.float(), stride=2, padding=1))
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+    err = (got.float() - ref).abs()
+    assert float((err - 1e-3 * ref.abs()).max()) <= 1e-3, float(err.max())
+    with pytest.raises(Exception):
+        ops.stem_conv(x.contiguous(), w, b)  # NCHW input is rejected, not silently re-laid-out
