@@ -194,6 +194,15 @@ def bench_k5():
         del x, buf, res
     buf = cl(96, 512, 32, 32)
     report("K5 SPPF pool 96 x 128ch 32x32 (read slot 0, write slots 1-3)", buf.numel() * 2, lambda: ops.sppf_pool_(buf))
+    x = cl(96, 3, 1024, 1024)
+    w = (torch.randn((16, 3, 3, 3), device=dev) * 0.4).half()
+    bias = torch.randn((16,), device=dev).half()
+    out = cl(96, 16, 512, 512)
+    report("K6 stem conv3x3 s2 + bias + SiLU 96 x 3ch 1024^2 -> 16ch 512^2", (x.numel() + out.numel()) * 2, lambda: ops.stem_conv(x, w, bias, out=out))
+    conv = lambda: ops.bias_act_(torch.nn.functional.conv2d(x, w.contiguous(memory_format=torch.channels_last), None, 2, 1), bias, "silu")  # noqa: E731
+    torch.backends.cudnn.benchmark = True
+    report("   (same layer as cuDNN conv + fsd_bias_act_inplace)", (x.numel() + out.numel()) * 2, conv)
+    del x, out
     a, b = cl(96, 128, 64, 64), cl(96, 64, 128, 128)
     report("K5 upsample2x+concat 96 x (128ch 64^2 , 64ch 128^2)", (a.numel() + b.numel() + 96 * 192 * 128 * 128) * 2,
            lambda: ops.upsample2x_concat(a, b))

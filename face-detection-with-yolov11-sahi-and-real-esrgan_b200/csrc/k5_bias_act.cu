@@ -3,6 +3,8 @@
 // SiLU / LeakyReLU kernel (two more read+write passes, the bias-add non-vectorised).  The ncu launch list of the
 // sliced-detection step showed those two passes costing ~3x the convolutions themselves (profiles/r1_launches_*).
 // Layout: channels-last ([N,H,W,C] dense, C % 8 == 0 for fp16 / C % 4 == 0 for fp32) so the bias index is idx % C.
+#include <algorithm>
+
 #include "fsd_common.cuh"
 
 namespace fsd {
@@ -133,17 +135,16 @@ __global__ void __launch_bounds__(K5_THREADS) k5_sppf_pool_kernel(uint4* __restr
 __global__ void __launch_bounds__(K5_THREADS)
 k5_upsample2x_concat_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
                             int N, int h, int w, int ca_vec, int cb_vec) {
+    // blockIdx.y = output row (n, y); threads run over the row's W * (ca+cb)/8 vectors: one 32-bit division per thread
     const int H = 2 * h, W = 2 * w, cv = ca_vec + cb_vec;
-    const size_t total = (size_t)N * H * W * cv;
-    for (size_t i = (size_t)blockIdx.x * K5_THREADS + threadIdx.x; i < total; i += (size_t)gridDim.x * K5_THREADS) {
-        const int c = (int)(i % cv);
-        const size_t pix = i / cv;
-        if (c < ca_vec) {
-            const int x = (int)(pix % W), y = (int)((pix / W) % H);
-            const size_t n = pix / ((size_t)W * H);
-            out[i] = __ldg(a + ((n * h + (y >> 1)) * w + (x >> 1)) * ca_vec + c);
-        } else {
-            out[i] = __ldg(b + pix * cb_vec + (c - ca_vec));
+    for (unsigned row = blockIdx.y; row < (unsigned)N * H; row += gridDim.y) {  // row = n * H + y
+        const unsigned n = row / (unsigned)H, y = row - n * (unsigned)H;
+        const uint4* arow = a + ((size_t)n * h + (y >> 1)) * w * ca_vec;
+        const uint4* brow = b + (size_t)row * W * cb_vec;
+        uint4* orow = out + (size_t)row * W * cv;
+        for (unsigned i = blockIdx.x * K5_THREADS + threadIdx.x; i < (unsigned)(W * cv); i += gridDim.x * K5_THREADS) {
+            const unsigned x = i / (unsigned)cv, c = i - x * (unsigned)cv;
+            orow[i] = c < (unsigned)ca_vec ? __ldg(arow + (x >> 1) * ca_vec + c) : __ldcs(brow + x * cb_vec + (c - ca_vec));
         }
     }
 }
@@ -161,12 +162,15 @@ extern "C" int fsd_upsample2x_concat(fsd_handle_t h, const void* a, const void* 
                   "fsd_upsample2x_concat: channel counts must be positive multiples of %d", per_vec);
     if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)out & 15)) { set_error("fsd_upsample2x_concat: pointers must be 16-byte aligned"); return FSD_ERR_ALIGN; }
     if (N == 0) return FSD_OK;
-    const size_t total = (size_t)N * 4 * ah * aw * ((ca + cb) / per_vec);
-    const size_t want = (total + K5_THREADS - 1) / K5_THREADS;
-    const int grid = (int)(want < (size_t)h->sm_count * 32 ? want : (size_t)h->sm_count * 32);
+    FSD_CHECK_ARG((int64_t)N * 2 * ah < (1ll << 31), "fsd_upsample2x_concat: too many rows for one launch");
+    const int row_vecs = 2 * aw * ((ca + cb) / per_vec);
+    const int rows = N * 2 * ah;
     FSD_CUDA(cudaSetDevice(h->device));
-    k5_upsample2x_concat_kernel<<<grid, K5_THREADS, 0, (cudaStream_t)stream_>>>((const uint4*)a, (const uint4*)b, (uint4*)out, N, ah, aw,
-                                                                               ca / per_vec, cb / per_vec);
+    {
+        dim3 grid(std::min((row_vecs + K5_THREADS - 1) / K5_THREADS, 8), std::min(rows, 65535));
+        k5_upsample2x_concat_kernel<<<grid, K5_THREADS, 0, (cudaStream_t)stream_>>>((const uint4*)a, (const uint4*)b, (uint4*)out, N, ah, aw,
+                                                                                   ca / per_vec, cb / per_vec);
+    }
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;
