@@ -264,9 +264,13 @@ def main():
                 a = (i * B) % n_host // B * B
                 yield [host[a + j] for j in range(B)]
 
+        host_stats = {}
+
         def run_e2e(count, start=0):
             d2h = 0
-            for res in predict_stream(batches(count, start), model, SLICE, SLICE, OVERLAP, OVERLAP, True, "GREEDYNMM", "IOS", 0.5):
+            host_stats.clear()
+            for res in predict_stream(batches(count, start), model, SLICE, SLICE, OVERLAP, OVERLAP, True, "GREEDYNMM", "IOS", 0.5,
+                                      stats=host_stats):
                 d2h += sum(len(r.object_prediction_list) for r in res) * ops.ROW * 4 + (B + 1) * 4
             return d2h
 
@@ -283,6 +287,7 @@ def main():
             dt = float(tt.item())
         e2e = {"value": world * e_steps * B / dt, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3,
                "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps,
+               "host_ms_per_step": {k: round(1e3 * v / e_steps, 2) for k, v in host_stats.items()},
                "api": "fsd_b200.api.predict_stream (pinned host images in, PredictionResult objects out; 2 batches in flight: "
                       "H2D of batch i+1 and D2H + object construction of batch i-1 overlap the device work of batch i)"}
 

@@ -45,9 +45,9 @@ def get_sliced_prediction_batch(images: Sequence, detection_model, slice_height:
 
 
 class _Slot:
-    def __init__(self, n, h, w, device, rows_cap):
+    def __init__(self, n, h, w, device, rows_cap, stream):
         self.pool = ops.ImagePool(n, h, w, device)
-        self.stream = torch.cuda.Stream(device=device)
+        self.stream = stream
         self.event = torch.cuda.Event()
         self.h_off = torch.empty((n + 1,), dtype=torch.int32).pin_memory()
         self.h_rows = torch.empty((rows_cap, ops.ROW), dtype=torch.float32).pin_memory()
@@ -60,18 +60,29 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
                    overlap_width_ratio: float = 0.2, perform_standard_pred: bool = True,
                    postprocess_type: str = "GREEDYNMM", postprocess_match_metric: str = "IOS",
                    postprocess_match_threshold: float = 0.5, postprocess_class_agnostic: bool = False, depth: int = 2,
-                   rows_per_image_hint: int = 256):
+                   rows_per_image_hint: int = 256, stats: dict | None = None, use_graphs: bool = True):
     """Pipelined batch prediction: yields one list[PredictionResult] per batch of `batches` (an iterable of equal-length
     lists of same-sized HWC uint8 images, ideally pinned CPU tensors), in order.
 
     `depth` batches are in flight: the H2D upload of batch i+1 and the D2H + result-object construction of batch i-1
-    overlap with the device pipeline of batch i (each batch on its own CUDA stream and image pool)."""
+    overlap with the device pipeline of batch i (each batch on its own CUDA stream and image pool).
+    `stats`, if given, accumulates host seconds: "enqueue" (uploads + kernel launches), "wait" (blocked on the device),
+    "build" (result-object construction)."""
+    import time as _time
+
+    if stats is not None:
+        for key in ("enqueue", "wait", "build"):
+            stats.setdefault(key, 0.0)
     eng = detection_model.engine()
     eng.truncate = True
+    graphs_before = eng.use_graphs
+    eng.use_graphs = bool(use_graphs)  # the backbone chunks are replayed as CUDA graphs (static per-stream input buffers)
     slots, pending, k = None, [], 0
 
     def finish(slot):
+        t_a = _time.perf_counter()
         slot.event.synchronize()
+        t_b = _time.perf_counter()
         n = slot.pool.n
         off = slot.h_off.numpy().copy()
         total = int(off[-1])
@@ -100,12 +111,19 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
                      for j, bx in zip(range(a, b), boxes_all[a:b])]
             out.append(PredictionResult(object_prediction_list=preds, image=slot.images[i], durations_in_seconds={}, image_size=(w, h)))
         slot.dev, slot.images = None, None
+        if stats is not None:
+            stats["wait"] += t_b - t_a
+            stats["build"] += _time.perf_counter() - t_b
         return out
 
     for images in batches:
         n, (h, w) = len(images), images[0].shape[:2]
         if slots is None:
-            slots = [_Slot(n, h, w, eng.device, n * rows_per_image_hint) for _ in range(depth)]
+            # the streams live on the engine: its captured backbone graphs and static buffers are keyed by stream
+            streams = eng.__dict__.setdefault("_pipeline_streams", [])
+            while len(streams) < depth:
+                streams.append(torch.cuda.Stream(device=eng.device))
+            slots = [_Slot(n, h, w, eng.device, n * rows_per_image_hint, streams[j]) for j in range(depth)]
         slot = slots[k % depth]
         k += 1
         if slot.dev is not None:
@@ -113,6 +131,7 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
         if (slot.pool.n, slot.pool.h, slot.pool.w) != (n, h, w):
             raise ValueError("predict_stream needs batches of one common size")
         slot.images = images
+        t_e = _time.perf_counter()
         with torch.cuda.stream(slot.stream):
             for i, im in enumerate(images):
                 slot.pool.upload(i, im, non_blocking=True)
@@ -126,5 +145,8 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
             slot.event.record(slot.stream)
         slot.dev = dev
         pending.append(slot)
+        if stats is not None:
+            stats["enqueue"] += _time.perf_counter() - t_e
     while pending:
         yield finish(pending.pop(0))
+    eng.use_graphs = graphs_before

@@ -64,7 +64,7 @@ class SlicedFaceDetector:
     def __init__(self, backbone: torch.nn.Module, device="cuda:0", imgsz: int = 1024, conf: float = 0.5,
                  half: bool = True, stride: int = 32, iou: float = 0.7, max_det: int = 300,
                  cap_per_entry: int = 1024, channels_last: bool = True, reverse_channels: bool = True,
-                 chunk_entries: int = 96, truncate: bool = True):
+                 chunk_entries: int = 96, truncate: bool = True, use_graphs: bool = False):
         if not torch.cuda.is_available():
             raise _cabi.FsdError("SlicedFaceDetector needs a CUDA device: fsd_b200 has no CPU fallback")
         self.device = torch.device(device)
@@ -84,6 +84,13 @@ class SlicedFaceDetector:
         self._dev_cache: Dict = {}
         self.handle = _cabi.get_handle(self.device.index or 0)
         self.head_hook = None  # tests: callable(entries_kind, x, levels) to record / replace head tensors
+        # CUDA-graph replay of the backbone (opt-in): one graph per (stream, chunk address, shape) over static network-input
+        # buffers, so a step enqueues a handful of graph launches instead of ~1300 kernel launches from Python
+        self.use_graphs = use_graphs
+        self._graphs: Dict = {}
+        self._graph_pools: Dict = {}
+        self._xbufs: Dict = {}
+        self.replayed_launches = 0  # fsd kernels executed through graph replays (the handle only counts direct launches)
 
     # ------------------------------------------------------------------------------------------ planning
     def plan(self, H, W, slice_h, slice_w, ov_h, ov_w, perform_standard_pred=True) -> SlicePlan:
@@ -130,12 +137,47 @@ class SlicedFaceDetector:
     def _forward_entries(self, kind: str, x: torch.Tensor, cand: torch.Tensor, count: torch.Tensor):
         """backbone + Kernel 2a over a batch of network inputs, in chunks that bound activation memory."""
         E = x.shape[0]
+        graphs = self.use_graphs and self.head_hook is None
         for a in range(0, E, self.chunk):
             xb = x[a:a + self.chunk]  # Kernel 1 already wrote the layout the backbone wants: no conversion pass
-            levels = self.backbone(xb)
+            levels = self._graph_forward(xb) if graphs else self.backbone(xb)
             if self.head_hook is not None:
                 levels = self.head_hook(kind, a, xb, levels)
             ops.pose_decode(levels, self.conf, cand=cand[a:a + self.chunk], count=count[a:a + self.chunk])
+
+    def _network_input(self, kind: str, shape):
+        """Static network-input buffer per (stream, kind, shape) when graphs are on (a captured graph reads fixed addresses)."""
+        if not self.use_graphs:
+            return None
+        key = (torch.cuda.current_stream(self.device).cuda_stream, kind, tuple(shape))
+        buf = self._xbufs.get(key)
+        if buf is None:
+            if len(self._xbufs) >= 16:
+                return None  # shapes keep changing: stay eager
+            buf = torch.empty(shape, dtype=self.dtype, device=self.device,
+                              memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+            self._xbufs[key] = buf
+        return buf
+
+    def _graph_forward(self, xb: torch.Tensor):
+        stream = torch.cuda.current_stream(self.device)
+        key = (stream.cuda_stream, xb.data_ptr(), tuple(xb.shape))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 64 or not any(xb.data_ptr() >= b.data_ptr() and xb.data_ptr() < b.data_ptr() + b.numel() * b.element_size()
+                                                   for b in self._xbufs.values()):
+                return self.backbone(xb)  # not one of the static buffers: a graph would read a stale address
+            self.backbone(xb)  # eager warm-up on this stream: cuDNN algorithm search must not run under capture
+            pool = self._graph_pools.setdefault(stream.cuda_stream, torch.cuda.graph_pool_handle())
+            graph = torch.cuda.CUDAGraph()
+            n0 = self.handle.launches
+            with torch.cuda.graph(graph, pool=pool):
+                levels = self.backbone(xb)
+            ent = (graph, levels, self.handle.launches - n0, xb)
+            self._graphs[key] = ent
+        ent[0].replay()
+        self.replayed_launches += ent[2]
+        return ent[1]
 
     def _stage1(self, cand, count, seg_off):
         return ops.merge_segments(cand.view(-1, ROW), seg_off, count, self.cap, merge_type="NMS", metric="IOU",
@@ -158,7 +200,8 @@ class SlicedFaceDetector:
             cand_s = torch.empty((E, self.cap, ROW), dtype=torch.float32, device=dev)
             count_s = torch.empty((E,), dtype=torch.int32, device=dev)
             x_s = ops.gather_letterbox(pool, t["ent_s"], plan.box_w, plan.box_h, self.imgsz, self.stride, self.reverse, self.dtype,
-                                       channels_last=self.channels_last)
+                                       channels_last=self.channels_last,
+                                       out=self._network_input("slices", (E, 3, plan.g_slice["out_h"], plan.g_slice["out_w"])))
             self._forward_entries("slices", x_s, cand_s, count_s)
             del x_s
             s1 = self._stage1(cand_s, count_s, t["seg_s"])
@@ -171,7 +214,8 @@ class SlicedFaceDetector:
                 cand_f = torch.empty((N, self.cap, ROW), dtype=torch.float32, device=dev)
                 count_f = torch.empty((N,), dtype=torch.int32, device=dev)
                 x_f = ops.gather_letterbox(pool, t["ent_f"], plan.W, plan.H, self.imgsz, self.stride, self.reverse, self.dtype,
-                                           channels_last=self.channels_last)
+                                           channels_last=self.channels_last,
+                                           out=self._network_input("full", (N, 3, plan.g_full["out_h"], plan.g_full["out_w"])))
                 self._forward_entries("full", x_f, cand_f, count_f)
                 del x_f
                 s1f = self._stage1(cand_f, count_f, t["seg_f"])

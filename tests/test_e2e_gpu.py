@@ -148,8 +148,10 @@ def test_batch_api_equals_single_image_api(cuda_device):
     assert n_all > 0 and n_kp >= n_all // 2
 
 
-def test_predict_stream_equals_batch_api(cuda_device):
-    """The pipelined API (2 batches in flight on separate streams) returns exactly what the synchronous batch call returns."""
+@pytest.mark.parametrize("use_graphs", [True, False])
+def test_predict_stream_equals_batch_api(cuda_device, use_graphs):
+    """The pipelined API (2 batches in flight on separate streams; backbone chunks replayed as CUDA graphs over static
+    per-stream buffers, or launched eagerly) returns exactly what the synchronous batch call returns."""
     from fsd_b200.api import get_sliced_prediction_batch, predict_stream
     from fsd_b200.plugins import YOLOv11PoseDetectionModel
     from fsd_b200.synthetic import make_image
@@ -159,7 +161,12 @@ def test_predict_stream_equals_batch_api(cuda_device):
     imgs = [torch.from_numpy(make_image(300 + i, 384, 512)[0]).pin_memory() for i in range(12)]
     groups = [imgs[0:4], imgs[4:8], imgs[8:12], imgs[0:4]]
     want = [get_sliced_prediction_batch(g, model, 256, 256, 0.2, 0.2) for g in groups]
-    got = list(predict_stream(iter(groups), model, 256, 256, 0.2, 0.2, depth=2, rows_per_image_hint=8))  # tiny window: exercises the refetch
+    stats = {}
+    got = list(predict_stream(iter(groups), model, 256, 256, 0.2, 0.2, depth=2, rows_per_image_hint=8,  # tiny window: exercises the refetch
+                              stats=stats, use_graphs=use_graphs))
+    eng = model.engine()
+    assert eng.use_graphs is False and (eng.replayed_launches > 0) == use_graphs or not use_graphs
+    assert set(stats) == {"enqueue", "wait", "build"} and all(v >= 0 for v in stats.values())
     assert len(got) == len(want)
     for gb, wb in zip(got, want):
         for gr, wr in zip(gb, wb):
