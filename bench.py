@@ -140,6 +140,8 @@ class ClockSampler:
 
 def main():
     args = parse()
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL would print its version banner on stdout, before the JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         return run_reference_arm(args)
 

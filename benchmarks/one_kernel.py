@@ -34,6 +34,21 @@ elif which == "k1_nhwc":
     out = torch.empty((ent.shape[0], 3, 1024, 1024), dtype=torch.float16, device=dev, memory_format=torch.channels_last)
     for _ in range(iters):
         ops.gather_letterbox(pool, ent, 512, 512, 1024, 32, True, torch.float16, out=out)
+elif which == "k6":
+    x = torch.rand((96, 3, 1024, 1024), device=dev).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((16, 3, 3, 3), device=dev) * 0.4).half()
+    b = torch.randn((16,), device=dev).half()
+    out = torch.empty((96, 16, 512, 512), device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    for _ in range(iters):
+        ops.stem_conv(x, w, b, out=out)
+elif which == "k5":
+    x = torch.randn((96, 64, 256, 256), device=dev).half().contiguous(memory_format=torch.channels_last)
+    buf = torch.empty((96, 128, 256, 256), device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    res = torch.randn((96, 64, 256, 256), device=dev).half().contiguous(memory_format=torch.channels_last)
+    b = torch.randn((64,), device=dev).half()
+    for _ in range(iters):
+        ops.bias_act(x, b, "silu", out=buf[:, 64:], residual=res)
+        ops.bias_act(x, b, "silu")
 elif which == "k2":
     B, H, W = 96, 1024, 1024
     g = torch.Generator(device=dev).manual_seed(0)
