@@ -203,6 +203,16 @@ def bench_k5():
     torch.backends.cudnn.benchmark = True
     report("   (same layer as cuDNN conv + fsd_bias_act_inplace)", (x.numel() + out.numel()) * 2, conv)
     del x, out
+    for name, k, n, hw in (("b2.cv1 32->32 256^2", 32, 32, 256), ("b2.cv2 48->64 256^2", 48, 64, 256), ("b4.cv2 96->128 128^2", 96, 128, 128),
+                           ("head.cv3 64->64 128^2", 64, 64, 128), ("b6.cv1 128->128 64^2", 128, 128, 64)):
+        x = cl(96, k, hw, hw)
+        w = (torch.randn((n, k, 1, 1), device=dev) / k ** 0.5).half().contiguous(memory_format=torch.channels_last)
+        bias = torch.randn((n,), device=dev).half()
+        out = cl(96, n, hw, hw)
+        nbytes = (x.numel() + out.numel()) * 2
+        report(f"K7 pointwise conv + bias + SiLU {name}", nbytes, lambda: ops.pointwise_conv(x, w, bias, "silu", out=out))
+        report("   (same layer as cuDNN conv + fsd_bias_act)", nbytes, lambda: ops.bias_act(torch.nn.functional.conv2d(x, w), bias, "silu", out=out))
+        del x, out
     a, b = cl(96, 128, 64, 64), cl(96, 64, 128, 128)
     report("K5 upsample2x+concat 96 x (128ch 64^2 , 64ch 128^2)", (a.numel() + b.numel() + 96 * 192 * 128 * 128) * 2,
            lambda: ops.upsample2x_concat(a, b))

@@ -42,6 +42,8 @@ SIGNATURES = {
     "fsd_bias_act": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                C.c_int, C.c_float, C.c_int, vp]),
     "fsd_stem_conv": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp]),
+    "fsd_pointwise_conv": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int,
+                                     C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
     "fsd_sppf_pool": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fsd_upsample2x_concat": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fsd_esrgan_tile_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int,

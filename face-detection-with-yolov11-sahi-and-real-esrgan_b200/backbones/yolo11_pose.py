@@ -17,6 +17,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+USE_POINTWISE_KERNEL = True  # fsd_pointwise_conv for the 1x1 layers it supports (False: cuDNN + fsd_bias_act everywhere)
+
+
 def _make_divisible(x, divisor=8):
     return int(math.ceil(x / divisor) * divisor)
 
@@ -52,12 +55,21 @@ class Conv(nn.Module):
                     cached = ((c.weight._version, c.weight.data_ptr()), c.weight.detach().contiguous().clone())
                     self._w_dense = cached
                 return stem_conv(x, cached[1], c.bias)
+            act = "silu" if isinstance(self.act, nn.SiLU) else "none"
+            if (c.kernel_size == (1, 1) and c.stride == (1, 1) and c.groups == 1 and USE_POINTWISE_KERNEL
+                    and x.stride(1) == 1 and x.shape[2] * x.shape[3] >= 1024):
+                # low-intensity 1x1 layers: one kernel does GEMM + bias + activation (+ residual) into the slot
+                from ..ops import pointwise_conv, pointwise_conv_supported
+
+                # measured (profiles/r1_kernels_k7.jsonl): it beats cuDNN + epilogue for K, N <= 64 (0.55 vs 0.34 of peak
+                # at 32->32); for N = 128 its SiLU epilogue is issue/MUFU-bound and the library pair is faster
+                if pointwise_conv_supported(c.in_channels, c.out_channels) and c.in_channels <= 64 and c.out_channels <= 64:
+                    return pointwise_conv(x, c.weight, c.bias, act, out=out, residual=residual, out2=out2)
             y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
             if y.is_contiguous(memory_format=torch.channels_last):
                 from ..ops import bias_act
 
-                return bias_act(y, c.bias, "silu" if isinstance(self.act, nn.SiLU) else "none", out=out,
-                                residual=residual, out2=out2)
+                return bias_act(y, c.bias, act, out=out, residual=residual, out2=out2)
             y = self.act(y + c.bias.view(1, -1, 1, 1))
         else:
             y = self.act(c(x))
@@ -252,6 +264,11 @@ class PoseHead(nn.Module):
         for m in seq[:-1]:
             x = m(x)
         if (x.is_cuda and x.dtype == torch.float16 and last.out_channels % 8 == 0 and not torch.is_grad_enabled()):
+            if USE_POINTWISE_KERNEL and x.stride(1) == 1 and x.shape[2] * x.shape[3] >= 1024:
+                from ..ops import pointwise_conv, pointwise_conv_supported
+
+                if pointwise_conv_supported(last.in_channels, last.out_channels) and last.in_channels <= 64 and last.out_channels <= 64:
+                    return pointwise_conv(x, last.weight, last.bias, "none")
             y = F.conv2d(x, last.weight, None, last.stride, last.padding, last.dilation, last.groups)
             if y.is_contiguous(memory_format=torch.channels_last):
                 from ..ops import bias_act

@@ -289,6 +289,40 @@ def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: to
     return out
 
 
+def pointwise_conv_supported(k: int, n: int) -> bool:
+    """Layer shapes Kernel 7 takes (the rest stays on the library convolution + fsd_bias_act)."""
+    return k % 16 == 0 and 16 <= k <= 128 and n in (16, 32, 64, 128)
+
+
+def pointwise_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: float = 0.2,
+                   out: torch.Tensor | None = None, residual: torch.Tensor | None = None,
+                   out2: torch.Tensor | None = None) -> torch.Tensor:
+    """(a5) act(conv1x1(x) + bias) (+ residual) in one kernel.  x [B,K,H,W] and out [B,N,H,W] (default: a new dense
+    tensor) / residual / out2 may be channel slots of channels-last fp16 buffers; weight [N,K] (or [N,K,1,1])."""
+    _require_cuda(x, "x")
+    b, k, hh, ww = x.shape
+    n = int(weight.shape[0])
+    if x.dtype != torch.float16:
+        raise ValueError("pointwise_conv needs fp16 tensors")
+    w2 = weight.reshape(n, k)
+    if not w2.is_contiguous():
+        w2 = w2.contiguous()
+    sx = _slot_stride(x, b, k, hh, ww, "x")
+    if out is None:
+        out = torch.empty((b, n, hh, ww), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    so = _slot_stride(out, b, n, hh, ww, "out")
+    sr = _slot_stride(residual, b, n, hh, ww, "residual") if residual is not None else 0
+    c2 = int(out2.shape[1]) if out2 is not None else 0
+    s2 = _slot_stride(out2, b, c2, hh, ww, "out2") if out2 is not None else 0
+    h = _handle_for(x)
+    check(h.lib.fsd_pointwise_conv(h.h, x.data_ptr(), sx, w2.data_ptr(), bias.data_ptr(), out.data_ptr(), so,
+                                   residual.data_ptr() if residual is not None else None, sr,
+                                   out2.data_ptr() if out2 is not None else None, s2, n - c2 if out2 is not None else 0,
+                                   b * hh * ww, k, n, _ACT[act], float(slope), _TORCH_DTYPE[x.dtype], _stream_ptr(x.device)),
+          "fsd_pointwise_conv")
+    return out
+
+
 def sppf_pool_(buf: torch.Tensor) -> torch.Tensor:
     """(a5) fills channel slots 1..3 of the dense channels-last [N,4c,H,W] fp16 buffer with the cascaded 5x5 max pools of
     slot 0 (ultralytics SPPF), one launch."""

@@ -177,6 +177,16 @@ int fsd_sppf_pool(fsd_handle_t h, void* buf, int N, int H, int W, int c, int dty
 int fsd_stem_conv(fsd_handle_t h, const void* x, int E, int H, int W, const void* weight, const void* bias,
                   int out_channels, int dtype, void* out, void* stream);
 
+/* ---- (a5) 1x1 convolution + bias + activation (+ residual) for the low-intensity layers, fp16 channels-last:
+ *      out[pix, :N] = act(x[pix, :K] . weight[N, K]^T + bias) (+ residual[pix, :N]); x / out / residual / out2 are channel slots
+ *      with their own pixel strides (elements), exactly as in fsd_bias_act.  K % 16 == 0, K <= 128, N in {16,32,64,128}
+ *      (the weight matrix and two staging tiles per warp live in shared memory).  Replaces cuDNN convolution + epilogue pass for
+ *      ultralytics Conv(c1, c2, 1, 1) layers (C3k2.cv1/cv2, C3k.cv1-3, head cv3; run from utils/yolo_wrapper.py:72). */
+int fsd_pointwise_conv(fsd_handle_t h, const void* x, int64_t x_pixel_stride, const void* weight, const void* bias,
+                       void* out, int64_t out_pixel_stride, const void* residual, int64_t residual_pixel_stride,
+                       void* out2, int64_t out2_pixel_stride, int out2_first_channel, int64_t n_pixels,
+                       int in_channels, int out_channels, int act, float slope, int dtype, void* stream);
+
 /* ---- (a5) YOLO neck: out = concat(nearest_upsample_2x(a), b) along channels, channels-last, in ONE pass.
  *      a [N,ah,aw,ca], b [N,2ah,2aw,cb], out [N,2ah,2aw,ca+cb]; replaces torch's upsample kernel + concat kernel. */
 int fsd_upsample2x_concat(fsd_handle_t h, const void* a, const void* b, void* out, int N, int ah, int aw, int ca,

@@ -224,3 +224,36 @@ def test_stem_conv_matches_torch(cuda_device, shape):
     assert float((err - 1e-3 * ref.abs()).max()) <= 1e-3, float(err.max())
     with pytest.raises(Exception):
         ops.stem_conv(x.contiguous(), w, b)  # NCHW input is rejected, not silently re-laid-out
+
+
+@pytest.mark.parametrize("kn", [(32, 32), (48, 64), (64, 64), (96, 128), (112, 32), (64, 16), (16, 128), (128, 128)])
+@pytest.mark.parametrize("act", ["silu", "none"])
+def test_pointwise_conv_matches_torch(cuda_device, kn, act):
+    """(a5) fsd_pointwise_conv == act(conv2d 1x1 + bias) (+ residual) computed in fp32 on the same fp16 inputs, written into
+    a concat slot with the trailing channels copied to a second destination; ragged pixel count (not a multiple of 32)."""
+    import fsd_b200.ops as ops
+
+    K, N = kn
+    g = torch.Generator().manual_seed(K * 1000 + N)
+    cl = lambda t: t.half().to(cuda_device).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    B, H, W = 3, 37, 29  # 3219 pixels
+    xbuf = cl(torch.randn((B, K + 16, H, W), generator=g))
+    x = xbuf[:, 8:8 + K]  # the input itself is a channel slot
+    w = (torch.randn((N, K, 1, 1), generator=g) / K ** 0.5).half().to(cuda_device)
+    bias = torch.randn((N,), generator=g).half().to(cuda_device)
+    res = cl(torch.randn((B, N, H, W), generator=g))
+    f = torch.nn.functional.silu if act == "silu" else (lambda t: t)
+    y = f(torch.nn.functional.conv2d(x.float(), w.float(), bias.float()))
+    want = y.half() + res  # act rounded to fp16, then the fp16 residual add — the order torch uses
+    buf = torch.full((B, N + 8, H, W), float("nan"), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    tail = torch.empty((B, 8, H, W), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    out = ops.pointwise_conv(x, w, bias, act, out=buf[:, 8:], residual=res, out2=tail)
+    assert out.data_ptr() == buf[:, 8:].data_ptr() and torch.isnan(buf[:, :8]).all()
+    err = (out.float() - want.float()).abs()
+    assert float((err - 2e-3 * want.float().abs()).max()) <= 2e-3, float(err.max())
+    assert torch.equal(tail, out[:, N - 8:])
+    plain = ops.pointwise_conv(x, w, bias, act)
+    assert plain.is_contiguous(memory_format=torch.channels_last)
+    err = (plain.float() - y).abs()
+    assert float((err - 1e-3 * y.abs()).max()) <= 1e-3, float(err.max())
+    assert not ops.pointwise_conv_supported(256, 64) and not ops.pointwise_conv_supported(24, 64)
