@@ -15,6 +15,8 @@ lives in third-party packages that are neither vendored under /root/reference no
     base}.py`, `utils/yolo_wrapper.py`, `utils/insightface_wrapper.py` and `utils/enhancer.py` are imported
     UNMODIFIED by `tests/golden/make_golden.py` (through thin `sahi`/`ultralytics`/`realesrgan` import shims)
     and their outputs are committed as fixtures under tests/golden/ — the oracle must reproduce them;
+  * the secondary evaluator: `eval/eval_dual.py` is imported unmodified by `tests/golden/make_golden_eval_dual.py` and the
+    results of its IoU / 11-point AP / matching methods are committed (tests/golden/eval_dual_outputs.json);
   * cv2.resize / copyMakeBorder (letterbox) and torchvision.ops.nms: the real libraries are in this image and
     the integer restatement in `oracle/letterbox.py` / `oracle/yolo_head.py` is checked against them.
 What is "parity unpinned": the published algorithms of sahi.slicing / sahi.postprocess / sahi.annotation,
