@@ -414,6 +414,11 @@ static int launch(fsd_context* h, const CUtensorMap& tmap, const K1Params& p, in
 
 int launch_upscale2x(fsd_context* h, const uint8_t* images, int64_t row_pitch, int64_t image_pitch, const int32_t* entries,
                      int B, int src_w, int src_h, int reverse, int nhwc, void* out, cudaStream_t stream);  // k1_upscale2x.cu
+bool pack_sixteenths_tables(const std::vector<int32_t>& xt, const std::vector<int32_t>& yt, int src_w, int src_h, int out_w,
+                            int out_h, std::vector<int32_t>& packed);
+int launch_sixteenths(fsd_context* h, const uint8_t* images, int64_t row_pitch, int64_t image_pitch, const int32_t* entries,
+                      int B, int src_w, const int32_t* packed_dev, int out_w, int out_h, int reverse, int nhwc, void* out,
+                      cudaStream_t stream);
 
 }  // namespace fsd
 
@@ -469,6 +474,31 @@ extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n
     if (rc) return rc;
     p.xtab = reinterpret_cast<const int2*>(xdev);
     p.ytab = reinterpret_cast<const int4*>(ydev);
+
+    // border-less up-scale (or copy) whose cv2 coefficients are all sixteenths (ratios 8/5, 4, 2, 1 ...), fp16 output:
+    // the packed 16-bit-lane path (k1_upscale2x.cu: k1_sixteenths_kernel)
+    if (mode == K1_MODE_LINEAR && dtype == FSD_F16 && p.pad_left == 0 && p.pad_top == 0 && p.out_w == p.new_w &&
+        p.out_h == p.new_h && p.new_w >= src_w && p.new_h >= src_h && !getenv("FSD_K1_GENERIC")) {
+        auto key = std::make_tuple(src_w * 65536 + src_h, p.new_w * 65536 + p.new_h, 1 << 20);
+        auto it = h->resize_tables.find(key);
+        if (it == h->resize_tables.end()) {
+            ResizeTable t;  // n = -1: this geometry does not qualify (remembered, so the check runs once)
+            std::vector<int32_t> packed;
+            if (pack_sixteenths_tables(xt, yt, src_w, src_h, p.new_w, p.new_h, packed)) {
+                t.n = (int)packed.size();
+                FSD_CUDA(cudaMalloc(&t.dev, packed.size() * sizeof(int32_t)));
+                FSD_CUDA(cudaMemcpy(t.dev, packed.data(), packed.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            } else {
+                t.n = -1;
+            }
+            it = h->resize_tables.emplace(key, t).first;
+        }
+        if (it->second.n > 0) {
+            if (n_images == 1) image_pitch = row_pitch * H;
+            return launch_sixteenths(h, images, row_pitch, image_pitch, entries, B, src_w, it->second.dev, p.new_w, p.new_h,
+                                     p.reverse, out_layout == FSD_CHANNELS_LAST, out, stream);
+        }
+    }
 
     // tile shape: widest TC whose source strip fits one 1024-byte TMA box row, tallest TR within the smem budget
     const int tcs[] = {256, 128, 64, 32, 16, 8};

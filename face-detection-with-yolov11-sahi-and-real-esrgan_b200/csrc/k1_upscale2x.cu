@@ -12,6 +12,8 @@
 // about 6 instructions per output element instead of 17 in the general kernel, which makes this path HBM-bound.
 // One thread produces 8 output columns x 3 channels and marches down the source rows, keeping A/B of the previous row
 // in registers; source bytes come straight from L1/L2 (they are 6 % of the traffic), stores are 128-bit.
+#include <vector>
+
 #include "fsd_common.cuh"
 
 namespace fsd {
@@ -155,6 +157,262 @@ int launch_upscale2x(fsd_context* h, const uint8_t* images, int64_t row_pitch, i
         TimedLaunch timed(h, FSD_KERNEL_GATHER, B, src_w, stream);
         if (nhwc) k1_upscale2x_kernel<true><<<grid, UP2_THREADS, 0, stream>>>(p);
         else k1_upscale2x_kernel<false><<<grid, UP2_THREADS, 0, stream>>>(p);
+    }
+    FSD_CUDA(cudaGetLastError());
+    h->launches += 1;
+    return FSD_OK;
+}
+
+
+// ---- "sixteenths" path: any border-less resize whose cv2 coefficients are all multiples of 128 (= k/16 weights) ----------
+// Ratios 8/5 (SAHI's default 640^2 slices at imgsz 1024), 4, 2, 1 (the full-image pass when the image is already a
+// multiple of the stride) have fractional source positions in sixteenths, so cv2's 11-bit coefficients are 128*k and the
+// two fixed-point passes reduce to
+//     s   = S[sx]*k0 + S[sx+1]*(16-k0)                          (<= 4080, horizontal pass; h = 8*s exactly)
+//     out = (((s[sy]*m0) >> 6) + ((s[sy1]*m1) >> 6) + 2) >> 2    (m0 + m1 = 16; every product < 65536)
+// i.e. the vertical pass and everything after it run on 16-bit lanes, two output columns per register, exactly as in
+// the 2x kernel above; the horizontal pass is evaluated once per source row and reused by the 1-4 output rows that
+// need it.  Indices and weights come from the cv2-exact host tables (border rules included), re-packed per column/row.
+struct K16Params {
+    const uint8_t* images;
+    int64_t row_pitch, image_pitch;
+    const int32_t* entries;
+    const int32_t* xk;  // [out_w]  byte offset of S0 | (S1 is 3 bytes further ? 1 : 0) << 20 | k0 << 24
+    const int32_t* yk;  // [out_h]  sy | (sy1 - sy) << 16 | m0 << 24
+    __half* out;
+    int out_w, out_h, reverse, rows_per_cta, src_w;
+};
+
+// Horizontal pattern of an 8-column output group when out_w * Q == 8 * src_w (ratios 8/Q: 8, 4, 8/3, 2, 8/5, 4/3, 8/7, 1):
+// every group maps to Q source pixels with the SAME relative indices and weights, so they are compile-time constants and
+// the group's Q + 2 source pixels are fetched as a few aligned 32-bit words (a byte load per tap costs ~4 L1 wavefronts
+// because neighbouring lanes are 3*Q bytes apart; the byte-load version of this kernel was bound by exactly that).
+template <int Q> struct K16Pat {
+    static constexpr int n(int i) { return (2 * i + 1) * Q - 8; }                       // source position in sixteenths
+    static constexpr int fl(int i) { return n(i) >= 0 ? n(i) / 16 : -((-n(i) + 15) / 16); }
+    static constexpr int rel(int i) { return fl(i) + 1; }                               // tap 0 = pixel rel(i) of the span (span starts at pixel v*Q - 1)
+    static constexpr int k1(int i) { return n(i) - 16 * fl(i); }                        // weight of tap 1 in sixteenths
+    static constexpr int SPAN = (Q + 2) * 3;                                            // bytes
+    static constexpr int NS = (SPAN + 3) / 4;                                           // words after alignment
+};
+
+template <bool NHWC, int Q>
+__global__ void __launch_bounds__(UP2_THREADS)
+k1_sixteenths_kernel(const K16Params p) {
+    const int b = blockIdx.z;
+    const int v = blockIdx.x * UP2_THREADS + threadIdx.x;  // 8-column output vector index
+    const int out_w = p.out_w, out_h = p.out_h;
+    if ((v & ~31) * 8 >= out_w) return;
+    const bool active = v * 8 < out_w;
+    const int img = __ldg(p.entries + 3 * b + 0), x0 = __ldg(p.entries + 3 * b + 1), y0 = __ldg(p.entries + 3 * b + 2);
+    const uint8_t* base = p.images + (size_t)img * p.image_pitch + (size_t)y0 * p.row_pitch + (size_t)x0 * 3;
+    int off0[Q == 0 ? 8 : 1], d1[Q == 0 ? 8 : 1], k0[Q == 0 ? 8 : 1];
+    if (Q == 0) {
+#pragma unroll
+        for (int i = 0; i < (Q == 0 ? 8 : 1); ++i) {
+            const int t = active ? __ldg(p.xk + v * 8 + i) : 0;
+            off0[i] = t & 0xfffff; d1[i] = ((t >> 20) & 1) * 3; k0[i] = (t >> 24) & 31;
+        }
+    }
+    // Q > 0: this thread's span = source pixels v*Q - 1 .. v*Q + Q (clamped to the slice: that IS cv2's border rule).  The
+    // word path needs the whole span inside the slice and its aligned window inside the row pitch.
+    using Pat = K16Pat<(Q > 0 ? Q : 1)>;
+    const int px_first = v * Q - 1;
+    const long long span_byte0 = (long long)x0 * 3 + (long long)px_first * 3;  // offset within the image row
+    const bool word_path = Q > 0 && active && px_first >= 0 && px_first + Q + 1 <= p.src_w - 1 &&
+                           (span_byte0 & ~3ll) + 4 * (Pat::NS + 1) <= p.row_pitch;
+    const int c0 = p.reverse ? 2 : 0, c2 = p.reverse ? 0 : 2;
+    const size_t plane = (size_t)out_h * out_w;
+    __half* out = p.out + (size_t)b * 3 * plane + (NHWC ? (size_t)v * 24 : (size_t)v * 8);
+    const int warp_byte0 = (v & ~31) * 48;
+    __half* out_warp = p.out + (size_t)b * 3 * plane + (size_t)(v & ~31) * 24;
+    __shared__ uint4 s_stage[NHWC ? UP2_THREADS * 3 : 1];
+
+    auto hrow = [&](int r, uint32_t (&dst)[3][4]) {  // packed s values of source row r for this thread's 8 columns
+        const uint8_t* row = base + (size_t)r * p.row_pitch;
+        if (Q == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[c][j] = 0;
+#pragma unroll
+            for (int i = 0; i < (Q == 0 ? 8 : 1); ++i) {
+                const uint8_t* px = row + off0[i];
+                const int k1 = 16 - k0[i];
+                const uint32_t sA = __ldg(px + c0) * k0[i] + __ldg(px + d1[i] + c0) * k1;
+                const uint32_t sB = __ldg(px + 1) * k0[i] + __ldg(px + d1[i] + 1) * k1;
+                const uint32_t sC = __ldg(px + c2) * k0[i] + __ldg(px + d1[i] + c2) * k1;
+                dst[0][i >> 1] |= sA << (16 * (i & 1));
+                dst[1][i >> 1] |= sB << (16 * (i & 1));
+                dst[2][i >> 1] |= sC << (16 * (i & 1));
+            }
+            return;
+        }
+        // ---- Q > 0: the span's bytes as a word stream st[] (byte 3*t + c = pixel t of the span, source channel c) ----------
+        uint32_t st[Pat::NS + 1];
+        if (word_path) {
+            const uint8_t* p0 = row + (long long)px_first * 3;
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p0);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+            const int sh = (int)(a & 3) * 8;
+            uint32_t w[Pat::NS + 1];
+#pragma unroll
+            for (int k = 0; k <= Pat::NS; ++k) w[k] = __ldg(wp + k);
+#pragma unroll
+            for (int k = 0; k < Pat::NS; ++k) st[k] = __funnelshift_r(w[k], w[k + 1], sh);
+        } else {  // border vectors (and idle lanes): clamped per-pixel byte loads, same stream layout
+#pragma unroll
+            for (int k = 0; k < Pat::NS; ++k) st[k] = 0;
+#pragma unroll
+            for (int t = 0; t < Q + 2; ++t) {
+                const int col = min(max(px_first + t, 0), p.src_w - 1);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) st[(3 * t + c) >> 2] |= (uint32_t)__ldg(row + col * 3 + c) << (8 * ((3 * t + c) & 3));
+            }
+        }
+        st[Pat::NS] = 0;
+        // s = S0*k0 + S1*k1 with the taps 3 bytes apart: ONE dp4a over the 4-byte window starting at tap 0, weights (k0,0,0,k1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            constexpr int dummy = 0; (void)dummy;
+            const int k1 = Pat::k1(i), k0w = 16 - k1;
+            const uint32_t wts = (uint32_t)k0w | ((uint32_t)k1 << 24);
+            uint32_t sv[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int b0 = 3 * Pat::rel(i) + c;  // stream byte of tap 0
+                const uint32_t win = (b0 & 3) == 0 ? st[b0 >> 2] : __funnelshift_r(st[b0 >> 2], st[(b0 >> 2) + 1], 8 * (b0 & 3));
+                sv[c] = __dp4a(win, wts, 0u);
+            }
+            // plane 0 <- source channel c0, plane 1 <- 1, plane 2 <- c2
+            const uint32_t pA = p.reverse ? sv[2] : sv[0], pC = p.reverse ? sv[0] : sv[2];
+            if (i & 1) {
+                dst[0][i >> 1] |= pA << 16; dst[1][i >> 1] |= sv[1] << 16; dst[2][i >> 1] |= pC << 16;
+            } else {
+                dst[0][i >> 1] = pA; dst[1][i >> 1] = sv[1]; dst[2][i >> 1] = pC;
+            }
+        }
+    };
+    auto store_row = [&](int Y, const uint32_t (&o)[3][4]) {
+        if (NHWC) {
+            uint32_t w[12];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w[3 * k + 0] = __byte_perm(o[0][k], o[1][k], 0x5410);
+                w[3 * k + 1] = __byte_perm(o[2][k], o[0][k], 0x7610);
+                w[3 * k + 2] = __byte_perm(o[1][k], o[2][k], 0x7632);
+            }
+            uint4* slab = s_stage + (threadIdx.x & ~31) * 3;
+            const int lane = threadIdx.x & 31;
+            slab[lane * 3 + 0] = make_uint4(w[0], w[1], w[2], w[3]);
+            slab[lane * 3 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+            slab[lane * 3 + 2] = make_uint4(w[8], w[9], w[10], w[11]);
+            __syncwarp();
+            uint4* d = reinterpret_cast<uint4*>(out_warp + (size_t)Y * out_w * 3);
+            const int nchunk = min(96, (out_w * 3 * 2 - warp_byte0) / 16);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k * 32 + lane < nchunk) d[k * 32 + lane] = slab[k * 32 + lane];
+            __syncwarp();
+        } else if (active) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                *reinterpret_cast<uint4*>(out + c * plane + (size_t)Y * out_w) = make_uint4(o[c][0], o[c][1], o[c][2], o[c][3]);
+        }
+    };
+
+    const int y_lo = blockIdx.y * p.rows_per_cta, y_hi = min(y_lo + p.rows_per_cta, out_h);
+    uint32_t cur[3][4], nxt[3][4];
+    int cur_i = -1, nxt_i = -1;
+    for (int y = y_lo; y < y_hi; ++y) {  // every branch below is uniform over the CTA (it depends on y only)
+        const int t = __ldg(p.yk + y);
+        const int sy = t & 0xffff, sy1 = sy + ((t >> 16) & 1);
+        const uint32_t m0 = (uint32_t)(t >> 24) & 31u, m1 = 16u - m0;
+        const uint32_t f0 = m0 << 26, f1 = m1 << 26;  // (x * m) >> 6 == umulhi(x, m << 26): multiply and shift in one IMAD.HI
+        if (sy != cur_i) {
+            if (sy == nxt_i) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cur[c][j] = nxt[c][j];
+            } else {
+                hrow(sy, cur);
+            }
+            cur_i = sy;
+        }
+        if (sy1 != nxt_i) {
+            if (sy1 == cur_i) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) nxt[c][j] = cur[c][j];
+            } else {
+                hrow(sy1, nxt);
+            }
+            nxt_i = sy1;
+        }
+        uint32_t o[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // A is masked to its 10-bit lanes; B may keep the <= 6 stray bits the shift moved into bits 10..15 of the
+                // low lane: A + B + 2 <= 1023 + (63 << 10) cannot carry into the high lane, and the final mask drops them
+                const uint32_t A = __umulhi(cur[c][j], f0) & 0x03ff03ffu;
+                const uint32_t B = __umulhi(nxt[c][j], f1);
+                o[c][j] = norm255_pair(((A + B + 0x00020002u) >> 2) & 0x00ff00ffu);
+            }
+        store_row(y, o);
+    }
+}
+
+// Packs the cv2-exact host tables for the sixteenths path; false when some coefficient is not a multiple of 128.
+bool pack_sixteenths_tables(const std::vector<int32_t>& xt, const std::vector<int32_t>& yt, int src_w, int src_h, int out_w,
+                            int out_h, std::vector<int32_t>& packed) {
+    packed.resize((size_t)out_w + out_h);
+    for (int x = 0; x < out_w; ++x) {
+        const int s = xt[2 * x], w0 = xt[2 * x + 1] & 0xffff, w1 = (xt[2 * x + 1] >> 16) & 0xffff;
+        if (w0 % 128 || w1 % 128 || w0 + w1 != 2048 || s < 0 || s >= src_w || s * 3 > 0xfffff) return false;
+        const int s1 = s + 1 < src_w ? s + 1 : src_w - 1;
+        packed[x] = (s * 3) | ((s1 != s ? 1 : 0) << 20) | ((w0 / 128) << 24);
+    }
+    for (int y = 0; y < out_h; ++y) {
+        const int s = yt[4 * y], s1 = yt[4 * y + 1], w0 = yt[4 * y + 2], w1 = yt[4 * y + 3];
+        if (w0 % 128 || w1 % 128 || w0 + w1 != 2048 || s < 0 || s >= src_h || s > 0xffff || (s1 != s && s1 != s + 1)) return false;
+        packed[out_w + y] = s | ((s1 - s) << 16) | ((w0 / 128) << 24);
+    }
+    return true;
+}
+
+int launch_sixteenths(fsd_context* h, const uint8_t* images, int64_t row_pitch, int64_t image_pitch, const int32_t* entries,
+                      int B, int src_w, const int32_t* packed_dev, int out_w, int out_h, int reverse, int nhwc, void* out,
+                      cudaStream_t stream) {
+    K16Params p;
+    p.images = images; p.row_pitch = row_pitch; p.image_pitch = image_pitch; p.entries = entries;
+    p.xk = packed_dev; p.yk = packed_dev + out_w; p.out = reinterpret_cast<__half*>(out);
+    p.out_w = out_w; p.out_h = out_h; p.reverse = reverse; p.rows_per_cta = 32; p.src_w = src_w;
+    const int vecs = out_w / 8;
+    dim3 grid((vecs + UP2_THREADS - 1) / UP2_THREADS, (out_h + p.rows_per_cta - 1) / p.rows_per_cta, B);
+    // uniform 8-column pattern (out_w * Q == 8 * src_w) -> compile-time taps; anything else -> the table-driven variant
+    int q = 0;
+    if ((8LL * src_w) % out_w == 0 && !getenv("FSD_K1_TABLE16")) q = (int)(8LL * src_w / out_w);
+    {
+        TimedLaunch timed(h, FSD_KERNEL_GATHER, B, src_w, stream);
+#define K16_GO(QQ)                                                                         \
+        if (nhwc) k1_sixteenths_kernel<true, QQ><<<grid, UP2_THREADS, 0, stream>>>(p);    \
+        else k1_sixteenths_kernel<false, QQ><<<grid, UP2_THREADS, 0, stream>>>(p);
+        switch (q) {
+            case 1: K16_GO(1) break;
+            case 2: K16_GO(2) break;
+            case 3: K16_GO(3) break;
+            case 4: K16_GO(4) break;
+            case 5: K16_GO(5) break;
+            case 6: K16_GO(6) break;
+            case 7: K16_GO(7) break;
+            case 8: K16_GO(8) break;
+            default: K16_GO(0) break;
+        }
+#undef K16_GO
     }
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;

@@ -121,6 +121,34 @@ def test_exact_2x_fast_path_equals_general_kernel_and_oracle(cuda_device, size, 
         assert torch.equal(general, fast)
 
 
+@pytest.mark.parametrize("case", [  # (slice h, slice w, imgsz): ratios 8/5, 4, 1 (copy), 8/5 non-square, 16/5 (NOT sixteenths)
+    (640, 640, 1024), (40, 40, 64), (64, 64, 256), (96, 128, 128), (768, 1024, 1024), (160, 200, 320), (20, 40, 128), (100, 100, 320),
+    (48, 48, 128), (96, 96, 128), (112, 112, 128), (16, 16, 128), (10, 10, 16), (5, 5, 32)])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_sixteenths_path_equals_general_kernel_and_oracle(cuda_device, case, channels_last, monkeypatch):
+    """Border-less resizes whose cv2 coefficients are multiples of 128 (ratios 8/5, 4, 1 ...) take the packed 16-bit-lane path
+    (k1_sixteenths_kernel); it must equal cv2 (oracle) AND the general TMA kernel bit for bit.  Geometries that do not
+    qualify (a letterbox border, 16/5) silently stay on the general kernel — same assertions."""
+    import fsd_b200.ops as ops
+
+    sh, sw, imgsz = case
+    H, W = sh + 19, sw + 11
+    rng = np.random.default_rng(sh * 7 + sw)
+    images = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(2)]
+    entries = [(0, 0, 0), (1, 11, 19), (0, 5, 2)]
+    pool = ops.ImagePool.from_numpy(images, cuda_device)
+    ent = torch.tensor(entries, dtype=torch.int32)
+    fast = ops.gather_letterbox(pool, ent, sw, sh, imgsz=imgsz, dtype=torch.float16, channels_last=channels_last)
+    ref = _oracle_batch(images, entries, sw, sh, imgsz, True, True)
+    assert torch.equal(fast.cpu(), ref)
+    monkeypatch.setenv("FSD_K1_TABLE16", "1")  # the table-driven variant of the same path (used for non-uniform column patterns)
+    table = ops.gather_letterbox(pool, ent, sw, sh, imgsz=imgsz, dtype=torch.float16, channels_last=channels_last)
+    assert torch.equal(table, fast)
+    monkeypatch.setenv("FSD_K1_GENERIC", "1")
+    general = ops.gather_letterbox(pool, ent, sw, sh, imgsz=imgsz, dtype=torch.float16, channels_last=channels_last)
+    assert torch.equal(general, fast)
+
+
 def test_in_library_kernel_timing(cuda_device):
     """fsd_kernel_timing_*: one sample per instrumented launch, tagged (kernel id, entries, src_w), positive device time;
     kernels outside the mask are not sampled and re-enabling clears the list."""
@@ -133,7 +161,7 @@ def test_in_library_kernel_timing(cuda_device):
     h = _cabi.get_handle(cuda_device.index or 0)
     h.timing_enable((_cabi.FSD_KERNEL_GATHER,))
     ops.gather_letterbox(pool, ent, 64, 64, 128, 32)              # exact-2x fast path
-    ops.gather_letterbox(pool, ent[:2], 48, 40, 128, 32)          # general TMA kernel
+    ops.gather_letterbox(pool, ent[:2], 48, 40, 128, 32)          # general TMA kernel (letterbox border)
     x = torch.randn((1, 16, 8, 8), device=cuda_device).half().contiguous(memory_format=torch.channels_last)
     ops.bias_act(x, torch.zeros(16, device=cuda_device).half(), "silu")  # not in the mask
     got = h.timing_read()
