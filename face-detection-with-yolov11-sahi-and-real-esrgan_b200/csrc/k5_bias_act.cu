@@ -12,7 +12,7 @@ namespace fsd {
 constexpr int K5_THREADS = 256;
 
 template <int ACT> __device__ __forceinline__ float activate(float v, float slope) {
-    if (ACT == 1) return __fdividef(v, 1.0f + __expf(-v));  // SiLU
+    if (ACT == 1) return fast_silu(v);  // SiLU
     if (ACT == 2) return v > 0.f ? v : v * slope;           // LeakyReLU
     return v;
 }

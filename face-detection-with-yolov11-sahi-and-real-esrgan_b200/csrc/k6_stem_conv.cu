@@ -4,7 +4,7 @@
 // is the one convolution cuDNN serves badly: a 3-channel channels-last input matches none of its tensor-core NHWC kernels
 // (profiles/r1_launches_bench_b32_slotcat.txt: 0.84 ms per 96 inputs, 8.8 % of the step, plus 0.28 ms for the epilogue
 // pass) although the layer moves only 1.4 GB (0.22 ms at HBM speed).  Here:
-//   * a CTA owns an 8 x 64 tile of output pixels; the 17 x 130 input pixels under it are staged in shared memory as
+//   * a CTA owns an 8 x 128 tile of output pixels; the 17 x 258 input pixels under it are staged in shared memory as
 //     [row][col][4 halfs] (channel 3 = 0), so the 3 x 4(cols) x 4(ch) window of an output pixel's kernel row is 16
 //     contiguous halfs and consecutive output pixels are 16 bytes apart: one `ldmatrix.x4` yields the 16 x 16 A tile
 //     (16 output pixels x one kernel row) without any bank conflict;
@@ -19,10 +19,10 @@ namespace fsd {
 
 constexpr int K6_THREADS = 256;
 constexpr int K6_TH = 8;     // output rows per CTA (one per warp)
-constexpr int K6_TW = 64;    // output columns per CTA
+constexpr int K6_TW = 128;   // output columns per CTA
 constexpr int K6_ROWS = 2 * K6_TH + 1;          // input rows staged
-constexpr int K6_PAIRS = K6_TW + 2;             // input column pairs staged: columns 2*x0-2 .. 2*x0+129
-constexpr int K6_PITCH = 2 * K6_PAIRS + 2;      // smem columns per row (index 0 unused; 8 bytes each; 1072 B = 67 * 16)
+constexpr int K6_PAIRS = K6_TW + 2;             // input column pairs staged: columns 2*x0-2 .. 2*x0+257
+constexpr int K6_PITCH = 2 * K6_PAIRS + 2;      // smem columns per row (index 0 unused; 8 bytes each; 2096 B = 131 * 16)
 
 struct K6Params {
     const __half* x;      // [E, H, W, 3]
@@ -32,7 +32,7 @@ struct K6Params {
     int H, W, OH, OW;
 };
 
-__device__ __forceinline__ float k6_silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float k6_silu(float v) { return fast_silu(v); }
 
 __global__ void __launch_bounds__(K6_THREADS) k6_stem_conv_kernel(const K6Params p) {
     __shared__ __align__(16) uint2 tile[K6_ROWS][K6_PITCH];
@@ -40,24 +40,22 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stem_conv_kernel(const K6Params
     const int x0 = blockIdx.x * K6_TW, y0 = blockIdx.y * K6_TH;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- weights -> B fragments (registers).  k = kx * 4 + c; zero for kx == 3 or c == 3 -------------------------------
+    // ---- weights -> B fragments.  k = kx * 4 + c; zero for kx == 3 or c == 3.  Built once per CTA in shared memory
+    // ([fragment][lane], conflict-free), then 12 LDS per thread (each thread used to assemble its 24 halfs itself: a
+    // quarter of the kernel's instructions, profiles/r1_k6_stem.summary.txt)
+    __shared__ uint32_t s_bfrag[12][32];
     const int g = lane >> 2, t = lane & 3;
-    uint32_t bfrag[3][2][2];
+    for (int i = tid; i < 12 * 32; i += K6_THREADS) {
+        const int f = i >> 5, ln = i & 31;          // f = (ky * 2 + j) * 2 + r
+        const int ky = f >> 2, j = (f >> 1) & 1, r = f & 1, n = 8 * j + (ln >> 2);
+        uint32_t word = 0;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int n = 8 * j + g;
-                unsigned short h2[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int k = 2 * t + 8 * r + q, kx = k >> 2, c = k & 3;
-                    h2[q] = (kx < 3 && c < 3) ? __half_as_ushort(__ldg(p.w + ((n * 3 + c) * 3 + ky) * 3 + kx)) : (unsigned short)0;
-                }
-                bfrag[ky][j][r] = (uint32_t)h2[0] | ((uint32_t)h2[1] << 16);
-            }
+        for (int q = 0; q < 2; ++q) {
+            const int k = 2 * (ln & 3) + 8 * r + q, kx = k >> 2, c = k & 3;
+            if (kx < 3 && c < 3) word |= (uint32_t)__half_as_ushort(__ldg(p.w + ((n * 3 + c) * 3 + ky) * 3 + kx)) << (16 * q);
+        }
+        s_bfrag[f][ln] = word;
+    }
     float bias[2][2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -82,8 +80,15 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stem_conv_kernel(const K6Params
     }
     if (tid < K6_ROWS) tile[tid][0] = make_uint2(0u, 0u);
     __syncthreads();
+    uint32_t bfrag[3][2][2];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) bfrag[ky][j][r] = s_bfrag[(ky * 2 + j) * 2 + r][lane];
 
-    // ---- one warp per output row; 4 groups of 16 output pixels ---------------------------------------------------------
+    // ---- one warp per output row; K6_TW / 16 groups of 16 output pixels ---------------------------------------------------------
     const int y = y0 + warp;
     if (y >= p.OH) return;
     __half* orow = p.out + ((size_t)e * p.OH + y) * p.OW * 16;

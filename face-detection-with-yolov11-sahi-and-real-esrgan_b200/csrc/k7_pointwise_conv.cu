@@ -47,7 +47,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 template <int ACT> __device__ __forceinline__ float k7_act(float v, float slope) {
-    if (ACT == 1) return __fdividef(v, 1.0f + __expf(-v));
+    if (ACT == 1) return fast_silu(v);
     if (ACT == 2) return v > 0.f ? v : v * slope;
     return v;
 }
