@@ -11,12 +11,16 @@
 //              them with the STRICT has_match re-check against the growing union box (A.2.5), in float64.
 // The match test is bit-faithful: fp64 divide/compare for sahi (exact on integral boxes), fp32 divide with the
 // result promoted to double for the torchvision rule.
+#include <cooperative_groups.h>
+
 #include "fsd_common.cuh"
 
 namespace fsd {
 
 constexpr int K3_SMEM_MAX_P = 4096;   // segments up to this many boxes live entirely in shared memory
-constexpr int K3_BYTES_PER_BOX = 48;  // keys 8 + vals 4 + box 16 + parent 4 + step 4 + cat 4 + keep 4 + run 4
+constexpr int K3_BYTES_PER_BOX = 48;
+constexpr int K3_CLUSTER = 8;          // CTAs (SMs) that share one large segment
+constexpr int K3_SCRATCH_BYTES = 2048;  // per-segment broadcast area of the cluster kernel (after the box arrays)  // keys 8 + vals 4 + box 16 + parent 4 + step 4 + cat 4 + keep 4 + run 4
 
 struct K3Params {
     const float* boxes; int box_stride;
@@ -109,6 +113,13 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     extern __shared__ __align__(16) uint8_t k3_smem[];
     __shared__ uint32_t s_diag[128];   // 64 rows x 2 halves of in-chunk match bits
     __shared__ int s_klist[64];
+    // staged per chunk so that the inner loops never touch the (possibly L2-resident) workspace: the chunk's 64 boxes,
+    // the boxes of its new keeps, and the removed-bit array of the whole segment (32768 bits)
+    __shared__ float4 s_cbox[64];
+    __shared__ int s_ccat[64];
+    __shared__ float4 s_kbox[64];
+    __shared__ int s_kcat[64];
+    __shared__ uint32_t s_rem[1024];
     __shared__ int s_kcount, s_ktotal, s_stop;
 
     const int s = blockIdx.x;
@@ -171,17 +182,18 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
 
     if (p.type != FSD_NMM) {
         // ---- 2a. greedy scan in chunks of 64 ranks --------------------------------------------------
-        // `step` doubles as the removed-bit array (32 ranks per word)
-        uint32_t* rem = reinterpret_cast<uint32_t*>(step);
+        uint32_t* rem = s_rem;
         for (int i = tid; i < (m + 31) / 32; i += T) rem[i] = 0;
         __syncthreads();
         for (int c0 = 0; c0 < m; c0 += 64) {
             const int cn = min(64, m - c0);
+            if (tid < cn) { s_cbox[tid] = sbox[c0 + tid]; s_ccat[tid] = scat[c0 + tid]; }
+            __syncthreads();
             // in-chunk match bits: 64 threads per row (two warps = two 32-bit halves)
             for (int r = tid >> 6; r < 64; r += T >> 6) {
                 const int q = tid & 63;
                 bool bit = false;
-                if (r < cn && q < cn && q > r) bit = match_pair(sbox[c0 + r], sbox[c0 + q], scat[c0 + r], scat[c0 + q], mc);
+                if (r < cn && q < cn && q > r) bit = match_pair(s_cbox[r], s_cbox[q], s_ccat[r], s_ccat[q], mc);
                 const uint32_t bal = __ballot_sync(0xffffffffu, bit);
                 if ((tid & 31) == 0) s_diag[r * 2 + (q >> 5)] = bal;
             }
@@ -213,16 +225,17 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
             __syncthreads();
             const int kc = s_kcount;
             if (s_stop) break;
+            if (tid < kc) { s_kbox[tid] = s_cbox[s_klist[tid] - c0]; s_kcat[tid] = s_ccat[s_klist[tid] - c0]; }
+            __syncthreads();
             // sweep: every not-yet-removed lower rank against this chunk's new keeps (first match claims it)
             for (int j = c0 + cn + tid; j < m; j += T) {
                 if ((rem[j >> 5] >> (j & 31)) & 1u) continue;
                 const float4 bj = sbox[j];
                 const int cj = scat[j];
                 for (int k = 0; k < kc; ++k) {
-                    const int kr = s_klist[k];
-                    if (match_pair(sbox[kr], bj, scat[kr], cj, mc)) {
+                    if (match_pair(s_kbox[k], bj, s_kcat[k], cj, mc)) {
                         atomicOr(&rem[j >> 5], 1u << (j & 31));
-                        parent[j] = kr;
+                        parent[j] = s_klist[k];
                         break;
                     }
                 }
@@ -340,6 +353,244 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     }
 }
 
+// ---- large segments (> 4096 boxes): one thread-block CLUSTER of 8 CTAs per segment -------------------------------------
+// The single-CTA path is bound by one SM's instruction throughput once a segment no longer fits shared memory (N = 9900:
+// ~27 M pair tests + two 16384-key sorts on one SM = 6.5-8.8 ms).  Here the same algorithm runs on 8 SMs: the arrays live
+// in the L2-resident workspace, every phase that is parallel over ranks (rank sort, sweep, replay sort, fold) is split
+// over the cluster's 4096 threads with cluster.sync() between dependent steps, and only the 64x64 in-chunk resolve stays
+// on CTA 0, which broadcasts the chunk's keeps through a small scratch area.  Arrays written by one CTA and read by
+// another are read with ld.global.cg (L2), never through a possibly stale L1 line.  NMS and GREEDYNMM only (NMM's
+// rank-by-rank walk would pay two cluster barriers per rank and keeps the single-CTA path).
+namespace cg = cooperative_groups;
+
+template <typename T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
+
+struct K3Scratch {  // lives in global memory, one per segment
+    int kcount, ktotal, stop, pad;
+    int klist[64];
+    int kcat[64];
+    float4 kbox[64];
+};
+static_assert(sizeof(K3Scratch) <= K3_SCRATCH_BYTES, "scratch area too small");
+
+__device__ void cluster_bitonic_sort(cg::cluster_group& cluster, uint64_t* keys, uint32_t* vals, int P, int gtid, int TT) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = gtid; t < (P >> 1); t += TT) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = (i & k) == 0;
+                const uint64_t ki = ld_cg(keys + i), kl = ld_cg(keys + l);
+                if ((ki > kl) == up) {
+                    __stcg(keys + i, kl); __stcg(keys + l, ki);
+                    if (vals) { const uint32_t vi = ld_cg(vals + i), vl = ld_cg(vals + l); __stcg(vals + i, vl); __stcg(vals + l, vi); }
+                }
+            }
+            cluster.sync();
+        }
+    }
+}
+
+__global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_merge_cluster_kernel(const K3Params p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ uint32_t s_diag[128];
+    __shared__ float4 s_cbox[64];
+    __shared__ int s_ccat[64];
+    __shared__ float4 s_kbox[64];
+    __shared__ int s_kcat[64];
+    __shared__ int s_klist[64];
+
+    const int s = blockIdx.x / K3_CLUSTER;
+    const int crank = (int)cluster.block_rank();
+    const int tid = threadIdx.x, T = blockDim.x, gtid = crank * T + tid, TT = K3_CLUSTER * T;
+    const int off = p.seg_offsets[s];
+    int n = p.seg_counts ? p.seg_counts[s] : p.seg_cap;
+    n = min(max(n, 0), p.seg_cap);
+    if (n == 0) {  // uniform over the cluster
+        if (gtid == 0) p.keep_count[s] = 0;
+        return;
+    }
+    int P = 64;
+    while (P < n) P <<= 1;
+    uint8_t* base = p.workspace + (size_t)s * p.ws_per_segment;
+    const size_t PP = (size_t)p.P;
+    float4* sbox = reinterpret_cast<float4*>(base);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(base + 16 * PP);
+    uint32_t* vals = reinterpret_cast<uint32_t*>(base + 24 * PP);
+    int* parent = reinterpret_cast<int*>(base + 28 * PP);
+    uint32_t* rem = reinterpret_cast<uint32_t*>(base + 32 * PP);  // removed bits (the `step` array of the NMM path)
+    int* scat = reinterpret_cast<int*>(base + 36 * PP);
+    int* keepr = reinterpret_cast<int*>(base + 40 * PP);
+    int* runs = reinterpret_cast<int*>(base + 44 * PP);
+    K3Scratch* sc = reinterpret_cast<K3Scratch*>(base + (size_t)K3_BYTES_PER_BOX * PP);
+
+    MatchCfg mc;
+    mc.metric = p.metric; mc.cmp_strict = p.cmp_strict; mc.precision = p.precision;
+    mc.class_agnostic = p.class_agnostic || p.cats == nullptr; mc.thr = p.thr;
+
+    // ---- 1. rank ----------------------------------------------------------------------------------------
+    for (int i = gtid; i < P; i += TT) {
+        uint64_t key = ~0ull;
+        uint32_t v = 0xffffffffu;
+        if (i < n) {
+            const float scv = p.scores[(size_t)(off + i) * p.score_stride];
+            const uint32_t tb = p.tie ? (uint32_t)p.tie[(size_t)(off + i) * p.tie_stride] : (uint32_t)i;
+            key = ((uint64_t)score_key_desc(scv) << 32) | tb;
+            v = (uint32_t)i;
+        }
+        __stcg(keys + i, key); __stcg(vals + i, v);
+    }
+    if (gtid == 0) { sc->ktotal = 0; sc->stop = 0; sc->kcount = 0; }
+    cluster.sync();
+    cluster_bitonic_sort(cluster, keys, vals, P, gtid, TT);
+    int m = n;
+    if (p.pre_cap > 0) m = min(m, p.pre_cap);
+    for (int r = gtid; r < n; r += TT) {
+        const int g = off + (int)ld_cg(vals + r);
+        if (r < m) {
+            const float* bp = p.boxes + (size_t)g * p.box_stride;
+            __stcg(sbox + r, make_float4(bp[0], bp[1], bp[2], bp[3]));
+            __stcg(scat + r, p.cats ? p.cats[(size_t)g * p.cat_stride] : 0);
+            __stcg(parent + r, -1);
+            __stcg(runs + r, -1);
+        } else {
+            p.parent[g] = -1;  // cut by the pre-NMS cap
+        }
+    }
+    for (int i = gtid; i < (m + 31) / 32; i += TT) __stcg(rem + i, 0u);
+    cluster.sync();
+
+    // ---- 2. greedy scan in chunks of 64 ranks ---------------------------------------------------------------
+    for (int c0 = 0; c0 < m; c0 += 64) {
+        const int cn = min(64, m - c0);
+        if (crank == 0) {
+            if (tid < cn) { s_cbox[tid] = ld_cg(sbox + c0 + tid); s_ccat[tid] = ld_cg(scat + c0 + tid); }
+            __syncthreads();
+            for (int r = tid >> 6; r < 64; r += T >> 6) {
+                const int q = tid & 63;
+                bool bit = false;
+                if (r < cn && q < cn && q > r) bit = match_pair(s_cbox[r], s_cbox[q], s_ccat[r], s_ccat[q], mc);
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                if ((tid & 31) == 0) s_diag[r * 2 + (q >> 5)] = bal;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const int words = (m + 31) / 32;
+                uint64_t remw = (uint64_t)ld_cg(rem + (c0 >> 5)) | ((uint64_t)(((c0 >> 5) + 1) < words ? ld_cg(rem + (c0 >> 5) + 1) : 0u) << 32);
+                int kc = 0, kt = sc->ktotal, stop = 0;
+                for (int b = 0; b < cn; ++b) {
+                    if ((remw >> b) & 1ull) continue;
+                    if (p.max_keep > 0 && kt + kc >= p.max_keep) { stop = 1; break; }
+                    const int kr = c0 + b;
+                    sc->klist[kc] = kr; sc->kbox[kc] = s_cbox[b]; sc->kcat[kc] = s_ccat[b];
+                    ++kc;
+                    __stcg(parent + kr, kr);
+                    const uint64_t row = (uint64_t)s_diag[2 * b] | ((uint64_t)s_diag[2 * b + 1] << 32);
+                    uint64_t fresh = row & ~remw;
+                    remw |= row;
+                    while (fresh) {
+                        const int q = __ffsll((long long)fresh) - 1;
+                        fresh &= fresh - 1;
+                        __stcg(parent + c0 + q, kr);
+                    }
+                    __stcg(keepr + kt + kc - 1, kr);
+                }
+                __stcg(rem + (c0 >> 5), (uint32_t)remw);
+                if (((c0 >> 5) + 1) < words) __stcg(rem + (c0 >> 5) + 1, (uint32_t)(remw >> 32));
+                sc->kcount = kc; sc->ktotal = kt + kc; sc->stop = stop;
+            }
+        }
+        cluster.sync();  // the chunk's keeps (scratch) and the updated removed bits are visible to every CTA
+        const int kc = ld_cg(&sc->kcount);
+        if (ld_cg(&sc->stop)) break;  // uniform over the cluster
+        if (tid < kc) { s_kbox[tid] = ld_cg(&sc->kbox[tid]); s_kcat[tid] = ld_cg(&sc->kcat[tid]); s_klist[tid] = ld_cg(&sc->klist[tid]); }
+        __syncthreads();
+        for (int j = c0 + cn + gtid; j < m; j += TT) {
+            if ((ld_cg(rem + (j >> 5)) >> (j & 31)) & 1u) continue;
+            const float4 bj = ld_cg(sbox + j);
+            const int cj = ld_cg(scat + j);
+            for (int k = 0; k < kc; ++k) {
+                if (match_pair(s_kbox[k], bj, s_kcat[k], cj, mc)) {
+                    atomicOr(rem + (j >> 5), 1u << (j & 31));
+                    __stcg(parent + j, s_klist[k]);
+                    break;
+                }
+            }
+        }
+        cluster.sync();  // all claims of this chunk are in place before the next chunk is resolved
+    }
+    cluster.sync();
+    const int K = ld_cg(&sc->ktotal);
+
+    // ---- 3. outputs + merge replay --------------------------------------------------------------------------------
+    if (p.parent) {
+        for (int r = gtid; r < m; r += TT) {
+            const int pr = ld_cg(parent + r);
+            p.parent[off + (int)ld_cg(vals + r)] = pr < 0 ? -1 : off + (int)ld_cg(vals + pr);
+        }
+    }
+    if (gtid == 0) p.keep_count[s] = K;
+    if (p.type == FSD_NMS) {
+        for (int i = gtid; i < K; i += TT) {
+            const int kr = ld_cg(keepr + i);
+            const int g = off + (int)ld_cg(vals + kr);
+            p.keep[off + i] = g;
+            const float4 b = ld_cg(sbox + kr);
+            float* mb = p.merged_boxes + (size_t)(off + i) * 4;
+            mb[0] = b.x; mb[1] = b.y; mb[2] = b.z; mb[3] = b.w;
+            p.merged_scores[off + i] = p.scores[(size_t)g * p.score_stride];
+            if (p.merged_cats) p.merged_cats[off + i] = ld_cg(scat + kr);
+        }
+        return;
+    }
+    // replay key = (keep rank : 15 bits | append sequence : 30 bits | candidate rank : 15 bits), ascending
+    for (int r = gtid; r < P; r += TT) {
+        uint64_t key = ~0ull;
+        if (r < m) {
+            const int pr = ld_cg(parent + r);
+            if (pr >= 0 && pr != r) key = ((uint64_t)pr << 45) | ((uint64_t)r << 15) | (uint64_t)r;
+        }
+        __stcg(keys + r, key);
+    }
+    cluster.sync();
+    cluster_bitonic_sort(cluster, keys, nullptr, P, gtid, TT);
+    for (int q = gtid; q < P; q += TT) {
+        const uint64_t key = ld_cg(keys + q);
+        if (key == ~0ull) continue;
+        const int pr = (int)(key >> 45);
+        if (q == 0 || (int)(ld_cg(keys + q - 1) >> 45) != pr) __stcg(runs + pr, q);
+    }
+    cluster.sync();
+    for (int i = gtid; i < K; i += TT) {
+        const int kr = ld_cg(keepr + i);
+        const int g = off + (int)ld_cg(vals + kr);
+        const float4 b = ld_cg(sbox + kr);
+        double kb[4] = {(double)b.x, (double)b.y, (double)b.z, (double)b.w};
+        const float kscore = p.scores[(size_t)g * p.score_stride];
+        int kcat = ld_cg(scat + kr);
+        int q = ld_cg(runs + kr);
+        if (q >= 0) {
+            for (; q < P; ++q) {
+                const uint64_t key = ld_cg(keys + q);
+                if (key == ~0ull || (int)(key >> 45) != kr) break;
+                const int cr = (int)(key & 32767ull);
+                const float4 c = ld_cg(sbox + cr);
+                if (has_match_f64(kb, c, p.metric, p.thr)) {
+                    kb[0] = fmin(kb[0], (double)c.x); kb[1] = fmin(kb[1], (double)c.y);
+                    kb[2] = fmax(kb[2], (double)c.z); kb[3] = fmax(kb[3], (double)c.w);
+                    const float cscore = p.scores[(size_t)(off + (int)ld_cg(vals + cr)) * p.score_stride];
+                    if (!(kscore > cscore)) kcat = ld_cg(scat + cr);
+                }
+            }
+        }
+        p.keep[off + i] = g;
+        float* mb = p.merged_boxes + (size_t)(off + i) * 4;
+        mb[0] = (float)kb[0]; mb[1] = (float)kb[1]; mb[2] = (float)kb[2]; mb[3] = (float)kb[3];
+        p.merged_scores[off + i] = kscore;
+        if (p.merged_cats) p.merged_cats[off + i] = kcat;
+    }
+}
+
 static int pow2_at_least(int n) {
     int P = 64;
     while (P < n) P <<= 1;
@@ -353,7 +604,7 @@ using namespace fsd;
 extern "C" int64_t fsd_merge_workspace_bytes(int64_t N, int S, int max_segment) {
     (void)N;
     if (max_segment <= K3_SMEM_MAX_P) return 256;  // unused, but keep the pointer non-null for callers
-    return (int64_t)S * pow2_at_least(max_segment) * K3_BYTES_PER_BOX + 256;
+    return (int64_t)S * ((int64_t)pow2_at_least(max_segment) * K3_BYTES_PER_BOX + K3_SCRATCH_BYTES) + 256;
 }
 
 extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, const float* scores, int score_stride,
@@ -387,7 +638,7 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     p.P = pow2_at_least(max_segment);
     p.use_global = p.P > K3_SMEM_MAX_P;
     p.workspace = reinterpret_cast<uint8_t*>(workspace);
-    p.ws_per_segment = (size_t)p.P * K3_BYTES_PER_BOX;
+    p.ws_per_segment = (size_t)p.P * K3_BYTES_PER_BOX + K3_SCRATCH_BYTES;
     if (p.use_global) {
         FSD_CHECK_ARG(workspace && workspace_bytes >= fsd_merge_workspace_bytes(0, S, max_segment),
                       "fsd_merge: workspace too small (%lld bytes needed)", (long long)fsd_merge_workspace_bytes(0, S, max_segment));
@@ -397,6 +648,13 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     const int threads = p.P <= 256 ? 128 : (p.P <= 1024 ? 256 : 512);
     FSD_CUDA(cudaSetDevice(h->device));
     FSD_CUDA(cudaFuncSetAttribute(k3_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_MAX_P * K3_BYTES_PER_BOX));
+    if (p.use_global && type != FSD_NMM && !getenv("FSD_K3_SINGLE_CTA")) {
+        // large segments: a cluster of 8 CTAs per segment (k3_merge_cluster_kernel)
+        k3_merge_cluster_kernel<<<S * K3_CLUSTER, 512, 0, (cudaStream_t)stream_>>>(p);
+        FSD_CUDA(cudaGetLastError());
+        h->launches += 1;
+        return FSD_OK;
+    }
     k3_merge_kernel<<<S, threads, smem, (cudaStream_t)stream_>>>(p);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;

@@ -12,6 +12,7 @@ CASES = [  # H, W, slice, overlap, imgsz, conf, postprocess, metric
     (384, 512, 256, 0.2, 512, 0.5, "GREEDYNMM", "IOS"),
     (384, 512, 256, 0.2, 512, 0.05, "NMS", "IOS"),        # evaluator settings: low confidence -> max_det pressure
     (300, 500, 320, 0.25, 640, 0.3, "NMM", "IOU"),         # non-square letterbox padding, NMM
+    (300, 500, 200, 0.2, 320, 0.4, "GREEDYNMM", "IOU"),    # 1.6x slices (SAHI's 640 -> 1024 ratio): Kernel 1's sixteenths path
 ]
 
 

@@ -207,3 +207,29 @@ def test_capacity_limit_is_an_error(cuda_device):
     t = torch.zeros((8, 6), device=cuda_device)
     with pytest.raises(cabi.FsdError):
         ops.merge_segments(t, torch.zeros(1, dtype=torch.int32, device=cuda_device), None, 40000)
+
+
+@pytest.mark.parametrize("ptype,metric,prec", [("NMS", "IOU", "fp64"), ("GREEDYNMM", "IOS", "fp64"), ("GREEDYNMM", "IOU", "fp64"),
+                                               ("NMS", "IOU", "fp32")])
+def test_cluster_path_equals_single_cta_path(cuda_device, ptype, metric, prec, monkeypatch):
+    """Segments above 4096 boxes run on a cluster of 8 CTAs (k3_merge_cluster_kernel); keeps, merge parents, merged boxes,
+    scores and categories must be identical to the single-CTA kernel on the same input — ragged segment sizes in one
+    launch (empty, tiny, just above the shared-memory limit, config 3's 9900), two categories, class-aware."""
+    rng = np.random.default_rng(77)
+    segs = []
+    for n in (0, 5, 4097, 9900, 700):
+        seg = sahi_like_boxes(rng, max(3, n // 2), dup=(1, 4), size=(10, 60), canvas=(2560, 1440))[:n] if n else np.zeros((0, 6), np.float32)
+        if len(seg):
+            seg[:, 5] = rng.integers(0, 2, len(seg))
+        segs.append(seg.astype(np.float32))
+    kw = dict(merge_type=ptype, metric=metric, thr=0.5, precision=prec, class_agnostic=False)
+    if prec == "fp32":
+        kw.update(cmp_strict=True, max_keep=300, pre_cap=30000)
+    multi = run_kernel(cuda_device, segs, **kw)
+    monkeypatch.setenv("FSD_K3_SINGLE_CTA", "1")
+    single = run_kernel(cuda_device, segs, **kw)
+    for a, b, seg in zip(multi, single, segs):
+        assert a["keep"] == b["keep"]
+        assert np.array_equal(a["parent"], b["parent"])
+        assert np.array_equal(a["boxes"], b["boxes"]) and np.array_equal(a["scores"], b["scores"]) and np.array_equal(a["cats"], b["cats"])
+    assert len(multi[3]["keep"]) > 300 or prec == "fp32"
