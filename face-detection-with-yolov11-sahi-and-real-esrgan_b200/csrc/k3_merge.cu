@@ -373,9 +373,38 @@ struct K3Scratch {  // lives in global memory, one per segment
 };
 static_assert(sizeof(K3Scratch) <= K3_SCRATCH_BYTES, "scratch area too small");
 
-__device__ void cluster_bitonic_sort(cg::cluster_group& cluster, uint64_t* keys, uint32_t* vals, int P, int gtid, int TT) {
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
+// Bitonic sort of P keys (P >= 8192, power of two) by the whole cluster.  Compare-exchange stages whose partner distance
+// j is smaller than the per-CTA block B = P / 8 never leave a block, so each CTA runs them on its block in shared memory
+// with block barriers only; just the log2(P/B) * (log2(P/B) + 1) / 2 = 6 stages with j >= B (for P = 16384) go through
+// L2 with a cluster barrier each — about 10 cluster barriers per sort instead of 105.
+__device__ void cluster_bitonic_sort(cg::cluster_group& cluster, uint64_t* keys, uint32_t* vals, int P, int crank, int tid, int T,
+                                     uint64_t* lk, uint32_t* lv) {
+    const int B = P / K3_CLUSTER, base = crank * B;
+    const int gtid = crank * T + tid, TT = K3_CLUSTER * T;
+    auto local_stages = [&](int k_first, int k_last) {  // all stages (k, j) with k_first <= k <= k_last and j < B
+        for (int i = tid; i < B; i += T) { lk[i] = ld_cg(keys + base + i); if (vals) lv[i] = ld_cg(vals + base + i); }
+        __syncthreads();
+        for (int k = k_first; k <= k_last; k <<= 1) {
+            for (int j = min(k >> 1, B >> 1); j > 0; j >>= 1) {
+                for (int t = tid; t < (B >> 1); t += T) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const bool up = ((base + i) & k) == 0;
+                    const uint64_t ki = lk[i], kl = lk[l];
+                    if ((ki > kl) == up) {
+                        lk[i] = kl; lk[l] = ki;
+                        if (vals) { const uint32_t vi = lv[i]; lv[i] = lv[l]; lv[l] = vi; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = tid; i < B; i += T) { __stcg(keys + base + i, lk[i]); if (vals) __stcg(vals + base + i, lv[i]); }
+    };
+    local_stages(2, B);
+    cluster.sync();
+    for (int k = 2 * B; k <= P; k <<= 1) {
+        for (int j = k >> 1; j >= B; j >>= 1) {
             for (int t = gtid; t < (P >> 1); t += TT) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int l = i | j;
@@ -388,6 +417,8 @@ __device__ void cluster_bitonic_sort(cg::cluster_group& cluster, uint64_t* keys,
             }
             cluster.sync();
         }
+        local_stages(k, k);
+        cluster.sync();
     }
 }
 
@@ -399,6 +430,7 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     __shared__ float4 s_kbox[64];
     __shared__ int s_kcat[64];
     __shared__ int s_klist[64];
+    extern __shared__ __align__(16) uint8_t k3c_smem[];  // sort block: P/8 keys (8 B) + values (4 B)
 
     const int s = blockIdx.x / K3_CLUSTER;
     const int crank = (int)cluster.block_rank();
@@ -442,7 +474,9 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     }
     if (gtid == 0) { sc->ktotal = 0; sc->stop = 0; sc->kcount = 0; }
     cluster.sync();
-    cluster_bitonic_sort(cluster, keys, vals, P, gtid, TT);
+    uint64_t* lk = reinterpret_cast<uint64_t*>(k3c_smem);
+    uint32_t* lv = reinterpret_cast<uint32_t*>(k3c_smem + (size_t)(p.P / K3_CLUSTER) * 8);
+    cluster_bitonic_sort(cluster, keys, vals, P, crank, tid, T, lk, lv);
     int m = n;
     if (p.pre_cap > 0) m = min(m, p.pre_cap);
     for (int r = gtid; r < n; r += TT) {
@@ -553,7 +587,7 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
         __stcg(keys + r, key);
     }
     cluster.sync();
-    cluster_bitonic_sort(cluster, keys, nullptr, P, gtid, TT);
+    cluster_bitonic_sort(cluster, keys, nullptr, P, crank, tid, T, lk, lv);
     for (int q = gtid; q < P; q += TT) {
         const uint64_t key = ld_cg(keys + q);
         if (key == ~0ull) continue;
@@ -650,7 +684,9 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     FSD_CUDA(cudaFuncSetAttribute(k3_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_MAX_P * K3_BYTES_PER_BOX));
     if (p.use_global && type != FSD_NMM && !getenv("FSD_K3_SINGLE_CTA")) {
         // large segments: a cluster of 8 CTAs per segment (k3_merge_cluster_kernel)
-        k3_merge_cluster_kernel<<<S * K3_CLUSTER, 512, 0, (cudaStream_t)stream_>>>(p);
+        const size_t csmem = (size_t)(p.P / K3_CLUSTER) * 12;
+        FSD_CUDA(cudaFuncSetAttribute(k3_merge_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        k3_merge_cluster_kernel<<<S * K3_CLUSTER, 512, csmem, (cudaStream_t)stream_>>>(p);
         FSD_CUDA(cudaGetLastError());
         h->launches += 1;
         return FSD_OK;
