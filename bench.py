@@ -242,7 +242,10 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "bytes_per_launch": k1_bytes, "launch_ms": k1_ms, "launches_timed": len(sl),
-                "timing": "CUDA events recorded inside libfsd_b200 around each launch (fsd_kernel_timing_*)"}
+                "timing": "CUDA events recorded inside libfsd_b200 around each launch (fsd_kernel_timing_*)",
+                "note": "Kernel 1 is the HBM-bound kernel SURVEY 8(d) defines the per-image algorithmic bytes for; by share of the "
+                        "step the largest hand-written kernel is the conv epilogue (other_kernels[0]); the step itself is bound by "
+                        "the PyTorch convolutions (profiles/r1_launches_bench_b32_end.txt)"}
     # the hand-written kernel with the largest share of the step: the conv epilogue (bias + SiLU [+ residual] -> concat slot)
     if k5:
         k5_bytes, k5_ms = sum(u for u, _ in k5), sum(t for _, t in k5)
