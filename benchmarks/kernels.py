@@ -66,11 +66,13 @@ def report(name, nbytes, fn, **extra):
 
 
 def bench_ref():
+    """The two reference points of this box: torch's device copy (the definition of MEASURED_PEAKS.hbm_gbs: bf16, read + write
+    bytes) and a write-only fill (what a >= 94 %-write kernel like K1 competes with)."""
     n = 1 << 30
-    a = torch.empty(n, dtype=torch.uint8, device=dev)
-    b = torch.empty(n, dtype=torch.uint8, device=dev)
-    report("torch copy_ 1 GiB (read+write)", 2 * n, lambda: b.copy_(a))
-    report("torch fill_ 1 GiB (write only)", n, lambda: b.fill_(7))
+    a = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    b = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    report("torch copy_ 1 Gi bf16 (read+write)", 4 * n, lambda: b.copy_(a))
+    report("torch fill_ 2 GiB (write only)", 2 * n, lambda: b.fill_(7))
 
 
 def bench_k1():
