@@ -302,8 +302,9 @@ def main():
         e2e = {"value": world * e_steps * B / dt, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3,
                "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps,
                "host_ms_per_step": {k: round(1e3 * v / e_steps, 2) for k, v in host_stats.items()},
-               "api": "fsd_b200.api.predict_stream (pinned host images in, PredictionResult objects out; 2 batches in flight: "
-                      "H2D of batch i+1 and D2H + object construction of batch i-1 overlap the device work of batch i)"}
+               "api": "fsd_b200.api.predict_stream (pinned host images in, PredictionResult objects out; 3 batches in flight: H2D of "
+                      "batch i+1 on a copy stream and D2H + object construction of batch i-1 overlap the device work of batch i on "
+                      "one compute stream; backbone chunks replayed as CUDA graphs)"}
 
     # ---- the one collective: all-gather of detections for evaluation (after the timed region) -------------
     gathered = None

@@ -49,6 +49,9 @@ class _Slot:
         self.pool = ops.ImagePool(n, h, w, device)
         self.stream = stream
         self.event = torch.cuda.Event()
+        self.uploaded = torch.cuda.Event()
+        self.t0 = torch.cuda.Event(enable_timing=True)   # device-side start / end of this batch's compute (stats only)
+        self.t1 = torch.cuda.Event(enable_timing=True)
         self.h_off = torch.empty((n + 1,), dtype=torch.int32).pin_memory()
         self.h_rows = torch.empty((rows_cap, ops.ROW), dtype=torch.float32).pin_memory()
         self.h_cmax = torch.empty((1,), dtype=torch.int32).pin_memory()
@@ -59,20 +62,25 @@ class _Slot:
 def predict_stream(batches, detection_model, slice_height: int, slice_width: int, overlap_height_ratio: float = 0.2,
                    overlap_width_ratio: float = 0.2, perform_standard_pred: bool = True,
                    postprocess_type: str = "GREEDYNMM", postprocess_match_metric: str = "IOS",
-                   postprocess_match_threshold: float = 0.5, postprocess_class_agnostic: bool = False, depth: int = 2,
+                   postprocess_match_threshold: float = 0.5, postprocess_class_agnostic: bool = False, depth: int = 3,
                    rows_per_image_hint: int = 256, stats: dict | None = None, use_graphs: bool = True):
     """Pipelined batch prediction: yields one list[PredictionResult] per batch of `batches` (an iterable of equal-length
     lists of same-sized HWC uint8 images, ideally pinned CPU tensors), in order.
 
-    `depth` batches are in flight: the H2D upload of batch i+1 and the D2H + result-object construction of batch i-1
-    overlap with the device pipeline of batch i (each batch on its own CUDA stream and image pool).
+    `depth` batches are in flight: the H2D upload of batch i+1 (copy stream) and the D2H + result-object construction of
+    batch i-1 (host) overlap with the device pipeline of batch i (one compute stream; each batch has its own image pool).
+    depth = 3 by default: under a bandwidth-saturating compute stream the 151 MB upload of a C2 batch takes ~18 ms instead
+    of 3 ms, and with only two batches in flight it was issued too late to finish before the compute stream needed it
+    (4.5 ms idle per batch, measured with `stats`).
     `stats`, if given, accumulates host seconds: "enqueue" (uploads + kernel launches), "wait" (blocked on the device),
-    "build" (result-object construction)."""
+    "build" (result-object construction), "device": seconds between the first and last kernel of each batch on the
+    compute stream, and "device_idle": seconds between one batch's last and the next batch's first kernel (CUDA events)."""
     import time as _time
 
     if stats is not None:
-        for key in ("enqueue", "wait", "build"):
+        for key in ("enqueue", "wait", "build", "device", "device_idle"):
             stats.setdefault(key, 0.0)
+    prev_t1 = [None]
     eng = detection_model.engine()
     eng.truncate = True
     graphs_before = eng.use_graphs
@@ -83,6 +91,11 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
         t_a = _time.perf_counter()
         slot.event.synchronize()
         t_b = _time.perf_counter()
+        if stats is not None:
+            stats["device"] += slot.t0.elapsed_time(slot.t1) * 1e-3
+            if prev_t1[0] is not None:  # compute-stream gap between the previous batch's last and this batch's first kernel
+                stats["device_idle"] += prev_t1[0].elapsed_time(slot.t0) * 1e-3
+            prev_t1[0] = slot.t1
         n = slot.pool.n
         off = slot.h_off.numpy().copy()
         total = int(off[-1])
@@ -119,11 +132,14 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
     for images in batches:
         n, (h, w) = len(images), images[0].shape[:2]
         if slots is None:
-            # the streams live on the engine: its captured backbone graphs and static buffers are keyed by stream
+            # ONE compute stream for every batch (kernels of two batches never interleave: the conv -> epilogue pairs keep
+            # their L2 reuse, and one set of captured graphs / static buffers serves all slots) + ONE copy stream on which
+            # the next batch's images are uploaded while the current batch computes.  The streams live on the engine: its
+            # captured backbone graphs are keyed by stream.
             streams = eng.__dict__.setdefault("_pipeline_streams", [])
-            while len(streams) < depth:
+            while len(streams) < 2:
                 streams.append(torch.cuda.Stream(device=eng.device))
-            slots = [_Slot(n, h, w, eng.device, n * rows_per_image_hint, streams[j]) for j in range(depth)]
+            slots = [_Slot(n, h, w, eng.device, n * rows_per_image_hint, streams[0]) for j in range(depth)]
         slot = slots[k % depth]
         k += 1
         if slot.dev is not None:
@@ -132,9 +148,15 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
             raise ValueError("predict_stream needs batches of one common size")
         slot.images = images
         t_e = _time.perf_counter()
-        with torch.cuda.stream(slot.stream):
+        with torch.cuda.stream(streams[1]):  # this slot's pool is free: finish() waited for the batch that last read it
             for i, im in enumerate(images):
                 slot.pool.upload(i, im, non_blocking=True)
+            slot.uploaded.record(streams[1])
+        with torch.cuda.stream(slot.stream):
+            slot.stream.wait_event(slot.uploaded)
+            if stats is not None:  # fresh events per batch: the previous batch's pair is still needed for the idle gap
+                slot.t0, slot.t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                slot.t0.record(slot.stream)
             dev = eng.detect(slot.pool, slice_height, slice_width, overlap_height_ratio, overlap_width_ratio,
                              perform_standard_pred, postprocess_type, postprocess_match_metric,
                              postprocess_match_threshold, postprocess_class_agnostic, to_host=False)
@@ -142,6 +164,8 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
             slot.h_rows.copy_(dev["rows"][: slot.h_rows.shape[0]], non_blocking=True)
             cmax = dev["count_s"].max() if dev["count_f"] is None else torch.maximum(dev["count_s"].max(), dev["count_f"].max())
             slot.h_cmax.copy_(cmax.reshape(1), non_blocking=True)
+            if stats is not None:
+                slot.t1.record(slot.stream)
             slot.event.record(slot.stream)
         slot.dev = dev
         pending.append(slot)

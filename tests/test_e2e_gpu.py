@@ -167,7 +167,7 @@ def test_predict_stream_equals_batch_api(cuda_device, use_graphs):
                               stats=stats, use_graphs=use_graphs))
     eng = model.engine()
     assert eng.use_graphs is False and (eng.replayed_launches > 0) == use_graphs or not use_graphs
-    assert set(stats) == {"enqueue", "wait", "build"} and all(v >= 0 for v in stats.values())
+    assert set(stats) == {"enqueue", "wait", "build", "device", "device_idle"} and all(v >= 0 for v in stats.values())
     assert len(got) == len(want)
     for gb, wb in zip(got, want):
         for gr, wr in zip(gb, wb):
