@@ -63,13 +63,15 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
                    overlap_width_ratio: float = 0.2, perform_standard_pred: bool = True,
                    postprocess_type: str = "GREEDYNMM", postprocess_match_metric: str = "IOS",
                    postprocess_match_threshold: float = 0.5, postprocess_class_agnostic: bool = False, depth: int = 3,
-                   rows_per_image_hint: int = 256, stats: dict | None = None, use_graphs: bool = True):
+                   rows_per_image_hint: int = 256, stats: dict | None = None, use_graphs: bool = True,
+                   overlap_post: bool = True):
     """Pipelined batch prediction: yields one list[PredictionResult] per batch of `batches` (an iterable of equal-length
     lists of same-sized HWC uint8 images, ideally pinned CPU tensors), in order.
 
     `depth` batches are in flight: the H2D upload of batch i+1 (copy stream) and the D2H + result-object construction of
     batch i-1 (host) overlap with the device pipeline of batch i (one compute stream; each batch has its own image pool).
-    depth = 3 by default: under a bandwidth-saturating compute stream the 151 MB upload of a C2 batch takes ~18 ms instead
+    With `overlap_post` the latency-bound post-processing kernels (stage-1 NMS, merge, attach: ~2 ms on 32-384 CTAs) run on
+    a third stream, overlapping the full-image pass and the next batch's backbone.  depth = 3 by default: under a bandwidth-saturating compute stream the 151 MB upload of a C2 batch takes ~18 ms instead
     of 3 ms, and with only two batches in flight it was issued too late to finish before the compute stream needed it
     (4.5 ms idle per batch, measured with `stats`).
     `stats`, if given, accumulates host seconds: "enqueue" (uploads + kernel launches), "wait" (blocked on the device),
@@ -92,9 +94,10 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
         slot.event.synchronize()
         t_b = _time.perf_counter()
         if stats is not None:
+            slot.t1.synchronize()
             stats["device"] += slot.t0.elapsed_time(slot.t1) * 1e-3
             if prev_t1[0] is not None:  # compute-stream gap between the previous batch's last and this batch's first kernel
-                stats["device_idle"] += prev_t1[0].elapsed_time(slot.t0) * 1e-3
+                stats["device_idle"] += max(0.0, prev_t1[0].elapsed_time(slot.t0)) * 1e-3
             prev_t1[0] = slot.t1
         n = slot.pool.n
         off = slot.h_off.numpy().copy()
@@ -137,7 +140,7 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
             # the next batch's images are uploaded while the current batch computes.  The streams live on the engine: its
             # captured backbone graphs are keyed by stream.
             streams = eng.__dict__.setdefault("_pipeline_streams", [])
-            while len(streams) < 2:
+            while len(streams) < 3:  # compute, copy (uploads), post (NMS / merge / attach / D2H of the previous batch)
                 streams.append(torch.cuda.Stream(device=eng.device))
             slots = [_Slot(n, h, w, eng.device, n * rows_per_image_hint, streams[0]) for j in range(depth)]
         slot = slots[k % depth]
@@ -159,14 +162,16 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
                 slot.t0.record(slot.stream)
             dev = eng.detect(slot.pool, slice_height, slice_width, overlap_height_ratio, overlap_width_ratio,
                              perform_standard_pred, postprocess_type, postprocess_match_metric,
-                             postprocess_match_threshold, postprocess_class_agnostic, to_host=False)
+                             postprocess_match_threshold, postprocess_class_agnostic, to_host=False,
+                             post_stream=streams[2] if overlap_post else None)
+            if stats is not None:
+                slot.t1.record(slot.stream)  # end of this batch's work on the compute stream
+        with torch.cuda.stream(dev.get("stream", slot.stream)):  # results live on the post stream
             slot.h_off.copy_(dev["offsets"], non_blocking=True)
             slot.h_rows.copy_(dev["rows"][: slot.h_rows.shape[0]], non_blocking=True)
             cmax = dev["count_s"].max() if dev["count_f"] is None else torch.maximum(dev["count_s"].max(), dev["count_f"].max())
             slot.h_cmax.copy_(cmax.reshape(1), non_blocking=True)
-            if stats is not None:
-                slot.t1.record(slot.stream)
-            slot.event.record(slot.stream)
+            slot.event.record(dev.get("stream", slot.stream))
         slot.dev = dev
         pending.append(slot)
         if stats is not None:

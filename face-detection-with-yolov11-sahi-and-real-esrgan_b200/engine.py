@@ -10,6 +10,8 @@ memory, streams and the conv backbone only.
 """
 from __future__ import annotations
 
+import contextlib
+
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -188,8 +190,13 @@ class SlicedFaceDetector:
     def detect(self, pool: ops.ImagePool, slice_h: int, slice_w: int, ov_h: float = 0.2, ov_w: float = 0.2,
                perform_standard_pred: bool = True, postprocess_type: str = "GREEDYNMM", match_metric: str = "IOS",
                match_threshold: float = 0.5, class_agnostic: bool = False, want_stage1: bool = False,
-               to_host: bool = True):
-        """Sliced detection of every image in `pool`; returns a DetectionBatch (or the device tensors if not to_host)."""
+               to_host: bool = True, post_stream: Optional[torch.cuda.Stream] = None):
+        """Sliced detection of every image in `pool`; returns a DetectionBatch (or the device tensors if not to_host).
+
+        With `post_stream` (only with to_host=False) everything after the network — stage-1 NMS, finalize, stage-2 merge,
+        key-point attach, packing: latency-bound kernels on 32-384 CTAs — is enqueued on that stream behind events, so it
+        overlaps the backbone of the full-image pass and of the NEXT batch on the calling stream.  The returned tensors
+        then belong to `post_stream` (the dict carries it under "stream")."""
         if postprocess_type not in ("NMS", "GREEDYNMM", "NMM"):
             raise ValueError(f"postprocess_type should be one of ['GREEDYNMM', 'NMM', 'NMS', 'LSNMS'] but given as {postprocess_type}")
         N, dev = pool.n, self.device
@@ -204,12 +211,29 @@ class SlicedFaceDetector:
                                        out=self._network_input("slices", (E, 3, plan.g_slice["out_h"], plan.g_slice["out_w"])))
             self._forward_entries("slices", x_s, cand_s, count_s)
             del x_s
-            s1 = self._stage1(cand_s, count_s, t["seg_s"])
-            det = torch.empty((N * t["det_cap"], ROW), dtype=torch.float32, device=dev)
-            dcount = torch.zeros((N,), dtype=torch.int32, device=dev)
-            ops.finalize_dets(cand_s, s1["keep"], s1["keep_count"], t["geo_s"], t["fgeo_s"], t["grange_s"], t["goff"],
-                              det, dcount, t["det_cap"], self.truncate)
+            main = torch.cuda.current_stream(dev)
+            post = post_stream if (post_stream is not None and not to_host) else None
+
+            def on_post(*tensors):
+                """Switch to the post stream behind everything enqueued so far; the caching allocator must not recycle
+                `tensors` (allocated on the main stream) until the post stream is done with them."""
+                if post is None:
+                    return contextlib.nullcontext()
+                ev = torch.cuda.Event()
+                ev.record(main)
+                post.wait_event(ev)
+                for x in tensors:
+                    x.record_stream(post)
+                return torch.cuda.stream(post)
+
+            with on_post(cand_s, count_s):
+                s1 = self._stage1(cand_s, count_s, t["seg_s"])
+                det = torch.empty((N * t["det_cap"], ROW), dtype=torch.float32, device=dev)
+                dcount = torch.zeros((N,), dtype=torch.int32, device=dev)
+                ops.finalize_dets(cand_s, s1["keep"], s1["keep_count"], t["geo_s"], t["fgeo_s"], t["grange_s"], t["goff"],
+                                  det, dcount, t["det_cap"], self.truncate)
             count_f = None
+            cand_f = None
             if plan.g_full is not None:
                 cand_f = torch.empty((N, self.cap, ROW), dtype=torch.float32, device=dev)
                 count_f = torch.empty((N,), dtype=torch.int32, device=dev)
@@ -218,16 +242,21 @@ class SlicedFaceDetector:
                                            out=self._network_input("full", (N, 3, plan.g_full["out_h"], plan.g_full["out_w"])))
                 self._forward_entries("full", x_f, cand_f, count_f)
                 del x_f
-                s1f = self._stage1(cand_f, count_f, t["seg_f"])
-                ops.finalize_dets(cand_f, s1f["keep"], s1f["keep_count"], t["geo_f"], t["fgeo_f"], t["grange_f"],
-                                  t["goff"], det, dcount, t["det_cap"], self.truncate)
-            # stage 2: cross-slice merge per image (skipped by the reference when an image has <= 1 prediction:
-            # a single box is its own keep, so running it is equivalent)
-            s2 = ops.merge_segments(det, t["goff"], dcount, t["det_cap"], merge_type=postprocess_type,
-                                    metric=match_metric, thr=match_threshold, cmp_strict=False, precision="fp64",
-                                    class_agnostic=True, want_parent=False)  # one class ("face") on this path
-            src = ops.attach_keypoints(s2["boxes"], t["goff"], s2["keep_count"], det, t["goff"], dcount)
-            rows, offsets = ops.pack_results(det, t["goff"], s2, src)
+            with on_post(*([cand_f, count_f] if cand_f is not None else [])):
+                if cand_f is not None:
+                    s1f = self._stage1(cand_f, count_f, t["seg_f"])
+                    ops.finalize_dets(cand_f, s1f["keep"], s1f["keep_count"], t["geo_f"], t["fgeo_f"], t["grange_f"],
+                                      t["goff"], det, dcount, t["det_cap"], self.truncate)
+                # stage 2: cross-slice merge per image (skipped by the reference when an image has <= 1 prediction:
+                # a single box is its own keep, so running it is equivalent)
+                s2 = ops.merge_segments(det, t["goff"], dcount, t["det_cap"], merge_type=postprocess_type,
+                                        metric=match_metric, thr=match_threshold, cmp_strict=False, precision="fp64",
+                                        class_agnostic=True, want_parent=False)  # one class ("face") on this path
+                src = ops.attach_keypoints(s2["boxes"], t["goff"], s2["keep_count"], det, t["goff"], dcount)
+                rows, offsets = ops.pack_results(det, t["goff"], s2, src)
+            if post is not None:
+                return dict(rows=rows, offsets=offsets, det=det, dcount=dcount, count_s=count_s, count_f=count_f, plan=plan,
+                            stream=post)
             if not to_host:
                 return dict(rows=rows, offsets=offsets, det=det, dcount=dcount, count_s=count_s, count_f=count_f, plan=plan)
             # ---- the only device->host traffic of the batch: counts, then exactly the packed rows

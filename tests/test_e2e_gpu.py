@@ -149,8 +149,8 @@ def test_batch_api_equals_single_image_api(cuda_device):
     assert n_all > 0 and n_kp >= n_all // 2
 
 
-@pytest.mark.parametrize("use_graphs", [True, False])
-def test_predict_stream_equals_batch_api(cuda_device, use_graphs):
+@pytest.mark.parametrize("use_graphs,overlap_post,depth", [(True, True, 3), (False, True, 2), (True, False, 2), (False, False, 1)])
+def test_predict_stream_equals_batch_api(cuda_device, use_graphs, overlap_post, depth):
     """The pipelined API (2 batches in flight on separate streams; backbone chunks replayed as CUDA graphs over static
     per-stream buffers, or launched eagerly) returns exactly what the synchronous batch call returns."""
     from fsd_b200.api import get_sliced_prediction_batch, predict_stream
@@ -160,11 +160,11 @@ def test_predict_stream_equals_batch_api(cuda_device, use_graphs):
 
     model = YOLOv11PoseDetectionModel(model=YOLO("random-init"), confidence_threshold=0.4, device="cuda:0", image_size=512)
     imgs = [torch.from_numpy(make_image(300 + i, 384, 512)[0]).pin_memory() for i in range(12)]
-    groups = [imgs[0:4], imgs[4:8], imgs[8:12], imgs[0:4]]
+    groups = [imgs[0:4], imgs[4:8], imgs[8:12], imgs[0:4], imgs[4:8], imgs[8:12]]
     want = [get_sliced_prediction_batch(g, model, 256, 256, 0.2, 0.2) for g in groups]
     stats = {}
-    got = list(predict_stream(iter(groups), model, 256, 256, 0.2, 0.2, depth=2, rows_per_image_hint=8,  # tiny window: exercises the refetch
-                              stats=stats, use_graphs=use_graphs))
+    got = list(predict_stream(iter(groups), model, 256, 256, 0.2, 0.2, depth=depth, rows_per_image_hint=8,  # tiny window: exercises the refetch
+                              stats=stats, use_graphs=use_graphs, overlap_post=overlap_post))
     eng = model.engine()
     assert eng.use_graphs is False and (eng.replayed_launches > 0) == use_graphs or not use_graphs
     assert set(stats) == {"enqueue", "wait", "build", "device", "device_idle"} and all(v >= 0 for v in stats.values())
