@@ -46,7 +46,9 @@ def get_sliced_prediction_batch(images: Sequence, detection_model, slice_height:
 
 class _Slot:
     def __init__(self, n, h, w, device, rows_cap, stream):
-        self.pool = ops.ImagePool(n, h, w, device)
+        self.shape, self.device = (n, h, w), device
+        self.own_pool = None   # upload target, allocated on first use (device-resident batches bring their own pool)
+        self.pool = None       # the pool the batch in flight reads
         self.stream = stream
         self.event = torch.cuda.Event()
         self.uploaded = torch.cuda.Event()
@@ -66,7 +68,8 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
                    rows_per_image_hint: int = 256, stats: dict | None = None, use_graphs: bool = True,
                    overlap_post: bool = True):
     """Pipelined batch prediction: yields one list[PredictionResult] per batch of `batches` (an iterable of equal-length
-    lists of same-sized HWC uint8 images, ideally pinned CPU tensors), in order.
+    lists of same-sized HWC uint8 images, ideally pinned CPU tensors — or of `ops.ImagePool`s already resident on the
+    device), in order.
 
     `depth` batches are in flight: the H2D upload of batch i+1 (copy stream) and the D2H + result-object construction of
     batch i-1 (host) overlap with the device pipeline of batch i (one compute stream; each batch has its own image pool).
@@ -133,7 +136,8 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
         return out
 
     for images in batches:
-        n, (h, w) = len(images), images[0].shape[:2]
+        resident = isinstance(images, ops.ImagePool)
+        n, h, w = (images.n, images.h, images.w) if resident else (len(images), *images[0].shape[:2])
         if slots is None:
             # ONE compute stream for every batch (kernels of two batches never interleave: the conv -> epilogue pairs keep
             # their L2 reuse, and one set of captured graphs / static buffers serves all slots) + ONE copy stream on which
@@ -147,13 +151,19 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
         k += 1
         if slot.dev is not None:
             yield finish(pending.pop(0))
-        if (slot.pool.n, slot.pool.h, slot.pool.w) != (n, h, w):
+        if slot.shape != (n, h, w):
             raise ValueError("predict_stream needs batches of one common size")
-        slot.images = images
         t_e = _time.perf_counter()
+        if resident:  # an ImagePool that already lives on the device: no upload, no host image behind the results
+            slot.pool, slot.images = images, [None] * n
+        else:
+            if slot.own_pool is None:
+                slot.own_pool = ops.ImagePool(n, h, w, eng.device)
+            slot.pool, slot.images = slot.own_pool, images
         with torch.cuda.stream(streams[1]):  # this slot's pool is free: finish() waited for the batch that last read it
-            for i, im in enumerate(images):
-                slot.pool.upload(i, im, non_blocking=True)
+            if not resident:
+                for i, im in enumerate(images):
+                    slot.pool.upload(i, im, non_blocking=True)
             slot.uploaded.record(streams[1])
         with torch.cuda.stream(slot.stream):
             slot.stream.wait_event(slot.uploaded)

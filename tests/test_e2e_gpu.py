@@ -167,6 +167,15 @@ def test_predict_stream_equals_batch_api(cuda_device, use_graphs, overlap_post, 
                               stats=stats, use_graphs=use_graphs, overlap_post=overlap_post))
     eng = model.engine()
     assert eng.use_graphs is False and (eng.replayed_launches > 0) == use_graphs or not use_graphs
+    # batches that already live on the device (ImagePool) go through the same pipeline without the upload
+    import fsd_b200.ops as ops
+
+    pools = [ops.ImagePool.from_numpy([im.numpy() for im in g], cuda_device) for g in groups[:3]]
+    res = list(predict_stream(iter(pools), model, 256, 256, 0.2, 0.2, depth=depth, use_graphs=use_graphs, overlap_post=overlap_post))
+    for gb, wb in zip(res, want[:3]):
+        for gr, wr in zip(gb, wb):
+            assert [p.bbox.to_xyxy() for p in gr.object_prediction_list] == [p.bbox.to_xyxy() for p in wr.object_prediction_list]
+            assert (gr.image_width, gr.image_height) == (512, 384)
     assert set(stats) == {"enqueue", "wait", "build", "device", "device_idle"} and all(v >= 0 for v in stats.values())
     assert len(got) == len(want)
     for gb, wb in zip(got, want):
