@@ -41,7 +41,7 @@ SIGNATURES = {
     "fsd_kernel_timing_read": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]),
     "fsd_bias_act": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                C.c_int, C.c_float, C.c_int, vp]),
-    "fsd_stem_conv": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp]),
+    "fsd_stem_conv": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "fsd_pointwise_conv": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int,
                                      C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
     "fsd_sppf_pool": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

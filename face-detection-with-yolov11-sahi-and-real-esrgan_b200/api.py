@@ -2,6 +2,8 @@
 dataset loop would use instead of calling get_sliced_prediction image by image)."""
 from __future__ import annotations
 
+import gc
+
 from typing import List, Sequence
 
 import numpy as np
@@ -123,12 +125,20 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
         boxes_all = host[:, :4].astype(np.int64).tolist()
         scores_all = host[:, 4].tolist()
         kp_all = host[:, 6:21].reshape(-1, 5, 3).copy()
-        for i in range(n):
-            a, b = int(off[i]), int(off[i + 1])
-            preds = [ObjectPrediction.from_merged_row(bx[0], bx[1], bx[2], bx[3], scores_all[j], _FACE,
-                                                      kp_all[j] if srcs[j] >= 0 else None)
-                     for j, bx in zip(range(a, b), boxes_all[a:b])]
-            out.append(PredictionResult(object_prediction_list=preds, image=slot.images[i], durations_in_seconds={}, image_size=(w, h)))
+        # a batch creates ~30 k small acyclic objects: with the cyclic collector enabled its generation-0 passes are 40 % of
+        # the construction time (measured), so it is paused for the loop
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            for i in range(n):
+                a, b = int(off[i]), int(off[i + 1])
+                preds = [ObjectPrediction.from_merged_row(bx[0], bx[1], bx[2], bx[3], scores_all[j], _FACE,
+                                                          kp_all[j] if srcs[j] >= 0 else None)
+                         for j, bx in zip(range(a, b), boxes_all[a:b])]
+                out.append(PredictionResult(object_prediction_list=preds, image=slot.images[i], durations_in_seconds={}, image_size=(w, h)))
+        finally:
+            if gc_was_on:
+                gc.enable()
         slot.dev, slot.images = None, None
         if stats is not None:
             stats["wait"] += t_b - t_a

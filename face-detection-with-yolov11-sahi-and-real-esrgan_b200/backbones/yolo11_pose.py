@@ -11,12 +11,14 @@ and the decode (DFL, anchors, sigmoid, key-points, NMS) is Kernel 2/3's job (or 
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 
+USE_S2D_STEM = not os.environ.get("FSD_NO_S2D_STEM")  # layers 0+1: fsd_stem_conv writes space-to-depth, layer 1 runs as a 2x2 stride-1 convolution (cuDNN fast path)
 USE_POINTWISE_KERNEL = True  # fsd_pointwise_conv for the 1x1 layers it supports (False: cuDNN + fsd_bias_act everywhere)
 
 
@@ -312,8 +314,42 @@ class YOLO11Pose(nn.Module):
         self.h22 = C3k2(c512 + c1024, c1024, rep(2), True)
         self.head = PoseHead(nc, kpt_shape, (c256, c512, c1024))
 
+    def _stem(self, x):
+        """b1(b0(x)).  On the GPU in fp16: layer 0 is the hand-written stem kernel, which can store its output already
+        folded space-to-depth ([E, 64, H/4 + 1, W/4 + 1], zero first row / column); on that tensor layer 1
+        (Conv(16, 32, 3, 2)) is algebraically a 2x2 stride-1 convolution over 64 channels — same products, same sums — for
+        which cuDNN has a tensor-core kernel (0.33 ms vs 0.52 ms per 96 inputs, benchmarks/b1_s2d_probe.py)."""
+        c0, c1 = self.b0.conv, self.b1.conv
+        if (USE_S2D_STEM and x.is_cuda and x.dtype == torch.float16 and not torch.is_grad_enabled()
+                and x.is_contiguous(memory_format=torch.channels_last) and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0
+                and (c0.in_channels, c0.out_channels, c0.kernel_size, c0.stride, c0.padding, c0.groups) == (3, 16, (3, 3), (2, 2), (1, 1), 1)
+                and (c1.in_channels, c1.kernel_size, c1.stride, c1.padding, c1.groups) == (16, (3, 3), (2, 2), (1, 1), 1)
+                and c1.out_channels % 8 == 0 and isinstance(self.b0.act, nn.SiLU) and isinstance(self.b1.act, nn.SiLU)):
+            from ..ops import bias_act, stem_conv
+
+            key = (c0.weight._version, c0.weight.data_ptr(), c1.weight._version, c1.weight.data_ptr())
+            cached = getattr(self, "_stem_weights", None)
+            if cached is None or cached[0] != key:
+                w0 = c0.weight.detach().contiguous().clone()
+                w1 = c1.weight.detach()
+                w2 = torch.zeros((c1.out_channels, 64, 2, 2), dtype=w1.dtype, device=w1.device)
+                tap = {0: (0, 1), 1: (1, 0), 2: (1, 1)}  # kernel row/col k -> (2x2 tap, parity inside the 2x2 block)
+                for ky in range(3):
+                    a, dy = tap[ky]
+                    for kx in range(3):
+                        b, dx = tap[kx]
+                        w2[:, (dy * 2 + dx) * 16:(dy * 2 + dx + 1) * 16, a, b] = w1[:, :, ky, kx]
+                cached = (key, w0, w2.contiguous(memory_format=torch.channels_last))
+                self._stem_weights = cached
+            s = stem_conv(x, cached[1], c0.bias, space_to_depth=True)
+            y = F.conv2d(s, cached[2], None, 1, 0)
+            if y.is_contiguous(memory_format=torch.channels_last):
+                return bias_act(y, c1.bias, "silu")
+            return self.b1.act(y + c1.bias.view(1, -1, 1, 1))
+        return self.b1(self.b0(x))
+
     def forward(self, x):
-        x = self.b1(self.b0(x))
+        x = self._stem(x)
         p3 = self.b4(self.b3(self.b2(x)))
         p4 = self.b6(self.b5(p3))
         c5 = self.b7.conv.out_channels

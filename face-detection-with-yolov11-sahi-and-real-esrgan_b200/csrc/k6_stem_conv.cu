@@ -28,8 +28,8 @@ struct K6Params {
     const __half* x;      // [E, H, W, 3]
     const __half* w;      // [16, 3, 3, 3] (o, c, ky, kx)
     const __half* bias;   // [16]
-    __half* out;          // [E, OH, OW, 16]
-    int H, W, OH, OW;
+    __half* out;          // [E, OH, OW, 16], or the space-to-depth form [E, OH/2 + 1, OW/2 + 1, 64] (s2d)
+    int H, W, OH, OW, s2d;
 };
 
 __device__ __forceinline__ float k6_silu(float v) { return fast_silu(v); }
@@ -91,7 +91,11 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stem_conv_kernel(const K6Params
     // ---- one warp per output row; K6_TW / 16 groups of 16 output pixels ---------------------------------------------------------
     const int y = y0 + warp;
     if (y >= p.OH) return;
-    __half* orow = p.out + ((size_t)e * p.OH + y) * p.OW * 16;
+    // plain: pixel (y, x) -> out[e][y][x][16].  s2d: -> out[e][y/2 + 1][x/2 + 1][((y&1)*2 + (x&1))*16 ..]: the layout in which
+    // the following 3x3 stride-2 convolution is a 2x2 stride-1 convolution over 64 channels (row 0 / column 0 = its zero padding)
+    const int OW2 = p.OW / 2 + 1;
+    __half* orow = p.s2d ? p.out + (((size_t)e * (p.OH / 2 + 1) + (y >> 1) + 1) * OW2) * 64 + (y & 1) * 32
+                         : p.out + ((size_t)e * p.OH + y) * p.OW * 16;
 #pragma unroll
     for (int grp = 0; grp < K6_TW / 16; ++grp) {
         const int xg = grp * 16;
@@ -122,7 +126,8 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stem_conv_kernel(const K6Params
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const __half2 o = __floats2half2_rn(k6_silu(acc[j][2 * half_] + bias[j][0]), k6_silu(acc[j][2 * half_ + 1] + bias[j][1]));
-                    *reinterpret_cast<__half2*>(orow + (size_t)x * 16 + 8 * j + 2 * t) = o;
+                    const size_t px = p.s2d ? (size_t)((x >> 1) + 1) * 64 + (x & 1) * 16 : (size_t)x * 16;
+                    *reinterpret_cast<__half2*>(orow + px + 8 * j + 2 * t) = o;
                 }
             }
         }
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stem_conv_kernel(const K6Params
 using namespace fsd;
 
 extern "C" int fsd_stem_conv(fsd_handle_t h, const void* x, int E, int H, int W, const void* weight, const void* bias,
-                             int out_channels, int dtype, void* out, void* stream_) {
+                             int out_channels, int dtype, int space_to_depth, void* out, void* stream_) {
     FSD_CHECK_ARG(h && x && weight && bias && out, "fsd_stem_conv: null argument");
     FSD_CHECK_ARG(dtype == FSD_F16, "fsd_stem_conv: only fp16 is implemented");
     FSD_CHECK_ARG(out_channels == 16, "fsd_stem_conv: the kernel is specialised for 16 output channels (YOLO11n), got %d", out_channels);
@@ -144,7 +149,8 @@ extern "C" int fsd_stem_conv(fsd_handle_t h, const void* x, int E, int H, int W,
     FSD_CHECK_ARG(E <= 65535, "fsd_stem_conv: at most 65535 inputs per launch");
     K6Params p;
     p.x = (const __half*)x; p.w = (const __half*)weight; p.bias = (const __half*)bias; p.out = (__half*)out;
-    p.H = H; p.W = W; p.OH = (H - 1) / 2 + 1; p.OW = (W - 1) / 2 + 1;
+    p.H = H; p.W = W; p.OH = (H - 1) / 2 + 1; p.OW = (W - 1) / 2 + 1; p.s2d = space_to_depth ? 1 : 0;
+    FSD_CHECK_ARG(!space_to_depth || (p.OH % 2 == 0 && p.OW % 2 == 0), "fsd_stem_conv: the space-to-depth output needs even output sizes");
     dim3 grid((p.OW + K6_TW - 1) / K6_TW, (p.OH + K6_TH - 1) / K6_TH, E);
     FSD_CUDA(cudaSetDevice(h->device));
     k6_stem_conv_kernel<<<grid, K6_THREADS, 0, (cudaStream_t)stream_>>>(p);

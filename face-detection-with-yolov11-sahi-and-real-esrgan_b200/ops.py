@@ -271,9 +271,11 @@ def bias_act(x: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: floa
     return out
 
 
-def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: torch.Tensor | None = None,
+              space_to_depth: bool = False) -> torch.Tensor:
     """(a5) SiLU(conv2d(x, weight, bias, stride=2, padding=1)) for the 3-channel fp16 channels-last network input, one kernel.
-    x [E,3,H,W] channels-last dense, weight [16,3,3,3] standard-contiguous, bias [16] -> [E,16,H/2,W/2] channels-last."""
+    x [E,3,H,W] channels-last dense, weight [16,3,3,3] standard-contiguous, bias [16] -> [E,16,H/2,W/2] channels-last, or with
+    `space_to_depth` -> [E,64,H/4+1,W/4+1] (zero first row / column, 2x2 blocks folded into channels: see fsd_stem_conv)."""
     _require_cuda(x, "x")
     e, c, hh, ww = x.shape
     if c != 3 or x.dtype != torch.float16 or not x.is_contiguous(memory_format=torch.channels_last) or ww % 2:
@@ -281,11 +283,22 @@ def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: to
     if tuple(weight.shape) != (16, 3, 3, 3) or not weight.is_contiguous() or weight.dtype != torch.float16:
         raise ValueError("stem_conv needs a contiguous fp16 [16,3,3,3] weight")
     oh, ow = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+    if space_to_depth:
+        if oh % 2 or ow % 2:
+            raise ValueError("stem_conv(space_to_depth=True) needs even output sizes")
+        shape = (e, 64, oh // 2 + 1, ow // 2 + 1)
+    else:
+        shape = (e, 16, oh, ow)
     if out is None:
-        out = torch.empty((e, 16, oh, ow), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        out = torch.empty(shape, dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        if space_to_depth:  # the kernel never writes the padding row / column
+            out[:, :, 0].zero_()
+            out[:, :, :, 0].zero_()
+    elif tuple(out.shape) != shape or not out.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError(f"stem_conv: out must be a dense channels_last {shape} tensor")
     h = _handle_for(x)
     check(h.lib.fsd_stem_conv(h.h, x.data_ptr(), e, hh, ww, weight.data_ptr(), bias.data_ptr(), 16, _TORCH_DTYPE[x.dtype],
-                              out.data_ptr(), _stream_ptr(x.device)), "fsd_stem_conv")
+                              1 if space_to_depth else 0, out.data_ptr(), _stream_ptr(x.device)), "fsd_stem_conv")
     return out
 
 

@@ -173,9 +173,12 @@ int fsd_sppf_pool(fsd_handle_t h, void* buf, int N, int H, int W, int c, int dty
 /* ---- (a5) YOLO stem: out = SiLU(conv3x3_stride2_pad1(x) + bias) for the 3-channel network input, fp16 channels-last:
  *      x [E,H,W,3] (Kernel 1's channels-last output), weight [16,3,3,3] (o,c,ky,kx dense), bias [16],
  *      out [E,(H-1)/2+1,(W-1)/2+1,16].  Replaces layer 0 of yolo11-pose.yaml (ultralytics Conv(3,16,3,2), run inside
- *      model.predict at utils/yolo_wrapper.py:72) as cuDNN convolution + epilogue pass; tensor cores via mma.sync. */
+ *      model.predict at utils/yolo_wrapper.py:72) as cuDNN convolution + epilogue pass; tensor cores via mma.sync.
+ *      space_to_depth != 0: out is [E, OH/2 + 1, OW/2 + 1, 64] with out[e][Y+1][X+1][(dy*2+dx)*16 + c] = result(e, 2Y+dy, 2X+dx, c)
+ *      (row 0 / column 0 are NOT written: the caller keeps them zero) — the layout in which layer 1 (Conv(16,32,3,2)) is a
+ *      2x2 stride-1 convolution over 64 channels, for which cuDNN has a fast kernel (benchmarks/b1_s2d_probe.py). */
 int fsd_stem_conv(fsd_handle_t h, const void* x, int E, int H, int W, const void* weight, const void* bias,
-                  int out_channels, int dtype, void* out, void* stream);
+                  int out_channels, int dtype, int space_to_depth, void* out, void* stream);
 
 /* ---- (a5) 1x1 convolution + bias + activation (+ residual) for the low-intensity layers, fp16 channels-last:
  *      out[pix, :N] = act(x[pix, :K] . weight[N, K]^T + bias) (+ residual[pix, :N]); x / out / residual / out2 are channel slots

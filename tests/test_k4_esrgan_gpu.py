@@ -257,3 +257,35 @@ def test_pointwise_conv_matches_torch(cuda_device, kn, act):
     err = (plain.float() - y).abs()
     assert float((err - 1e-3 * y.abs()).max()) <= 1e-3, float(err.max())
     assert not ops.pointwise_conv_supported(256, 64) and not ops.pointwise_conv_supported(24, 64)
+
+
+def test_space_to_depth_stem_equals_plain_layers(cuda_device):
+    """(a5) layers 0+1 through the space-to-depth stem (fsd_stem_conv(space_to_depth) + 2x2 convolution) vs the plain
+    pair (fsd_stem_conv + cuDNN 3x3 stride-2 convolution): same products and sums, so the results agree to fp16 rounding of
+    the accumulation order; the folded tensor itself is an exact re-arrangement of the plain stem output."""
+    import fsd_b200.ops as ops
+    from fsd_b200.backbones import yolo11_pose as yp
+
+    g = torch.Generator().manual_seed(3)
+    model = yp.build_yolo11n_pose().half().to(cuda_device).to(memory_format=torch.channels_last)
+    x = torch.rand((3, 3, 96, 160), generator=g).half().to(cuda_device).contiguous(memory_format=torch.channels_last)
+    w0 = model.b0.conv.weight.detach().contiguous().clone()
+    plain = ops.stem_conv(x, w0, model.b0.conv.bias)
+    folded = ops.stem_conv(x, w0, model.b0.conv.bias, space_to_depth=True)
+    assert folded.shape == (3, 64, 25, 41) and float(folded[:, :, 0].abs().max()) == 0 and float(folded[:, :, :, 0].abs().max()) == 0
+    for dy in range(2):
+        for dx in range(2):
+            assert torch.equal(folded[:, (dy * 2 + dx) * 16:(dy * 2 + dx + 1) * 16, 1:, 1:], plain[:, :, dy::2, dx::2])
+    with torch.no_grad():
+        got = model._stem(x)
+        old = yp.USE_S2D_STEM
+        yp.USE_S2D_STEM = False
+        try:
+            want = model._stem(x)
+        finally:
+            yp.USE_S2D_STEM = old
+    assert got.shape == want.shape == (3, 32, 24, 40)
+    err = (got.float() - want.float()).abs()
+    assert float((err - 4e-3 * want.float().abs()).max()) <= 4e-3, float(err.max())
+    with pytest.raises(Exception):
+        ops.stem_conv(x[:, :, :90], w0, model.b0.conv.bias, space_to_depth=True)  # 45 output rows: not foldable
