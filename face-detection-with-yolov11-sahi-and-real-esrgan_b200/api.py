@@ -36,13 +36,19 @@ def get_sliced_prediction_batch(images: Sequence, detection_model, slice_height:
     if not as_objects:
         return batch
     out: List[PredictionResult] = []
-    for i in range(len(images)):
-        boxes, scores, kpts, has_k = batch.image(i)
-        ib, sc, hk = boxes.astype(np.int64).tolist(), scores.tolist(), has_k.tolist()
-        preds = [ObjectPrediction.from_merged_row(b[0], b[1], b[2], b[3], sc[j], _FACE, kpts[j] if hk[j] else None)
-                 for j, b in enumerate(ib)]
-        out.append(PredictionResult(object_prediction_list=preds, image=images[i], durations_in_seconds={},
-                                    image_size=(w, h)))
+    gc_was_on = gc.isenabled()
+    gc.disable()  # thousands of small acyclic objects: the cyclic collector's generation-0 passes would dominate
+    try:
+        for i in range(len(images)):
+            boxes, scores, kpts, has_k = batch.image(i)
+            ib, sc, hk = boxes.astype(np.int64).tolist(), scores.tolist(), has_k.tolist()
+            preds = [ObjectPrediction.from_merged_row(b[0], b[1], b[2], b[3], sc[j], _FACE, kpts[j] if hk[j] else None)
+                     for j, b in enumerate(ib)]
+            out.append(PredictionResult(object_prediction_list=preds, image=images[i], durations_in_seconds={},
+                                        image_size=(w, h)))
+    finally:
+        if gc_was_on:
+            gc.enable()
     return out
 
 
