@@ -173,6 +173,7 @@ def main():
     pool = make_pool_on_device(n_resident, H, W, dev, seed=1234 + rank * 100003)
     model = YOLOv11PoseDetectionModel(model=YOLO("random-init"), confidence_threshold=CONF, device=str(dev), image_size=IMGSZ)
     eng = model.engine()
+    eng.overlap_post = True  # synchronous detect(): the slices' stage-1 NMS runs on a side stream under the full-image pass
     h = _cabi.get_handle(local)
     kw = dict(postprocess_type="GREEDYNMM", match_metric="IOS", match_threshold=0.5)
 

@@ -66,7 +66,7 @@ class SlicedFaceDetector:
     def __init__(self, backbone: torch.nn.Module, device="cuda:0", imgsz: int = 1024, conf: float = 0.5,
                  half: bool = True, stride: int = 32, iou: float = 0.7, max_det: int = 300,
                  cap_per_entry: int = 1024, channels_last: bool = True, reverse_channels: bool = True,
-                 chunk_entries: int = 96, truncate: bool = True, use_graphs: bool = False):
+                 chunk_entries: int = 96, truncate: bool = True, use_graphs: bool = False, overlap_post: bool = False):
         if not torch.cuda.is_available():
             raise _cabi.FsdError("SlicedFaceDetector needs a CUDA device: fsd_b200 has no CPU fallback")
         self.device = torch.device(device)
@@ -89,6 +89,9 @@ class SlicedFaceDetector:
         # CUDA-graph replay of the backbone (opt-in): one graph per (stream, chunk address, shape) over static network-input
         # buffers, so a step enqueues a handful of graph launches instead of ~1300 kernel launches from Python
         self.use_graphs = use_graphs
+        # synchronous detect(): run the slices' stage-1 NMS / finalize on a side stream under the full-image pass
+        self.overlap_post = overlap_post
+        self._own_post_stream = None
         self._graphs: Dict = {}
         self._graph_pools: Dict = {}
         self._xbufs: Dict = {}
@@ -212,7 +215,11 @@ class SlicedFaceDetector:
             self._forward_entries("slices", x_s, cand_s, count_s)
             del x_s
             main = torch.cuda.current_stream(dev)
-            post = post_stream if (post_stream is not None and not to_host) else None
+            post = post_stream if not to_host else None
+            if post is None and self.overlap_post:
+                if self._own_post_stream is None:
+                    self._own_post_stream = torch.cuda.Stream(device=dev)
+                post = self._own_post_stream
 
             def on_post(*tensors):
                 """Switch to the post stream behind everything enqueued so far; the caching allocator must not recycle
@@ -254,9 +261,11 @@ class SlicedFaceDetector:
                                         class_agnostic=True, want_parent=False)  # one class ("face") on this path
                 src = ops.attach_keypoints(s2["boxes"], t["goff"], s2["keep_count"], det, t["goff"], dcount)
                 rows, offsets = ops.pack_results(det, t["goff"], s2, src)
-            if post is not None:
+            if post is not None and not to_host:
                 return dict(rows=rows, offsets=offsets, det=det, dcount=dcount, count_s=count_s, count_f=count_f, plan=plan,
                             stream=post)
+            if post is not None:
+                main.wait_stream(post)  # synchronous form: the results are read on the calling stream below
             if not to_host:
                 return dict(rows=rows, offsets=offsets, det=det, dcount=dcount, count_s=count_s, count_f=count_f, plan=plan)
             # ---- the only device->host traffic of the batch: counts, then exactly the packed rows

@@ -162,6 +162,12 @@ def test_predict_stream_equals_batch_api(cuda_device, use_graphs, overlap_post, 
     imgs = [torch.from_numpy(make_image(300 + i, 384, 512)[0]).pin_memory() for i in range(12)]
     groups = [imgs[0:4], imgs[4:8], imgs[8:12], imgs[0:4], imgs[4:8], imgs[8:12]]
     want = [get_sliced_prediction_batch(g, model, 256, 256, 0.2, 0.2) for g in groups]
+    # the synchronous call with its slices' stage-1 work on a side stream (engine.overlap_post) returns the same objects
+    model.engine().overlap_post = True
+    again = get_sliced_prediction_batch(groups[1], model, 256, 256, 0.2, 0.2)
+    model.engine().overlap_post = False
+    for gr, wr in zip(again, want[1]):
+        assert [(p.bbox.to_xyxy(), p.score.value) for p in gr.object_prediction_list] == [(p.bbox.to_xyxy(), p.score.value) for p in wr.object_prediction_list]
     stats = {}
     got = list(predict_stream(iter(groups), model, 256, 256, 0.2, 0.2, depth=depth, rows_per_image_hint=8,  # tiny window: exercises the refetch
                               stats=stats, use_graphs=use_graphs, overlap_post=overlap_post))
