@@ -34,6 +34,33 @@ elif which == "k1_nhwc":
     out = torch.empty((ent.shape[0], 3, 1024, 1024), dtype=torch.float16, device=dev, memory_format=torch.channels_last)
     for _ in range(iters):
         ops.gather_letterbox(pool, ent, 512, 512, 1024, 32, True, torch.float16, out=out)
+elif which == "k1_c1":  # C1 slices 640^2 -> 1024^2: the sixteenths path
+    N = 24
+    pool = ops.ImagePool(N, 1080, 1920, dev)
+    pool.buf.random_(0, 256)
+    boxes = _cabi.slice_plan(1080, 1920, 640, 640, 0.2, 0.2)
+    ent = torch.tensor([[i, b[0], b[1]] for i in range(N) for b in boxes], dtype=torch.int32, device=dev)
+    out = torch.empty((ent.shape[0], 3, 1024, 1024), dtype=torch.float16, device=dev, memory_format=torch.channels_last)
+    for _ in range(iters):
+        ops.gather_letterbox(pool, ent, 640, 640, 1024, 32, True, torch.float16, out=out)
+elif which == "k7":
+    x = torch.randn((96, 48, 256, 256), device=dev).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((64, 48, 1, 1), device=dev) / 7).half()
+    b = torch.randn((64,), device=dev).half()
+    out = torch.empty((96, 64, 256, 256), device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    for _ in range(iters):
+        ops.pointwise_conv(x, w, b, "silu", out=out)
+elif which == "k3_big":  # config 3: 9900 boxes per image -> the cluster kernel
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_k3_merge_gpu import sahi_like_boxes
+
+    rng = np.random.default_rng(0)
+    seg = sahi_like_boxes(rng, 5000, dup=(1, 4), size=(10, 40), canvas=(3840, 2160))[:9900]
+    S = 8
+    rows = torch.from_numpy(np.tile(seg, (S, 1))).to(dev)
+    offs = torch.arange(S, dtype=torch.int32, device=dev) * len(seg)
+    for _ in range(iters):
+        ops.merge_segments(rows, offs, None, len(seg), merge_type="GREEDYNMM", metric="IOS", thr=0.5, want_parent=False)
 elif which == "k6":
     x = torch.rand((96, 3, 1024, 1024), device=dev).half().contiguous(memory_format=torch.channels_last)
     w = (torch.randn((16, 3, 3, 3), device=dev) * 0.4).half()
