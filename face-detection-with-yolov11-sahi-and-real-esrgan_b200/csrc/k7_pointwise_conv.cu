@@ -18,7 +18,6 @@ namespace fsd {
 
 constexpr int K7_THREADS = 256;
 constexpr int K7_WARPS = K7_THREADS / 32;
-constexpr int K7_TILE = 32;  // pixels per warp tile
 
 struct K7Params {
     const __half* x; const __half* w; const __half* bias;
@@ -52,8 +51,12 @@ template <int ACT> __device__ __forceinline__ float k7_act(float v, float slope)
     return v;
 }
 
-template <int N, int ACT>
-__global__ void __launch_bounds__(K7_THREADS) k7_pointwise_conv_kernel(const K7Params p) {
+// MT = 16-pixel m-tiles per warp tile.  MT = 2 halves the weight-fragment traffic per pixel; MT = 1 halves the accumulator
+// registers (N = 64: 128 -> ~80 per thread), which doubles the resident warps — tried because the N = 64 variant runs at 23 %
+// occupancy (profiles/r1_k7_pointwise_48x64.summary.txt), but it was slower: the kernel is MUFU/issue-bound, not latency-bound.
+template <int N, int ACT, int MT>
+__global__ void __launch_bounds__(K7_THREADS, N <= 32 ? 3 : (N <= 64 ? 2 : 1)) k7_pointwise_conv_kernel(const K7Params p) {
+    constexpr int K7_TILE = 16 * MT;  // pixels per warp tile
     extern __shared__ __align__(16) uint8_t k7_smem[];
     const int K = p.K;
     const int wpitch = K + 8;                       // halfs; +16 B keeps ldmatrix rows on distinct banks
@@ -102,17 +105,17 @@ __global__ void __launch_bounds__(K7_THREADS) k7_pointwise_conv_kernel(const K7P
         cp_async_wait_but_one();
         __syncwarp();
 
-        float acc[2][N / 8][4];
+        float acc[MT][N / 8][4];
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int m = 0; m < MT; ++m)
 #pragma unroll
             for (int j = 0; j < N / 8; ++j)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
         for (int ks = 0; ks < K; ks += 16) {
-            uint32_t a[2][4];
+            uint32_t a[MT][4];
 #pragma unroll
-            for (int m = 0; m < 2; ++m)  // lanes 0-15 -> rows, lanes 16-31 -> the k+8 half
+            for (int m = 0; m < MT; ++m)  // lanes 0-15 -> rows, lanes 16-31 -> the k+8 half
                 ldsm4(a[m], stage + (size_t)(16 * m + (lane & 15)) * spitch + ks + 8 * (lane >> 4));
 #pragma unroll
             for (int jp = 0; jp < N / 16; ++jp) {
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(K7_THREADS) k7_pointwise_conv_kernel(const K7P
                 uint32_t b[4];
                 ldsm4(b, Ws + (size_t)(16 * jp + (lane & 7) + 8 * (lane >> 4)) * wpitch + ks + 8 * ((lane >> 3) & 1));
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < MT; ++m) {
                     mma16816(acc[m][2 * jp], a[m], b[0], b[1]);
                     mma16816(acc[m][2 * jp + 1], a[m], b[2], b[3]);
                 }
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(K7_THREADS) k7_pointwise_conv_kernel(const K7P
         }
         __syncwarp();  // every lane is done reading the activations: the staging rows now take the outputs
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int m = 0; m < MT; ++m)
 #pragma unroll
             for (int j = 0; j < N / 8; ++j)
 #pragma unroll
@@ -161,6 +164,8 @@ __global__ void __launch_bounds__(K7_THREADS) k7_pointwise_conv_kernel(const K7P
 
 template <int N>
 static int k7_launch(fsd_context* h, const K7Params& p, cudaStream_t s) {
+    constexpr int MT = 2;  // MT = 1 (half the accumulators, twice the resident warps) measured slower for N = 64: 0.50 vs 0.54 of peak
+    constexpr int K7_TILE = 16 * MT;
     const int K = p.K;
     const size_t smem = ((size_t)N * (K + 8) + (size_t)2 * K7_WARPS * K7_TILE * ((K > N ? K : N) + 8)) * sizeof(__half);
     const long long tiles = (p.P + K7_TILE - 1) / K7_TILE;
@@ -171,7 +176,7 @@ static int k7_launch(fsd_context* h, const K7Params& p, cudaStream_t s) {
     const int grid = (int)(want < (long long)h->sm_count * per_sm ? want : (long long)h->sm_count * per_sm);
 #define K7_GO(ACT)                                                                                                   \
     {                                                                                                                \
-        auto kern = k7_pointwise_conv_kernel<N, ACT>;                                                                \
+        auto kern = k7_pointwise_conv_kernel<N, ACT, MT>;                                                                \
         FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
         kern<<<grid, K7_THREADS, smem, s>>>(p);                                                                      \
     }
