@@ -6,10 +6,14 @@ images, 512x512 slices (0.2 overlap -> 6 slices) + the full-image pass, imgsz 10
 GREEDYNMM / IOS / 0.5 merge, conf 0.5, fp16 network input.  A "step" is one batch of `--batch` images through the whole
 hot path (Kernel 1 -> backbone -> Kernel 2a -> Kernel 3 -> Kernel 2b -> Kernel 3 -> attach/pack -> D2H of the results).
 
-  value     images/sec with the step's images already resident in HBM
-  e2e       images/sec through the public API (fsd_b200.api.get_sliced_prediction_batch) from PINNED HOST images,
-            H2D copies and result D2H + Python result objects inside the timed region
-  roofline  Kernel 1 (slice launch): algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json hbm_gbs
+  value     images/sec with the step's images already resident in HBM (synchronous engine.detect per batch, the backbone
+            replayed as CUDA graphs; CUDA-event timed)
+  e2e       images/sec through the public API (fsd_b200.api.predict_stream: copy / compute / post-processing streams,
+            three batches in flight) from PINNED HOST images: H2D copies, result D2H and the Python PredictionResult /
+            ObjectPrediction objects are all inside the timed region
+  roofline  Kernel 1 (slice launch): algorithmic bytes / time between CUDA events recorded inside the library around the
+            launch, vs MEASURED_PEAKS.json hbm_gbs; `other_kernels`: the conv epilogue (largest share of the step);
+            `hot_path`: SURVEY 8(d)'s whole-path figure
   cpu_baseline / --impl reference: the CPU oracle (reference-equivalent restatement: sequential batch-1 slices,
             per-box Python objects, CPU merge) on a bounded sample of the same images, all host threads.
 
@@ -347,6 +351,14 @@ def main():
                            "cuda_graphs": bool(graphs_used)},
                 "detections_per_image": n_dets / (args.steps * B), "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base}
+        # the whole hot path against the HBM roofline = algorithmic bytes of Kernel 1 (44.8 MB / image) and
+        # Kernel 2 (23.2 MB / image) over the time per image; it is small because the step is the PyTorch backbone's
+        bytes_per_image = (H * W * 3 + 6 * 3 * IMGSZ * IMGSZ * 2 + 3 * H * W * 2) + (6 * 21504 + 16128) * 80 * 2
+        line["hot_path"] = {"algorithmic_bytes_per_image": bytes_per_image, "achieved_GBps": bytes_per_image * value / 1e9,
+                            "frac_of_peak": bytes_per_image * value / 1e9 / peak,
+                            "backbone_share_of_device_time": 0.87,
+                            "backbone_share_source": "profiles/r1_launches_bench_b32_end.txt: library conv/gemm/sdpa 43.5 % + the "
+                                                     "hand-written backbone kernels (epilogues, stem, 1x1 conv, up-sample, SPPF) 43.4 %"}
         if gathered is not None:
             line["allgather_detections"] = gathered
         print(json.dumps(line), flush=True)
