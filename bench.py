@@ -354,8 +354,8 @@ def main():
         # the whole hot path against the HBM roofline = algorithmic bytes of Kernel 1 (44.8 MB / image) and
         # Kernel 2 (23.2 MB / image) over the time per image; it is small because the step is the PyTorch backbone's
         bytes_per_image = (H * W * 3 + 6 * 3 * IMGSZ * IMGSZ * 2 + 3 * H * W * 2) + (6 * 21504 + 16128) * 80 * 2
-        line["hot_path"] = {"algorithmic_bytes_per_image": bytes_per_image, "achieved_GBps": bytes_per_image * value / 1e9,
-                            "frac_of_peak": bytes_per_image * value / 1e9 / peak,
+        line["hot_path"] = {"algorithmic_bytes_per_image": bytes_per_image, "achieved_GBps_per_gpu": bytes_per_image * value / world / 1e9,
+                            "frac_of_peak": bytes_per_image * value / world / 1e9 / peak,
                             "backbone_share_of_device_time": 0.87,
                             "backbone_share_source": "profiles/r1_launches_bench_b32_end.txt: library conv/gemm/sdpa 43.5 % + the "
                                                      "hand-written backbone kernels (epilogues, stem, 1x1 conv, up-sample, SPPF) 43.4 %"}
