@@ -220,3 +220,53 @@ def test_fused_path_edge_cases(cuda_device):
     want = opred.get_sliced_prediction(img, omodel, slice_height=512, slice_width=512, verbose=0)
     assert [r[0] for r in as_rows(got.object_prediction_list)] == [r[0] for r in as_rows(want.object_prediction_list)]
     assert len(got.object_prediction_list) > 0
+
+
+@pytest.mark.parametrize("cfg", [("C2", 768, 1024, 512, 4), ("C1", 1080, 1920, 640, 2)], ids=lambda c: c[0])
+def test_full_size_properties(cuda_device, cfg):
+    """BASELINE configs at their FULL sizes (imgsz 1024), through properties that do not need the CPU oracle to finish:
+    determinism (two runs, and graph replay vs eager launches, give identical rows), geometric sanity of every box,
+    stage-1 caps, and idempotence of the merge (merging the merged NMS output again keeps everything)."""
+    import fsd_b200.ops as ops
+    from fsd_b200.plugins import YOLOv11PoseDetectionModel
+    from fsd_b200.synthetic import make_image
+    from fsd_b200.yolo import YOLO
+
+    name, H, W, sl, n = cfg
+    torch.backends.cudnn.deterministic = True
+    model = YOLOv11PoseDetectionModel(model=YOLO("random-init"), confidence_threshold=0.5, device="cuda:0", image_size=1024)
+    eng = model.engine()
+    eng.truncate = True  # the plug-in's int() truncation (utils/yolo_wrapper.py:138), as the reference-facing API sets it
+    pool = ops.ImagePool.from_numpy([make_image(900 + i, H, W, mean_faces=12)[0] for i in range(n)], cuda_device)
+    kw = dict(postprocess_type="NMS", match_metric="IOS", match_threshold=0.5)
+    a = eng.detect(pool, sl, sl, 0.2, 0.2, True, want_stage1=True, **kw)
+    b = eng.detect(pool, sl, sl, 0.2, 0.2, True, **kw)
+    eng.use_graphs = True
+    try:
+        c = eng.detect(pool, sl, sl, 0.2, 0.2, True, **kw)   # first call captures the graphs, second replays them
+        d = eng.detect(pool, sl, sl, 0.2, 0.2, True, **kw)
+    finally:
+        eng.use_graphs = False
+        torch.backends.cudnn.deterministic = False
+    for other in (b, c, d):
+        assert np.array_equal(a.offsets, other.offsets) and np.array_equal(a.boxes, other.boxes) and np.array_equal(a.scores, other.scores)
+        assert np.array_equal(a.keypoints, other.keypoints)
+    S = a.counters["slices"]
+    assert S == {"C2": 6, "C1": 8}[name] and a.counters["entries"] == n * (S + 1)
+    assert int(a.offsets[-1]) > 0
+    bx = a.boxes
+    assert (bx == np.floor(bx)).all() and (bx[:, 0] >= 0).all() and (bx[:, 1] >= 0).all()
+    assert (bx[:, 2] <= W).all() and (bx[:, 3] <= H).all() and (bx[:, 2] > bx[:, 0]).all() and (bx[:, 3] > bx[:, 1]).all()
+    assert (a.scores >= 0.5).all() and (a.scores <= 1.0).all()
+    assert all(int(cnt) <= (S + 1) * 300 for cnt in a.stage1["count"])
+    # idempotence: the NMS/IOS output of every image, merged again with the same rule, keeps every box
+    for i in range(n):
+        lo, hi = int(a.offsets[i]), int(a.offsets[i + 1])
+        if hi - lo < 2:
+            continue
+        rows = torch.zeros((hi - lo, 6), device=cuda_device)
+        rows[:, :4] = torch.from_numpy(bx[lo:hi]).to(cuda_device)
+        rows[:, 4] = torch.from_numpy(a.scores[lo:hi]).to(cuda_device)
+        res = ops.merge_segments(rows, torch.zeros(1, dtype=torch.int32, device=cuda_device), None, hi - lo, merge_type="NMS",
+                                 metric="IOS", thr=0.5, precision="fp64")
+        assert int(res["keep_count"][0]) == hi - lo
