@@ -10,6 +10,29 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+FAST_INFERENCE = True  # GPU fp16 inference: channels-last convolutions + the one-pass bias/LeakyReLU epilogue (fsd_bias_act_inplace)
+
+
+def _fast(x):
+    return FAST_INFERENCE and x.is_cuda and x.dtype == torch.float16 and not torch.is_grad_enabled()
+
+
+def _conv_act(conv, x, act):
+    """conv(x) + bias followed by LeakyReLU(0.2) (act="lrelu") or nothing (act="none").  On the fast path cuDNN produces the
+    raw channels-last convolution and ONE hand-written pass applies bias and activation in place; eager PyTorch launches a
+    bias-add kernel and an activation kernel after every convolution (2 x 115 convolutions in the 23-block network)."""
+    if _fast(x) and conv.out_channels % 8 == 0:
+        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
+        if y.is_contiguous(memory_format=torch.channels_last):
+            from ..ops import bias_act_
+
+            return bias_act_(y, conv.bias, act, 0.2)
+        y = y + conv.bias.view(1, -1, 1, 1)
+    else:
+        y = conv(x)
+    return F.leaky_relu(y, 0.2) if act == "lrelu" else y
+
+
 def pixel_unshuffle(x, scale):
     b, c, hh, hw = x.size()
     h, w = hh // scale, hw // scale
@@ -31,12 +54,12 @@ class ResidualDenseBlock(nn.Module):
             nn.init.zeros_(m.bias)
 
     def forward(self, x):
-        x1 = self.lrelu(self.conv1(x))
-        x2 = self.lrelu(self.conv2(torch.cat((x, x1), 1)))
-        x3 = self.lrelu(self.conv3(torch.cat((x, x1, x2), 1)))
-        x4 = self.lrelu(self.conv4(torch.cat((x, x1, x2, x3), 1)))
-        x5 = self.conv5(torch.cat((x, x1, x2, x3, x4), 1))
-        return x5 * 0.2 + x
+        x1 = _conv_act(self.conv1, x, "lrelu")
+        x2 = _conv_act(self.conv2, torch.cat((x, x1), 1), "lrelu")
+        x3 = _conv_act(self.conv3, torch.cat((x, x1, x2), 1), "lrelu")
+        x4 = _conv_act(self.conv4, torch.cat((x, x1, x2, x3), 1), "lrelu")
+        x5 = _conv_act(self.conv5, torch.cat((x, x1, x2, x3, x4), 1), "none")
+        return torch.add(x, x5, alpha=0.2) if _fast(x) else x5 * 0.2 + x
 
 
 class RRDB(nn.Module):
@@ -47,7 +70,8 @@ class RRDB(nn.Module):
         self.rdb3 = ResidualDenseBlock(num_feat, num_grow_ch)
 
     def forward(self, x):
-        return self.rdb3(self.rdb2(self.rdb1(x))) * 0.2 + x
+        y = self.rdb3(self.rdb2(self.rdb1(x)))
+        return torch.add(x, y, alpha=0.2) if _fast(x) else y * 0.2 + x
 
 
 class RRDBNet(nn.Module):
@@ -74,8 +98,15 @@ class RRDBNet(nn.Module):
             feat = pixel_unshuffle(x, 4)
         else:
             feat = x
-        feat = self.conv_first(feat)
-        feat = feat + self.conv_body(self.body(feat))
-        feat = self.lrelu(self.conv_up1(F.interpolate(feat, scale_factor=2, mode="nearest")))
-        feat = self.lrelu(self.conv_up2(F.interpolate(feat, scale_factor=2, mode="nearest")))
-        return self.conv_last(self.lrelu(self.conv_hr(feat)))
+        if _fast(feat):
+            # channels-last from here on (the weights are converted once): cuDNN's tensor-core kernels are NHWC
+            if not getattr(self, "_cl_weights", False):
+                self.to(memory_format=torch.channels_last)
+                self._cl_weights = True
+            feat = feat.contiguous(memory_format=torch.channels_last)
+        feat = _conv_act(self.conv_first, feat, "none")
+        feat = feat + _conv_act(self.conv_body, self.body(feat), "none")
+        feat = _conv_act(self.conv_up1, F.interpolate(feat, scale_factor=2, mode="nearest"), "lrelu")
+        feat = _conv_act(self.conv_up2, F.interpolate(feat, scale_factor=2, mode="nearest"), "lrelu")
+        out = self.conv_last(_conv_act(self.conv_hr, feat, "lrelu"))
+        return out.contiguous() if _fast(x) else out

@@ -289,3 +289,30 @@ def test_space_to_depth_stem_equals_plain_layers(cuda_device):
     assert float((err - 4e-3 * want.float().abs()).max()) <= 4e-3, float(err.max())
     with pytest.raises(Exception):
         ops.stem_conv(x[:, :, :90], w0, model.b0.conv.bias, space_to_depth=True)  # 45 output rows: not foldable
+
+
+@pytest.mark.parametrize("scale", [2, 4])
+def test_rrdbnet_fast_inference_path(cuda_device, scale):
+    """RRDBNet's GPU fp16 path (channels-last convolutions + fsd_bias_act_inplace LeakyReLU epilogue, fused residual scaling) vs
+    the plain eager module with the same weights: same network, results agree to fp16 accumulation noise; and vs fp32 on the CPU."""
+    from fsd_b200.backbones import rrdbnet
+
+    torch.manual_seed(scale)
+    net = rrdbnet.RRDBNet(scale=scale, num_block=3).eval()
+    x = torch.rand((2, 3, 40, 56))
+    with torch.no_grad():
+        want32 = net(x)
+        gpu = rrdbnet.RRDBNet(scale=scale, num_block=3).eval()
+        gpu.load_state_dict(net.state_dict())
+        gpu = gpu.half().to(cuda_device)
+        xg = x.half().to(cuda_device)
+        rrdbnet.FAST_INFERENCE = False
+        try:
+            plain = gpu(xg)
+        finally:
+            rrdbnet.FAST_INFERENCE = True
+        fast = gpu(xg)
+    assert fast.shape == plain.shape == (2, 3, 40 * scale, 56 * scale) and fast.is_contiguous()
+    scale_ref = float(want32.abs().max())
+    assert float((fast.float() - plain.float()).abs().max()) <= 2e-2 * scale_ref
+    assert float((fast.float().cpu() - want32).abs().max()) <= 3e-2 * scale_ref
