@@ -39,8 +39,8 @@ SIGNATURES = {
     "fsd_bias_act_inplace": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
     "fsd_kernel_timing_enable": (C.c_int, [vp, C.c_uint]),
     "fsd_kernel_timing_read": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]),
-    "fsd_bias_act": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int64, C.c_int,
-                               C.c_int, C.c_float, C.c_int, vp]),
+    "fsd_bias_act": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, vp, C.c_int64, C.c_int, C.c_int,
+                               C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
     "fsd_stem_conv": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "fsd_pointwise_conv": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int,
                                      C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]),

@@ -38,15 +38,15 @@ class Conv(nn.Module):
         self.conv = nn.Conv2d(c1, c2, k, s, k // 2, groups=g, bias=True)
         self.act = nn.SiLU(inplace=True) if act else nn.Identity()
 
-    def forward(self, x, out=None, residual=None, out2=None):
-        """act(conv(x) + bias) (+ residual).  On the GPU in fp16 the convolution runs in cuDNN without bias and ONE
+    def forward(self, x, out=None, residual=None, out2=None, up2=None):
+        """act(conv(x) + bias) (+ residual); `up2` [N,C,2H,2W] additionally receives the result up-sampled 2x (nearest).  On the GPU in fp16 the convolution runs in cuDNN without bias and ONE
         hand-written pass (fsd_bias_act) applies bias, activation and the residual and stores the result into `out` —
         which may be a channel slot of a concat buffer — and the trailing channels into `out2` as well."""
         c = self.conv
         if (x.is_cuda and x.dtype == torch.float16 and c.out_channels % 8 == 0 and not torch.is_grad_enabled()):
             if (c.in_channels == 3 and c.out_channels == 16 and c.kernel_size == (3, 3) and c.stride == (2, 2)
                     and c.padding == (1, 1) and c.groups == 1 and isinstance(self.act, nn.SiLU) and out is None
-                    and residual is None and out2 is None and x.shape[3] % 2 == 0
+                    and residual is None and out2 is None and up2 is None and x.shape[3] % 2 == 0
                     and x.is_contiguous(memory_format=torch.channels_last)):
                 # the stem: cuDNN has no good kernel for a 3-channel channels-last input; one hand-written tensor-core
                 # kernel does convolution + bias + SiLU (fsd_stem_conv)
@@ -58,7 +58,7 @@ class Conv(nn.Module):
                     self._w_dense = cached
                 return stem_conv(x, cached[1], c.bias)
             act = "silu" if isinstance(self.act, nn.SiLU) else "none"
-            if (c.kernel_size == (1, 1) and c.stride == (1, 1) and c.groups == 1 and USE_POINTWISE_KERNEL
+            if (c.kernel_size == (1, 1) and c.stride == (1, 1) and c.groups == 1 and USE_POINTWISE_KERNEL and up2 is None
                     and x.stride(1) == 1 and x.shape[2] * x.shape[3] >= 1024):
                 # low-intensity 1x1 layers: one kernel does GEMM + bias + activation (+ residual) into the slot
                 from ..ops import pointwise_conv, pointwise_conv_supported
@@ -71,7 +71,7 @@ class Conv(nn.Module):
             if y.is_contiguous(memory_format=torch.channels_last):
                 from ..ops import bias_act
 
-                return bias_act(y, c.bias, act, out=out, residual=residual, out2=out2)
+                return bias_act(y, c.bias, act, out=out, residual=residual, out2=out2, up2=up2)
             y = self.act(y + c.bias.view(1, -1, 1, 1))
         else:
             y = self.act(c(x))
@@ -79,6 +79,8 @@ class Conv(nn.Module):
             y = residual + y
         if out2 is not None:
             out2.copy_(y[:, y.shape[1] - out2.shape[1]:])
+        if up2 is not None:
+            up2.copy_(F.interpolate(y, scale_factor=2.0, mode="nearest"))
         if out is not None:
             out.copy_(y)
             return out
@@ -130,7 +132,7 @@ class C3k2(nn.Module):
         self.m = nn.ModuleList(C3k(self.c, self.c, 2, shortcut) if c3k else Bottleneck(self.c, self.c, shortcut)
                                for _ in range(n))
 
-    def forward(self, x, out=None, out2=None):
+    def forward(self, x, out=None, out2=None, up2=None):
         c, n = self.c, len(self.m)
         buf = _cat_buffer(x, (2 + n) * c)
         y = torch.empty((x.shape[0], c, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
@@ -141,7 +143,7 @@ class C3k2(nn.Module):
             y = m(y, out=buf[:, (2 + i) * c:(3 + i) * c])
             if i + 1 < n:
                 y = y.contiguous(memory_format=torch.channels_last)
-        return self.cv2(buf, out=out, out2=out2)
+        return self.cv2(buf, out=out, out2=out2, up2=up2)
 
 
 class SPPF(nn.Module):
@@ -220,7 +222,7 @@ class C2PSA(nn.Module):
         self.cv1, self.cv2 = Conv(c1, 2 * self.c, 1, 1), Conv(2 * self.c, c1, 1)
         self.m = nn.ModuleList(PSABlock(self.c, attn_ratio=0.5, num_heads=max(1, self.c // 64)) for _ in range(n))
 
-    def forward(self, x, out2=None):
+    def forward(self, x, out=None, out2=None, up2=None):
         c = self.c
         buf = _cat_buffer(x, 2 * c)
         b = torch.empty((x.shape[0], c, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
@@ -228,7 +230,7 @@ class C2PSA(nn.Module):
         self.cv1(x, out=buf, out2=b)  # slot 0 = a, slot 1 is overwritten by m(b) below
         for i, m in enumerate(self.m):
             b = m(b, out=buf[:, c:] if i == len(self.m) - 1 else None)
-        return self.cv2(buf, out2=out2)
+        return self.cv2(buf, out=out, out2=out2, up2=up2)
 
 
 def _up_cat(a, b):
@@ -349,20 +351,31 @@ class YOLO11Pose(nn.Module):
         return self.b1(self.b0(x))
 
     def forward(self, x):
+        """Every concatenation of the FPN / PAN neck is a pre-allocated buffer that its producers fill: the conv epilogues
+        store p3 / p4 (second destination), the nearest-2x up-sampled p5 / n4 (`up2`) and the PAN inputs straight into their
+        channel slots, so neither `torch.cat` nor an up-sampling kernel runs."""
         x = self._stem(x)
-        p3 = self.b4(self.b3(self.b2(x)))
-        p4 = self.b6(self.b5(p3))
-        c5 = self.b7.conv.out_channels
-        h5, w5 = (p4.shape[2] - 1) // 2 + 1, (p4.shape[3] - 1) // 2 + 1
-        cat22 = _cat_buffer(x, self.h20.conv.out_channels + c5, h5, w5)  # cat(h20(m4), p5): p5 stored by its producer
-        p5 = self.b10(self.b9(self.b8(self.b7(p4))), out2=cat22[:, self.h20.conv.out_channels:])
-        c17 = self.h17.conv.out_channels
-        cat19 = _cat_buffer(x, c17 + self.h13.cv2.conv.out_channels, p4.shape[2], p4.shape[3])  # cat(h17(n3), n4)
-        n4 = self.h13(_up_cat(p5, p4), out2=cat19[:, c17:])
-        n3 = self.h16(_up_cat(n4, p3))
+        down = lambda v: (v - 1) // 2 + 1  # noqa: E731  (3x3 stride-2 pad-1 convolution)
+        h8, w8 = down(x.shape[2]), down(x.shape[3])
+        h16, w16 = down(h8), down(w8)
+        h32, w32 = down(h16), down(w16)
+        if (2 * h32, 2 * w32, 2 * h16, 2 * w16) != (h16, w16, h8, w8):
+            raise ValueError("the network input must be a multiple of 32 (ultralytics pads to the stride before inference)")
+        c3, c4, c5 = self.b4.cv2.conv.out_channels, self.b6.cv2.conv.out_channels, self.b10.cv2.conv.out_channels
+        cn4 = self.h13.cv2.conv.out_channels
+        c17, c20 = self.h17.conv.out_channels, self.h20.conv.out_channels
+        cat16 = _cat_buffer(x, cn4 + c3, h8, w8)      # cat(up(n4), p3)
+        p3 = self.b4(self.b3(self.b2(x)), out2=cat16[:, cn4:])
+        cat13 = _cat_buffer(x, c5 + c4, h16, w16)     # cat(up(p5), p4)
+        p4 = self.b6(self.b5(p3), out2=cat13[:, c5:])
+        cat22 = _cat_buffer(x, c20 + c5, h32, w32)    # cat(h20(m4), p5)
+        self.b10(self.b9(self.b8(self.b7(p4))), out=cat22[:, c20:], up2=cat13[:, :c5])      # p5
+        cat19 = _cat_buffer(x, c17 + cn4, h16, w16)   # cat(h17(n3), n4)
+        self.h13(cat13, out=cat19[:, c17:], up2=cat16[:, :cn4])                               # n4
+        n3 = self.h16(cat16)
         self.h17(n3, out=cat19[:, :c17])
         m4 = self.h19(cat19)
-        self.h20(m4, out=cat22[:, :self.h20.conv.out_channels])
+        self.h20(m4, out=cat22[:, :c20])
         m5 = self.h22(cat22)
         return self.head([n3, m4, m5])
 

@@ -54,6 +54,7 @@ k5_bias_act_float_kernel(float4* __restrict__ x, const float4* __restrict__ bias
 struct K5GenArgs {
     const uint4* x; const uint4* bias; uint4* out; const uint4* res; uint4* out2;
     unsigned n_vec; int c_vec; int out_stride; int res_stride; int out2_stride; int out2_c0; float slope;
+    uint4* up; int up_stride; int H, W;  // optional nearest-2x up-sampled destination ([N, 2H, 2W] pixels, own stride)
 };
 
 template <int ACT>
@@ -79,6 +80,14 @@ __global__ void __launch_bounds__(K5_THREADS) k5_bias_act_general_half_kernel(co
         }
         a.out[(size_t)pix * a.out_stride + c] = v;
         if (a.out2 && c >= a.out2_c0) a.out2[(size_t)pix * a.out2_stride + (c - a.out2_c0)] = v;
+        if (a.up) {  // FPN: the next stage concatenates the nearest-2x up-sampled map — store the four copies here
+            const unsigned hw = (unsigned)(a.H * a.W);
+            const unsigned n = pix / hw, rem = pix - n * hw;
+            const unsigned y = rem / (unsigned)a.W, x = rem - y * (unsigned)a.W;
+            uint4* d = a.up + (((size_t)n * 2 * a.H + 2 * y) * 2 * a.W + 2 * x) * a.up_stride + c;
+            const size_t row = (size_t)2 * a.W * a.up_stride;
+            d[0] = v; d[a.up_stride] = v; d[row] = v; d[row + a.up_stride] = v;
+        }
     }
 }
 
@@ -205,8 +214,8 @@ extern "C" int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, i
 
 extern "C" int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, void* out, int64_t out_pixel_stride,
                             const void* residual, int64_t residual_pixel_stride, void* out2, int64_t out2_pixel_stride,
-                            int out2_first_channel, int64_t n_pixels, int channels, int act, float slope, int dtype,
-                            void* stream_) {
+                            int out2_first_channel, void* up2x, int64_t up2x_pixel_stride, int height, int width,
+                            int64_t n_pixels, int channels, int act, float slope, int dtype, void* stream_) {
     FSD_CHECK_ARG(h && x && bias && out, "fsd_bias_act: null argument");
     FSD_CHECK_ARG(dtype == FSD_F16, "fsd_bias_act: only fp16 is implemented (use fsd_bias_act_inplace for fp32)");
     FSD_CHECK_ARG(n_pixels >= 0 && channels > 0 && channels % 8 == 0 && act >= 0 && act <= 2, "fsd_bias_act: bad sizes / activation");
@@ -215,7 +224,11 @@ extern "C" int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, voi
     FSD_CHECK_ARG(!out2 || (out2_first_channel >= 0 && out2_first_channel < channels && out2_first_channel % 8 == 0 &&
                             out2_pixel_stride >= channels - out2_first_channel && out2_pixel_stride % 8 == 0),
                   "fsd_bias_act: bad second destination");
-    if (((uintptr_t)x & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)out & 15) || ((uintptr_t)residual & 15) || ((uintptr_t)out2 & 15)) {
+    FSD_CHECK_ARG(!up2x || (height > 0 && width > 0 && n_pixels % ((int64_t)height * width) == 0 && up2x_pixel_stride >= channels &&
+                            up2x_pixel_stride % 8 == 0),
+                  "fsd_bias_act: the up-sampled destination needs height * width dividing n_pixels and a stride >= channels");
+    if (((uintptr_t)x & 15) || ((uintptr_t)bias & 15) || ((uintptr_t)out & 15) || ((uintptr_t)residual & 15) || ((uintptr_t)out2 & 15) ||
+        ((uintptr_t)up2x & 15)) {
         set_error("fsd_bias_act: pointers must be 16-byte aligned");
         return FSD_ERR_ALIGN;
     }
@@ -227,13 +240,14 @@ extern "C" int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, voi
     a.n_vec = (unsigned)n_vec; a.c_vec = channels / 8; a.out_stride = (int)(out_pixel_stride / 8);
     a.res_stride = (int)(residual_pixel_stride / 8); a.out2_stride = (int)(out2_pixel_stride / 8);
     a.out2_c0 = out2_first_channel / 8; a.slope = slope;
+    a.up = (uint4*)up2x; a.up_stride = (int)(up2x_pixel_stride / 8); a.H = height; a.W = width;
     const size_t want = (n_vec + K5_THREADS - 1) / K5_THREADS;
     const int grid = (int)(want < (size_t)h->sm_count * 16 ? want : (size_t)h->sm_count * 16);
     cudaStream_t s = (cudaStream_t)stream_;
     FSD_CUDA(cudaSetDevice(h->device));
     {
         // units = bytes this launch moves (read x [+ residual], write out [+ out2])
-        const int64_t bytes = (int64_t)n_pixels * 2 * ((residual ? 3 : 2) * channels + (out2 ? channels - out2_first_channel : 0));
+        const int64_t bytes = (int64_t)n_pixels * 2 * ((residual ? 3 : 2) * channels + (out2 ? channels - out2_first_channel : 0) + (up2x ? 4 * channels : 0));
         TimedLaunch timed(h, FSD_KERNEL_BIAS_ACT, bytes, channels, s);
         if (act == 0) k5_bias_act_general_half_kernel<0><<<grid, K5_THREADS, 0, s>>>(a);
         else if (act == 1) k5_bias_act_general_half_kernel<1><<<grid, K5_THREADS, 0, s>>>(a);

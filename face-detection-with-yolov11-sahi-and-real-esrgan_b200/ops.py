@@ -248,10 +248,12 @@ def _slot_stride(t: torch.Tensor, n: int, c: int, hh: int, ww: int, name: str) -
 
 
 def bias_act(x: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: float = 0.2, out: torch.Tensor | None = None,
-             residual: torch.Tensor | None = None, out2: torch.Tensor | None = None) -> torch.Tensor:
+             residual: torch.Tensor | None = None, out2: torch.Tensor | None = None,
+             up2: torch.Tensor | None = None) -> torch.Tensor:
     """(a5) general fp16 conv epilogue: out = act(x + bias[c]) (+ residual).  `x` is the dense channels-last raw
     convolution [N,C,H,W]; `out` (default: x itself), `residual` and `out2` may be channel slots (views `buf[:, a:b]`) of
-    wider channels-last buffers.  `out2` [N,C2,H,W] additionally receives the LAST C2 channels.  Returns `out`."""
+    wider channels-last buffers.  `out2` [N,C2,H,W] additionally receives the LAST C2 channels; `up2` [N,C,2H,2W] (a slot
+    too) receives the result up-sampled 2x (nearest).  Returns `out`."""
     _require_cuda(x, "x")
     n, c, hh, ww = x.shape
     if x.dtype != torch.float16 or not x.is_contiguous(memory_format=torch.channels_last):
@@ -262,10 +264,12 @@ def bias_act(x: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: floa
     sr = _slot_stride(residual, n, c, hh, ww, "residual") if residual is not None else 0
     c2 = int(out2.shape[1]) if out2 is not None else 0
     s2 = _slot_stride(out2, n, c2, hh, ww, "out2") if out2 is not None else 0
+    su = _slot_stride(up2, n, c, 2 * hh, 2 * ww, "up2") if up2 is not None else 0
     h = _handle_for(x)
     check(h.lib.fsd_bias_act(h.h, x.data_ptr(), bias.data_ptr(), out.data_ptr(), so,
                              residual.data_ptr() if residual is not None else None, sr,
                              out2.data_ptr() if out2 is not None else None, s2, c - c2 if out2 is not None else 0,
+                             up2.data_ptr() if up2 is not None else None, su, hh, ww,
                              n * hh * ww, c, _ACT[act], float(slope), _TORCH_DTYPE[x.dtype], _stream_ptr(x.device)),
           "fsd_bias_act")
     return out

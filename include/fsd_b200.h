@@ -161,10 +161,13 @@ int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, int64_t n_pi
  *      `out` / `residual` / `out2` may be channel slots of wider channels-last buffers: each has its own pixel stride
  *      (elements).  Channels >= out2_first_channel are also stored to out2 (NULL = none).  With it the epilogue of
  *      ultralytics' Conv writes straight into the concat buffer of C3k2 / SPPF / C2PSA (`torch.cat((...), 1)` in
- *      ultralytics/nn/modules/block.py, reached from utils/yolo_wrapper.py:72) and folds Bottleneck's `x + cv2(cv1(x))`. */
+ *      ultralytics/nn/modules/block.py, reached from utils/yolo_wrapper.py:72) and folds Bottleneck's `x + cv2(cv1(x))`.
+ *      up2x (NULL = none): a [N, 2*height, 2*width] pixel grid (own pixel stride) that receives every result pixel four times
+ *      = `nn.Upsample(2, "nearest")` of the output, stored straight into the FPN's next concat buffer. */
 int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, void* out, int64_t out_pixel_stride,
                  const void* residual, int64_t residual_pixel_stride, void* out2, int64_t out2_pixel_stride,
-                 int out2_first_channel, int64_t n_pixels, int channels, int act, float slope, int dtype, void* stream);
+                 int out2_first_channel, void* up2x, int64_t up2x_pixel_stride, int height, int width,
+                 int64_t n_pixels, int channels, int act, float slope, int dtype, void* stream);
 
 /* ---- (a5) SPPF pooling: buf is the [N,H,W,4c] fp16 channels-last concat buffer whose channel slot 0 holds y; fills
  *      slots 1..3 with m(y), m(m(y)), m(m(m(y))), m = MaxPool2d(kernel 5, stride 1, padding 2) (ultralytics SPPF). */

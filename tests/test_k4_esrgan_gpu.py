@@ -155,6 +155,11 @@ def test_bias_act_into_concat_slot_with_residual(cuda_device, act):
     assert torch.equal(tail, want[:, 40:])
     # in place, no extras == the dedicated in-place kernel
     assert torch.equal(ops.bias_act(x.clone(memory_format=torch.channels_last), bias, act), y)
+    # third destination: the result up-sampled 2x (nearest) into a slot of the FPN's next concat buffer
+    upbuf = torch.full((3, 40, 18, 26), float("nan"), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    dense = ops.bias_act(x.clone(memory_format=torch.channels_last), bias, act, up2=upbuf[:, :32])
+    assert torch.equal(dense, y) and torch.equal(upbuf[:, :32], torch.nn.functional.interpolate(y, scale_factor=2.0, mode="nearest"))
+    assert torch.isnan(upbuf[:, 32:]).all()
     with pytest.raises(Exception):
         ops.bias_act(x, bias, act, out=buf[:, 16:].contiguous())  # NCHW-dense is not a channels-last slot
     with pytest.raises(Exception):
