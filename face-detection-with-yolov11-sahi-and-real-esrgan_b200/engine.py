@@ -11,6 +11,7 @@ memory, streams and the conv backbone only.
 from __future__ import annotations
 
 import contextlib
+import os
 
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
@@ -82,6 +83,8 @@ class SlicedFaceDetector:
             bb = bb.to(memory_format=torch.channels_last)
         self.backbone = bb
         torch.backends.cudnn.benchmark = True  # per-shape algorithm search: the batched shapes repeat for every step
+        if os.environ.get("FSD_CUDNN_BENCHMARK_LIMIT") is not None:  # 0 = try every algorithm (default: the first 10)
+            torch.backends.cudnn.benchmark_limit = int(os.environ["FSD_CUDNN_BENCHMARK_LIMIT"])
         self._plans: Dict = {}
         self._dev_cache: Dict = {}
         self.handle = _cabi.get_handle(self.device.index or 0)
