@@ -64,7 +64,7 @@ class _Slot:
         self.t1 = torch.cuda.Event(enable_timing=True)
         self.h_off = torch.empty((n + 1,), dtype=torch.int32).pin_memory()
         self.h_rows = torch.empty((rows_cap, ops.ROW), dtype=torch.float32).pin_memory()
-        self.h_cmax = torch.empty((1,), dtype=torch.int32).pin_memory()
+        self.h_cmax = torch.empty((2,), dtype=torch.int32).pin_memory()  # max candidates per entry, max stage-1 rows per image
         self.dev = None
         self.images = None
 
@@ -113,7 +113,9 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
         n = slot.pool.n
         off = slot.h_off.numpy().copy()
         total = int(off[-1])
-        if int(slot.h_cmax[0]) > eng.cap:  # a slice overflowed the candidate capacity: redo this batch synchronously
+        eng.check_det_overflow(int(slot.h_cmax[1]), slot.dev["tables"]["det_cap"])
+        # compared with the capacity THIS batch was enqueued with (eng.cap may have grown since, through another batch's redo)
+        if int(slot.h_cmax[0]) > slot.dev["cap"]:  # a slice overflowed the candidate capacity: redo this batch synchronously
             batch = eng.detect(slot.pool, slice_height, slice_width, overlap_height_ratio, overlap_width_ratio,
                                perform_standard_pred, postprocess_type, postprocess_match_metric, postprocess_match_threshold)
             off, total = batch.offsets, int(batch.offsets[-1])
@@ -196,7 +198,7 @@ def predict_stream(batches, detection_model, slice_height: int, slice_width: int
             slot.h_off.copy_(dev["offsets"], non_blocking=True)
             slot.h_rows.copy_(dev["rows"][: slot.h_rows.shape[0]], non_blocking=True)
             cmax = dev["count_s"].max() if dev["count_f"] is None else torch.maximum(dev["count_s"].max(), dev["count_f"].max())
-            slot.h_cmax.copy_(cmax.reshape(1), non_blocking=True)
+            slot.h_cmax.copy_(torch.stack((cmax, dev["dmax"])).to(torch.int32), non_blocking=True)
             slot.event.record(dev.get("stream", slot.stream))
         slot.dev = dev
         pending.append(slot)

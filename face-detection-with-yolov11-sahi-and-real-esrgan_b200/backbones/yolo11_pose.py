@@ -289,8 +289,12 @@ class PoseHead(nn.Module):
 class YOLO11Pose(nn.Module):
     strides = (8, 16, 32)
 
-    def __init__(self, nc=1, kpt_shape=(5, 3), depth=0.50, width=0.25, max_channels=1024):
+    def __init__(self, nc=1, kpt_shape=(5, 3), depth=0.50, width=0.25, max_channels=1024, c3k_all=False):
+        """yolo11.yaml scales: n (0.50, 0.25, 1024), s (0.50, 0.50, 1024), m (0.50, 1.00, 512), l (1.00, 1.00, 512),
+        x (1.00, 1.50, 512); the m/l/x scales use C3k inside every C3k2 (`c3k_all`, ultralytics parse_model)."""
         super().__init__()
+        self.arch = dict(nc=nc, kpt_shape=tuple(kpt_shape), depth=depth, width=width, max_channels=max_channels, c3k_all=c3k_all)
+        k = bool(c3k_all)
         ch = lambda c: _make_divisible(min(c, max_channels) * width, 8)  # noqa: E731
         rep = lambda n: max(round(n * depth), 1)  # noqa: E731
         c64, c128, c256, c512, c1024 = ch(64), ch(128), ch(256), ch(512), ch(1024)
@@ -298,9 +302,9 @@ class YOLO11Pose(nn.Module):
         # backbone
         self.b0 = Conv(3, c64, 3, 2)
         self.b1 = Conv(c64, c128, 3, 2)
-        self.b2 = C3k2(c128, c256, rep(2), False, 0.25)
+        self.b2 = C3k2(c128, c256, rep(2), k, 0.25)
         self.b3 = Conv(c256, c256, 3, 2)
-        self.b4 = C3k2(c256, c512, rep(2), False, 0.25)
+        self.b4 = C3k2(c256, c512, rep(2), k, 0.25)
         self.b5 = Conv(c512, c512, 3, 2)
         self.b6 = C3k2(c512, c512, rep(2), True)
         self.b7 = Conv(c512, c1024, 3, 2)
@@ -308,10 +312,10 @@ class YOLO11Pose(nn.Module):
         self.b9 = SPPF(c1024, c1024, 5)
         self.b10 = C2PSA(c1024, c1024, rep(2))
         # neck
-        self.h13 = C3k2(c1024 + c512, c512, rep(2), False)
-        self.h16 = C3k2(c512 + c512, c256, rep(2), False)
+        self.h13 = C3k2(c1024 + c512, c512, rep(2), k)
+        self.h16 = C3k2(c512 + c512, c256, rep(2), k)
         self.h17 = Conv(c256, c256, 3, 2)
-        self.h19 = C3k2(c256 + c512, c512, rep(2), False)
+        self.h19 = C3k2(c256 + c512, c512, rep(2), k)
         self.h20 = Conv(c512, c512, 3, 2)
         self.h22 = C3k2(c512 + c1024, c1024, rep(2), True)
         self.head = PoseHead(nc, kpt_shape, (c256, c512, c1024))

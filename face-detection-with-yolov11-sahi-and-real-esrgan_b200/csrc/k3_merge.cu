@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
             parent[r] = -1;
             runs[r] = -1;
         } else {
-            p.parent[g] = -1;  // cut by the pre-NMS cap
+            if (p.parent) p.parent[g] = -1;  // cut by the pre-NMS cap
         }
     }
     if (tid == 0) { s_ktotal = 0; s_stop = 0; }
@@ -488,7 +488,7 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
             __stcg(parent + r, -1);
             __stcg(runs + r, -1);
         } else {
-            p.parent[g] = -1;  // cut by the pre-NMS cap
+            if (p.parent) p.parent[g] = -1;  // cut by the pre-NMS cap
         }
     }
     for (int i = gtid; i < (m + 31) / 32; i += TT) __stcg(rem + i, 0u);

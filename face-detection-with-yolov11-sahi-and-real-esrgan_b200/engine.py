@@ -22,6 +22,7 @@ import torch
 from . import _cabi, ops
 
 ROW = ops.ROW
+MAX_STAGE2_SEGMENT = 32768  # fsd_merge's max_segment limit
 
 
 @dataclass
@@ -82,9 +83,11 @@ class SlicedFaceDetector:
         if channels_last:
             bb = bb.to(memory_format=torch.channels_last)
         self.backbone = bb
-        torch.backends.cudnn.benchmark = True  # per-shape algorithm search: the batched shapes repeat for every step
-        if os.environ.get("FSD_CUDNN_BENCHMARK_LIMIT") is not None:  # 0 = try every algorithm (default: the first 10)
-            torch.backends.cudnn.benchmark_limit = int(os.environ["FSD_CUDNN_BENCHMARK_LIMIT"])
+        # per-shape cuDNN algorithm search (the batched shapes repeat for every step) is switched on around the backbone
+        # calls only (_cudnn_scope): constructing a detector does not change the process-wide torch.backends.cudnn flags
+        self.cudnn_benchmark = True
+        self._cudnn_limit = (int(os.environ["FSD_CUDNN_BENCHMARK_LIMIT"])  # 0 = try every algorithm (default: the first 10)
+                             if os.environ.get("FSD_CUDNN_BENCHMARK_LIMIT") is not None else None)
         self._plans: Dict = {}
         self._dev_cache: Dict = {}
         self.handle = _cabi.get_handle(self.device.index or 0)
@@ -98,6 +101,7 @@ class SlicedFaceDetector:
         self._graphs: Dict = {}
         self._graph_pools: Dict = {}
         self._xbufs: Dict = {}
+        self.last_stage1 = None
         self.replayed_launches = 0  # fsd kernels executed through graph replays (the handle only counts direct launches)
 
     # ------------------------------------------------------------------------------------------ planning
@@ -128,7 +132,10 @@ class SlicedFaceDetector:
         t = dict(ent_s=ent_s, geo_s=geo_s, fgeo_s=fgeo_s,
                  grange_s=torch.tensor([[i * S, (i + 1) * S] for i in range(N)], **i32),
                  seg_s=torch.arange(N * S, **i32) * self.cap)
-        det_cap = (S + (1 if plan.g_full else 0)) * self.max_det
+        # worst case (S+1)*max_det per image, bounded by Kernel 3's segment limit: images with >= 109 slices (e.g. 8000x6000
+        # at 640/0.2 = 192 slices) are accepted, and only an image that really produces more than 32768 per-slice detections
+        # is refused (check_det_overflow) — never truncated silently
+        det_cap = min((S + (1 if plan.g_full else 0)) * self.max_det, MAX_STAGE2_SEGMENT)
         t["det_cap"] = det_cap
         t["goff"] = torch.arange(N, **i32) * det_cap
         if plan.g_full is not None:
@@ -141,14 +148,25 @@ class SlicedFaceDetector:
         self._dev_cache[key] = t
         return t
 
+    @staticmethod
+    def check_det_overflow(dmax: int, det_cap: int):
+        if dmax > det_cap:
+            raise _cabi.FsdError(f"an image produced {dmax} per-slice detections, more than the {det_cap} one stage-2 merge "
+                                 "segment holds (Kernel 3 limit 32768): raise the confidence threshold or use merge_buffer_length")
+
     # ------------------------------------------------------------------------------------------ stages
+    def _cudnn_scope(self):
+        """cudnn.benchmark (and the optional search limit) for the backbone calls of this engine only."""
+        return ops.cudnn_benchmark(self.cudnn_benchmark, self._cudnn_limit)
+
     def _forward_entries(self, kind: str, x: torch.Tensor, cand: torch.Tensor, count: torch.Tensor):
         """backbone + Kernel 2a over a batch of network inputs, in chunks that bound activation memory."""
         E = x.shape[0]
         graphs = self.use_graphs and self.head_hook is None
         for a in range(0, E, self.chunk):
             xb = x[a:a + self.chunk]  # Kernel 1 already wrote the layout the backbone wants: no conversion pass
-            levels = self._graph_forward(xb) if graphs else self.backbone(xb)
+            with self._cudnn_scope():
+                levels = self._graph_forward(xb) if graphs else self.backbone(xb)
             if self.head_hook is not None:
                 levels = self.head_hook(kind, a, xb, levels)
             ops.pose_decode(levels, self.conf, cand=cand[a:a + self.chunk], count=count[a:a + self.chunk])
@@ -259,21 +277,30 @@ class SlicedFaceDetector:
                                       t["goff"], det, dcount, t["det_cap"], self.truncate)
                 # stage 2: cross-slice merge per image (skipped by the reference when an image has <= 1 prediction:
                 # a single box is its own keep, so running it is equivalent)
+                # (this path has ONE category, "face": without a category array Kernel 3 treats every pair as same-class, so
+                # class_agnostic True and False give the same result — exactly as sahi's batched_* variants do for one class)
                 s2 = ops.merge_segments(det, t["goff"], dcount, t["det_cap"], merge_type=postprocess_type,
                                         metric=match_metric, thr=match_threshold, cmp_strict=False, precision="fp64",
-                                        class_agnostic=True, want_parent=False)  # one class ("face") on this path
+                                        class_agnostic=bool(class_agnostic), want_parent=False)
+                # per-image stage-1 detections BEFORE the det_cap clamp (overflow is reported, never silently truncated)
+                dmax = s1["keep_count"].view(N, S).sum(1)
+                if cand_f is not None:
+                    dmax = dmax + s1f["keep_count"]
+                dmax = dmax.max()
                 src = ops.attach_keypoints(s2["boxes"], t["goff"], s2["keep_count"], det, t["goff"], dcount)
                 rows, offsets = ops.pack_results(det, t["goff"], s2, src)
             if post is not None and not to_host:
                 return dict(rows=rows, offsets=offsets, det=det, dcount=dcount, count_s=count_s, count_f=count_f, plan=plan,
-                            stream=post)
+                            stream=post, cap=self.cap, tables=t, dmax=dmax)
             if post is not None:
                 main.wait_stream(post)  # synchronous form: the results are read on the calling stream below
             if not to_host:
-                return dict(rows=rows, offsets=offsets, det=det, dcount=dcount, count_s=count_s, count_f=count_f, plan=plan)
+                return dict(rows=rows, offsets=offsets, det=det, dcount=dcount, count_s=count_s, count_f=count_f, plan=plan,
+                            cap=self.cap, tables=t, dmax=dmax)
             # ---- the only device->host traffic of the batch: counts, then exactly the packed rows
             off_h = offsets.cpu().numpy()
             cmax = int(count_s.max()) if count_f is None else max(int(count_s.max()), int(count_f.max()))
+            self.check_det_overflow(int(dmax), t["det_cap"])
             if cmax > self.cap:
                 self.cap = 1 << (cmax - 1).bit_length()
                 self._dev_cache.clear()
@@ -290,6 +317,7 @@ class SlicedFaceDetector:
             dc = dcount.cpu().numpy()
             d = det.cpu().numpy().reshape(N, t["det_cap"], ROW)
             out.stage1 = dict(count=dc, rows=[d[i, : dc[i]].copy() for i in range(N)])
+            self.last_stage1 = out.stage1  # parity tests compare the per-slice detections behind the reference-facing call
         return out
 
     # ------------------------------------------------------------------------------------------ single entry

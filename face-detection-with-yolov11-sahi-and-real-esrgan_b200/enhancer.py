@@ -26,10 +26,12 @@ class RealESRGANer:
         self.device = torch.device(device) if device is not None else torch.device(f"cuda:{gpu_id or 0}")
         if model is None:
             model = RRDBNet(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=23, num_grow_ch=32, scale=scale)
-        if model_path and isinstance(model_path, str) and os.path.isfile(model_path):
-            state = torch.load(model_path, map_location="cpu", weights_only=True)
-            key = "params_ema" if "params_ema" in state else ("params" if "params" in state else None)
-            model.load_state_dict(state[key] if key else state, strict=True)
+        self.weights = "random-init"
+        if model_path:  # like RealESRGANer: a given path is loaded ('params_ema' preferred) or the call raises
+            from .checkpoints import load_rrdbnet_state
+
+            model.load_state_dict(load_rrdbnet_state(str(model_path)), strict=True)
+            self.weights = str(model_path)
         model = model.to(self.device).eval()
         for p in model.parameters():
             p.requires_grad_(False)
@@ -63,7 +65,8 @@ class RealESRGANer:
                 part = idxs[a:a + self.max_tile_batch]
                 views = [ops.tile_view(tiles[n], table[i]) for n, i in part]
                 x = torch.cat(views, 0) if len(part) > 1 else views[0]
-                y = self.model(x)
+                with ops.cudnn_benchmark():  # tile shapes repeat frame after frame
+                    y = self.model(x)
                 for j, (n, i) in enumerate(part):
                     ops.tile_view(outbuf[n], table[i], s, out=True).copy_(y[j:j + 1])
         out = ops.esrgan_stitch(outbuf, table, tab_dev, s, H, W)
@@ -80,8 +83,12 @@ class RealESRGANer:
 
 
 class FaceEnhancer:
-    def __init__(self, model_name="RealESRGAN_x4plus", model_path=None, scale=4, tile=400, half=True):
+    def __init__(self, model_name="RealESRGAN_x4plus", model_path=None, scale=4, tile=400, half=True,
+                 allow_random_init=False):
+        """As utils/enhancer.py:21-60: the constructor raises when the weights cannot be found — unless
+        `allow_random_init=True` (tests / bench: there is no network for the real weights)."""
         self.model_name, self.scale, self.tile, self.half = model_name, scale, tile, half
+        self.allow_random_init = allow_random_init
         self.upsampler = None
         self.device = self._check_device()
         self._setup_model(model_name, model_path)
@@ -100,6 +107,13 @@ class FaceEnhancer:
             raise _cabi.FsdError("fsd_b200.FaceEnhancer needs a CUDA device: the tile crop/stitch kernels have no CPU fallback")
         if model_path is None:
             model_path = self._find_model_path(model_name)
+        if model_path is None or not os.path.isfile(str(model_path)):
+            # the reference cannot continue either: RealESRGANer(model_path=None) raises inside the constructor
+            # (utils/enhancer.py:131-186 retries once, then re-raises); there is no network here to download weights
+            if not self.allow_random_init:
+                raise FileNotFoundError(f"Real-ESRGAN weights for {model_name} not found ({model_path}); pass model_path=... "
+                                        "(or allow_random_init=True for tests / benchmarks)")
+            model_path = None
         blocks = 6 if "anime_6B" in model_name else 23
         if "x2" in model_name and "anime_6B" not in model_name:
             self.scale = 2

@@ -5,7 +5,9 @@ path is done by the hand-written sm_100a kernels in csrc/.  All functions raise 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
@@ -14,6 +16,39 @@ from . import _cabi
 from ._cabi import FSD_F16, FSD_F32, check, get_handle
 
 _TORCH_DTYPE = {torch.float16: FSD_F16, torch.float32: FSD_F32}
+
+
+@contextlib.contextmanager
+def cudnn_benchmark(on: bool = True, limit: int | None = None):
+    """Per-shape cuDNN algorithm search around the library convolutions of the backbones, restored on exit: the product
+    never leaves process-wide torch.backends.cudnn flags changed behind the caller's back."""
+    cud = torch.backends.cudnn
+    old = (cud.benchmark, cud.benchmark_limit)
+    cud.benchmark = bool(on)
+    if limit is not None:
+        cud.benchmark_limit = int(limit)
+    try:
+        yield
+    finally:
+        cud.benchmark, cud.benchmark_limit = old
+
+
+_WARNED_CPU = []
+
+
+def resolve_device(device) -> str:
+    """The CUDA device a plug-in runs on.  The reference's plug-ins default to device='cpu' (utils/yolo_wrapper.py:8); this
+    library has no CPU path, so a CPU request is redirected to cuda:0 with ONE warning per process (never silently), and
+    raises when no CUDA device is visible."""
+    d = str(device)
+    if d in ("cpu", "None", ""):
+        if not torch.cuda.is_available():
+            raise _cabi.FsdError("fsd_b200 runs on CUDA only (no CPU fallback) and no CUDA device is visible")
+        if not _WARNED_CPU:
+            _WARNED_CPU.append(d)
+            warnings.warn(f"device={device!r} requested, but fsd_b200 has no CPU path: running on cuda:0", RuntimeWarning, stacklevel=3)
+        return "cuda:0"
+    return d
 
 
 def _require_cuda(t: torch.Tensor, name: str):

@@ -62,12 +62,9 @@ class YOLOv11PoseDetectionModel(DetectionModel):
         self.keypoints_cache = {}
 
     def _cuda_device(self):
-        d = str(self.device)
-        if d == "cpu" or d == "None":
-            if not torch.cuda.is_available():
-                raise RuntimeError("fsd_b200 plug-ins run on CUDA only (no CPU fallback)")
-            return "cuda:0"
-        return d
+        from . import ops
+
+        return ops.resolve_device(self.device)
 
     def engine(self):
         eng = self.model.engine(self._cuda_device(), self.half)

@@ -74,9 +74,7 @@ def _fused_sliced_prediction(image_as_pil, detection_model, slice_height, slice_
     from .. import ops
 
     model = detection_model.model
-    dev = str(getattr(detection_model, "device", "cuda:0"))
-    if dev in ("cpu", "None"):
-        dev = "cuda:0"
+    dev = ops.resolve_device(getattr(detection_model, "device", "cuda:0"))
     eng = model.engine(dev, getattr(detection_model, "half", True))
     eng.conf, eng.imgsz, eng.truncate = detection_model.confidence_threshold, detection_model.image_size, True
     arr = np.ascontiguousarray(image_as_pil)  # what get_prediction hands to perform_inference (channel order as-is)

@@ -1,13 +1,12 @@
 """`ultralytics.YOLO`-shaped front end over the B200 pipeline (the `.model` attribute of the reference plugin,
 utils/yolo_wrapper.py:55,74-80; also called raw by eval/eval_official_widerface.py:149,219).
 
-`YOLO(path)` loads a state_dict saved by `YOLO.save()`; ultralytics pickles cannot be read without ultralytics, so
-any other path yields the deterministic random-init YOLO11n-pose of backbones/yolo11_pose.py (there is no network
-for real checkpoints; parity is judged after the backbone).  `predict()` runs Kernel 1 -> backbone -> Kernel 2a ->
+`YOLO(path)` loads a file saved by `YOLO.save()` or an ultralytics checkpoint (checkpoints.py reads the pickle without
+ultralytics and folds Conv+BN); an unloadable path raises.  `YOLO("random-init")` is the deterministic random-init
+YOLO11n-pose of backbones/yolo11_pose.py (there is no network for real checkpoints; parity is judged after the backbone).  `predict()` runs Kernel 1 -> backbone -> Kernel 2a ->
 Kernel 3 (per-image NMS) -> Kernel 2b on the GPU and returns `Results` with CUDA tensors."""
 from __future__ import annotations
 
-import os
 from typing import Optional
 
 import numpy as np
@@ -62,23 +61,38 @@ class Results:
 class YOLO:
     names = {0: "face"}
 
-    def __init__(self, model="yolo11n-pose.pt", task: Optional[str] = None, verbose: bool = False, seed: int = 0):
+    def __init__(self, model="yolo11n-pose.pt", task: Optional[str] = None, verbose: bool = False, seed: int = 0,
+                 allow_random_init: bool = False):
+        """`model`: a checkpoint path (this package's `save()` format or an ultralytics `best.pt`, read without
+        ultralytics by checkpoints.read_ultralytics_checkpoint), a torch module, or the literal "random-init".
+        Like `ultralytics.YOLO(path)` (utils/yolo_wrapper.py:55) a path that cannot be loaded RAISES — FileNotFoundError
+        or checkpoints.CheckpointError; the deterministic random-init YOLO11n-pose (there is no network for real weights
+        here: tests, bench) must be requested explicitly with model="random-init" or allow_random_init=True."""
         self.ckpt_path = model if isinstance(model, str) else None
+        self.info = dict(scale="n", nc=1, kpt_shape=(5, 3), names=dict(self.names), source="random-init")
         if isinstance(model, torch.nn.Module):
             self.model = model
-        else:
+            self.info["source"] = "module"
+        elif model == "random-init":
             self.model = build_yolo11n_pose(seed=seed)
-            if isinstance(model, str) and os.path.isfile(model):
-                try:
-                    state = torch.load(model, map_location="cpu", weights_only=True)
-                    self.model.load_state_dict(state["model"] if "model" in state else state)
-                except Exception as e:  # an ultralytics pickle or a foreign file
-                    print(f"[fsd_b200] {model}: not a fsd_b200 state_dict ({type(e).__name__}); using random-init YOLO11n-pose")
+        else:
+            from .checkpoints import load_yolo
+
+            try:
+                self.model, info = load_yolo(model)
+                self.info.update(info, source=model)
+                self.names = dict(info.get("names") or self.names)
+            except (FileNotFoundError, ValueError):
+                if not allow_random_init:
+                    raise
+                print(f"[fsd_b200] {model}: not loadable, allow_random_init=True -> random-init YOLO11n-pose")
+                self.model = build_yolo11n_pose(seed=seed)
         self.task = "pose"
         self._engines = {}
 
     def save(self, path: str):
-        torch.save({"model": self.model.state_dict()}, path)
+        torch.save({"model": self.model.state_dict(), "arch": {k: (list(v) if isinstance(v, tuple) else v)
+                                                             for k, v in getattr(self.model, "arch", {}).items()}}, path)
 
     def to(self, device):
         return self

@@ -102,7 +102,7 @@ def test_enhancer_matches_reference(cuda_device):
 def test_face_enhancer_contract(cuda_device):
     from fsd_b200.enhancer import FaceEnhancer
 
-    fe = FaceEnhancer(model_name="RealESRGAN_x2plus", model_path=None, scale=4, tile=64, half=True)
+    fe = FaceEnhancer(model_name="RealESRGAN_x2plus", model_path=None, scale=4, tile=64, half=True, allow_random_init=True)
     assert fe.scale == 2 and fe.device == "cuda" and fe.get_model_info()["is_loaded"]
     img = np.random.default_rng(0).integers(0, 256, (70, 90, 3), dtype=np.uint8)
     out, ok = fe.enhance_image(img)

@@ -1,0 +1,204 @@
+"""Oracle-checked parity at BASELINE.json's OWN configurations, full size (VERDICT r1 "next" item 1):
+
+  C2  768x1024, 512^2 slices, imgsz 1024: GREEDYNMM/IOS/0.5 at conf 0.5 and the evaluator variant NMS/IOS at conf 0.01
+      (eval/eval_official_widerface.py:69,200-207), 8 images each;
+  C1  1080x1920, 640^2 slices, imgsz 1024, GREEDYNMM/IOS (docs sahi/predict.py:142-345 defaults), 2 images;
+  C3  2160x3840, 32+1 slices of 640^2, a synthetic >= 1000-box detector through the InsightFaceDetectionModel contract
+      (utils/insightface_wrapper.py:52-98), NMS/IOU — one image with > 4096 stage-2 boxes so that the 8-CTA cluster
+      kernel is checked against the ORACLE (not against the single-CTA kernel);
+  C4  detections of a C1 image -> crops (save_face_crops rules) -> x4 tiled enhancement (tile 256, pad 10), plus three
+      600x500 crops (3x2 tiles), with the exact affine up-sampler: bit-exact vs the oracle RealESRGANer;
+  C5  1080x1920 -> x2 tiled (tile 400, pad 10) -> 2160x3840 -> SAHI 640^2 (32+1 slices) with the YOLO plug-in;
+  fp16 device pipeline vs the fp32 CPU flow (own backbone, nothing replayed): AP-level comparison on 32 C2 images.
+
+Bars as everywhere: bit-exact boxes / keeps / groupings, <= 1e-4 px (or 2 ulp) on key-points, <= 1e-3 on scores, identical
+WIDER-FACE-protocol AP; int() flips are handled as described in tests/parity_utils.py (no image is skipped)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import fake_detectors as fd  # noqa: E402
+from parity_utils import as_rows, run_sliced_case  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,conf,ptype,metric,n", [
+    ("C2-greedynmm-ios-conf0.5", 0.5, "GREEDYNMM", "IOS", 8),
+    ("C2-evaluator-nms-ios-conf0.01", 0.01, "NMS", "IOS", 8),
+], ids=lambda v: v if isinstance(v, str) and v.startswith("C2") else None)
+def test_c2_full_size_equals_oracle(cuda_device, name, conf, ptype, metric, n):
+    out = run_sliced_case(768, 1024, 512, 0.2, 1024, conf, ptype, metric, n_images=n, seed0=1234, mean_faces=12, face_px=(6, 200))
+    print(name, out)
+    assert out["stage1"] > (1000 if conf < 0.1 else 50) and out["boxes"] > 20
+
+
+def test_c1_full_size_equals_oracle(cuda_device):
+    out = run_sliced_case(1080, 1920, 640, 0.2, 1024, 0.5, "GREEDYNMM", "IOS", n_images=2, seed0=1234, mean_faces=40, face_px=(12, 120))
+    print("C1", out)
+    assert out["stage1"] > 50 and out["boxes"] > 20
+
+
+def _dense_faces(height, width, pitch, seed, lo=10, hi=40):
+    """dense grid of lo..hi px boxes with jitter"""
+    rng = np.random.default_rng(seed)
+    faces = []
+    for y in range(4, height - hi - 4, pitch):
+        for x in range(4, width - hi - 4, pitch):
+            w, h = rng.uniform(lo, hi), rng.uniform(lo, hi)
+            jx, jy = rng.uniform(0, pitch - hi), rng.uniform(0, pitch - hi)
+            faces.append((x + jx, y + jy, x + jx + w, y + jy + h))
+    return faces
+
+
+@pytest.mark.parametrize("pitch,ptype,metric,min_stage2", [(100, "NMS", "IOU", 1000), (46, "NMS", "IOU", 4097), (46, "GREEDYNMM", "IOS", 4097)])
+def test_c3_crowd_scale_insightface_contract_equals_oracle(cuda_device, pitch, ptype, metric, min_stage2):
+    from fsd_b200.plugins import InsightFaceDetectionModel
+    from fsd_b200.sahi_api import get_sliced_prediction
+    from oracle import predict as opred
+    from oracle import yolo_wrapper as owrap
+
+    H, W = 2160, 3840
+    img = fd.coordinate_image(H, W)
+    fd.FakeFaceAnalysis.faces = _dense_faces(H, W, pitch, seed=pitch)
+    kw = dict(slice_height=640, slice_width=640, overlap_height_ratio=0.2, overlap_width_ratio=0.2, postprocess_type=ptype,
+              postprocess_match_metric=metric, postprocess_match_threshold=0.5, verbose=0)
+    omodel = owrap.InsightFaceDetectionModel(model=fd.FakeFaceAnalysis(), confidence_threshold=0.4)
+    counter = {"n": 0}
+    orig = omodel._create_object_prediction_list_from_original_predictions
+
+    def counting(*a, **k):
+        orig(*a, **k)
+        counter["n"] += len(omodel._object_prediction_list_per_image[0])
+
+    omodel._create_object_prediction_list_from_original_predictions = counting
+    want = opred.get_sliced_prediction(img, omodel, **kw)
+    assert counter["n"] >= min_stage2, f"only {counter['n']} stage-2 boxes"
+    got = get_sliced_prediction(img, InsightFaceDetectionModel(model=fd.FakeFaceAnalysis(), confidence_threshold=0.4), **kw)
+    a, b = as_rows(got.object_prediction_list), as_rows(want.object_prediction_list)
+    assert len(a) == len(b) and len(a) >= 400
+    assert [r[0] for r in a] == [r[0] for r in b], "merged boxes / kept set / order differ from the oracle"
+    assert [r[1] for r in a] == [r[1] for r in b]
+    print(f"C3 pitch {pitch} {ptype}/{metric}: {counter['n']} stage-2 boxes -> {len(a)} kept")
+
+
+def test_c4_detection_first_crops_x4_equals_oracle(cuda_device):
+    """Config 4 with the exact up-sampler: every crop the reference would cut (utils/visualization.py:206-221 rules) from the
+    detections of a C1 image, plus three 600x500 crops (3x2 tiles at tile 256), enhanced x4 by Kernel 4 crop -> network ->
+    Kernel 4 stitch, bit-exact against the oracle's RealESRGANer (pre_pad 0, tile_pad 10, as utils/enhancer.py:131-148)."""
+    import fsd_b200.pipelines as pp
+    from fsd_b200.enhancer import RealESRGANer
+    from fsd_b200.plugins import YOLOv11PoseDetectionModel
+    from fsd_b200.synthetic import make_image
+    from fsd_b200.yolo import YOLO
+    from oracle import esrgan as oesr
+    from oracle import pipelines as opipe
+
+    img, _ = make_image(1234, 1080, 1920, mean_faces=40, face_px=(12, 120))
+    model = YOLOv11PoseDetectionModel(model=YOLO("random-init"), confidence_threshold=0.5, device="cuda:0", image_size=1024)
+    up = RealESRGANer(scale=4, model=fd.AffineUpsampler(scale=4), tile=256, tile_pad=10, pre_pad=0, half=False)
+    res, crops = pp.detect_then_enhance(img, model, up, slice_params=(640, 640))
+    rects = opipe.crop_rectangles([p.bbox.to_xyxy() for p in res.object_prediction_list], 1920, 1080)
+    assert len(rects) == len(crops) and len(rects) >= 10
+    oup = oesr.RealESRGANer(scale=4, model=fd.AffineUpsampler(scale=4), tile=256, tile_pad=10, pre_pad=0, half=False)
+    n_big = 0
+    for (x1, y1, x2, y2), got in zip(rects, crops):
+        src = img[y1:y2, x1:x2]
+        if y2 - y1 < 4 or x2 - x1 < 4:
+            assert np.array_equal(got, src)
+            continue
+        want, _ = oup.enhance(np.ascontiguousarray(src), outscale=4)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        n_big += 1
+    assert n_big >= 5
+    for k in range(3):  # 600x500 crops: ceil(500/256) x ceil(600/256) = 2 x 3 tiles
+        y0, x0 = 100 + 150 * k, 200 + 400 * k
+        src = np.ascontiguousarray(img[y0:y0 + 600, x0:x0 + 500])
+        got = up.enhance_device(torch.from_numpy(src).to(cuda_device)).cpu().numpy()
+        want, _ = oup.enhance(src, outscale=4)
+        assert got.shape == (2400, 2000, 3) and np.array_equal(got, want)
+
+
+def test_c5_enhancement_first_x2_then_sahi_equals_oracle(cuda_device):
+    """Config 5: 1080x1920 -> x2 (tile 400, pad 10: 15 tiles; exact affine up-sampler) -> 2160x3840, bit-exact against the
+    oracle RealESRGANer; then SAHI 640^2 (32 + 1 slices, imgsz 1024) on the enhanced image against the oracle flow."""
+    from fsd_b200.enhancer import RealESRGANer
+    from fsd_b200.synthetic import make_image
+    from oracle import esrgan as oesr
+
+    img, gt = make_image(1234, 1080, 1920, mean_faces=40, face_px=(12, 120))
+    up = RealESRGANer(scale=2, model=fd.AffineUpsampler(scale=2), tile=400, tile_pad=10, pre_pad=0, half=False)
+    big = up.enhance_device(torch.from_numpy(img).to(cuda_device)).cpu().numpy()
+    want_big, _ = oesr.RealESRGANer(scale=2, model=fd.AffineUpsampler(scale=2), tile=400, tile_pad=10, pre_pad=0, half=False).enhance(img, outscale=2)
+    assert big.shape == (2160, 3840, 3) and np.array_equal(big, want_big)
+    gt2 = gt * 2.0
+    out = run_sliced_case(2160, 3840, 640, 0.2, 1024, 0.5, "GREEDYNMM", "IOS", n_images=1, images=[(big, gt2)])
+    print("C5", out)
+    assert out["stage1"] > 100 and out["boxes"] > 40
+
+
+def test_fp16_device_pipeline_vs_fp32_cpu_flow_ap(cuda_device):
+    """The shipped fp16 pipeline against the fp32 CPU flow ON THE SAME IMAGES with each side's OWN backbone (nothing is
+    replayed): what the precision change costs, as WIDER-FACE-protocol AP and as a box-level match rate.  The fp32 device
+    pipeline (half=False) is compared as well.  32 C2-shaped images (512^2 slices; imgsz 512 keeps the CPU side in
+    seconds — the arithmetic under test is the same at 1024)."""
+    from fsd_b200.api import get_sliced_prediction_batch
+    from fsd_b200.plugins import YOLOv11PoseDetectionModel
+    from fsd_b200.synthetic import make_image
+    from fsd_b200.yolo import YOLO
+    from oracle import predict as opred
+    from oracle import widerface_eval as oe
+    from oracle.yolo11_pose_plain import build_plain_yolo11n_pose
+    from oracle.yolo_head import OracleYOLO
+    from oracle.yolo_wrapper import YOLOv11PoseDetectionModel as OracleModel
+
+    n, conf = 32, 0.25
+    pairs = [make_image(5000 + i, 768, 1024, mean_faces=12) for i in range(n)]
+    imgs, gts = [p[0] for p in pairs], [p[1] for p in pairs]
+    yolo = YOLO("random-init")
+    plain = build_plain_yolo11n_pose(state_dict={k: v.float() for k, v in yolo.model.state_dict().items()})
+    omodel = OracleModel(model=OracleYOLO(plain, half=False), confidence_threshold=conf, device="cpu", image_size=512)
+    kw = dict(slice_height=512, slice_width=512, overlap_height_ratio=0.2, overlap_width_ratio=0.2)
+    cpu = [as_rows(opred.get_sliced_prediction(im, omodel, verbose=0, **kw).object_prediction_list) for im in imgs]
+    res = {}
+    for name, half in (("fp16", True), ("fp32", False)):
+        model = YOLOv11PoseDetectionModel(model=yolo, confidence_threshold=conf, device="cuda:0", image_size=512, half=half)
+        out = get_sliced_prediction_batch(imgs, model, 512, 512, 0.2, 0.2)
+        res[name] = [as_rows(r.object_prediction_list) for r in out]
+
+    def xywh(rows):
+        return np.array([[r[0][0], r[0][1], r[0][2] - r[0][0], r[0][3] - r[0][1], r[1]] for r in rows], dtype=float).reshape(-1, 5)
+
+    def match_rate(a_rows, b_rows):
+        hit = tot = 0
+        for a, b in zip(a_rows, b_rows):
+            tot += len(b)
+            if not a or not b:
+                continue
+            A = np.array([r[0] for r in a], dtype=float); B = np.array([r[0] for r in b], dtype=float)
+            ix = np.clip(np.minimum(A[:, None, 2], B[None, :, 2]) - np.maximum(A[:, None, 0], B[None, :, 0]), 0, None)
+            iy = np.clip(np.minimum(A[:, None, 3], B[None, :, 3]) - np.maximum(A[:, None, 1], B[None, :, 1]), 0, None)
+            inter = ix * iy
+            ua = (A[:, 2] - A[:, 0]) * (A[:, 3] - A[:, 1]); ub = (B[:, 2] - B[:, 0]) * (B[:, 3] - B[:, 1])
+            iou = inter / np.maximum(ua[:, None] + ub[None, :] - inter, 1e-9)
+            hit += int((iou.max(0) >= 0.9).sum())
+        return hit / max(tot, 1)
+
+    report = {}
+    for setting in ("easy", "medium", "hard"):
+        keeps = [oe.difficulty_keep_lists(g)[setting] for g in gts]
+        ap_cpu, _ = oe.evaluate_setting([xywh(r) for r in cpu], gts, keeps, thresh_num=1000)
+        for name in res:
+            ap, _ = oe.evaluate_setting([xywh(r) for r in res[name]], gts, keeps, thresh_num=1000)
+            report[(setting, name)] = (ap, ap_cpu)
+            assert abs(ap - ap_cpu) <= 0.02, f"{setting} {name}: AP {ap} vs fp32 CPU {ap_cpu}"
+    rates = {name: match_rate(res[name], cpu) for name in res}
+    print("AP (device, fp32 CPU):", report, "box match rate (IoU >= 0.9):", rates, "boxes:", sum(len(r) for r in cpu))
+    assert sum(len(r) for r in cpu) > 200
+    assert rates["fp32"] >= 0.97 and rates["fp16"] >= 0.90, rates

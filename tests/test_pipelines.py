@@ -73,7 +73,7 @@ def test_device_pipelines_run_end_to_end(cuda_device):
 
     img, _ = make_image(11, 160, 224)
     model = YOLOv11PoseDetectionModel(model=YOLO("random-init"), confidence_threshold=0.4, device="cuda:0", image_size=512)
-    fe = FaceEnhancer(model_name="RealESRGAN_x2plus", scale=2, tile=96, half=True)
+    fe = FaceEnhancer(model_name="RealESRGAN_x2plus", scale=2, tile=96, half=True, allow_random_init=True)
     res, big = pp.enhance_then_detect(img, fe, model, slice_params=(256, 256, 0.2, 0.2))
     assert tuple(big.shape) == (320, 448, 3) and (res.image_width, res.image_height) == (224, 160)
     for p in res.object_prediction_list:

@@ -33,13 +33,18 @@ def compat():
     sys.modules.update(saved)
 
 
-def test_reference_plugin_and_enhancer_import_unmodified(compat):
+def test_reference_plugin_and_enhancer_import_unmodified(compat, tmp_path):
     yw = _load("ref_yolo_wrapper_compat", "utils/yolo_wrapper.py")
     from fsd_b200.sahi_api import DetectionModel
     from fsd_b200.yolo import YOLO
 
     assert issubclass(yw.YOLOv11PoseDetectionModel, DetectionModel) and yw.YOLO is YOLO
-    m = yw.YOLOv11PoseDetectionModel(model_path="weights-that-do-not-exist.pt", confidence_threshold=0.6, device="cuda:0")
+    # like ultralytics.YOLO(path), a missing checkpoint raises out of the reference's load_model (utils/yolo_wrapper.py:55)
+    with pytest.raises(FileNotFoundError):
+        yw.YOLOv11PoseDetectionModel(model_path="weights-that-do-not-exist.pt", confidence_threshold=0.6, device="cuda:0")
+    ckpt = str(tmp_path / "best.pt")
+    YOLO("random-init").save(ckpt)
+    m = yw.YOLOv11PoseDetectionModel(model_path=ckpt, confidence_threshold=0.6, device="cuda:0")
     assert isinstance(m.model, YOLO) and m.image_size == 1024 and m.category_mapping == {"0": "face"}
     assert m.category_names == ["face"] and m.has_mask is False and m.keypoints_cache == {}
     from fsd_b200.sahi_api.predict import _fused_capable
