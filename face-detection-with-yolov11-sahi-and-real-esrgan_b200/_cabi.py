@@ -53,6 +53,9 @@ SIGNATURES = {
     "fsd_esrgan_stitch": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int64,
                                     C.c_int, C.c_int64, C.c_int64, vp]),
     "fsd_bbox_overlaps_p1": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, vp]),
+    "fsd_widerface_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "fsd_widerface_pr_curve": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_double, vp, C.c_int, vp, vp,
+                                         vp, C.c_int64, vp, vp]),
     "fsd_attach_keypoints": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
 }
 

@@ -312,30 +312,6 @@ k4_stitch_kernel(const InT* __restrict__ tiles_out, const int32_t* __restrict__ 
     }
 }
 
-// ---- (f1) WIDER-FACE bbox_overlaps with the "+1" pixel convention ------------------------------------
-__global__ void bbox_overlaps_p1_kernel(const double* __restrict__ boxes, int N, const double* __restrict__ query,
-                                        int K, double* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)N * K) return;
-    const int n = (int)(i / K), k = (int)(i % K);
-    const double* b = boxes + 4 * (size_t)n;
-    const double* q = query + 4 * (size_t)k;
-    // explicitly rounded operations in the Cython source's order (no FMA contraction: bit-identical to the CPU result)
-    const double qa = __dmul_rn(__dadd_rn(__dsub_rn(q[2], q[0]), 1.0), __dadd_rn(__dsub_rn(q[3], q[1]), 1.0));
-    const double iw = __dadd_rn(__dsub_rn(fmin(b[2], q[2]), fmax(b[0], q[0])), 1.0);
-    double v = 0.0;
-    if (iw > 0) {
-        const double ih = __dadd_rn(__dsub_rn(fmin(b[3], q[3]), fmax(b[1], q[1])), 1.0);
-        if (ih > 0) {
-            const double ba = __dmul_rn(__dadd_rn(__dsub_rn(b[2], b[0]), 1.0), __dadd_rn(__dsub_rn(b[3], b[1]), 1.0));
-            const double inter = __dmul_rn(iw, ih);
-            const double ua = __dsub_rn(__dadd_rn(ba, qa), inter);
-            v = __ddiv_rn(inter, ua);
-        }
-    }
-    out[i] = v;
-}
-
 // ---- (f2) key-point attach (utils/yolo_wrapper.py:168-217): one CTA per image, one WARP per merged box ----
 // lanes stride over the image's detections; the reference's sequential rule (exact key -> LAST detection with that box;
 // else the FIRST detection reaching the maximum IoU, if > 0.5, then the LAST detection sharing that box) is recovered
@@ -476,19 +452,6 @@ extern "C" int fsd_esrgan_stitch(fsd_handle_t h, const void* tiles_out, const in
     FSD_CUDA(cudaSetDevice(h->device));
     if (dtype == FSD_F16) k4_stitch_kernel<__half><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>((const __half*)tiles_out, table_dev, scale, out_bgr, out_h, out_w, out_pitch, tiles_image_stride, out_image_pitch);
     else k4_stitch_kernel<float><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>((const float*)tiles_out, table_dev, scale, out_bgr, out_h, out_w, out_pitch, tiles_image_stride, out_image_pitch);
-    FSD_CUDA(cudaGetLastError());
-    h->launches += 1;
-    return FSD_OK;
-}
-
-extern "C" int fsd_bbox_overlaps_p1(fsd_handle_t h, const double* boxes, int N, const double* query, int K,
-                                    double* overlaps, void* stream_) {
-    FSD_CHECK_ARG(h && N >= 0 && K >= 0, "fsd_bbox_overlaps_p1: bad arguments");
-    if (N == 0 || K == 0) return FSD_OK;
-    FSD_CHECK_ARG(boxes && query && overlaps, "fsd_bbox_overlaps_p1: null argument");
-    const int64_t total = (int64_t)N * K;
-    FSD_CUDA(cudaSetDevice(h->device));
-    bbox_overlaps_p1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(boxes, N, query, K, overlaps);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

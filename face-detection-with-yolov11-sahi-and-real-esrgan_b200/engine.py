@@ -157,7 +157,7 @@ class SlicedFaceDetector:
     # ------------------------------------------------------------------------------------------ stages
     def _cudnn_scope(self):
         """cudnn.benchmark (and the optional search limit) for the backbone calls of this engine only."""
-        return ops.cudnn_benchmark(self.cudnn_benchmark, self._cudnn_limit)
+        return ops.cudnn_benchmark(self.cudnn_benchmark, self._cudnn_limit, tf32=None if self.dtype == torch.float16 else False)
 
     def _forward_entries(self, kind: str, x: torch.Tensor, cand: torch.Tensor, count: torch.Tensor):
         """backbone + Kernel 2a over a batch of network inputs, in chunks that bound activation memory."""

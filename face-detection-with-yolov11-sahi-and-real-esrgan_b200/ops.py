@@ -19,18 +19,22 @@ _TORCH_DTYPE = {torch.float16: FSD_F16, torch.float32: FSD_F32}
 
 
 @contextlib.contextmanager
-def cudnn_benchmark(on: bool = True, limit: int | None = None):
+def cudnn_benchmark(on: bool = True, limit: int | None = None, tf32: bool | None = None):
     """Per-shape cuDNN algorithm search around the library convolutions of the backbones, restored on exit: the product
-    never leaves process-wide torch.backends.cudnn flags changed behind the caller's back."""
-    cud = torch.backends.cudnn
-    old = (cud.benchmark, cud.benchmark_limit)
+    never leaves process-wide torch.backends flags changed behind the caller's back.  `tf32=False` additionally forces true
+    fp32 convolutions / matmuls inside the scope (the fp32 engine: the reference's CPU path computes in IEEE fp32, and
+    TF32's 10-bit mantissa is fp16-grade noise)."""
+    cud, mm = torch.backends.cudnn, torch.backends.cuda.matmul
+    old = (cud.benchmark, cud.benchmark_limit, cud.allow_tf32, mm.allow_tf32)
     cud.benchmark = bool(on)
     if limit is not None:
         cud.benchmark_limit = int(limit)
+    if tf32 is not None:
+        cud.allow_tf32 = mm.allow_tf32 = bool(tf32)
     try:
         yield
     finally:
-        cud.benchmark, cud.benchmark_limit = old
+        cud.benchmark, cud.benchmark_limit, cud.allow_tf32, mm.allow_tf32 = old
 
 
 _WARNED_CPU = []
@@ -500,6 +504,30 @@ def bbox_overlaps_p1(boxes: torch.Tensor, query: torch.Tensor) -> torch.Tensor:
                                      int(query.shape[0]), out.data_ptr(), _stream_ptr(boxes.device)),
           "fsd_bbox_overlaps_p1")
     return out
+
+
+def widerface_pr_curve(pred: torch.Tensor, pred_off: torch.Tensor, gt: torch.Tensor, gt_off: torch.Tensor,
+                       evaluate: torch.Tensor, thresh: torch.Tensor, iou_thresh: float = 0.5):
+    """(f1) one launch: greedy matching of every image + PR accumulation.  pred [Np,5] / gt [Ng,4] float64 xywh(+score)
+    rows with int32 CSR offsets [G+1], evaluate [Ng] int32, thresh [T] float64 (all CUDA).
+    Returns (pr_curve [T,2], pred_recall [Np], proposal [Np]) float64."""
+    _require_cuda(pred_off, "offsets")
+    dev = pred_off.device
+    G, n_pred, n_gt, T = int(pred_off.shape[0]) - 1, int(pred.shape[0]), int(gt.shape[0]), int(thresh.shape[0])
+    for t, dt in ((pred, torch.float64), (gt, torch.float64), (thresh, torch.float64), (pred_off, torch.int32),
+                  (gt_off, torch.int32), (evaluate, torch.int32)):
+        assert t.dtype == dt and t.is_contiguous() and t.device == dev
+    pr_curve = torch.empty((T, 2), dtype=torch.float64, device=dev)
+    pred_recall = torch.zeros((n_pred,), dtype=torch.float64, device=dev)
+    proposal = torch.ones((n_pred,), dtype=torch.float64, device=dev)
+    h = get_handle(dev.index if dev.index is not None else torch.cuda.current_device())
+    nbytes = int(h.lib.fsd_widerface_scratch_bytes(n_pred, n_gt))
+    scratch = torch.empty((nbytes // 8 + 1,), dtype=torch.float64, device=dev)
+    check(h.lib.fsd_widerface_pr_curve(h.h, _ptr(pred), pred_off.data_ptr(), _ptr(gt), gt_off.data_ptr(), _ptr(evaluate), G,
+                                       n_pred, n_gt, float(iou_thresh), thresh.data_ptr(), T, pred_recall.data_ptr(),
+                                       proposal.data_ptr(), scratch.data_ptr(), nbytes, pr_curve.data_ptr(), _stream_ptr(dev)),
+          "fsd_widerface_pr_curve")
+    return pr_curve, pred_recall, proposal
 
 
 def attach_keypoints(merged: torch.Tensor, m_off, m_cnt, dets: torch.Tensor, d_off, d_cnt) -> torch.Tensor:

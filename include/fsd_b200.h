@@ -228,6 +228,20 @@ int fsd_esrgan_stitch(fsd_handle_t h, const void* tiles_out, const int32_t* tabl
 int fsd_bbox_overlaps_p1(fsd_handle_t h, const double* boxes, int N, const double* query, int K,
                          double* overlaps, void* stream);
 
+/* ---- (f1) WIDER-FACE official-protocol PR curve in ONE launch — replaces _image_eval, _img_pr_info and the
+ *      `pr_curve += ...` accumulation of _evaluate_setting (eval/eval_official_widerface.py:302-377, 398-445).
+ *      pred [n_pred,5] f64 rows (x,y,w,h,score) of all G images, image g = rows pred_off[g] .. pred_off[g+1]-1 in the
+ *      order the evaluator stores them; gt [n_gt,4] f64 (x,y,w,h) with gt_off likewise; evaluate [n_gt] int32 =
+ *      1 for ground-truth boxes that count in this setting (the `ignore` array of :432-434), 0 for ignored ones;
+ *      thresh [T] f64 = 1 - (t+1)/T as the host computes them.  Outputs: pred_recall / proposal [n_pred] f64 (what
+ *      _image_eval returns per image: cumulative matched count, and 1 / -1 flags) and pr_curve [T,2] f64 =
+ *      sum over images of _img_pr_info (zeroed by this call).  scratch: fsd_widerface_scratch_bytes() bytes. */
+int64_t fsd_widerface_scratch_bytes(int64_t n_pred, int64_t n_gt);
+int fsd_widerface_pr_curve(fsd_handle_t h, const double* pred, const int32_t* pred_off, const double* gt,
+                           const int32_t* gt_off, const int32_t* evaluate, int G, int64_t n_pred, int64_t n_gt,
+                           double iou_thresh, const double* thresh, int T, double* pred_recall, double* proposal,
+                           void* scratch, int64_t scratch_bytes, double* pr_curve, void* stream);
+
 /* ---- (f2) keypoint attach — replaces YOLOv11PoseDetectionModel.attach_keypoints_to_predictions
  *      (utils/yolo_wrapper.py:168-217), batched over S images: for each merged box pick the LAST stage-1
  *      detection of the same image with the identical box, else the detection whose box has the largest IoU

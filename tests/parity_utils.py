@@ -152,7 +152,9 @@ def run_sliced_case(H, W, sl, ov, imgsz, conf, ptype, metric, n_images, seed0=10
             want_list = omodel.attach_keypoints_to_predictions(want.object_prediction_list)
             boxes = oslice.get_slice_bboxes(img.shape[0], img.shape[1], sl, sl, True, ov, ov)
             shifts = [b[:2] for b in boxes] + ([[0, 0]] if len(boxes) > 1 else [])
-            assert len(oyolo.calls) == len(shifts) == len(rec.items)
+            # (the engine re-runs a batch once when a slice overflowed the candidate capacity: the hook then saw every input twice)
+            assert len(oyolo.calls) == len(shifts) and len(rec.items) % len(shifts) == 0 and len(rec.items) > 0, \
+                (len(oyolo.calls), len(shifts), len(rec.items))
             flips = compare_stage1(stage1, oyolo.calls, shifts)
             a, b = as_rows(got_list), as_rows(want_list)
             # the merge on identical inputs: always bit-exact
