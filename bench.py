@@ -5,17 +5,23 @@ Workload (config.workload): BASELINE.json configs[1] — YOLOv11n-face SAHI on s
 images, 512x512 slices (0.2 overlap -> 6 slices) + the full-image pass, imgsz 1024 (the reference plug-in default),
 GREEDYNMM / IOS / 0.5 merge, conf 0.5, fp16 network input.  A "step" is one batch of `--batch` images through the whole
 hot path (Kernel 1 -> backbone -> Kernel 2a -> Kernel 3 -> Kernel 2b -> Kernel 3 -> attach/pack -> D2H of the results).
+With no flags: 64 steps x 64 images = the whole 4096-image data set, resident in HBM.
 
-  value     images/sec with the step's images already resident in HBM (synchronous engine.detect per batch, the backbone
-            replayed as CUDA graphs; CUDA-event timed)
-  e2e       images/sec through the public API (fsd_b200.api.predict_stream: copy / compute / post-processing streams,
-            three batches in flight) from PINNED HOST images: H2D copies, result D2H and the Python PredictionResult /
-            ObjectPrediction objects are all inside the timed region
-  roofline  Kernel 1 (slice launch): algorithmic bytes / time between CUDA events recorded inside the library around the
-            launch, vs MEASURED_PEAKS.json hbm_gbs; `other_kernels`: the conv epilogue (largest share of the step);
-            `hot_path`: SURVEY 8(d)'s whole-path figure
+  parity_gate   BEFORE any timing: one C2 and one C1 image through the fused path against the oracle flow (bit-exact boxes /
+                merge / AP), Kernel 3 vs the sahi oracle on 1024 and 9900 boxes, Kernel 4 bit-exact (oracle = checker only)
+  value         images/sec with the step's images already resident in HBM (synchronous engine.detect per batch, the backbone
+                replayed as CUDA graphs; CUDA-event timed)
+  e2e           images/sec through the public API (fsd_b200.api.predict_stream: copy / compute / post-processing streams,
+                three batches in flight) from PINNED HOST images: H2D copies, result D2H and the Python PredictionResult /
+                ObjectPrediction objects are all inside the timed region
+  roofline      Kernel 1 (slice launch): algorithmic bytes / time between CUDA events recorded inside the library around the
+                launch, vs MEASURED_PEAKS.json hbm_gbs; `other_kernels`: K2a decode, K3 merge (us per launch / segment), K2b,
+                attach, pack measured in the SAME timed region, the backbone's own kernels (K5/K6/K7/SPPF) in one eager step
+                (launches inside replayed graphs cannot be bracketed), K4 crop/stitch in the C5 leg
+  hot_path      SURVEY 8(d)'s whole-path figure; the backbone's share is MEASURED in this run (backbone-only replays)
+  extra         short legs: fp32 pipeline (TF32 off), C1 (1080p, 640^2 slices) incl. its CPU time, C3 merge us vs N, C5
   cpu_baseline / --impl reference: the CPU oracle (reference-equivalent restatement: sequential batch-1 slices,
-            per-box Python objects, CPU merge) on a bounded sample of the same images, all host threads.
+                per-box Python objects, CPU merge; the oracle's own plain PyTorch network) on a bounded sample, all host threads.
 
 Multi-GPU: launched by torchrun with one rank per GPU; images are sharded by index (weak scaling: every rank runs
 `steps` batches of its own shard), no collective on the hot path, one all-gather of detections after the timed region.
@@ -41,7 +47,7 @@ WORKLOAD = "C2: YOLOv11n-face SAHI, synthetic 1024x768 images, 512x512 slices (0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="images per step and per GPU")
     ap.add_argument("--images", type=int, default=4096, help="size of the synthetic data set (all GPUs together)")
@@ -49,30 +55,32 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=6, help="images of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short fp32 / C1 / C3 / C5 legs")
+    ap.add_argument("--no-parity-gate", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch the backbone eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
 def cpu_arm_setup():
+    """The reference-equivalent CPU path: oracle plug-in over the oracle's OWN plain PyTorch YOLO11n-pose (nothing from the
+    product's backbones), fp32, all host threads."""
     import torch
 
-    import fsd_b200  # noqa: F401
-    from fsd_b200.backbones.yolo11_pose import build_yolo11n_pose
+    from oracle.yolo11_pose_plain import build_plain_yolo11n_pose
     from oracle.yolo_head import OracleYOLO
     from oracle.yolo_wrapper import YOLOv11PoseDetectionModel
 
     torch.set_num_threads(os.cpu_count() or 1)
-    model = YOLOv11PoseDetectionModel(model=OracleYOLO(build_yolo11n_pose(), half=False), confidence_threshold=CONF,
-                                      device="cpu", image_size=IMGSZ)
-    return model
+    return YOLOv11PoseDetectionModel(model=OracleYOLO(build_plain_yolo11n_pose(), half=False), confidence_threshold=CONF,
+                                     device="cpu", image_size=IMGSZ)
 
 
-def cpu_arm_image(model, img):
+def cpu_arm_image(model, img, slice_px=SLICE):
     from oracle.predict import get_sliced_prediction
 
     model.keypoints_cache = {}
-    res = get_sliced_prediction(img, model, slice_height=SLICE, slice_width=SLICE, overlap_height_ratio=OVERLAP,
+    res = get_sliced_prediction(img, model, slice_height=slice_px, slice_width=slice_px, overlap_height_ratio=OVERLAP,
                                 overlap_width_ratio=OVERLAP, postprocess_type="GREEDYNMM", postprocess_match_metric="IOS",
                                 postprocess_match_threshold=0.5, verbose=0)
     return model.attach_keypoints_to_predictions(res.object_prediction_list)
@@ -102,8 +110,9 @@ def run_reference_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_step": 1},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} images (1 per step) of the C2 workload, oracle port of the reference CPU path "
-                                       f"(sahi/ultralytics/realesrgan are not installable here); os.cpu_count()={os.cpu_count()}"},
+                             "sample": f"{args.steps} images (1 per step) of the C2 workload, oracle port of the reference CPU path over "
+                                       f"the oracle's own plain PyTorch YOLO11n-pose (sahi/ultralytics/realesrgan are not installable "
+                                       f"here); os.cpu_count()={os.cpu_count()}"},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
@@ -143,6 +152,50 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+# ----------------------------------------------------------------------------------------------- parity gate
+def parity_gate(dev):
+    """One image per BASELINE config that fits a few seconds + the stand-alone kernels, against the oracle (checker only)."""
+    from oracle import parity
+
+    checks, t0 = {}, time.perf_counter()
+    try:
+        for name, kw in (("C2", dict(H=768, W=1024, sl=512, mean_faces=12, face_px=(6, 200))),
+                         ("C1", dict(H=1080, W=1920, sl=640, mean_faces=40, face_px=(12, 120)))):
+            out = parity.run_sliced_case(kw["H"], kw["W"], kw["sl"], OVERLAP, IMGSZ, CONF, "GREEDYNMM", "IOS", n_images=1, seed0=1234,
+                                         mean_faces=kw["mean_faces"], face_px=kw["face_px"])
+            checks[name] = {"per_slice_boxes": out["stage1"], "merged_boxes": out["boxes"], "int_flips": out["flips"]}
+        checks["K3_greedynmm_ios_1024"] = parity.merge_gate(dev, 1024)
+        checks["K3_nms_iou_9900"] = parity.merge_gate(dev, 9900, merge_type="NMS", metric="IOU")
+        checks["K4_crop_stitch"] = parity.esrgan_gate(dev)
+        status = "pass"
+    except AssertionError as e:
+        status = f"fail: {str(e)[:300]}"
+    return status, {"checks": checks, "seconds": round(time.perf_counter() - t0, 1),
+                    "bar": "bit-exact per-slice boxes, merged boxes and AP vs the oracle flow (backbone factored out by replaying the "
+                           "recorded head tensors); K3 / K4 bit-exact vs the oracle"}
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def timed_steps(fn, steps, sync):
+    import torch
+
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    t0.record()
+    for i in range(steps):
+        fn(i)
+    t1.record()
+    sync()
+    return t0.elapsed_time(t1)
+
+
+def by_kernel(samples):
+    out = {}
+    for kid, units, tag, ms_ in samples:
+        out.setdefault(kid, []).append((units, tag, ms_))
+    return out
+
+
 def main():
     args = parse()
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL would print its version banner on stdout, before the JSON line
@@ -156,11 +209,11 @@ def main():
 
     import fsd_b200  # noqa: F401
     from fsd_b200 import _cabi, ops
-    from fsd_b200.api import get_sliced_prediction_batch
     from fsd_b200.plugins import YOLOv11PoseDetectionModel
-    from fsd_b200.synthetic import make_image, make_pool_on_device
+    from fsd_b200.synthetic import make_pool_on_device
     from fsd_b200.yolo import YOLO
 
+    K = _cabi
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -170,109 +223,167 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
-    n_local = max(B, (args.images // world) // B * B)   # images this rank owns (index i*world + rank)
-    n_resident = min(n_local, max(B, (args.steps + args.warmup) * B))
-    # ---- synthetic data: generated in HBM (device RNG), mirrored into pinned host memory for the e2e leg
-    pool = make_pool_on_device(n_resident, H, W, dev, seed=1234 + rank * 100003)
-    model = YOLOv11PoseDetectionModel(model=YOLO("random-init"), confidence_threshold=CONF, device=str(dev), image_size=IMGSZ)
-    eng = model.engine()
-    eng.overlap_post = True  # synchronous detect(): the slices' stage-1 NMS runs on a side stream under the full-image pass
-    h = _cabi.get_handle(local)
-    kw = dict(postprocess_type="GREEDYNMM", match_metric="IOS", match_threshold=0.5)
-
-    def step_resident(i):
-        a = (i % (n_resident // B)) * B
-        return eng.detect(pool.subpool(a, a + B), SLICE, SLICE, OVERLAP, OVERLAP, True, **kw)
-
     def sync_all():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # ---- parity gate: before any timing ----------------------------------------------------------------------
+    gate_status, gate_info = "skipped", None
+    if not args.no_parity_gate and rank == 0:
+        gate_status, gate_info = parity_gate(dev)
+    sync_all()
+
+    B = args.batch
+    n_local = max(B, (args.images // world) // B * B)   # images this rank owns (index i*world + rank)
+    n_resident = min(n_local, max(B, (args.steps + args.warmup) * B))
+    # ---- synthetic data: generated in HBM (device RNG), mirrored into pinned host memory for the e2e leg
+    pool = make_pool_on_device(n_resident, H, W, dev, seed=1234 + rank * 100003)
+    yolo = YOLO("random-init")
+    model = YOLOv11PoseDetectionModel(model=yolo, confidence_threshold=CONF, device=str(dev), image_size=IMGSZ)
+    eng = model.engine()
+    eng.overlap_post = True  # synchronous detect(): the slices' stage-1 NMS runs on a side stream under the full-image pass
+    h = _cabi.get_handle(local)
+    kw = dict(postprocess_type="GREEDYNMM", match_metric="IOS", match_threshold=0.5)
+    n_batches = n_resident // B
+
+    def step_resident(i):
+        a = (i % n_batches) * B
+        return eng.detect(pool.subpool(a, a + B), SLICE, SLICE, OVERLAP, OVERLAP, True, **kw)
+
     # ---- leg 1: inputs resident in HBM -------------------------------------------------------------------
     # The backbone chunks are replayed as CUDA graphs (static network-input buffers; captured during the first warm-up
-    # steps).  The last warm-up step runs eagerly once more with the conv-epilogue launches (~450 per step) timed by the
-    # library: kernels inside a replayed graph are not individually bracketed.
+    # steps).  One eager step with the backbone's own kernels timed by the library comes first: launches inside a replayed
+    # graph cannot be bracketed individually.
     use_graphs = not args.no_graphs
-    step_resident(0)  # cold eager step: cuDNN algorithm search, module loads (so that the timed eager step below is warm)
-    for i in range(args.warmup):
-        eng.use_graphs = use_graphs and i < args.warmup - 1
-        if i == args.warmup - 1:
-            h.timing_enable((_cabi.FSD_KERNEL_BIAS_ACT,))
+    backbone_ids = (K.FSD_KERNEL_BIAS_ACT, K.FSD_KERNEL_STEM, K.FSD_KERNEL_POINTWISE, K.FSD_KERNEL_SPPF)
+    path_ids = (K.FSD_KERNEL_GATHER, K.FSD_KERNEL_DECODE, K.FSD_KERNEL_MERGE, K.FSD_KERNEL_FINALIZE, K.FSD_KERNEL_ATTACH, K.FSD_KERNEL_PACK)
+    step_resident(0)  # cold eager step: cuDNN algorithm search, module loads
+    step_resident(1)
+    h.timing_enable(backbone_ids)
+    eager_ms = timed_steps(lambda i: step_resident(2), 1, sync_all)
+    eager = by_kernel(h.timing_read())
+    h.timing_enable(())
+    eng.use_graphs = use_graphs
+    for i in range(max(args.warmup, 3)):
         step_resident(i)
-    eng.use_graphs = use_graphs and args.warmup >= 2
-    k5 = [(units, ms_) for (kid, units, tag, ms_) in h.timing_read() if kid == _cabi.FSD_KERNEL_BIAS_ACT]
-    # kernel timing: CUDA events recorded by the library itself right around each launch, on the launching stream
-    # (= torch's current stream), so no host-side preparation falls inside a sample
-    h.timing_enable((_cabi.FSD_KERNEL_GATHER,))
+    # kernel timing: CUDA events recorded by the library itself right around each launch, on the launching stream, so no
+    # host-side preparation falls inside a sample; the hot-path kernels (K1, K2a, K3, K2b, attach, pack) are launched outside
+    # the captured graphs and are timed INSIDE the timed region
+    h.timing_enable(path_ids)
     sampler = ClockSampler(local)
     sync_all()
     sampler.start()
     torch.cuda.profiler.start()  # ncu --profile-from-start off captures exactly the timed region
     launches0 = h.launches + eng.replayed_launches  # direct launches + the library's kernels inside replayed graphs
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    n_dets = 0
-    for i in range(args.steps):
-        n_dets += int(step_resident(args.warmup + i).offsets[-1])
-    t1.record()
-    sync_all()
+    n_dets = [0]
+
+    def timed_step(i):
+        n_dets[0] += int(step_resident(args.warmup + i).offsets[-1])
+
+    ms = timed_steps(timed_step, args.steps, sync_all)
     torch.cuda.profiler.stop()
     launches = h.launches + eng.replayed_launches - launches0
     graphs_used = eng.use_graphs
-    eng.use_graphs = False
     clocks = sampler.stop()
-    samples = h.timing_read()
+    path = by_kernel(h.timing_read())
     h.timing_enable(())
-    ms = t0.elapsed_time(t1)
     if world > 1:
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     value = world * args.steps * B / (ms / 1000.0)
+    step_ms = ms / args.steps
+    # the backbone alone (same graphs, same buffers), measured here instead of quoted from a profile
+    plan = eng.plan(H, W, SLICE, SLICE, OVERLAP, OVERLAP, True)
+    backbone_ms = eng.measure_backbone_ms(plan, B, steps=3)
+    eng.use_graphs = False
 
-    # roofline of the dominant kernel: Kernel 1 slice launch
-    sl = [(units, ms_) for (kid, units, tag, ms_) in samples if kid == _cabi.FSD_KERNEL_GATHER and tag == SLICE]
-    k1_ms = sum(t for _, t in sl) / max(len(sl), 1)
-    n_entries = sl[0][0] if sl else 0
-    k1_bytes = n_entries * 3 * IMGSZ * IMGSZ * 2 + (n_entries // 6) * H * W * 3  # every network input once + the source once
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of the same launch (ncu --set full capture under profiles/)
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))
-        if tj.get("entries") == n_entries:
-            traffic = tj["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    gbs = lambda nbytes, ms_: nbytes / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0  # noqa: E731
+
+    # roofline of the dominant north-star kernel: Kernel 1 slice launch
+    sl = [(u, t) for (u, tag, t) in path.get(K.FSD_KERNEL_GATHER, []) if tag == SLICE]
+    k1_ms = sum(t for _, t in sl) / max(len(sl), 1)
+    n_entries = sl[0][0] if sl else 0
+    k1_bytes = n_entries * 3 * IMGSZ * IMGSZ * 2 + (n_entries // 6) * H * W * 3  # every network input once + the source once
+    traffic, traffic_src = None, None
+    for name in ("r2_k1_traffic.json", "r1_k1_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if tj.get("entries") == n_entries:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], f"profiles/{name}: ncu --set full capture of the same launch, NOT measured in this run"
+                break
+        except Exception:
+            pass
+    achieved = gbs(k1_bytes, k1_ms)
     roofline = {"bound": "hbm", "kernel": "k1_upscale2x_kernel<channels_last> via fsd_gather_letterbox (slice launch: 6 slices x B images, exact-2x path)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "bytes_per_launch": k1_bytes, "launch_ms": k1_ms, "launches_timed": len(sl),
-                "timing": "CUDA events recorded inside libfsd_b200 around each launch (fsd_kernel_timing_*)",
-                "note": "Kernel 1 is the HBM-bound kernel SURVEY 8(d) defines the per-image algorithmic bytes for; by share of the "
-                        "step the largest hand-written kernel is the conv epilogue (other_kernels[0]); the step itself is bound by "
-                        "the PyTorch convolutions (profiles/r1_launches_bench_b32_end.txt)"}
-    # the hand-written kernel with the largest share of the step: the conv epilogue (bias + SiLU [+ residual] -> concat slot)
-    if k5:
-        k5_bytes, k5_ms = sum(u for u, _ in k5), sum(t for _, t in k5)
-        roofline["other_kernels"] = [{
-            "kernel": "k5_bias_act_general_half_kernel via fsd_bias_act (all launches of the last warm-up step)", "bound": "hbm",
-            "achieved": k5_bytes / (k5_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": k5_bytes / (k5_ms * 1e-3) / 1e9 / peak,
-            "launches_timed": len(k5), "ms_per_step": k5_ms, "share_of_step": k5_ms / (ms / args.steps)}]
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_source, "bytes_per_launch": k1_bytes, "launch_ms": k1_ms, "launches_timed": len(sl),
+                "timing": "CUDA events recorded inside libfsd_b200 around each launch (fsd_kernel_timing_*), inside the timed region",
+                "note": "Kernel 1 is the HBM-bound kernel SURVEY 8(d) defines the per-image algorithmic bytes for; the step itself is "
+                        "bound by the PyTorch convolutions (hot_path.backbone_share_of_step, measured in this run)"}
+    others = []
+    fl = [(u, t) for (u, tag, t) in path.get(K.FSD_KERNEL_GATHER, []) if tag == W]
+    if fl:
+        fb = fl[0][0] * (H * W * 3 + 3 * H * W * 2)
+        fms = sum(t for _, t in fl) / len(fl)
+        others.append({"kernel": "k1 full-image launch (768x1024 copy-convert, sixteenths path)", "bound": "hbm", "achieved": gbs(fb, fms),
+                       "peak": peak, "unit": "GB/s", "frac": gbs(fb, fms) / peak, "launch_ms": fms, "bytes_per_launch": fb,
+                       "ms_per_step": fms, "share_of_step": fms / step_ms})
+    dec = path.get(K.FSD_KERNEL_DECODE, [])
+    if dec:
+        dbytes, dms = sum(u for u, _, _ in dec), sum(t for _, _, t in dec)
+        others.append({"kernel": "k2_pose_decode_kernel<half, channels_last> via fsd_pose_decode (all launches of the timed region)",
+                       "bound": "hbm", "achieved": gbs(dbytes, dms), "peak": peak, "unit": "GB/s", "frac": gbs(dbytes, dms) / peak,
+                       "bytes": "full head tensors, 80 values x anchors x 2 B per entry (SURVEY 8d; the confidence gate touches far fewer)",
+                       "launches_timed": len(dec), "ms_per_step": dms / args.steps, "share_of_step": dms / args.steps / step_ms})
+    mer = path.get(K.FSD_KERNEL_MERGE, [])
+    if mer:
+        groups = {}
+        for segs, tag, t in mer:
+            groups.setdefault((segs, tag), []).append(t)
+        rows = []
+        for (segs, tag), ts in sorted(groups.items()):
+            kind = "stage 2 (cross-slice merge per image, GREEDYNMM/IOS fp64)" if tag == plan_det_cap(eng, plan) else \
+                ("stage 1 (per-slice NMS, torchvision rule) over the slices" if segs > B else "stage 1 over the full-image entries")
+            rows.append({"launch": kind, "segments": segs, "max_segment": tag, "us_per_launch": 1e3 * sum(ts) / len(ts),
+                         "us_per_segment": 1e3 * sum(ts) / len(ts) / max(segs, 1), "launches_timed": len(ts)})
+        mms = sum(t for _, _, t in mer)
+        others.append({"kernel": "k3_merge_kernel via fsd_merge (all launches of the timed region; latency-bound: absolute time)",
+                       "bound": "latency", "launches": rows, "ms_per_step": mms / args.steps, "share_of_step": mms / args.steps / step_ms,
+                       "note": "runs on the post-processing stream concurrently with the next chunk's backbone"})
+    for kid, label in ((K.FSD_KERNEL_FINALIZE, "k2_finalize_kernel via fsd_finalize_dets"), (K.FSD_KERNEL_ATTACH, "attach_keypoints_kernel"),
+                       (K.FSD_KERNEL_PACK, "k2_pack_kernel via fsd_pack_results")):
+        ss = path.get(kid, [])
+        if ss:
+            tms = sum(t for _, _, t in ss)
+            others.append({"kernel": label, "bound": "latency", "us_per_launch": 1e3 * tms / len(ss), "launches_timed": len(ss),
+                           "ms_per_step": tms / args.steps, "share_of_step": tms / args.steps / step_ms})
+    ours_backbone_ms = 0.0
+    for kid, label in ((K.FSD_KERNEL_BIAS_ACT, "k5_bias_act kernels via fsd_bias_act (conv epilogue: bias + SiLU [+ residual] -> concat slot)"),
+                       (K.FSD_KERNEL_STEM, "k6_stem_conv_kernel via fsd_stem_conv"), (K.FSD_KERNEL_POINTWISE, "k7_pointwise_conv_kernel via fsd_pointwise_conv"),
+                       (K.FSD_KERNEL_SPPF, "k5_sppf_pool_kernel via fsd_sppf_pool")):
+        ss = eager.get(kid, [])
+        if ss:
+            tb, tms = sum(u for u, _, _ in ss), sum(t for _, _, t in ss)
+            ours_backbone_ms += tms
+            others.append({"kernel": label, "bound": "hbm", "achieved": gbs(tb, tms), "peak": peak, "unit": "GB/s", "frac": gbs(tb, tms) / peak,
+                           "launches_timed": len(ss), "ms_per_step": tms, "share_of_step": tms / eager_ms,
+                           "source": "one eager step before the timed region (launches inside replayed CUDA graphs cannot be bracketed)"})
+    roofline["other_kernels"] = others
 
     # ---- leg 2: end to end through the public API from pinned host memory ---------------------------------
     e2e = None
     if not args.skip_e2e:
-        n_host = min(n_resident, 4 * B)
+        n_host = min(n_resident, 16 * B)
         host = torch.empty((n_host, H, W, 3), dtype=torch.uint8).pin_memory()
         for i in range(n_host):
             host[i].copy_(pool.view(i))
@@ -296,7 +407,7 @@ def main():
 
         run_e2e(max(2, args.warmup))
         sync_all()
-        e_steps = max(4, args.steps)  # the 2-deep pipeline starts empty and is drained inside the timed region
+        e_steps = max(4, args.steps)  # the pipeline starts empty and is drained inside the timed region
         w0 = time.perf_counter()
         d2h = run_e2e(e_steps, start=3)
         sync_all()
@@ -306,11 +417,12 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = {"value": world * e_steps * B / dt, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3,
-               "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps,
+               "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps, "pinned_host_images": n_host,
                "host_ms_per_step": {k: round(1e3 * v / e_steps, 2) for k, v in host_stats.items()},
                "api": "fsd_b200.api.predict_stream (pinned host images in, PredictionResult objects out; 3 batches in flight: H2D of "
                       "batch i+1 on a copy stream and D2H + object construction of batch i-1 overlap the device work of batch i on "
                       "one compute stream; backbone chunks replayed as CUDA graphs)"}
+        del host
 
     # ---- the one collective: all-gather of detections for evaluation (after the timed region) -------------
     gathered = None
@@ -324,10 +436,18 @@ def main():
         gi, gr = gather_detections(ids.long(), rows)
         gathered = int(gi.shape[0])
 
+    # ---- extra legs (single GPU): fp32 line, C1, C3 merge vs N, C5 ------------------------------------------
+    extra = None
+    sample_imgs = [pool.view(i).cpu().numpy().copy() for i in range(max(args.cpu_sample, 1))] if rank == 0 else []
+    pool = None  # release the resident data set before the extra legs allocate theirs
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_extras:
+        extra = run_extras(args, dev, yolo, eng, h, peak, use_graphs)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         model_cpu = cpu_arm_setup()
-        imgs = [pool.view(i).cpu().numpy().copy() for i in range(args.cpu_sample)]
+        imgs = sample_imgs[: args.cpu_sample]
         cpu_arm_image(model_cpu, imgs[0])
         c0 = time.perf_counter()
         for im in imgs:
@@ -335,36 +455,192 @@ def main():
         cdt = time.perf_counter() - c0
         cpu_base = {"value": len(imgs) / cdt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                     "sample": f"first {len(imgs)} images of this run's data set through the oracle port of the reference CPU path "
-                              f"(sequential batch-1 slices at imgsz {IMGSZ}, fp32, per-box Python objects, CPU GREEDYNMM); "
-                              f"os.cpu_count()={os.cpu_count()}"}
+                              f"(sequential batch-1 slices at imgsz {IMGSZ}, fp32, per-box Python objects, CPU GREEDYNMM, the oracle's "
+                              f"own plain PyTorch network); os.cpu_count()={os.cpu_count()}"}
+        if extra is not None and "c1" in extra:  # BASELINE configs[0]: the reference's own CPU-runnable case
+            from fsd_b200.synthetic import make_image
+
+            img1 = make_image(1234, 1080, 1920, mean_faces=40, face_px=(12, 120))[0]
+            cpu_arm_image(model_cpu, img1, 640)
+            ts = []
+            for _ in range(3):
+                c0 = time.perf_counter()
+                cpu_arm_image(model_cpu, img1, 640)
+                ts.append(time.perf_counter() - c0)
+            extra["c1"]["cpu_port_seconds_per_image"] = sorted(ts)[1]
+            extra["c1"]["cpu_port_images_per_s"] = 1.0 / sorted(ts)[1]
+            extra["c1"]["cpu_cores"] = torch.get_num_threads()
 
     if rank == 0:
         line = {"metric": "sliced face-detect images/sec", "value": value, "unit": "images/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "images_per_step_per_gpu": B, "data_set_images": args.images,
-                           "resident_images_per_gpu": n_resident, "slices_per_image": 6, "network_inputs_per_image": 7,
+                           "resident_images_per_gpu": n_resident, "images_timed_per_gpu": args.steps * B,
+                           "slices_per_image": 6, "network_inputs_per_image": 7,
                            "conf": CONF, "weights": "random-init YOLO11n-pose (calibrated head), seed 0",
                            "l2": "inputs larger than L2: each step gathers %.0f MB of source pixels into %.1f GB of network input"
                                  % (B * H * W * 3 / 1e6, B * (6 * 3 * IMGSZ * IMGSZ + 3 * H * W) * 2 / 1e9),
                            "parallelism": f"image-index sharding x{world}, no hot-path collective",
                            "cuda_graphs": bool(graphs_used)},
-                "detections_per_image": n_dets / (args.steps * B), "gpu_launches": int(launches), "clocks": clocks,
+                "parity_gate": gate_status, "parity": gate_info,
+                "detections_per_image": n_dets[0] / (args.steps * B), "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base}
         # the whole hot path against the HBM roofline = algorithmic bytes of Kernel 1 (44.8 MB / image) and
         # Kernel 2 (23.2 MB / image) over the time per image; it is small because the step is the PyTorch backbone's
         bytes_per_image = (H * W * 3 + 6 * 3 * IMGSZ * IMGSZ * 2 + 3 * H * W * 2) + (6 * 21504 + 16128) * 80 * 2
+        ns_ms = sum(sum(t for _, _, t in path.get(kid, [])) for kid in path_ids) / args.steps
         line["hot_path"] = {"algorithmic_bytes_per_image": bytes_per_image, "achieved_GBps_per_gpu": bytes_per_image * value / world / 1e9,
                             "frac_of_peak": bytes_per_image * value / world / 1e9 / peak,
-                            "backbone_share_of_device_time": 0.87,
-                            "backbone_share_source": "profiles/r1_launches_bench_b32_end.txt: library conv/gemm/sdpa 43.5 % + the "
-                                                     "hand-written backbone kernels (epilogues, stem, 1x1 conv, up-sample, SPPF) 43.4 %"}
+                            "north_star_kernels_ms_per_step": ns_ms, "north_star_kernels_share_of_step": ns_ms / step_ms,
+                            "backbone_ms_per_step": backbone_ms, "backbone_share_of_step": backbone_ms / step_ms,
+                            "backbone_own_kernels_ms_per_eager_step": ours_backbone_ms, "eager_step_ms": eager_ms,
+                            "source": "measured in this run: backbone = the step's backbone graph replays alone over the same buffers "
+                                      "(CUDA events); north-star kernels = in-library event timing inside the timed region (K3/K2b/attach/"
+                                      "pack overlap the backbone on a second stream, so the shares need not add up to 1)"}
+        if extra is not None:
+            line["extra"] = extra
         if gathered is not None:
             line["allgather_detections"] = gathered
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def plan_det_cap(eng, plan):
+    return min((plan.S + (1 if plan.g_full else 0)) * eng.max_det, 32768)
+
+
+# ----------------------------------------------------------------------------------------------- extra legs
+def run_extras(args, dev, yolo, eng, h, peak, use_graphs):
+    import numpy as np
+    import torch
+
+    from fsd_b200 import _cabi as K
+    from fsd_b200 import ops
+    from fsd_b200.plugins import YOLOv11PoseDetectionModel
+    from fsd_b200.synthetic import make_pool_on_device
+
+    def sync():
+        torch.cuda.synchronize(dev)
+
+    gbs = lambda nbytes, ms_: nbytes / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0  # noqa: E731
+    kw = dict(postprocess_type="GREEDYNMM", match_metric="IOS", match_threshold=0.5)
+    extra = {}
+
+    # ---- (d) the same C2 workload in fp32 (what the reference computes in: utils/yolo_wrapper.py:74-80, half=False) ----
+    Bf = 32
+    pool32 = make_pool_on_device(2 * Bf, H, W, dev, seed=99)
+    m32 = YOLOv11PoseDetectionModel(model=yolo, confidence_threshold=CONF, device=str(dev), image_size=IMGSZ, half=False)
+    e32 = m32.engine()
+    e32.overlap_post = True
+    run32 = lambda i: e32.detect(pool32.subpool((i % 2) * Bf, (i % 2) * Bf + Bf), SLICE, SLICE, OVERLAP, OVERLAP, True, **kw)  # noqa: E731
+    run32(0)
+    e32.use_graphs = use_graphs
+    for i in range(3):
+        run32(i)
+    ms32 = timed_steps(run32, 6, sync)
+    extra["f32"] = {"value": 6 * Bf / (ms32 * 1e-3), "unit": "images/s", "dtype": "f32", "images_per_step": Bf, "steps": 6,
+                    "ms_per_step": ms32 / 6, "workload": "C2 as the headline, network input / backbone / decode in fp32 with TF32 disabled "
+                                                        "(the reference's own arithmetic); inputs resident in HBM"}
+    e32.use_graphs = False
+    del pool32, e32, m32
+    yolo._engines.pop((str(dev), False), None)
+    torch.cuda.empty_cache()
+
+    # ---- (c1) BASELINE configs[0] on the GPU: 1920x1080, 640^2 slices (8 + 1 network inputs), imgsz 1024 -------------
+    B1 = 32
+    pool1 = make_pool_on_device(2 * B1, 1080, 1920, dev, seed=7)
+    run1 = lambda i: eng.detect(pool1.subpool((i % 2) * B1, (i % 2) * B1 + B1), 640, 640, OVERLAP, OVERLAP, True, **kw)  # noqa: E731
+    eng.use_graphs = False
+    run1(0)
+    eng.use_graphs = use_graphs
+    for i in range(3):
+        run1(i)
+    h.timing_enable((K.FSD_KERNEL_GATHER, K.FSD_KERNEL_DECODE, K.FSD_KERNEL_MERGE))
+    ms1 = timed_steps(run1, 6, sync)
+    s1 = by_kernel(h.timing_read())
+    h.timing_enable(())
+    eng.use_graphs = False
+    c1 = {"value": 6 * B1 / (ms1 * 1e-3), "unit": "images/s", "images_per_step": B1, "steps": 6, "ms_per_step": ms1 / 6,
+          "workload": "C1: 1920x1080 images, 640x640 slices (0.2 overlap, 8 slices) + full-image pass (576x1024), imgsz 1024, GREEDYNMM/IOS/0.5, fp16"}
+    g = s1.get(K.FSD_KERNEL_GATHER, [])
+    sl = [t for (u, tag, t) in g if tag == 640]
+    fl = [t for (u, tag, t) in g if tag == 1920]
+    if sl:
+        nb = 8 * B1 * 3 * 1024 * 1024 * 2 + B1 * 1080 * 1920 * 3
+        c1["k1_slices_640_to_1024"] = {"achieved": gbs(nb, sum(sl) / len(sl)), "frac": gbs(nb, sum(sl) / len(sl)) / peak, "unit": "GB/s",
+                                       "launch_ms": sum(sl) / len(sl), "bytes_per_launch": nb}
+    if fl:
+        nb = B1 * (1080 * 1920 * 3 + 3 * 576 * 1024 * 2)
+        c1["k1_full_1080p_to_576x1024"] = {"achieved": gbs(nb, sum(fl) / len(fl)), "frac": gbs(nb, sum(fl) / len(fl)) / peak, "unit": "GB/s",
+                                           "launch_ms": sum(fl) / len(fl), "bytes_per_launch": nb}
+    extra["c1"] = c1
+    del pool1
+    torch.cuda.empty_cache()
+
+    # ---- (c3) merge-kernel time vs N: dense crowd boxes (config 3), NMS / IOU / 0.5, fp64 metric ----------------------
+    def crowd(n, seed):
+        rng = np.random.default_rng(seed)
+        side = int(30 * np.sqrt(n))
+        xy = rng.integers(0, side, (n, 2))
+        wh = rng.integers(10, 41, (n, 2))
+        return np.concatenate([xy, xy + wh, rng.uniform(0.4, 1.0, (n, 1)), np.zeros((n, 1))], 1).astype(np.float32)
+
+    c3 = []
+    for n in (256, 1024, 4096, 9900):
+        for segs in (1, 32):
+            rows = torch.from_numpy(np.concatenate([crowd(n, 100 * n + s) for s in range(segs)])).to(dev)
+            off = torch.arange(segs, dtype=torch.int32, device=dev) * n
+            for mt, metric in (("NMS", "IOU"), ("GREEDYNMM", "IOS")):
+                for _ in range(2):
+                    res = ops.merge_segments(rows, off, None, n, merge_type=mt, metric=metric, thr=0.5, precision="fp64", want_parent=False)
+                sync()
+                h.timing_enable((K.FSD_KERNEL_MERGE,))
+                for _ in range(5):
+                    res = ops.merge_segments(rows, off, None, n, merge_type=mt, metric=metric, thr=0.5, precision="fp64", want_parent=False)
+                ts = sorted(t for (_, _, t) in by_kernel(h.timing_read()).get(K.FSD_KERNEL_MERGE, []))
+                h.timing_enable(())
+                c3.append({"N": n, "segments": segs, "type": f"{mt}/{metric}", "us_median": 1e3 * ts[len(ts) // 2], "us_min": 1e3 * ts[0],
+                           "kept_first_segment": int(res["keep_count"][0])})
+    extra["c3_merge_us"] = {"rows": c3, "note": "one fsd_merge launch over `segments` independent segments of N boxes each (dense 10-40 px "
+                                                "crowd boxes, scores U(0.4,1)); in-library CUDA-event timing, median / min of 5 launches"}
+
+    # ---- (c5) enhancement-first: 1080p -> x2 RRDBNet (random-init, fp16, tile 400) -> 2160x3840 -> SAHI 640^2 ---------
+    from fsd_b200.enhancer import RealESRGANer
+
+    F = 2
+    frames = make_pool_on_device(F, 1080, 1920, dev, seed=11)
+    fr = torch.stack([frames.view(i) for i in range(F)]).contiguous()
+    torch.manual_seed(0)
+    up = RealESRGANer(scale=2, tile=400, tile_pad=10, pre_pad=0, half=True, device=dev, max_tile_batch=15)
+    big = up.enhance_device(fr)
+    h.timing_enable((K.FSD_KERNEL_ESRGAN_CROP, K.FSD_KERNEL_ESRGAN_STITCH))
+    ms_enh = timed_steps(lambda i: up.enhance_device(fr), 3, sync)
+    s5 = by_kernel(h.timing_read())
+    h.timing_enable(())
+    pool5 = ops.ImagePool(F, 2160, 3840, dev)
+    pool5.buf[:, :, : 3840 * 3].copy_(big.reshape(F, 2160, 3840 * 3))
+    run5 = lambda i: eng.detect(pool5, 640, 640, OVERLAP, OVERLAP, True, **kw)  # noqa: E731
+    run5(0)
+    eng.use_graphs = use_graphs
+    for i in range(3):
+        run5(i)
+    ms_det = timed_steps(run5, 4, sync)
+    eng.use_graphs = False
+    c5 = {"enhance_ms_per_frame": ms_enh / 3 / F, "detect_ms_per_frame": ms_det / 4 / F,
+          "value": 1e3 / (ms_enh / 3 / F + ms_det / 4 / F), "unit": "frames/s", "frames_per_step": F,
+          "workload": "C5: 1920x1080 -> Real-ESRGAN x2 (random-init 23-block RRDBNet in PyTorch fp16, tile 400, pad 10: 15 tiles) -> 3840x2160 "
+                      "-> YOLOv11n SAHI 640x640 (32 slices + full image), GREEDYNMM/IOS/0.5; both stages on one GPU, back to back"}
+    for kid, name in ((K.FSD_KERNEL_ESRGAN_CROP, "k4_crop"), (K.FSD_KERNEL_ESRGAN_STITCH, "k4_stitch")):
+        ss = s5.get(kid, [])
+        if ss:
+            nb, t = ss[0][0], sum(t for _, _, t in ss) / len(ss)
+            c5[name] = {"achieved": gbs(nb, t), "frac": gbs(nb, t) / peak, "unit": "GB/s", "launch_us": 1e3 * t, "bytes_per_launch": nb,
+                        "frames_per_launch": F, "share_of_enhance_stage": t / (ms_enh / 3)}
+    extra["c5"] = c5
+    return extra
 
 
 if __name__ == "__main__":

@@ -71,6 +71,8 @@ struct TimedLaunch {
     fsd_context* h; cudaStream_t stream; cudaEvent_t e1 = nullptr;
     TimedLaunch(fsd_context* h_, int kernel, int64_t units, int64_t tag, cudaStream_t s) : h(h_), stream(s) {
         if (!(h->timing >> kernel & 1u) || h->timing_samples.size() >= (1u << 20)) return;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;  // a launch being captured into a CUDA graph cannot be bracketed
+        if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return;
         cudaEvent_t ev[2];
         for (int i = 0; i < 2; ++i) {
             if (!h->event_pool.empty()) { ev[i] = h->event_pool.back(); h->event_pool.pop_back(); }

@@ -250,6 +250,7 @@ extern "C" int fsd_pack_results(fsd_handle_t h, const float* det, const int32_t*
     FSD_CHECK_ARG(G >= 0, "fsd_pack_results: bad G");
     if (G == 0) return FSD_OK;
     FSD_CUDA(cudaSetDevice(h->device));
+    TimedLaunch timed(h, FSD_KERNEL_PACK, G, 0, (cudaStream_t)stream_);
     k2_pack_kernel<<<G, K2_THREADS, 0, (cudaStream_t)stream_>>>(det, group_offsets, keep, keep_count, merged_boxes,
                                                                merged_scores, src_index, G, out, out_offsets);
     FSD_CUDA(cudaGetLastError());
@@ -280,6 +281,7 @@ extern "C" int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const v
     FSD_CUDA(cudaSetDevice(h->device));
     FSD_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * B, stream));
     dim3 grid((a + K2_THREADS - 1) / K2_THREADS, B);
+    TimedLaunch timed(h, FSD_KERNEL_DECODE, (int64_t)B * a * 80 * (dtype == FSD_F16 ? 2 : 4), a, stream);
     if (dtype == FSD_F16) {
         if (layout == FSD_PLANAR) k2_pose_decode_kernel<__half, FSD_PLANAR><<<grid, K2_THREADS, 0, stream>>>(L, B, conf, cand, cap_per_entry, count);
         else k2_pose_decode_kernel<__half, FSD_CHANNELS_LAST><<<grid, K2_THREADS, 0, stream>>>(L, B, conf, cand, cap_per_entry, count);
@@ -306,6 +308,7 @@ extern "C" int fsd_finalize_dets(fsd_handle_t h, const float* cand, int cap_per_
     p.group_range = group_range; p.group_offsets = group_offsets; p.det = det; p.out_count = out_count;
     p.cap = cap_per_entry; p.det_cap = det_cap_per_group; p.truncate = truncate;
     FSD_CUDA(cudaSetDevice(h->device));
+    TimedLaunch timed(h, FSD_KERNEL_FINALIZE, B, G, (cudaStream_t)stream_);
     k2_finalize_kernel<<<G, K2_THREADS, 0, (cudaStream_t)stream_>>>(p);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;

@@ -686,11 +686,13 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
         // large segments: a cluster of 8 CTAs per segment (k3_merge_cluster_kernel)
         const size_t csmem = (size_t)(p.P / K3_CLUSTER) * 12;
         FSD_CUDA(cudaFuncSetAttribute(k3_merge_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, (cudaStream_t)stream_);
         k3_merge_cluster_kernel<<<S * K3_CLUSTER, 512, csmem, (cudaStream_t)stream_>>>(p);
         FSD_CUDA(cudaGetLastError());
         h->launches += 1;
         return FSD_OK;
     }
+    TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, (cudaStream_t)stream_);
     k3_merge_kernel<<<S, threads, smem, (cudaStream_t)stream_>>>(p);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;

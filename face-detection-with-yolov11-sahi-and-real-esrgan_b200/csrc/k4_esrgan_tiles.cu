@@ -426,6 +426,9 @@ extern "C" int fsd_esrgan_crop(fsd_handle_t h, const uint8_t* bgr, int H, int W,
     }
     dim3 grid((max_items + K4_THREADS - 1) / K4_THREADS, T, n_images);
     FSD_CUDA(cudaSetDevice(h->device));
+    int64_t crop_bytes = (int64_t)H * W * 3;  // algorithmic: source once + every tile once
+    for (int i = 0; i < T; ++i) crop_bytes += (int64_t)3 * table_host[i * TT + 2] * table_host[i * TT + 3] * (dtype == FSD_F16 ? 2 : 4);
+    TimedLaunch timed(h, FSD_KERNEL_ESRGAN_CROP, crop_bytes * n_images, n_images, (cudaStream_t)stream_);
     if (dtype == FSD_F16) k4_crop_kernel<__half><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>(bgr, H, W, row_pitch, pre_h, pre_w, table_dev, (__half*)tiles, image_pitch, tiles_image_stride);
     else k4_crop_kernel<float><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>(bgr, H, W, row_pitch, pre_h, pre_w, table_dev, (float*)tiles, image_pitch, tiles_image_stride);
     FSD_CUDA(cudaGetLastError());
@@ -450,6 +453,9 @@ extern "C" int fsd_esrgan_stitch(fsd_handle_t h, const void* tiles_out, const in
     }
     dim3 grid((max_items + K4_THREADS - 1) / K4_THREADS, T, n_images);
     FSD_CUDA(cudaSetDevice(h->device));
+    int64_t stitch_bytes = (int64_t)out_h * out_w * 3;  // algorithmic: every tile interior once + the output once
+    for (int i = 0; i < T; ++i) stitch_bytes += (int64_t)3 * table_host[i * TT + 6] * scale * table_host[i * TT + 7] * scale * (dtype == FSD_F16 ? 2 : 4);
+    TimedLaunch timed(h, FSD_KERNEL_ESRGAN_STITCH, stitch_bytes * n_images, n_images, (cudaStream_t)stream_);
     if (dtype == FSD_F16) k4_stitch_kernel<__half><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>((const __half*)tiles_out, table_dev, scale, out_bgr, out_h, out_w, out_pitch, tiles_image_stride, out_image_pitch);
     else k4_stitch_kernel<float><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>((const float*)tiles_out, table_dev, scale, out_bgr, out_h, out_w, out_pitch, tiles_image_stride, out_image_pitch);
     FSD_CUDA(cudaGetLastError());
@@ -465,6 +471,7 @@ extern "C" int fsd_attach_keypoints(fsd_handle_t h, const float* merged, int mer
                   "fsd_attach_keypoints: row strides must be multiples of 4 floats (16-byte rows)");
     if (S == 0) return FSD_OK;
     FSD_CUDA(cudaSetDevice(h->device));
+    TimedLaunch timed(h, FSD_KERNEL_ATTACH, S, 0, (cudaStream_t)stream_);
     attach_keypoints_kernel<<<S, 256, 0, (cudaStream_t)stream_>>>(merged, merged_stride, m_off, m_cnt, dets, det_stride, d_off, d_cnt, src_index);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;

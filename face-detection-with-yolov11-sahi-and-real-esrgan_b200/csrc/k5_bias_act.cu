@@ -205,6 +205,7 @@ extern "C" int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, i
     if (act == 0) K<0><<<grid, K5_THREADS, 0, s>>>((T*)x, (const T*)bias, n_vec, c_vec, slope); \
     else if (act == 1) K<1><<<grid, K5_THREADS, 0, s>>>((T*)x, (const T*)bias, n_vec, c_vec, slope); \
     else K<2><<<grid, K5_THREADS, 0, s>>>((T*)x, (const T*)bias, n_vec, c_vec, slope);
+    TimedLaunch timed(h, FSD_KERNEL_BIAS_ACT, (int64_t)n_vec * 32, channels, s);  // read + write once
     if (dtype == FSD_F16) { LAUNCH(k5_bias_act_half_kernel, uint4) } else { LAUNCH(k5_bias_act_float_kernel, float4) }
 #undef LAUNCH
     FSD_CUDA(cudaGetLastError());
@@ -268,6 +269,7 @@ extern "C" int fsd_sppf_pool(fsd_handle_t h, void* buf, int N, int H, int W, int
     if (N == 0) return FSD_OK;
     FSD_CUDA(cudaSetDevice(h->device));
     if (smem > 48 * 1024) FSD_CUDA(cudaFuncSetAttribute(k5_sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TimedLaunch timed(h, FSD_KERNEL_SPPF, (int64_t)N * H * W * c * 4 * 2, c, (cudaStream_t)stream_);  // read slot 0, write slots 1..3
     k5_sppf_pool_kernel<<<N * (c / 8), K5_THREADS, smem, (cudaStream_t)stream_>>>((uint4*)buf, H, W, c / 8);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;

@@ -153,6 +153,8 @@ extern "C" int fsd_stem_conv(fsd_handle_t h, const void* x, int E, int H, int W,
     FSD_CHECK_ARG(!space_to_depth || (p.OH % 2 == 0 && p.OW % 2 == 0), "fsd_stem_conv: the space-to-depth output needs even output sizes");
     dim3 grid((p.OW + K6_TW - 1) / K6_TW, (p.OH + K6_TH - 1) / K6_TH, E);
     FSD_CUDA(cudaSetDevice(h->device));
+    // algorithmic bytes: the 3-channel input once + the 16-channel output once
+    TimedLaunch timed(h, FSD_KERNEL_STEM, (int64_t)E * ((int64_t)H * W * 3 + (int64_t)p.OH * p.OW * 16) * 2, 16, (cudaStream_t)stream_);
     k6_stem_conv_kernel<<<grid, K6_THREADS, 0, (cudaStream_t)stream_>>>(p);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;

@@ -180,6 +180,8 @@ static int k7_launch(fsd_context* h, const K7Params& p, cudaStream_t s) {
         FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
         kern<<<grid, K7_THREADS, smem, s>>>(p);                                                                      \
     }
+    // algorithmic bytes: input + output (+ residual, + second destination) once
+    TimedLaunch timed(h, FSD_KERNEL_POINTWISE, (int64_t)p.P * (K + N + (p.res ? N : 0) + (p.out2 ? N - p.out2_c0 : 0)) * 2, N, s);
     if (p.act == 0) K7_GO(0) else if (p.act == 1) K7_GO(1) else K7_GO(2)
 #undef K7_GO
     FSD_CUDA(cudaGetLastError());

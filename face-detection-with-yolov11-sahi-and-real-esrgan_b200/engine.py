@@ -205,6 +205,37 @@ class SlicedFaceDetector:
         self.replayed_launches += ent[2]
         return ent[1]
 
+    @torch.no_grad()
+    def measure_backbone_ms(self, plan: SlicePlan, N: int, steps: int = 3) -> float:
+        """Device milliseconds per batch spent in the PyTorch backbone ALONE (all slice chunks + the full-image chunk, graph
+        replays when enabled) over whatever the network-input buffers hold — measurement only: bench.py uses it for the
+        backbone's share of the step instead of quoting a profile."""
+        shapes = [("slices", (N * plan.S, 3, plan.g_slice["out_h"], plan.g_slice["out_w"]))]
+        if plan.g_full is not None:
+            shapes.append(("full", (N, 3, plan.g_full["out_h"], plan.g_full["out_w"])))
+        bufs = []
+        for kind, shape in shapes:
+            x = self._network_input(kind, shape)
+            if x is None:
+                x = torch.zeros(shape, dtype=self.dtype, device=self.device,
+                                memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+            bufs.append(x)
+
+        def once():
+            for x in bufs:
+                for a in range(0, x.shape[0], self.chunk):
+                    with self._cudnn_scope():
+                        self._graph_forward(x[a:a + self.chunk]) if self.use_graphs else self.backbone(x[a:a + self.chunk])
+
+        once()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            once()
+        t1.record()
+        t1.synchronize()
+        return t0.elapsed_time(t1) / steps
+
     def _stage1(self, cand, count, seg_off):
         return ops.merge_segments(cand.view(-1, ROW), seg_off, count, self.cap, merge_type="NMS", metric="IOU",
                                   thr=self.iou, cmp_strict=True, precision="fp32", class_agnostic=True,

@@ -52,10 +52,17 @@ int64_t fsd_launch_count(fsd_handle_t h);
  * by CUDA events recorded on the launching stream INSIDE the library, right around the launch, so host-side preparation
  * never falls inside a sample.  enable() clears earlier samples; read() waits for each sample's end event and
  * returns rows [kernel id (FSD_KERNEL_*), units, tag, milliseconds]:
- *   FSD_KERNEL_GATHER   units = entries of the launch, tag = src_w
- *   FSD_KERNEL_BIAS_ACT units = bytes the launch moves, tag = channels
+ *   FSD_KERNEL_GATHER         units = entries of the launch, tag = src_w
+ *   FSD_KERNEL_DECODE         units = bytes of the head tensors (80 values per anchor), tag = anchors per entry
+ *   FSD_KERNEL_MERGE          units = segments, tag = max_segment
+ *   FSD_KERNEL_ESRGAN_CROP / _STITCH   units = algorithmic bytes, tag = images of the launch
+ *   FSD_KERNEL_BIAS_ACT / _STEM / _POINTWISE / _SPPF   units = bytes the launch moves, tag = channels
+ *   FSD_KERNEL_FINALIZE / _ATTACH / _PACK   units = entries / images
+ * Launches captured into a CUDA graph cannot be bracketed (bench.py times the backbone's kernels in an eager step).
  * (the reference has no counterpart; its timing is wall-clock around model.predict, utils/yolo_wrapper.py:67-80) */
-enum { FSD_KERNEL_GATHER = 1, FSD_KERNEL_BIAS_ACT = 5 };
+enum { FSD_KERNEL_GATHER = 1, FSD_KERNEL_DECODE = 2, FSD_KERNEL_MERGE = 3, FSD_KERNEL_ESRGAN_CROP = 4, FSD_KERNEL_BIAS_ACT = 5,
+       FSD_KERNEL_STEM = 6, FSD_KERNEL_POINTWISE = 7, FSD_KERNEL_FINALIZE = 8, FSD_KERNEL_ATTACH = 9, FSD_KERNEL_PACK = 10,
+       FSD_KERNEL_ESRGAN_STITCH = 11, FSD_KERNEL_SPPF = 12 };
 int fsd_kernel_timing_enable(fsd_handle_t h, unsigned kernel_mask /* OR of (1u << FSD_KERNEL_*); 0 = off */);
 int fsd_kernel_timing_read(fsd_handle_t h, double* samples /* [cap,4] or NULL */, int cap, int* n);
 

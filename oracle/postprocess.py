@@ -4,8 +4,9 @@ Restates [EXT sahi==0.11.34] sahi.postprocess.combine / sahi.postprocess.utils a
 App. A.2 — selected by the reference at docs sahi/predict.py:44-49,250-259 and run at :297,:319.
 Parity unpinned (upstream source and its shapely/GEOS dependency are absent).  Defaults chosen where upstream
 generations differ: float64 metric, match when metric >= threshold, zero-area boxes never match,
-rank order = score descending with ties broken by the lower original index, candidates of a keep listed in rank
-order (GREEDYNMM) / in append order of the transitive walk (NMM).
+visiting order = score descending with ties visited in original index order, equal scores handled by variant N's
+lexicographic box rule (`tie_rule="box_lex"`, the default; `"index"` is the plain greedy loop), candidates of a keep listed
+in rank order (GREEDYNMM) / in append order of the transitive walk (NMM).
 """
 from __future__ import annotations
 
@@ -48,8 +49,47 @@ def metric_row(boxes: np.ndarray, i: int, js: np.ndarray, match_metric: str, dty
     return out
 
 
-def nms(preds: np.ndarray, match_metric="IOU", match_threshold=0.5):
+TIE_RULE = "box_lex"  # module default: what sahi 0.11.34 is believed to ship (SURVEY A.2.4 variant N); "index" = plain order
+
+
+def lex_greater(boxes: np.ndarray, ref: np.ndarray) -> np.ndarray:
+    """tuple(box) > tuple(ref), row by row (python tuple comparison of the four coordinates)."""
+    out = np.zeros(len(boxes), dtype=bool)
+    undecided = np.ones(len(boxes), dtype=bool)
+    for c in range(4):
+        out |= undecided & (boxes[:, c] > ref[c])
+        undecided &= boxes[:, c] == ref[c]
+    return out
+
+
+def _candidates(order, r, boxes, scores, suppressed, tie_rule):
+    """Indices the current box order[r] is tested against, in rank order.
+
+    tie_rule "index": every not yet suppressed box of lower rank (ties broken by the lower original index) — the greedy
+    loop of the pure-torch generations.
+    tie_rule "box_lex" (SURVEY A.2.4 variant N, lines 606-617): every not suppressed box whose score is not higher, EXCEPT
+    equal-score boxes whose coordinate tuple is lexicographically larger than the current one's.  Two consequences, both
+    restated faithfully: (a) an equal-score, lexicographically larger box of lower rank is NOT suppressed by the current
+    box, so both can be kept; (b) when that box is visited later it DOES test — and can "suppress" — the earlier equal-score
+    keep, which for GREEDYNMM puts an already kept box into the later keep's merge list."""
+    cur = order[r]
+    if tie_rule == "index":
+        cand = order[r + 1:]
+        return cand[~suppressed[cand]]
+    if tie_rule != "box_lex":
+        raise ValueError(f"unknown tie_rule {tie_rule}")
+    lo = r
+    while lo > 0 and scores[order[lo - 1]] == scores[cur]:
+        lo -= 1
+    cand = np.concatenate((order[lo:r], order[r + 1:]))
+    cand = cand[~suppressed[cand]]
+    skip = (scores[cand] == scores[cur]) & lex_greater(boxes[cand], boxes[cur])
+    return cand[~skip]
+
+
+def nms(preds: np.ndarray, match_metric="IOU", match_threshold=0.5, tie_rule=None):
     boxes, scores = preds[:, :4], preds[:, 4]
+    tie_rule = tie_rule or TIE_RULE
     order = rank_order(scores)
     suppressed = np.zeros(len(preds), dtype=bool)
     keep = []
@@ -57,24 +97,23 @@ def nms(preds: np.ndarray, match_metric="IOU", match_threshold=0.5):
         if suppressed[cur]:
             continue
         keep.append(int(cur))
-        rest = order[r + 1:]
-        rest = rest[~suppressed[rest]]
+        rest = _candidates(order, r, boxes, scores, suppressed, tie_rule)
         if len(rest):
             m = metric_row(boxes, cur, rest, match_metric) >= match_threshold
             suppressed[rest[m]] = True
     return keep
 
 
-def greedy_nmm(preds: np.ndarray, match_metric="IOU", match_threshold=0.5):
+def greedy_nmm(preds: np.ndarray, match_metric="IOU", match_threshold=0.5, tie_rule=None):
     boxes, scores = preds[:, :4], preds[:, 4]
+    tie_rule = tie_rule or TIE_RULE
     order = rank_order(scores)
     suppressed = np.zeros(len(preds), dtype=bool)
     keep_to_merge = {}
     for r, cur in enumerate(order):
         if suppressed[cur]:
             continue
-        rest = order[r + 1:]
-        rest = rest[~suppressed[rest]]
+        rest = _candidates(order, r, boxes, scores, suppressed, tie_rule)
         merged = []
         if len(rest):
             m = metric_row(boxes, cur, rest, match_metric) >= match_threshold
@@ -84,7 +123,7 @@ def greedy_nmm(preds: np.ndarray, match_metric="IOU", match_threshold=0.5):
     return keep_to_merge
 
 
-def nmm(preds: np.ndarray, match_metric="IOU", match_threshold=0.5):
+def nmm(preds: np.ndarray, match_metric="IOU", match_threshold=0.5, tie_rule=None):
     """Transitive merge (SURVEY A.2.4 `nmm`): every box is visited in rank order; a box already claimed by a keep
     forwards its own unclaimed matches to that keep.  Matches are listed in ascending-score order (`flip`)."""
     boxes, scores = preds[:, :4], preds[:, 4]
@@ -110,34 +149,34 @@ def nmm(preds: np.ndarray, match_metric="IOU", match_threshold=0.5):
     return keep_to_merge
 
 
-def _batched(fn_dict_or_list, preds, match_metric, match_threshold, is_dict):
+def _batched(fn_dict_or_list, preds, match_metric, match_threshold, is_dict, **kw):
     cats = preds[:, 5]
     if is_dict:
         out = {}
         for c in np.unique(cats):
             idx = np.where(cats == c)[0]
-            sub = fn_dict_or_list(preds[idx], match_metric, match_threshold)
+            sub = fn_dict_or_list(preds[idx], match_metric, match_threshold, **kw)
             for k, lst in sub.items():
                 out[int(idx[k])] = [int(idx[j]) for j in lst]
         return out
     mask = np.zeros(len(preds), dtype=bool)
     for c in np.unique(cats):
         idx = np.where(cats == c)[0]
-        mask[idx[fn_dict_or_list(preds[idx], match_metric, match_threshold)]] = True
+        mask[idx[fn_dict_or_list(preds[idx], match_metric, match_threshold, **kw)]] = True
     keep = np.where(mask)[0]
     return [int(i) for i in keep[rank_order(preds[keep, 4])]]
 
 
-def batched_nms(preds, match_metric="IOU", match_threshold=0.5):
-    return _batched(nms, preds, match_metric, match_threshold, False)
+def batched_nms(preds, match_metric="IOU", match_threshold=0.5, tie_rule=None):
+    return _batched(nms, preds, match_metric, match_threshold, False, tie_rule=tie_rule)
 
 
-def batched_greedy_nmm(preds, match_metric="IOU", match_threshold=0.5):
-    return _batched(greedy_nmm, preds, match_metric, match_threshold, True)
+def batched_greedy_nmm(preds, match_metric="IOU", match_threshold=0.5, tie_rule=None):
+    return _batched(greedy_nmm, preds, match_metric, match_threshold, True, tie_rule=tie_rule)
 
 
-def batched_nmm(preds, match_metric="IOU", match_threshold=0.5):
-    return _batched(nmm, preds, match_metric, match_threshold, True)
+def batched_nmm(preds, match_metric="IOU", match_threshold=0.5, tie_rule=None):
+    return _batched(nmm, preds, match_metric, match_threshold, True)  # variant N's nmm has no tie rule (A.2.4)
 
 
 # ---- object level: has_match / merge (sahi.postprocess.utils) ----------------------------
@@ -175,8 +214,9 @@ def merge_object_prediction_pair(p1, p2):
 
 
 class PostprocessPredictions:
-    def __init__(self, match_threshold=0.5, match_metric="IOU", class_agnostic=True):
+    def __init__(self, match_threshold=0.5, match_metric="IOU", class_agnostic=True, tie_rule=None):
         self.match_threshold, self.match_metric, self.class_agnostic = match_threshold, match_metric, class_agnostic
+        self.tie_rule = tie_rule  # None: the module default TIE_RULE
 
     def __call__(self, object_predictions):
         raise NotImplementedError()
@@ -186,7 +226,7 @@ class NMSPostprocess(PostprocessPredictions):
     def __call__(self, object_predictions):
         preds = to_array(object_predictions)
         fn = nms if self.class_agnostic else batched_nms
-        keep = fn(preds, self.match_metric, self.match_threshold)
+        keep = fn(preds, self.match_metric, self.match_threshold, tie_rule=self.tie_rule)
         self.last_keep = keep
         return [object_predictions[i] for i in keep]
 
@@ -198,7 +238,7 @@ class _MergePostprocess(PostprocessPredictions):
         opl = list(object_predictions)
         preds = to_array(opl)
         fn = type(self)._plain if self.class_agnostic else type(self)._batched_fn
-        keep_to_merge = fn(preds, self.match_metric, self.match_threshold)
+        keep_to_merge = fn(preds, self.match_metric, self.match_threshold, tie_rule=self.tie_rule)
         self.last_keep_to_merge = keep_to_merge
         selected = []
         for keep_ind, merge_list in keep_to_merge.items():

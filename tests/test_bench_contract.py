@@ -31,7 +31,7 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = _run(["--steps", "3", "--warmup", "3", "--batch", "8", "--images", "64", "--cpu-sample", "1"], 900)
+    d = _run(["--steps", "3", "--warmup", "3", "--batch", "8", "--images", "64", "--cpu-sample", "1"], 1500)
     assert BASE_KEYS | {"roofline", "clocks", "gpu_launches"} <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["dtype"] == "f16" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["gpu_launches"] > 0 and d["vs_baseline"] is None and d["scaling"] == "weak"
@@ -42,3 +42,14 @@ def test_gpu_arm_line():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["value"] > 0 and c["cores"] >= 1 and "sample" in c
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    # round 2: parity gate before timing, the other north-star kernels in the same line, measured shares, extra legs
+    assert d["parity_gate"] == "pass" and set(d["parity"]["checks"]) >= {"C2", "C1", "K3_greedynmm_ios_1024", "K3_nms_iou_9900", "K4_crop_stitch"}
+    names = " ".join(k["kernel"] for k in r["other_kernels"])
+    for part in ("k2_pose_decode", "k3_merge", "k2_finalize", "attach_keypoints", "k5_bias_act"):
+        assert part in names
+    hp = d["hot_path"]
+    assert 0 < hp["backbone_share_of_step"] < 1.5 and hp["backbone_ms_per_step"] > 0 and hp["north_star_kernels_ms_per_step"] > 0
+    x = d["extra"]
+    assert x["f32"]["value"] > 0 and x["c1"]["value"] > 0 and x["c5"]["value"] > 0 and x["c1"]["cpu_port_seconds_per_image"] > 0
+    assert {row["N"] for row in x["c3_merge_us"]["rows"]} == {256, 1024, 4096, 9900}
+    assert 0 < x["c5"]["k4_crop"]["frac"] < 1.2 and 0 < x["c5"]["k4_stitch"]["frac"] < 1.2

@@ -156,9 +156,25 @@ def test_threshold_equality_is_dropped_not_merged():
 
 def test_zero_area_and_equal_scores():
     preds = [P([10, 10, 10, 40], 0.7), P([0, 0, 50, 50], 0.7), P([5, 5, 45, 45], 0.7)]
-    pp = opp.GreedyNMMPostprocess(0.5, "IOS", True)
+    pp = opp.GreedyNMMPostprocess(0.5, "IOS", True, tie_rule="index")
     out = pp(preds)
     assert pp.last_keep_to_merge == {0: [], 1: [2]} and [o.bbox.to_xyxy() for o in out] == [[10, 10, 10, 40], [0, 0, 50, 50]]
+    # variant N (lines 606-617), the default: box 1 must not test box 2 (equal score, lexicographically larger
+    # tuple), so box 2 is kept as well — and, visited later, claims the already kept box 1 into its own merge list
+    pp = opp.GreedyNMMPostprocess(0.5, "IOS", True)
+    out = pp(preds)
+    assert pp.last_keep_to_merge == {0: [], 1: [], 2: [1]}
+    assert [o.bbox.to_xyxy() for o in out] == [[10, 10, 10, 40], [0, 0, 50, 50], [0, 0, 50, 50]]
+    assert opp.nms(opp.to_array(preds), "IOS", 0.5) == [0, 1, 2] and opp.nms(opp.to_array(preds), "IOS", 0.5, tie_rule="index") == [0, 1]
+    # equal scores, lexicographically SMALLER later box: the plain rule applies
+    rev = [P([5, 5, 45, 45], 0.7), P([0, 0, 50, 50], 0.7)]
+    assert opp.greedy_nmm(opp.to_array(rev), "IOS", 0.5) == {0: [1]}
+    # a chain inside one tie group: 0 <- 1 <- 2 are each claimed by the next (lexicographically larger) keep
+    chain = [P([0, 0, 40, 40], 0.5), P([1, 0, 41, 40], 0.5), P([2, 0, 42, 40], 0.5)]
+    pp = opp.GreedyNMMPostprocess(0.5, "IOU", True)
+    out = pp(chain)
+    assert pp.last_keep_to_merge == {0: [], 1: [0], 2: [1]}
+    assert [o.bbox.to_xyxy() for o in out] == [[0, 0, 40, 40], [0, 0, 41, 40], [0, 0, 42, 40]]  # 2 merges the MERGED box 1
 
 
 def test_chain_greedy_vs_transitive():
