@@ -595,11 +595,11 @@ def run_extras(args, dev, yolo, eng, h, peak, use_graphs):
             off = torch.arange(segs, dtype=torch.int32, device=dev) * n
             for mt, metric in (("NMS", "IOU"), ("GREEDYNMM", "IOS")):
                 for _ in range(2):
-                    res = ops.merge_segments(rows, off, None, n, merge_type=mt, metric=metric, thr=0.5, precision="fp64", want_parent=False)
+                    res = ops.merge_segments(rows, off, None, n, merge_type=mt, metric=metric, thr=0.5, precision="fp64", want_parent=False, tie_rule="box_lex")
                 sync()
                 h.timing_enable((K.FSD_KERNEL_MERGE,))
                 for _ in range(5):
-                    res = ops.merge_segments(rows, off, None, n, merge_type=mt, metric=metric, thr=0.5, precision="fp64", want_parent=False)
+                    res = ops.merge_segments(rows, off, None, n, merge_type=mt, metric=metric, thr=0.5, precision="fp64", want_parent=False, tie_rule="box_lex")
                 ts = sorted(t for (_, _, t) in by_kernel(h.timing_read()).get(K.FSD_KERNEL_MERGE, []))
                 h.timing_enable(())
                 c3.append({"N": n, "segments": segs, "type": f"{mt}/{metric}", "us_median": 1e3 * ts[len(ts) // 2], "us_min": 1e3 * ts[0],

@@ -31,7 +31,7 @@ SIGNATURES = {
                                   C.c_int, C.c_float, vp, C.c_int, vp, vp]),
     "fsd_merge_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "fsd_merge": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int,
-                            C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
+                            C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                             vp, vp, vp, vp, C.c_int64, vp]),
     "fsd_finalize_dets": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp,
                                     C.c_int, vp, vp]),

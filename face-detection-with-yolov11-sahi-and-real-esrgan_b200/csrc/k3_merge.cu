@@ -1,14 +1,23 @@
 // Kernel 3 — batched segment NMS / GREEDYNMM / NMM with IOU | IOS match metrics.
 //
 // One CTA per segment (a slice for stage 1 = torchvision.ops.nms semantics inside ultralytics' NMS; an image for
-// stage 2 = sahi.postprocess.combine semantics).  Phases, all on-chip for segments up to 4096 boxes:
-//   1. rank:   64-bit keys (score descending, tie-break key ascending) sorted by an in-CTA bitonic network;
-//   2. scan:   greedy suppression in chunks of 64 ranks: the 64x64 in-chunk match bits come from warp ballots,
-//              one thread resolves the chunk with 64-bit mask operations, then every thread sweeps the not yet
-//              removed lower ranks against the chunk's (<= 64) new keeps — no N x N mask is ever materialised;
+// stage 2 = sahi.postprocess.combine semantics); segments above 4096 boxes get a cluster of 8 CTAs.  The launch is sized
+// by the caller's CAPACITY, the work by each segment's actual count read on the device: a CTA trims itself to the warps its
+// segment needs, and the two kernels (shared-memory / cluster) are launched back to back, each leaving the other's segments
+// alone — no host round trip decides the path.  Phases of the shared-memory kernel (k3_merge_kernel, <= 4096 boxes):
+//   1. rank:   64-bit keys (score descending, tie-break key ascending), bitonic network whose stages with partner distance
+//              < 32 run in registers through warp shuffles (20 block barriers for 1024 keys instead of 55);
+//   2. scan:   greedy suppression in chunks of 64 ranks, TWO block barriers per chunk: one warp resolves the chunk from its
+//              64x64 match bits held in registers (64 shuffle steps, no memory on the dependent chain), then all threads
+//              assign in-chunk parents, sweep the not yet removed lower ranks against the chunk's (<= 64) new keeps (first
+//              match claims) AND compute the next chunk's match bits in the same phase — no N x N mask is ever materialised;
 //              NMM instead walks every rank and propagates claims transitively (A.2.4 `nmm`);
-//   3. replay: a second bitonic sort groups merge candidates by keep in append order, one thread per keep folds
-//              them with the STRICT has_match re-check against the growing union box (A.2.5), in float64.
+//   3. replay: every keep folds its candidates in append order with the STRICT has_match re-check against the growing
+//              union box (A.2.5), in float64: one thread per keep, all threads scanning the claim array in lockstep
+//              (broadcast reads) — no second sort for GREEDYNMM; NMM's step-major order still uses one.
+// tie_rule 1 = sahi 0.11.34's lexicographic box rule for equal scores (SURVEY A.2.4 variant N, oracle/postprocess.py
+// `_candidates`): an equal-score candidate whose coordinate tuple is larger is not tested, so both boxes can be kept, and
+// the later keep claims the earlier equal-score keep into its merge list (then folds that keep's MERGED box).
 // The match test is bit-faithful: fp64 divide/compare for sahi (exact on integral boxes), fp32 divide with the
 // result promoted to double for the torchvision rule.
 #include <cooperative_groups.h>
@@ -30,7 +39,7 @@ struct K3Params {
     const int32_t* seg_offsets;
     const int32_t* seg_counts;
     int seg_cap;
-    int type, metric, cmp_strict, precision, class_agnostic, pre_cap, max_keep;
+    int type, metric, cmp_strict, precision, class_agnostic, pre_cap, max_keep, tie_rule;
     double thr;
     int32_t* keep; int32_t* keep_count; int32_t* parent;
     float* merged_boxes; float* merged_scores; int32_t* merged_cats;
@@ -46,9 +55,25 @@ __device__ __forceinline__ uint32_t score_key_desc(float s) {
 }
 
 struct MatchCfg {
-    int metric, cmp_strict, precision, class_agnostic;
+    int metric, cmp_strict, precision, class_agnostic, tie_rule;
     double thr;
 };
+
+__device__ __forceinline__ MatchCfg match_cfg(const K3Params& p) {
+    MatchCfg mc;
+    mc.metric = p.metric; mc.cmp_strict = p.cmp_strict; mc.precision = p.precision;
+    mc.class_agnostic = p.class_agnostic || p.cats == nullptr; mc.thr = p.thr;
+    mc.tie_rule = (p.tie_rule != 0 && p.type != FSD_NMM) ? 1 : 0;  // variant N's nmm has no tie rule
+    return mc;
+}
+
+// tuple(a) > tuple(b), python tuple comparison of (x1, y1, x2, y2)
+__device__ __forceinline__ bool lex_greater(const float4 a, const float4 b) {
+    if (a.x != b.x) return a.x > b.x;
+    if (a.y != b.y) return a.y > b.y;
+    if (a.z != b.z) return a.z > b.z;
+    return a.w > b.w;
+}
 
 __device__ __forceinline__ bool match_pair(const float4 a, const float4 b, int ca, int cb, const MatchCfg& m) {
     if (!m.class_agnostic && ca != cb) return false;
@@ -77,6 +102,14 @@ __device__ __forceinline__ bool match_pair(const float4 a, const float4 b, int c
     const double den = m.metric == FSD_IOU ? aa + ab - inter : fmin(aa, ab);
     const double v = den > 0.0 ? inter / den : 0.0;
     return m.cmp_strict ? v > m.thr : v >= m.thr;
+}
+
+// What the greedy loop applies to (current box, candidate): the match test, minus variant N's exclusion of an equal-score
+// candidate whose coordinate tuple is lexicographically larger.  kcur / kcand = the score halves of the rank keys.
+__device__ __forceinline__ bool suppresses(const float4 cur, const float4 cand, int ccur, int ccand, uint32_t kcur,
+                                           uint32_t kcand, const MatchCfg& m) {
+    if (m.tie_rule && kcur == kcand && lex_greater(cand, cur)) return false;
+    return match_pair(cur, cand, ccur, ccand, m);
 }
 
 // sahi.postprocess.utils.has_match: numpy float64, STRICT >, nan (0/0) compares false
@@ -109,8 +142,392 @@ __device__ void bitonic_sort(uint64_t* keys, uint32_t* vals, int P) {
     }
 }
 
+
+constexpr int K3_HASB = 1 << 30;  // step[] flag: this keep has an earlier equal-score keep in its merge list (tie_rule 1)
+
+// barrier over the first T threads of the CTA (the warps a small segment does not need have already returned)
+__device__ __forceinline__ void k3_bar(int T) { asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory"); }
+
+// Bitonic sort of P keys (power of two >= 64) by T threads.  Stages with partner distance j < 32 stay inside one 32-key
+// group: a warp holds the group in registers and exchanges through shuffles, all stages j = 16..1 of a phase back to back
+// with no barrier; only the stages with j >= 32 go through shared memory with one barrier each.
+__device__ void bitonic_sort_hybrid(uint64_t* keys, uint32_t* vals, int P, int tid, int T) {
+    const int lane = tid & 31, warp = tid >> 5, warps = T >> 5, groups = P >> 5;
+    auto reg_pass = [&](int k_first, int k_last) {
+        for (int g = warp; g < groups; g += warps) {
+            const int i = (g << 5) | lane;
+            uint64_t key = keys[i];
+            uint32_t val = vals ? vals[i] : 0u;
+            for (int k = k_first; k <= k_last; k <<= 1) {
+                const bool up = (i & k) == 0;
+                for (int j = min(k >> 1, 16); j > 0; j >>= 1) {
+                    const uint64_t ok = __shfl_xor_sync(0xffffffffu, key, j);
+                    const uint32_t ov = __shfl_xor_sync(0xffffffffu, val, j);
+                    const bool take_min = ((lane & j) == 0) == up;
+                    if (take_min ? (ok < key) : (ok > key)) { key = ok; val = ov; }
+                }
+            }
+            keys[i] = key;
+            if (vals) vals[i] = val;
+        }
+        k3_bar(T);
+    };
+    reg_pass(2, 32);
+    for (int k = 64; k <= P; k <<= 1) {
+        for (int j = k >> 1; j >= 32; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += T) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = (i & k) == 0;
+                const uint64_t ki = keys[i], kl = keys[l];
+                if ((ki > kl) == up) {
+                    keys[i] = kl; keys[l] = ki;
+                    if (vals) { const uint32_t vi = vals[i]; vals[i] = vals[l]; vals[l] = vi; }
+                }
+            }
+            k3_bar(T);
+        }
+        reg_pass(k, k);
+    }
+}
+
 __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     extern __shared__ __align__(16) uint8_t k3_smem[];
+    __shared__ uint32_t s_diag[2][128];  // 64 rows x 2 halves of in-chunk match bits, double buffered (chunk c / c + 1)
+    __shared__ int s_klist[64];
+    __shared__ float4 s_kbox[64];
+    __shared__ int s_kcat[64];
+    __shared__ uint32_t s_kkey[64];
+    __shared__ uint32_t s_rem[130];      // removed bits of the whole segment (4096) + slack for the 64-bit window
+    __shared__ unsigned long long s_keepmask, s_rembefore, s_remafter;
+    __shared__ int s_kcount, s_ktotal, s_stop;
+
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int off = p.seg_offsets[s];
+    int n = p.seg_counts ? p.seg_counts[s] : p.seg_cap;
+    n = min(max(n, 0), p.seg_cap);
+    if (n > K3_SMEM_MAX_P) return;  // the cluster launch owns this segment
+    if (n == 0) {
+        if (tid == 0) p.keep_count[s] = 0;
+        return;
+    }
+    int P = 64;
+    while (P < n) P <<= 1;
+    // the launch is sized for the capacity; the segment decides how many warps stay
+    const int T = min((int)blockDim.x, P <= 64 ? 64 : (P <= 256 ? 128 : (P <= 1024 ? 256 : 512)));
+    if (tid >= T) return;
+    const int lane = tid & 31;
+
+    uint8_t* base = k3_smem;
+    const size_t PP = (size_t)P;
+    float4* sbox = reinterpret_cast<float4*>(base);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(base + 16 * PP);
+    uint32_t* vals = reinterpret_cast<uint32_t*>(base + 24 * PP);
+    int* parent = reinterpret_cast<int*>(base + 28 * PP);   // rank of the claiming keep, own rank for keeps, -1 none
+    int* step = reinterpret_cast<int*>(base + 32 * PP);     // NMM: rank whose visit produced the claim; tie rule: backward claims
+    int* scat = reinterpret_cast<int*>(base + 36 * PP);
+    int* keepr = reinterpret_cast<int*>(base + 40 * PP);    // ranks of keeps in output order
+    int* runs = reinterpret_cast<int*>(base + 44 * PP);     // NMM: first replay-list position of each keep rank
+
+    const MatchCfg mc = match_cfg(p);
+
+    // ---- 1. rank ------------------------------------------------------------------------------------
+    for (int i = tid; i < P; i += T) {
+        uint64_t key = ~0ull;
+        uint32_t v = 0xffffffffu;
+        if (i < n) {
+            const float sc = p.scores[(size_t)(off + i) * p.score_stride];
+            const uint32_t tb = p.tie ? (uint32_t)p.tie[(size_t)(off + i) * p.tie_stride] : (uint32_t)i;
+            key = ((uint64_t)score_key_desc(sc) << 32) | tb;
+            v = (uint32_t)i;
+        }
+        keys[i] = key; vals[i] = v;
+    }
+    k3_bar(T);
+    bitonic_sort_hybrid(keys, vals, P, tid, T);
+    int m = n;
+    if (p.pre_cap > 0) m = min(m, p.pre_cap);
+    for (int r = tid; r < n; r += T) {
+        const int g = off + (int)vals[r];
+        if (r < m) {
+            const float* bp = p.boxes + (size_t)g * p.box_stride;
+            sbox[r] = make_float4(bp[0], bp[1], bp[2], bp[3]);
+            scat[r] = p.cats ? p.cats[(size_t)g * p.cat_stride] : 0;
+            parent[r] = -1;
+            step[r] = 0;
+            runs[r] = -1;
+        } else if (p.parent) {
+            p.parent[g] = -1;  // cut by the pre-NMS cap
+        }
+    }
+    for (int i = tid; i < 130; i += T) s_rem[i] = 0;
+    if (tid == 0) { s_ktotal = 0; s_stop = 0; s_kcount = 0; }
+    k3_bar(T);
+    auto keyhi = [&](int r) -> uint32_t { return mc.tie_rule ? (uint32_t)(keys[r] >> 32) : 0u; };
+
+    if (p.type != FSD_NMM) {
+        // ---- 2a. greedy scan in chunks of 64 ranks --------------------------------------------------
+        // match bits of one chunk: 64 threads per row (two warps = the two 32-bit halves), rows spread over the thread groups
+        auto chunk_bits = [&](int c0, uint32_t* dg) {
+            const int cn = min(64, m - c0);
+            const int q = tid & 63;
+            for (int r = tid >> 6; r < cn; r += T >> 6) {
+                bool bit = false;
+                if (q < cn && q > r)
+                    bit = suppresses(sbox[c0 + r], sbox[c0 + q], scat[c0 + r], scat[c0 + q], keyhi(c0 + r), keyhi(c0 + q), mc);
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                if (lane == 0) dg[r * 2 + (q >> 5)] = bal;
+            }
+        };
+        chunk_bits(0, s_diag[0]);
+        k3_bar(T);
+        for (int c0 = 0, c = 0; c0 < m; c0 += 64, ++c) {
+            const int cn = min(64, m - c0);
+            const uint32_t* dg = s_diag[c & 1];
+            if (tid < 32) {
+                // resolve: lane l holds rows l and l + 32 in registers; the dependent chain is 64 shuffle + mask steps
+                const uint64_t rowA = lane < cn ? ((uint64_t)dg[2 * lane] | ((uint64_t)dg[2 * lane + 1] << 32)) : 0ull;
+                const uint64_t rowB = lane + 32 < cn ? ((uint64_t)dg[2 * lane + 64] | ((uint64_t)dg[2 * lane + 65] << 32)) : 0ull;
+                const int w0 = c0 >> 5;
+                uint64_t remw = (uint64_t)s_rem[w0] | ((uint64_t)s_rem[w0 + 1] << 32);
+                const uint64_t before = remw;
+                uint64_t keepmask = 0;
+                const int kt = s_ktotal;
+                int cnt = 0, stop = 0;
+                for (int b = 0; b < cn; ++b) {
+                    const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
+                    if (!((remw >> b) & 1ull)) {
+                        if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
+                        keepmask |= 1ull << b;
+                        ++cnt;
+                        remw |= row;
+                    }
+                }
+                for (int pos = lane; pos < 64; pos += 32) {
+                    if ((keepmask >> pos) & 1ull) {
+                        const int idx = __popcll(keepmask & ((1ull << pos) - 1ull));
+                        const int kr = c0 + pos;
+                        s_klist[idx] = kr;
+                        keepr[kt + idx] = kr;
+                        s_kbox[idx] = sbox[kr];
+                        s_kcat[idx] = scat[kr];
+                        s_kkey[idx] = keyhi(kr);
+                        parent[kr] = kr;
+                    }
+                }
+                if (lane == 0) {
+                    s_rem[w0] = (uint32_t)remw;
+                    s_rem[w0 + 1] = (uint32_t)(remw >> 32);
+                    s_keepmask = keepmask; s_rembefore = before; s_remafter = remw;
+                    s_kcount = cnt; s_ktotal = kt + cnt; s_stop = stop;
+                }
+            }
+            k3_bar(T);
+            const int kc = s_kcount, stop = s_stop;
+            if (tid < cn) {
+                // parents of the ranks this chunk's own keeps removed: the FIRST keep whose row holds the rank
+                const uint64_t keepmask = s_keepmask;
+                const int q = tid;
+                if (!((s_rembefore >> q) & 1ull) && !((keepmask >> q) & 1ull) && ((s_remafter >> q) & 1ull)) {
+                    uint64_t km = keepmask & ((1ull << q) - 1ull);
+                    while (km) {
+                        const int b = __ffsll((long long)km) - 1;
+                        km &= km - 1;
+                        if ((dg[2 * b + (q >> 5)] >> (q & 31)) & 1u) { parent[c0 + q] = c0 + b; break; }
+                    }
+                }
+            }
+            if (!stop) {
+                // sweep: every not-yet-removed lower rank against this chunk's new keeps (first match claims it)
+                for (int j = c0 + cn + tid; j < m; j += T) {
+                    if ((s_rem[j >> 5] >> (j & 31)) & 1u) continue;
+                    const float4 bj = sbox[j];
+                    const int cj = scat[j];
+                    const uint32_t kj = keyhi(j);
+                    for (int k = 0; k < kc; ++k) {
+                        if (suppresses(s_kbox[k], bj, s_kcat[k], cj, s_kkey[k], kj, mc)) {
+                            atomicOr(&s_rem[j >> 5], 1u << (j & 31));
+                            parent[j] = s_klist[k];
+                            break;
+                        }
+                    }
+                }
+                if (c0 + 64 < m) chunk_bits(c0 + 64, s_diag[(c + 1) & 1]);  // off the critical path: same phase as the sweep
+            }
+            k3_bar(T);
+            if (stop) break;
+        }
+    } else {
+        // ---- 2b. NMM: visit every rank; a claimed rank forwards its unclaimed matches to its keep -------
+        for (int i = 0; i < m; ++i) {
+            if (tid == 0 && parent[i] == -1) {
+                parent[i] = i;
+                keepr[s_ktotal] = i;
+                s_ktotal = s_ktotal + 1;
+            }
+            k3_bar(T);
+            const int k = parent[i];
+            const float4 bi = sbox[i];
+            const int ci = scat[i];
+            for (int j = tid; j < m; j += T) {
+                if (j == i || parent[j] != -1) continue;
+                if (match_pair(bi, sbox[j], ci, scat[j], mc)) { parent[j] = k; step[j] = i; }
+            }
+            k3_bar(T);
+        }
+    }
+    k3_bar(T);
+    const int K = s_ktotal;
+    const bool tie_merge = mc.tie_rule && p.type == FSD_GREEDYNMM;
+
+    // ---- tie rule: a keep claims the earlier equal-score keeps it matches (each keep is claimed by the first such keep) ----
+    if (tie_merge) {
+        for (int i = tid; i < K; i += T) {
+            const int kr = keepr[i];
+            const uint32_t kk = keyhi(kr);
+            for (int q = kr + 1; q < m && keyhi(q) == kk; ++q) {
+                if (parent[q] == q && suppresses(sbox[q], sbox[kr], scat[q], scat[kr], kk, kk, mc)) {
+                    atomicOr(&step[kr], q + 1);
+                    atomicOr(&step[q], K3_HASB);
+                    break;
+                }
+            }
+        }
+        k3_bar(T);
+    }
+
+    // ---- 3. outputs + merge replay ------------------------------------------------------------------
+    if (p.parent) {
+        for (int r = tid; r < m; r += T) {
+            int pr = parent[r];
+            if (tie_merge && pr == r && (step[r] & ~K3_HASB)) pr = (step[r] & ~K3_HASB) - 1;  // claimed by a later equal-score keep
+            p.parent[off + (int)vals[r]] = pr < 0 ? -1 : off + (int)vals[pr];
+        }
+    }
+    if (tid == 0) p.keep_count[s] = K;
+    if (p.type == FSD_NMS) {
+        for (int i = tid; i < K; i += T) {
+            const int kr = keepr[i];
+            const int g = off + (int)vals[kr];
+            p.keep[off + i] = g;
+            const float4 b = sbox[kr];
+            float* mb = p.merged_boxes + (size_t)(off + i) * 4;
+            mb[0] = b.x; mb[1] = b.y; mb[2] = b.z; mb[3] = b.w;
+            p.merged_scores[off + i] = p.scores[(size_t)g * p.score_stride];
+            if (p.merged_cats) p.merged_cats[off + i] = scat[kr];
+        }
+        return;
+    }
+    auto emit = [&](int i, int kr, const double (&kb)[4], float kscore, int kcat) {
+        p.keep[off + i] = off + (int)vals[kr];
+        float* mb = p.merged_boxes + (size_t)(off + i) * 4;
+        mb[0] = (float)kb[0]; mb[1] = (float)kb[1]; mb[2] = (float)kb[2]; mb[3] = (float)kb[3];
+        p.merged_scores[off + i] = kscore;
+        if (p.merged_cats) p.merged_cats[off + i] = kcat;
+    };
+    auto fold_one = [&](double (&kb)[4], float kscore, int& kcat, int cr) {
+        const float4 c = sbox[cr];
+        if (has_match_f64(kb, c, p.metric, p.thr)) {
+            kb[0] = fmin(kb[0], (double)c.x); kb[1] = fmin(kb[1], (double)c.y);
+            kb[2] = fmax(kb[2], (double)c.z); kb[3] = fmax(kb[3], (double)c.w);
+            // merged category: the keep's unless the candidate's score is not lower (sahi get_merged_category)
+            const float cscore = p.scores[(size_t)(off + (int)vals[cr]) * p.score_stride];
+            if (!(kscore > cscore)) kcat = scat[cr];
+        }
+    };
+    if (p.type == FSD_GREEDYNMM) {
+        // candidates of a keep in append order = ascending rank: every thread owns one keep, all threads walk the claim array
+        // together (uniform addresses: broadcast reads), a hit folds into the growing union box
+        for (int i0 = 0; i0 < K; i0 += T) {
+            const int i = i0 + tid;
+            const int kr = i < K ? keepr[i] : -1;
+            const bool mine = kr >= 0 && !(tie_merge && (step[kr] & K3_HASB));
+            double kb[4] = {0, 0, 0, 0};
+            float kscore = 0.f;
+            int kcat = 0;
+            if (mine) {
+                const float4 b = sbox[kr];
+                kb[0] = b.x; kb[1] = b.y; kb[2] = b.z; kb[3] = b.w;
+                kscore = p.scores[(size_t)(off + (int)vals[kr]) * p.score_stride];
+                kcat = scat[kr];
+            }
+            for (int r = keepr[i0] + 1; r < m; ++r)
+                if (parent[r] == kr && r != kr && mine) fold_one(kb, kscore, kcat, r);
+            if (mine) {
+                emit(i, kr, kb, kscore, kcat);
+                if (tie_merge) {  // a later equal-score keep may fold THIS keep's merged box (only that keep reads it)
+                    sbox[kr] = make_float4((float)kb[0], (float)kb[1], (float)kb[2], (float)kb[3]);
+                    scat[kr] = kcat;
+                }
+            }
+        }
+        if (tie_merge) {
+            k3_bar(T);
+            if (tid == 0) {  // keeps with backward claims, in rank order (they are rare: exact score ties between overlapping keeps)
+                for (int i = 0; i < K; ++i) {
+                    const int kr = keepr[i];
+                    if (!(step[kr] & K3_HASB)) continue;
+                    const float4 b = sbox[kr];
+                    double kb[4] = {(double)b.x, (double)b.y, (double)b.z, (double)b.w};
+                    const float kscore = p.scores[(size_t)(off + (int)vals[kr]) * p.score_stride];
+                    int kcat = scat[kr];
+                    for (int r = 0; r < m; ++r) {
+                        const bool fwd = parent[r] == kr && r != kr;
+                        const bool bwd = parent[r] == r && (step[r] & ~K3_HASB) == kr + 1;
+                        if (fwd || bwd) fold_one(kb, kscore, kcat, r);
+                    }
+                    emit(i, kr, kb, kscore, kcat);
+                    sbox[kr] = make_float4((float)kb[0], (float)kb[1], (float)kb[2], (float)kb[3]);
+                    scat[kr] = kcat;
+                }
+            }
+        }
+        return;
+    }
+    // ---- NMM replay: key = (keep rank : 15 bits | append sequence : 30 bits | candidate rank : 15 bits), ascending ----
+    for (int r = tid; r < P; r += T) {
+        uint64_t key = ~0ull;
+        if (r < m) {
+            const int pr = parent[r];
+            if (pr >= 0 && pr != r) {
+                const uint64_t seq = (uint64_t)step[r] * 32768ull + (uint64_t)(32767 - r);
+                key = ((uint64_t)pr << 45) | (seq << 15) | (uint64_t)r;
+            }
+        }
+        keys[r] = key;
+    }
+    k3_bar(T);
+    bitonic_sort_hybrid(keys, nullptr, P, tid, T);
+    for (int q = tid; q < P; q += T) {
+        const uint64_t key = keys[q];
+        if (key == ~0ull) continue;
+        const int pr = (int)(key >> 45);
+        if (q == 0 || (int)(keys[q - 1] >> 45) != pr) runs[pr] = q;
+    }
+    k3_bar(T);
+    for (int i = tid; i < K; i += T) {
+        const int kr = keepr[i];
+        const float4 b = sbox[kr];
+        double kb[4] = {(double)b.x, (double)b.y, (double)b.z, (double)b.w};
+        const float kscore = p.scores[(size_t)(off + (int)vals[kr]) * p.score_stride];
+        int kcat = scat[kr];
+        int q = runs[kr];
+        if (q >= 0) {
+            for (; q < P; ++q) {
+                const uint64_t key = keys[q];
+                if (key == ~0ull || (int)(key >> 45) != kr) break;
+                fold_one(kb, kscore, kcat, (int)(key & 32767ull));
+            }
+        }
+        emit(i, kr, kb, kscore, kcat);
+    }
+}
+
+// ---- fallback: one CTA per segment with the arrays in the (L2-resident) workspace ---------------------------------------
+// Used for NMM above 4096 boxes (its rank-by-rank walk would pay two cluster barriers per rank) and as the cross-check of
+// the cluster kernel (FSD_K3_SINGLE_CTA=1).  Plain rank order, no tie rule.
+__global__ void __launch_bounds__(512) k3_merge_global_kernel(const K3Params p) {
     __shared__ uint32_t s_diag[128];   // 64 rows x 2 halves of in-chunk match bits
     __shared__ int s_klist[64];
     // staged per chunk so that the inner loops never touch the (possibly L2-resident) workspace: the chunk's 64 boxes,
@@ -127,6 +544,7 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     const int off = p.seg_offsets[s];
     int n = p.seg_counts ? p.seg_counts[s] : p.seg_cap;
     n = min(max(n, 0), p.seg_cap);
+    if (n <= K3_SMEM_MAX_P && !p.use_global) return;  // the shared-memory launch owns this segment
     if (n == 0) {
         if (tid == 0) p.keep_count[s] = 0;
         return;
@@ -134,8 +552,8 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     int P = 64;
     while (P < n) P <<= 1;
 
-    uint8_t* base = p.use_global ? p.workspace + (size_t)s * p.ws_per_segment : k3_smem;
-    const size_t PP = p.use_global ? (size_t)p.P : (size_t)P;
+    uint8_t* base = p.workspace + (size_t)s * p.ws_per_segment;
+    const size_t PP = (size_t)p.P;
     float4* sbox = reinterpret_cast<float4*>(base);
     uint64_t* keys = reinterpret_cast<uint64_t*>(base + 16 * PP);
     uint32_t* vals = reinterpret_cast<uint32_t*>(base + 24 * PP);
@@ -145,9 +563,8 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     int* keepr = reinterpret_cast<int*>(base + 40 * PP);    // ranks of keeps in output order
     int* runs = reinterpret_cast<int*>(base + 44 * PP);     // first replay-list position of each keep rank
 
-    MatchCfg mc;
-    mc.metric = p.metric; mc.cmp_strict = p.cmp_strict; mc.precision = p.precision;
-    mc.class_agnostic = p.class_agnostic || p.cats == nullptr; mc.thr = p.thr;
+    MatchCfg mc = match_cfg(p);
+    mc.tie_rule = 0;
 
     // ---- 1. rank ------------------------------------------------------------------------------------
     for (int i = tid; i < P; i += T) {
@@ -360,7 +777,8 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
 // over the cluster's 4096 threads with cluster.sync() between dependent steps, and only the 64x64 in-chunk resolve stays
 // on CTA 0, which broadcasts the chunk's keeps through a small scratch area.  Arrays written by one CTA and read by
 // another are read with ld.global.cg (L2), never through a possibly stale L1 line.  NMS and GREEDYNMM only (NMM's
-// rank-by-rank walk would pay two cluster barriers per rank and keeps the single-CTA path).
+// rank-by-rank walk would pay two cluster barriers per rank and keeps the single-CTA path).  CTA 0 resolves a chunk with one
+// warp holding the 64x64 match bits in registers, and computes the NEXT chunk's match bits while the cluster sweeps.
 namespace cg = cooperative_groups;
 
 template <typename T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
@@ -369,6 +787,7 @@ struct K3Scratch {  // lives in global memory, one per segment
     int kcount, ktotal, stop, pad;
     int klist[64];
     int kcat[64];
+    uint32_t kkey[64];
     float4 kbox[64];
 };
 static_assert(sizeof(K3Scratch) <= K3_SCRATCH_BYTES, "scratch area too small");
@@ -424,12 +843,15 @@ __device__ void cluster_bitonic_sort(cg::cluster_group& cluster, uint64_t* keys,
 
 __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_merge_cluster_kernel(const K3Params p) {
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ uint32_t s_diag[128];
-    __shared__ float4 s_cbox[64];
-    __shared__ int s_ccat[64];
+    __shared__ uint32_t s_diag[2][128];
+    __shared__ float4 s_cbox[2][64];
+    __shared__ int s_ccat[2][64];
+    __shared__ uint32_t s_ckey[2][64];
     __shared__ float4 s_kbox[64];
     __shared__ int s_kcat[64];
+    __shared__ uint32_t s_kkey[64];
     __shared__ int s_klist[64];
+    __shared__ unsigned long long s_keepmask, s_rembefore, s_remafter;
     extern __shared__ __align__(16) uint8_t k3c_smem[];  // sort block: P/8 keys (8 B) + values (4 B)
 
     const int s = blockIdx.x / K3_CLUSTER;
@@ -438,10 +860,7 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     const int off = p.seg_offsets[s];
     int n = p.seg_counts ? p.seg_counts[s] : p.seg_cap;
     n = min(max(n, 0), p.seg_cap);
-    if (n == 0) {  // uniform over the cluster
-        if (gtid == 0) p.keep_count[s] = 0;
-        return;
-    }
+    if (n <= K3_SMEM_MAX_P) return;  // uniform over the cluster: the shared-memory launch owns this segment
     int P = 64;
     while (P < n) P <<= 1;
     uint8_t* base = p.workspace + (size_t)s * p.ws_per_segment;
@@ -450,15 +869,14 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     uint64_t* keys = reinterpret_cast<uint64_t*>(base + 16 * PP);
     uint32_t* vals = reinterpret_cast<uint32_t*>(base + 24 * PP);
     int* parent = reinterpret_cast<int*>(base + 28 * PP);
-    uint32_t* rem = reinterpret_cast<uint32_t*>(base + 32 * PP);  // removed bits (the `step` array of the NMM path)
+    uint32_t* rem = reinterpret_cast<uint32_t*>(base + 32 * PP);  // removed bits: the first PP / 8 bytes of the NMM path's `step` slot
     int* scat = reinterpret_cast<int*>(base + 36 * PP);
     int* keepr = reinterpret_cast<int*>(base + 40 * PP);
     int* runs = reinterpret_cast<int*>(base + 44 * PP);
     K3Scratch* sc = reinterpret_cast<K3Scratch*>(base + (size_t)K3_BYTES_PER_BOX * PP);
 
-    MatchCfg mc;
-    mc.metric = p.metric; mc.cmp_strict = p.cmp_strict; mc.precision = p.precision;
-    mc.class_agnostic = p.class_agnostic || p.cats == nullptr; mc.thr = p.thr;
+    const MatchCfg mc = match_cfg(p);
+    const int lane = tid & 31;
 
     // ---- 1. rank ----------------------------------------------------------------------------------------
     for (int i = gtid; i < P; i += TT) {
@@ -491,70 +909,129 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
             if (p.parent) p.parent[g] = -1;  // cut by the pre-NMS cap
         }
     }
-    for (int i = gtid; i < (m + 31) / 32; i += TT) __stcg(rem + i, 0u);
+    for (int i = gtid; i < (m + 31) / 32 + 2; i += TT) __stcg(rem + i, 0u);
     cluster.sync();
+    auto keyhi = [&](int r) -> uint32_t { return mc.tie_rule ? (uint32_t)(ld_cg(keys + r) >> 32) : 0u; };
+    // CTA 0: stage a chunk's boxes and compute its 64x64 match bits (double buffered: chunk c + 1 while chunk c is swept)
+    auto stage_chunk = [&](int c0, int buf) {
+        const int cn = min(64, m - c0);
+        if (tid < cn) { s_cbox[buf][tid] = ld_cg(sbox + c0 + tid); s_ccat[buf][tid] = ld_cg(scat + c0 + tid); s_ckey[buf][tid] = keyhi(c0 + tid); }
+        __syncthreads();
+        const int q = tid & 63;
+        for (int r = tid >> 6; r < cn; r += T >> 6) {
+            bool bit = false;
+            if (q < cn && q > r)
+                bit = suppresses(s_cbox[buf][r], s_cbox[buf][q], s_ccat[buf][r], s_ccat[buf][q], s_ckey[buf][r], s_ckey[buf][q], mc);
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) s_diag[buf][r * 2 + (q >> 5)] = bal;
+        }
+        __syncthreads();
+    };
+    if (crank == 0) stage_chunk(0, 0);
 
     // ---- 2. greedy scan in chunks of 64 ranks ---------------------------------------------------------------
-    for (int c0 = 0; c0 < m; c0 += 64) {
+    for (int c0 = 0, c = 0; c0 < m; c0 += 64, ++c) {
         const int cn = min(64, m - c0);
+        const int buf = c & 1;
         if (crank == 0) {
-            if (tid < cn) { s_cbox[tid] = ld_cg(sbox + c0 + tid); s_ccat[tid] = ld_cg(scat + c0 + tid); }
-            __syncthreads();
-            for (int r = tid >> 6; r < 64; r += T >> 6) {
-                const int q = tid & 63;
-                bool bit = false;
-                if (r < cn && q < cn && q > r) bit = match_pair(s_cbox[r], s_cbox[q], s_ccat[r], s_ccat[q], mc);
-                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                if ((tid & 31) == 0) s_diag[r * 2 + (q >> 5)] = bal;
+            const uint32_t* dg = s_diag[buf];
+            if (tid < 32) {
+                const uint64_t rowA = lane < cn ? ((uint64_t)dg[2 * lane] | ((uint64_t)dg[2 * lane + 1] << 32)) : 0ull;
+                const uint64_t rowB = lane + 32 < cn ? ((uint64_t)dg[2 * lane + 64] | ((uint64_t)dg[2 * lane + 65] << 32)) : 0ull;
+                const int w0 = c0 >> 5;
+                uint64_t remw = (uint64_t)ld_cg(rem + w0) | ((uint64_t)ld_cg(rem + w0 + 1) << 32);
+                const uint64_t before = remw;
+                uint64_t keepmask = 0;
+                const int kt = ld_cg(&sc->ktotal);
+                int cnt = 0, stop = 0;
+                for (int b = 0; b < cn; ++b) {
+                    const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
+                    if (!((remw >> b) & 1ull)) {
+                        if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
+                        keepmask |= 1ull << b;
+                        ++cnt;
+                        remw |= row;
+                    }
+                }
+                for (int pos = lane; pos < 64; pos += 32) {
+                    if ((keepmask >> pos) & 1ull) {
+                        const int idx = __popcll(keepmask & ((1ull << pos) - 1ull));
+                        const int kr = c0 + pos;
+                        sc->klist[idx] = kr; sc->kbox[idx] = s_cbox[buf][pos]; sc->kcat[idx] = s_ccat[buf][pos]; sc->kkey[idx] = s_ckey[buf][pos];
+                        __stcg(keepr + kt + idx, kr);
+                        __stcg(parent + kr, kr);
+                    }
+                }
+                if (lane == 0) {
+                    __stcg(rem + w0, (uint32_t)remw);
+                    __stcg(rem + w0 + 1, (uint32_t)(remw >> 32));
+                    s_keepmask = keepmask; s_rembefore = before; s_remafter = remw;
+                    sc->kcount = cnt; sc->ktotal = kt + cnt; sc->stop = stop;
+                }
             }
             __syncthreads();
-            if (tid == 0) {
-                const int words = (m + 31) / 32;
-                uint64_t remw = (uint64_t)ld_cg(rem + (c0 >> 5)) | ((uint64_t)(((c0 >> 5) + 1) < words ? ld_cg(rem + (c0 >> 5) + 1) : 0u) << 32);
-                int kc = 0, kt = sc->ktotal, stop = 0;
-                for (int b = 0; b < cn; ++b) {
-                    if ((remw >> b) & 1ull) continue;
-                    if (p.max_keep > 0 && kt + kc >= p.max_keep) { stop = 1; break; }
-                    const int kr = c0 + b;
-                    sc->klist[kc] = kr; sc->kbox[kc] = s_cbox[b]; sc->kcat[kc] = s_ccat[b];
-                    ++kc;
-                    __stcg(parent + kr, kr);
-                    const uint64_t row = (uint64_t)s_diag[2 * b] | ((uint64_t)s_diag[2 * b + 1] << 32);
-                    uint64_t fresh = row & ~remw;
-                    remw |= row;
-                    while (fresh) {
-                        const int q = __ffsll((long long)fresh) - 1;
-                        fresh &= fresh - 1;
-                        __stcg(parent + c0 + q, kr);
+            if (tid < cn) {  // parents of the ranks this chunk's own keeps removed: the first keep whose row holds the rank
+                const uint64_t keepmask = s_keepmask;
+                const int q = tid;
+                if (!((s_rembefore >> q) & 1ull) && !((keepmask >> q) & 1ull) && ((s_remafter >> q) & 1ull)) {
+                    uint64_t km = keepmask & ((1ull << q) - 1ull);
+                    while (km) {
+                        const int b = __ffsll((long long)km) - 1;
+                        km &= km - 1;
+                        if ((dg[2 * b + (q >> 5)] >> (q & 31)) & 1u) { __stcg(parent + c0 + q, c0 + b); break; }
                     }
-                    __stcg(keepr + kt + kc - 1, kr);
                 }
-                __stcg(rem + (c0 >> 5), (uint32_t)remw);
-                if (((c0 >> 5) + 1) < words) __stcg(rem + (c0 >> 5) + 1, (uint32_t)(remw >> 32));
-                sc->kcount = kc; sc->ktotal = kt + kc; sc->stop = stop;
             }
         }
         cluster.sync();  // the chunk's keeps (scratch) and the updated removed bits are visible to every CTA
         const int kc = ld_cg(&sc->kcount);
         if (ld_cg(&sc->stop)) break;  // uniform over the cluster
-        if (tid < kc) { s_kbox[tid] = ld_cg(&sc->kbox[tid]); s_kcat[tid] = ld_cg(&sc->kcat[tid]); s_klist[tid] = ld_cg(&sc->klist[tid]); }
+        if (tid < kc) { s_kbox[tid] = ld_cg(&sc->kbox[tid]); s_kcat[tid] = ld_cg(&sc->kcat[tid]); s_klist[tid] = ld_cg(&sc->klist[tid]); s_kkey[tid] = ld_cg(&sc->kkey[tid]); }
         __syncthreads();
         for (int j = c0 + cn + gtid; j < m; j += TT) {
             if ((ld_cg(rem + (j >> 5)) >> (j & 31)) & 1u) continue;
             const float4 bj = ld_cg(sbox + j);
             const int cj = ld_cg(scat + j);
+            const uint32_t kj = keyhi(j);
             for (int k = 0; k < kc; ++k) {
-                if (match_pair(s_kbox[k], bj, s_kcat[k], cj, mc)) {
+                if (suppresses(s_kbox[k], bj, s_kcat[k], cj, s_kkey[k], kj, mc)) {
                     atomicOr(rem + (j >> 5), 1u << (j & 31));
                     __stcg(parent + j, s_klist[k]);
                     break;
                 }
             }
         }
+        if (crank == 0 && c0 + 64 < m) stage_chunk(c0 + 64, buf ^ 1);  // next chunk's match bits, off the critical path
         cluster.sync();  // all claims of this chunk are in place before the next chunk is resolved
     }
     cluster.sync();
     const int K = ld_cg(&sc->ktotal);
+    const bool tie_merge = mc.tie_rule && p.type == FSD_GREEDYNMM;
+
+    // ---- tie rule: a keep claims the earlier equal-score keeps it matches (see k3_merge_kernel).  Here the claim is written
+    // into parent[] itself (the claimed keep then enters the claimer's replay list like any other candidate); what a rank IS
+    // lives in runs[]: K3C_ISKEEP, K3_HASB (this keep's list holds an earlier keep), K3C_HASLIST | first list position.
+    constexpr int K3C_ISKEEP = 1 << 29, K3C_HASLIST = 1 << 28;
+    for (int r = gtid; r < m; r += TT) __stcg(runs + r, 0);
+    cluster.sync();
+    for (int i = gtid; i < K; i += TT) atomicOr(runs + ld_cg(keepr + i), K3C_ISKEEP);
+    cluster.sync();
+    if (tie_merge) {
+        for (int i = gtid; i < K; i += TT) {
+            const int kr = ld_cg(keepr + i);
+            const uint32_t kk = keyhi(kr);
+            const float4 bk = ld_cg(sbox + kr);
+            const int ck = ld_cg(scat + kr);
+            for (int q = kr + 1; q < m && keyhi(q) == kk; ++q) {
+                if ((ld_cg(runs + q) & K3C_ISKEEP) && suppresses(ld_cg(sbox + q), bk, ld_cg(scat + q), ck, kk, kk, mc)) {
+                    __stcg(parent + kr, q);
+                    atomicOr(runs + q, K3_HASB);
+                    break;
+                }
+            }
+        }
+        cluster.sync();
+    }
 
     // ---- 3. outputs + merge replay --------------------------------------------------------------------------------
     if (p.parent) {
@@ -577,7 +1054,8 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
         }
         return;
     }
-    // replay key = (keep rank : 15 bits | append sequence : 30 bits | candidate rank : 15 bits), ascending
+    // replay key = (keep rank : 15 bits | append sequence : 30 bits | candidate rank : 15 bits), ascending; a keep claimed
+    // through the tie rule carries its claimer in parent[] and is listed like every other candidate
     for (int r = gtid; r < P; r += TT) {
         uint64_t key = ~0ull;
         if (r < m) {
@@ -592,19 +1070,19 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
         const uint64_t key = ld_cg(keys + q);
         if (key == ~0ull) continue;
         const int pr = (int)(key >> 45);
-        if (q == 0 || (int)(ld_cg(keys + q - 1) >> 45) != pr) __stcg(runs + pr, q);
+        if (q == 0 || (int)(ld_cg(keys + q - 1) >> 45) != pr) atomicOr(runs + pr, K3C_HASLIST | q);
     }
     cluster.sync();
-    for (int i = gtid; i < K; i += TT) {
+    auto fold_keep = [&](int i) {
         const int kr = ld_cg(keepr + i);
         const int g = off + (int)ld_cg(vals + kr);
         const float4 b = ld_cg(sbox + kr);
         double kb[4] = {(double)b.x, (double)b.y, (double)b.z, (double)b.w};
         const float kscore = p.scores[(size_t)g * p.score_stride];
         int kcat = ld_cg(scat + kr);
-        int q = ld_cg(runs + kr);
-        if (q >= 0) {
-            for (; q < P; ++q) {
+        const int w = ld_cg(runs + kr);
+        if (w & K3C_HASLIST) {
+            for (int q = w & 0xffff; q < P; ++q) {
                 const uint64_t key = ld_cg(keys + q);
                 if (key == ~0ull || (int)(key >> 45) != kr) break;
                 const int cr = (int)(key & 32767ull);
@@ -622,6 +1100,18 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
         mb[0] = (float)kb[0]; mb[1] = (float)kb[1]; mb[2] = (float)kb[2]; mb[3] = (float)kb[3];
         p.merged_scores[off + i] = kscore;
         if (p.merged_cats) p.merged_cats[off + i] = kcat;
+        if (tie_merge) {  // a later equal-score keep may fold THIS keep's merged box
+            __stcg(sbox + kr, make_float4((float)kb[0], (float)kb[1], (float)kb[2], (float)kb[3]));
+            __stcg(scat + kr, kcat);
+        }
+    };
+    for (int i = gtid; i < K; i += TT)
+        if (!(ld_cg(runs + ld_cg(keepr + i)) & K3_HASB)) fold_keep(i);
+    if (tie_merge) {
+        cluster.sync();
+        if (gtid == 0)  // keeps whose list holds an earlier keep, in rank order (rare: exact score ties between overlapping keeps)
+            for (int i = 0; i < K; ++i)
+                if (ld_cg(runs + ld_cg(keepr + i)) & K3_HASB) fold_keep(i);
     }
 }
 
@@ -645,7 +1135,7 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
                          const int32_t* cats, int cat_stride, const int32_t* tie, int tie_stride,
                          const int32_t* seg_offsets, const int32_t* seg_counts, int S, int max_segment, int type,
                          int metric, double thr, int cmp_strict, int precision, int class_agnostic, int pre_cap,
-                         int max_keep, int32_t* keep, int32_t* keep_count, int32_t* parent, float* merged_boxes,
+                         int max_keep, int tie_rule, int32_t* keep, int32_t* keep_count, int32_t* parent, float* merged_boxes,
                          float* merged_scores, int32_t* merged_cats, void* workspace, int64_t workspace_bytes,
                          void* stream_) {
     FSD_CHECK_ARG(h && boxes && scores && seg_offsets && keep && keep_count && merged_boxes && merged_scores,
@@ -653,6 +1143,7 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     FSD_CHECK_ARG(type == FSD_NMS || type == FSD_GREEDYNMM || type == FSD_NMM, "fsd_merge: unknown merge type %d", type);
     FSD_CHECK_ARG(metric == FSD_IOU || metric == FSD_IOS, "fsd_merge: unknown match metric %d", metric);
     FSD_CHECK_ARG(S >= 0 && max_segment >= 0 && box_stride >= 4 && score_stride >= 1, "fsd_merge: bad sizes");
+    FSD_CHECK_ARG(tie_rule == 0 || tie_rule == 1, "fsd_merge: unknown tie rule %d", tie_rule);
     if (S == 0 || max_segment == 0) {
         if (S > 0) FSD_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int32_t) * S, (cudaStream_t)stream_));
         return FSD_OK;
@@ -666,7 +1157,7 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     p.cats = cats; p.cat_stride = cat_stride > 0 ? cat_stride : 1; p.tie = tie; p.tie_stride = tie_stride > 0 ? tie_stride : 1;
     p.seg_offsets = seg_offsets; p.seg_counts = seg_counts; p.seg_cap = max_segment;
     p.type = type; p.metric = metric; p.cmp_strict = cmp_strict; p.precision = precision;
-    p.class_agnostic = class_agnostic; p.pre_cap = pre_cap; p.max_keep = max_keep; p.thr = thr;
+    p.class_agnostic = class_agnostic; p.pre_cap = pre_cap; p.max_keep = max_keep; p.thr = thr; p.tie_rule = tie_rule;
     p.keep = keep; p.keep_count = keep_count; p.parent = parent; p.merged_boxes = merged_boxes;
     p.merged_scores = merged_scores; p.merged_cats = merged_cats;
     p.P = pow2_at_least(max_segment);
@@ -678,23 +1169,38 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
                       "fsd_merge: workspace too small (%lld bytes needed)", (long long)fsd_merge_workspace_bytes(0, S, max_segment));
         if (((uintptr_t)workspace & 15) != 0) { set_error("fsd_merge: workspace must be 16-byte aligned"); return FSD_ERR_ALIGN; }
     }
-    const size_t smem = p.use_global ? 0 : (size_t)p.P * K3_BYTES_PER_BOX;
-    const int threads = p.P <= 256 ? 128 : (p.P <= 1024 ? 256 : 512);
+    cudaStream_t stream = (cudaStream_t)stream_;
     FSD_CUDA(cudaSetDevice(h->device));
-    FSD_CUDA(cudaFuncSetAttribute(k3_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_MAX_P * K3_BYTES_PER_BOX));
-    if (p.use_global && type != FSD_NMM && !getenv("FSD_K3_SINGLE_CTA")) {
-        // large segments: a cluster of 8 CTAs per segment (k3_merge_cluster_kernel)
-        const size_t csmem = (size_t)(p.P / K3_CLUSTER) * 12;
-        FSD_CUDA(cudaFuncSetAttribute(k3_merge_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, (cudaStream_t)stream_);
-        k3_merge_cluster_kernel<<<S * K3_CLUSTER, 512, csmem, (cudaStream_t)stream_>>>(p);
+    const bool force_single = getenv("FSD_K3_SINGLE_CTA") != nullptr;
+    // the path is chosen per segment ON THE DEVICE from its actual count: both kernels are launched over all S segments when
+    // the capacity allows large ones, and each returns at once for the segments that belong to the other
+    if (p.use_global && (type == FSD_NMM || force_single)) {
+        // NMM above 4096 boxes / cross-check mode: one CTA per segment over the workspace (takes EVERY segment of the launch)
+        TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, stream);
+        k3_merge_global_kernel<<<S, 512, 0, stream>>>(p);
         FSD_CUDA(cudaGetLastError());
         h->launches += 1;
         return FSD_OK;
     }
-    TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, (cudaStream_t)stream_);
-    k3_merge_kernel<<<S, threads, smem, (cudaStream_t)stream_>>>(p);
-    FSD_CUDA(cudaGetLastError());
-    h->launches += 1;
+    {
+        const int Psm = p.P < K3_SMEM_MAX_P ? p.P : K3_SMEM_MAX_P;
+        const size_t smem = (size_t)Psm * K3_BYTES_PER_BOX;
+        const int threads = Psm <= 64 ? 64 : (Psm <= 256 ? 128 : (Psm <= 1024 ? 256 : 512));
+        FSD_CUDA(cudaFuncSetAttribute(k3_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_MAX_P * K3_BYTES_PER_BOX));
+        p.use_global = 0;
+        TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, stream);
+        k3_merge_kernel<<<S, threads, smem, stream>>>(p);
+        FSD_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
+    if (p.P > K3_SMEM_MAX_P) {
+        // segments above 4096 boxes: a cluster of 8 CTAs each (k3_merge_cluster_kernel)
+        const size_t csmem = (size_t)(p.P / K3_CLUSTER) * 12;
+        FSD_CUDA(cudaFuncSetAttribute(k3_merge_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        TimedLaunch timed(h, FSD_KERNEL_MERGE, S, -max_segment, stream);
+        k3_merge_cluster_kernel<<<S * K3_CLUSTER, 512, csmem, stream>>>(p);
+        FSD_CUDA(cudaGetLastError());
+        h->launches += 1;
+    }
     return FSD_OK;
 }

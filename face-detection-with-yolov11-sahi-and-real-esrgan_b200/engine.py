@@ -11,6 +11,7 @@ memory, streams and the conv backbone only.
 from __future__ import annotations
 
 import contextlib
+import copy
 import os
 
 from dataclasses import dataclass, field
@@ -76,7 +77,8 @@ class SlicedFaceDetector:
         self.imgsz, self.conf, self.stride, self.iou, self.max_det = imgsz, conf, stride, iou, max_det
         self.cap, self.reverse, self.chunk, self.truncate = cap_per_entry, reverse_channels, chunk_entries, truncate
         self.channels_last = channels_last
-        bb = backbone.to(self.device).eval()
+        # a private copy: Module.half() / .float() convert in place, and one YOLO front end may own an fp16 and an fp32 engine
+        bb = copy.deepcopy(backbone).to(self.device).eval()
         bb = bb.half() if half else bb.float()
         for p in bb.parameters():
             p.requires_grad_(False)
@@ -102,6 +104,7 @@ class SlicedFaceDetector:
         self._graph_pools: Dict = {}
         self._xbufs: Dict = {}
         self.last_stage1 = None
+        self.tie_rule = "box_lex"  # stage 2: sahi 0.11.34's equal-score rule (SURVEY A.2.4 variant N); "index" = plain greedy order
         self.replayed_launches = 0  # fsd kernels executed through graph replays (the handle only counts direct launches)
 
     # ------------------------------------------------------------------------------------------ planning
@@ -312,7 +315,7 @@ class SlicedFaceDetector:
                 # class_agnostic True and False give the same result — exactly as sahi's batched_* variants do for one class)
                 s2 = ops.merge_segments(det, t["goff"], dcount, t["det_cap"], merge_type=postprocess_type,
                                         metric=match_metric, thr=match_threshold, cmp_strict=False, precision="fp64",
-                                        class_agnostic=bool(class_agnostic), want_parent=False)
+                                        class_agnostic=bool(class_agnostic), want_parent=False, tie_rule=self.tie_rule)
                 # per-image stage-1 detections BEFORE the det_cap clamp (overflow is reported, never silently truncated)
                 dmax = s1["keep_count"].view(N, S).sum(1)
                 if cand_f is not None:

@@ -196,14 +196,16 @@ def pose_decode(levels, conf: float, cap_per_entry: int = 1024, cand: torch.Tens
 # ---- Kernel 3 -------------------------------------------------------------------------------------------
 _MERGE_TYPE = {"NMS": _cabi.FSD_NMS, "GREEDYNMM": _cabi.FSD_GREEDYNMM, "NMM": _cabi.FSD_NMM}
 _METRIC = {"IOU": _cabi.FSD_IOU, "IOS": _cabi.FSD_IOS}
+_TIE_RULE = {"index": 0, "box_lex": 1}  # include/fsd_b200.h: fsd_merge tie_rule
 
 
 def merge_segments(rows: torch.Tensor, seg_offsets: torch.Tensor, seg_counts: torch.Tensor | None, max_segment: int,
                    merge_type="NMS", metric="IOU", thr=0.5, cmp_strict=False, precision="fp64", class_agnostic=True,
                    pre_cap=0, max_keep=0, box_col=0, score_col=4, tie_col=None, cats: torch.Tensor | None = None,
-                   want_parent=True):
+                   want_parent=True, tie_rule="index"):
     """Kernel 3 over a [N, R] float32 row matrix (boxes at box_col..+3, score at score_col, optional int-bits
-    tie-break key at tie_col).  Returns dict(keep, keep_count, parent, boxes, scores, cats)."""
+    tie-break key at tie_col).  tie_rule "box_lex" = sahi 0.11.34's equal-score rule (stage 2), "index" = the plain greedy
+    loop (torchvision / stage 1).  Returns dict(keep, keep_count, parent, boxes, scores, cats)."""
     _require_cuda(rows, "rows")
     assert rows.dtype == torch.float32 and rows.dim() == 2 and rows.is_contiguous()
     N, R = rows.shape
@@ -224,7 +226,7 @@ def merge_segments(rows: torch.Tensor, seg_offsets: torch.Tensor, seg_counts: to
                           seg_offsets.data_ptr(), _ptr(seg_counts), S, int(max_segment),
                           _MERGE_TYPE[merge_type], _METRIC[metric], float(thr), 1 if cmp_strict else 0,
                           0 if precision == "fp64" else 1, 1 if class_agnostic else 0, int(pre_cap), int(max_keep),
-                          keep.data_ptr(), keep_count.data_ptr(), _ptr(parent), mboxes.data_ptr(),
+                          _TIE_RULE[tie_rule], keep.data_ptr(), keep_count.data_ptr(), _ptr(parent), mboxes.data_ptr(),
                           mscores.data_ptr(), _ptr(mcats), ws.data_ptr(), ws_bytes, _stream_ptr(dev)), "fsd_merge")
     return dict(keep=keep, keep_count=keep_count, parent=parent, boxes=mboxes, scores=mscores, cats=mcats)
 

@@ -30,12 +30,15 @@ class PostprocessPredictions:
 
     merge_type = None
 
-    def __init__(self, match_threshold: float = 0.5, match_metric: str = "IOU", class_agnostic: bool = True):
+    def __init__(self, match_threshold: float = 0.5, match_metric: str = "IOU", class_agnostic: bool = True,
+                 tie_rule: str = "box_lex"):
         if match_metric not in ("IOU", "IOS"):
             raise ValueError(f"'match_metric' should be one of ['IOU', 'IOS'] but given as {match_metric}")
         self.match_threshold = match_threshold
         self.match_metric = match_metric
         self.class_agnostic = class_agnostic
+        # equal scores: "box_lex" = sahi 0.11.34's lexicographic rule (SURVEY A.2.4 variant N), "index" = plain greedy order
+        self.tie_rule = tie_rule
         self.device = None  # set by get_sliced_prediction; defaults to the current CUDA device
 
     def _run(self, object_predictions):
@@ -48,7 +51,7 @@ class PostprocessPredictions:
         res = ops.merge_segments(rows, torch.zeros(1, dtype=torch.int32, device=dev), None, n,
                                  merge_type=self.merge_type, metric=self.match_metric, thr=self.match_threshold,
                                  cmp_strict=False, precision="fp64", class_agnostic=self.class_agnostic, cats=cats,
-                                 want_parent=False)
+                                 want_parent=False, tie_rule=self.tie_rule)
         k = int(res["keep_count"][0])
         keep = res["keep"][:k].cpu().numpy()
         order = np.arange(k)

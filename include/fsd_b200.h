@@ -115,18 +115,26 @@ int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const void* const 
  *      segment s covers rows seg_offsets[s] .. +min(seg_counts[s], max_segment)-1 (seg_counts NULL: all full).
  *      cmp_strict: 0 -> match if metric >= thr (sahi), 1 -> metric > thr (torchvision).
  *      precision:  0 -> fp64 metric (sahi 0.11.34), 1 -> fp32 metric (torchvision).
- *      Rank order inside a segment: score descending, ties by ascending tie key.
+ *      Rank (visiting) order inside a segment: score descending, ties by ascending tie key.
+ *      tie_rule: 0 -> plain greedy loop (torchvision; sahi's older pure-torch generations);
+ *                1 -> sahi 0.11.34's rule for EQUAL scores (SURVEY A.2.4 variant N): the current box does not test an
+ *                     equal-score candidate whose (x1,y1,x2,y2) tuple is lexicographically larger — both may be kept — and a
+ *                     keep visited later does test, and for GREEDYNMM claims into its merge list, the earlier equal-score
+ *                     keeps it matches (it then folds their MERGED boxes).  Ignored for NMM (variant N's nmm has no such rule).
  *      Outputs (dev): keep [.] global row ids in rank order, written from seg_offsets[s]; keep_count [S];
- *      parent [.] (may be NULL) = global row id of the keep that claimed a row (its own id for keeps, -1 for
- *      rows cut by pre_cap/max_keep); merged_boxes [.,4], merged_scores [.], merged_cats [.] (may be NULL) are
- *      indexed like keep: the union box after the has_match replay (NMS: the kept row itself).
- *      workspace: dev scratch of fsd_merge_workspace_bytes() bytes (only touched when max_segment > 4096).
+ *      parent [.] (may be NULL) = global row id of the keep that claimed a row (its own id for keeps — or, with tie_rule 1,
+ *      the later equal-score keep that claimed this keep; -1 for rows cut by pre_cap/max_keep); merged_boxes [.,4],
+ *      merged_scores [.], merged_cats [.] (may be NULL) are indexed like keep: the union box after the has_match replay
+ *      (NMS: the kept row itself).
+ *      The path is chosen per segment on the device from its actual count (no host round trip): segments up to 4096 boxes
+ *      run in one CTA's shared memory, larger ones on a cluster of 8 CTAs over `workspace`
+ *      (fsd_merge_workspace_bytes() bytes; only touched when max_segment > 4096).
  *      Limit: max_segment <= 32768 (FSD_ERR_CAPACITY beyond). */
 int64_t fsd_merge_workspace_bytes(int64_t N, int S, int max_segment);
 int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, const float* scores, int score_stride,
               const int32_t* cats, int cat_stride, const int32_t* tie, int tie_stride,
               const int32_t* seg_offsets, const int32_t* seg_counts, int S, int max_segment, int type, int metric,
-              double thr, int cmp_strict, int precision, int class_agnostic, int pre_cap, int max_keep,
+              double thr, int cmp_strict, int precision, int class_agnostic, int pre_cap, int max_keep, int tie_rule,
               int32_t* keep, int32_t* keep_count, int32_t* parent, float* merged_boxes, float* merged_scores,
               int32_t* merged_cats, void* workspace, int64_t workspace_bytes, void* stream);
 

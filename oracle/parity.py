@@ -206,7 +206,7 @@ def merge_gate(device, n=1024, seed=0, merge_type="GREEDYNMM", metric="IOS"):
     wh = rng.integers(8, 60, (n, 2))
     rows = np.concatenate([xy, xy + wh, rng.uniform(0.3, 1.0, (n, 1)).astype(np.float32), np.zeros((n, 1))], 1).astype(np.float32)
     res = ops.merge_segments(torch.from_numpy(rows).to(device), torch.zeros(1, dtype=torch.int32, device=device), None, n,
-                             merge_type=merge_type, metric=metric, thr=0.5, precision="fp64")
+                             merge_type=merge_type, metric=metric, thr=0.5, precision="fp64", tie_rule="box_lex")
     k = int(res["keep_count"][0])
     got = res["boxes"][:k].cpu().numpy().astype(np.int64).tolist()
     preds = [OracleOP(bbox=[int(v) for v in r[:4]], score=float(r[4]), category_id=0, category_name="face") for r in rows]

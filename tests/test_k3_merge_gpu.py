@@ -104,10 +104,10 @@ def test_stage1_pre_cap(cuda_device):
 
 
 # ---------------------------------------------------------------------------------------------- stage 2
-def _oracle(seg, ptype, metric, thr, agnostic):
+def _oracle(seg, ptype, metric, thr, agnostic, tie_rule="box_lex"):
     preds = [ObjectPrediction(bbox=[int(v) for v in r[:4]], score=float(r[4]), category_id=int(r[5]),
                               category_name=str(int(r[5]))) for r in seg]
-    pp = opp.POSTPROCESS_NAME_TO_CLASS[ptype](match_threshold=thr, match_metric=metric, class_agnostic=agnostic)
+    pp = opp.POSTPROCESS_NAME_TO_CLASS[ptype](match_threshold=thr, match_metric=metric, class_agnostic=agnostic, tie_rule=tie_rule)
     out = pp(preds) if len(preds) else []
     if ptype == "NMS":
         keep, groups = (pp.last_keep if len(preds) else []), None
@@ -120,14 +120,16 @@ def _oracle(seg, ptype, metric, thr, agnostic):
 @pytest.mark.parametrize("ptype", ["NMS", "GREEDYNMM", "NMM"])
 @pytest.mark.parametrize("metric", ["IOS", "IOU"])
 @pytest.mark.parametrize("thr", [0.3, 0.5, 0.7])
-def test_stage2_matches_sahi_oracle(cuda_device, ptype, metric, thr):
-    rng = np.random.default_rng(hash((ptype, metric)) % 1000 + int(thr * 10))
+@pytest.mark.parametrize("tie_rule", ["box_lex", "index"])
+def test_stage2_matches_sahi_oracle(cuda_device, ptype, metric, thr, tie_rule):
+    rng = np.random.default_rng({"NMS": 1, "GREEDYNMM": 2, "NMM": 3}[ptype] * 100 + (7 if metric == "IOS" else 0) + int(thr * 10))
     segs = [sahi_like_boxes(rng, nf) for nf in (0, 1, 3, 40, 150)]
-    segs.append(sahi_like_boxes(rng, 60, score_ties=True))
+    segs.append(sahi_like_boxes(rng, 60, score_ties=True))       # scores rounded to one decimal: large tie groups
+    segs.append(sahi_like_boxes(rng, 400, dup=(2, 6), size=(20, 120), canvas=(1200, 800), score_ties=True))  # dense + ties, > 1024 boxes
     got = run_kernel(cuda_device, segs, merge_type=ptype, metric=metric, thr=thr, cmp_strict=False, precision="fp64",
-                     class_agnostic=True)
+                     class_agnostic=True, tie_rule=tie_rule)
     for seg, g in zip(segs, got):
-        keep, groups, out = _oracle(seg, ptype, metric, thr, True)
+        keep, groups, out = _oracle(seg, ptype, metric, thr, True, tie_rule)
         assert g["keep"] == keep
         if groups is not None:
             gg = groups_from_parent(g["parent"], g["keep"])
@@ -142,7 +144,7 @@ def test_stage2_per_category(cuda_device, ptype):
     rng = np.random.default_rng(77)
     seg = sahi_like_boxes(rng, 80, ncat=3)
     g = run_kernel(cuda_device, [seg], merge_type=ptype, metric="IOS", thr=0.5, cmp_strict=False, precision="fp64",
-                   class_agnostic=False)[0]
+                   class_agnostic=False, tie_rule="box_lex")[0]
     keep, groups, out = _oracle(seg, ptype, "IOS", 0.5, False)
     # the kernel emits one score-descending list; sahi's batched_* variants list category by category
     assert sorted(g["keep"]) == sorted(keep)
@@ -166,10 +168,22 @@ def test_hand_made_edge_cases(cuda_device):
     assert g["keep"] == [0]
     g = run_kernel(cuda_device, [seg], merge_type="NMS", metric="IOU", thr=0.5, cmp_strict=True, precision="fp32")[0]
     assert g["keep"] == [0, 1]  # torchvision rule: strictly greater
-    # zero-area box never matches; equal scores keep input order
+    # zero-area box never matches; equal scores keep input order (plain rule)
     seg = np.array([[10, 10, 10, 40, 0.7, 0], [0, 0, 50, 50, 0.7, 0], [5, 5, 45, 45, 0.7, 0]], dtype=np.float32)
     g = run_kernel(cuda_device, [seg], merge_type="GREEDYNMM", metric="IOS", thr=0.5, precision="fp64")[0]
     assert g["keep"] == [0, 1] and g["parent"].tolist() == [0, 1, 1]
+    # sahi 0.11.34's equal-score rule (SURVEY A.2.4 variant N): box 1 does not test the lexicographically larger box 2, so
+    # both are kept; box 2, visited later, claims the already kept box 1 and merges it (its output equals box 1's)
+    g = run_kernel(cuda_device, [seg], merge_type="GREEDYNMM", metric="IOS", thr=0.5, precision="fp64", tie_rule="box_lex")[0]
+    assert g["keep"] == [0, 1, 2] and g["parent"].tolist() == [0, 2, 2]
+    assert g["boxes"].tolist() == [[10, 10, 10, 40], [0, 0, 50, 50], [0, 0, 50, 50]]
+    g = run_kernel(cuda_device, [seg], merge_type="NMS", metric="IOS", thr=0.5, precision="fp64", tie_rule="box_lex")[0]
+    assert g["keep"] == [0, 1, 2]
+    # a chain inside one tie group: each keep is claimed by the next one, which folds the MERGED box of its predecessor
+    seg = np.array([[0, 0, 40, 40, 0.5, 0], [1, 0, 41, 40, 0.5, 0], [2, 0, 42, 40, 0.5, 0]], dtype=np.float32)
+    keep, groups, out = _oracle(seg, "GREEDYNMM", "IOU", 0.5, True)
+    g = run_kernel(cuda_device, [seg], merge_type="GREEDYNMM", metric="IOU", thr=0.5, precision="fp64", tie_rule="box_lex")[0]
+    assert g["keep"] == keep == [0, 1, 2] and g["boxes"].tolist() == [o.bbox.to_xyxy() for o in out] == [[0, 0, 40, 40], [0, 0, 41, 40], [0, 0, 42, 40]]
     # chain A~B~C, A!~C: greedy keeps A(+B) and C; NMM pulls C in through B
     seg = np.array([[0, 0, 100, 100, 0.9, 0], [60, 0, 160, 100, 0.8, 0], [120, 0, 220, 100, 0.7, 0]], dtype=np.float32)
     keep_g, groups_g, out_g = _oracle(seg, "GREEDYNMM", "IOU", 0.2, True)
@@ -194,7 +208,7 @@ def test_dense_stress_nms_iou(cuda_device, n_faces):
     seg = sahi_like_boxes(rng, n_faces, dup=(1, 4), size=(10, 40), canvas=(3840, 2160))
     assert len(seg) > 1000 or n_faces < 1000
     for ptype in ("NMS", "GREEDYNMM"):
-        g = run_kernel(cuda_device, [seg], merge_type=ptype, metric="IOU", thr=0.5, precision="fp64")[0]
+        g = run_kernel(cuda_device, [seg], merge_type=ptype, metric="IOU", thr=0.5, precision="fp64", tie_rule="box_lex")[0]
         keep, groups, out = _oracle(seg, ptype, "IOU", 0.5, True)
         assert g["keep"] == keep
         assert np.array_equal(g["boxes"], np.array([o.bbox.to_xyxy() for o in out], dtype=np.float32))
@@ -233,3 +247,57 @@ def test_cluster_path_equals_single_cta_path(cuda_device, ptype, metric, prec, m
         assert np.array_equal(a["parent"], b["parent"])
         assert np.array_equal(a["boxes"], b["boxes"]) and np.array_equal(a["scores"], b["scores"]) and np.array_equal(a["cats"], b["cats"])
     assert len(multi[3]["keep"]) > 300 or prec == "fp32"
+
+
+@pytest.mark.parametrize("ptype", ["NMS", "GREEDYNMM"])
+def test_cluster_path_with_score_ties_matches_oracle(cuda_device, ptype):
+    """> 4096 boxes with scores rounded to two decimals (thousands of exact ties between overlapping boxes): the cluster kernel's
+    equal-score rule, backward claims and deferred folds against the ORACLE."""
+    rng = np.random.default_rng(123)
+    seg = sahi_like_boxes(rng, 2600, dup=(1, 4), size=(10, 60), canvas=(2560, 1440))[:6000]
+    seg[:, 4] = np.round(seg[:, 4], 2)
+    assert len(seg) > 4096
+    g = run_kernel(cuda_device, [seg], merge_type=ptype, metric="IOS", thr=0.5, precision="fp64", tie_rule="box_lex")[0]
+    keep, groups, out = _oracle(seg, ptype, "IOS", 0.5, True)
+    assert g["keep"] == keep
+    assert np.array_equal(g["boxes"], np.array([o.bbox.to_xyxy() for o in out], dtype=np.float32))
+    if groups is not None:
+        gg = groups_from_parent(g["parent"], g["keep"])
+        assert {k: sorted(v) for k, v in gg.items()} == {k: sorted(v) for k, v in groups.items()}
+        assert sum(1 for k in keep for j in groups[k] if j in groups) > 0, "the case must contain a keep claimed by a later keep"
+
+
+def test_null_parent_with_pre_cap(cuda_device):
+    """ranks cut by pre_cap must not be written through a NULL parent pointer (engine._stage1 passes none)."""
+    import fsd_b200.ops as ops
+
+    rng = np.random.default_rng(4)
+    n = 900
+    xy = rng.uniform(0, 3000, (n, 2)).astype(np.float32)
+    rows = torch.from_numpy(np.concatenate([xy, xy + 9, rng.uniform(0, 1, (n, 1)).astype(np.float32), np.zeros((n, 1), np.float32)], 1)).to(cuda_device)
+    res = ops.merge_segments(rows, torch.zeros(1, dtype=torch.int32, device=cuda_device), None, n, merge_type="NMS", metric="IOU",
+                             thr=0.7, cmp_strict=True, precision="fp32", pre_cap=500, max_keep=300, want_parent=False)
+    torch.cuda.synchronize()
+    assert int(res["keep_count"][0]) == 300 and res["parent"] is None
+
+
+def test_small_segments_in_a_large_capacity_launch(cuda_device):
+    """The launch is sized by the capacity (9900 -> cluster-capable), the path by each segment's actual count: tiny, medium and
+    > 4096-box segments in ONE call (what engine.detect does for configs 3 / 5 with few detections) all match the oracle."""
+    rng = np.random.default_rng(8)
+    segs = [sahi_like_boxes(rng, nf, dup=(1, 4), size=(10, 60), canvas=(2560, 1440)) for nf in (2, 30, 700)]
+    segs.append(sahi_like_boxes(rng, 2500, dup=(1, 4), size=(10, 60), canvas=(2560, 1440))[:5000])
+    import fsd_b200.ops as ops
+
+    cap = 9900
+    rows = np.zeros((len(segs) * cap, 6), dtype=np.float32)
+    for i, sg in enumerate(segs):
+        rows[i * cap: i * cap + len(sg)] = sg
+    res = ops.merge_segments(torch.from_numpy(rows).to(cuda_device), torch.arange(len(segs), dtype=torch.int32, device=cuda_device) * cap,
+                             torch.tensor([len(sg) for sg in segs], dtype=torch.int32, device=cuda_device), cap, merge_type="GREEDYNMM",
+                             metric="IOS", thr=0.5, precision="fp64", tie_rule="box_lex")
+    kc = res["keep_count"].cpu().numpy()
+    for i, sg in enumerate(segs):
+        keep, groups, out = _oracle(sg, "GREEDYNMM", "IOS", 0.5, True)
+        assert (res["keep"].cpu().numpy()[i * cap: i * cap + kc[i]] - i * cap).tolist() == keep
+        assert np.array_equal(res["boxes"].cpu().numpy()[i * cap: i * cap + kc[i]], np.array([o.bbox.to_xyxy() for o in out], dtype=np.float32))
