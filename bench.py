@@ -347,15 +347,17 @@ def main():
                        "launches_timed": len(dec), "ms_per_step": dms / args.steps, "share_of_step": dms / args.steps / step_ms})
     mer = path.get(K.FSD_KERNEL_MERGE, [])
     if mer:
-        groups = {}
-        for segs, tag, t in mer:
-            groups.setdefault((segs, tag), []).append(t)
+        groups, calls = {}, {}
+        for segs, tag, t in mer:  # one fsd_merge call = up to three launches (two shared-memory tiers + the cluster kernel): tag < 0 marks the followers
+            groups[(segs, abs(tag))] = groups.get((segs, abs(tag)), 0.0) + t
+            calls[(segs, abs(tag))] = calls.get((segs, abs(tag)), 0) + (1 if tag > 0 else 0)
         rows = []
-        for (segs, tag), ts in sorted(groups.items()):
-            kind = "stage 2 (cross-slice merge per image, GREEDYNMM/IOS fp64)" if tag == plan_det_cap(eng, plan) else \
+        for (segs, tag), tsum in sorted(groups.items()):
+            kind = "stage 2 (cross-slice merge per image, GREEDYNMM/IOS fp64, sahi 0.11.34 tie rule)" if tag == plan_det_cap(eng, plan) else \
                 ("stage 1 (per-slice NMS, torchvision rule) over the slices" if segs > B else "stage 1 over the full-image entries")
-            rows.append({"launch": kind, "segments": segs, "max_segment": tag, "us_per_launch": 1e3 * sum(ts) / len(ts),
-                         "us_per_segment": 1e3 * sum(ts) / len(ts) / max(segs, 1), "launches_timed": len(ts)})
+            nc = max(calls[(segs, tag)], 1)
+            rows.append({"launch": kind, "segments": segs, "max_segment": tag, "us_per_call": 1e3 * tsum / nc,
+                         "us_per_segment": 1e3 * tsum / nc / max(segs, 1), "calls_timed": nc})
         mms = sum(t for _, _, t in mer)
         others.append({"kernel": "k3_merge_kernel via fsd_merge (all launches of the timed region; latency-bound: absolute time)",
                        "bound": "latency", "launches": rows, "ms_per_step": mms / args.steps, "share_of_step": mms / args.steps / step_ms,

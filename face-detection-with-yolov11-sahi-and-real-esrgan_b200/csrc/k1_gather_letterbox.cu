@@ -477,8 +477,13 @@ extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n
 
     // border-less up-scale (or copy) whose cv2 coefficients are all sixteenths (ratios 8/5, 4, 2, 1 ...), fp16 output:
     // the packed 16-bit-lane path (k1_upscale2x.cu: k1_sixteenths_kernel)
+    // (down-scales qualify too when their coefficients are sixteenths — 1080p -> 576x1024 is 15/8 — but only with a
+    // compile-time tap pattern: the table-driven variant's byte loads lose to the TMA kernel there)
+    const long long q8 = (8LL * src_w) % p.new_w == 0 ? 8LL * src_w / p.new_w : 0;
+    const bool down_ok = q8 == 10 || q8 == 12 || q8 == 15;
     if (mode == K1_MODE_LINEAR && dtype == FSD_F16 && p.pad_left == 0 && p.pad_top == 0 && p.out_w == p.new_w &&
-        p.out_h == p.new_h && p.new_w >= src_w && p.new_h >= src_h && !getenv("FSD_K1_GENERIC")) {
+        p.out_h == p.new_h && ((p.new_w >= src_w && p.new_h >= src_h) || (down_ok && !getenv("FSD_K1_TABLE16"))) &&
+        !getenv("FSD_K1_GENERIC")) {
         auto key = std::make_tuple(src_w * 65536 + src_h, p.new_w * 65536 + p.new_h, 1 << 20);
         auto it = h->resize_tables.find(key);
         if (it == h->resize_tables.end()) {

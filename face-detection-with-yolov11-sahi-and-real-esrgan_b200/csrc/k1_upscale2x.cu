@@ -39,6 +39,22 @@ __device__ __forceinline__ uint32_t norm255_pair(uint32_t w) {  // (vB << 16 | v
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// t = two 16-bit lanes holding A + B + 2 (<= 1022 each; stray bits above bit 9 of the low lane allowed): the cv2 result
+// v = t >> 2 (8 bits) normalised to half(v / 255), without ever forming v as an integer: (t & 0x03fc) | 0x6400 is the half
+// 1024 + 4v (exact, ulp 1), one FMA turns it into v (x 0.25 - 256, exact), then the two-term product of norm255_pair.
+// One LOP3 + three half2 operations per pair instead of SHF + LOP + LOP + three: the integer ops run on the half-rate ALU
+// pipe that bounds these kernels (profiles/r1_k1_sixteenths_c1.summary.txt: ALU 54 %, issue 71 %).
+__device__ __forceinline__ uint32_t quant_norm_pair(uint32_t t) {
+    uint32_t m = (t & 0x03fc03fcu) | 0x64006400u;
+    const __half2 q = __halves2half2(__ushort_as_half(0x3400), __ushort_as_half(0x3400));      // 0.25
+    const __half2 z = __halves2half2(__ushort_as_half(0xDC00), __ushort_as_half(0xDC00));      // -256
+    const __half2 v = __hfma2(*reinterpret_cast<__half2*>(&m), q, z);
+    const __half2 c_hi = __halves2half2(__ushort_as_half(0x1C04), __ushort_as_half(0x1C04));  // fp16(1/255)
+    const __half2 c_lo = __halves2half2(__ushort_as_half(0x0001), __ushort_as_half(0x0001));  // 2^-24
+    const __half2 r = __hfma2(v, c_hi, __hmul2(v, c_lo));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 // A/B words of one source row for one channel: 4 words = output columns (2j..2j+7), two columns per word
 struct RowAB { uint32_t a[4], b[4]; };
 
@@ -54,7 +70,7 @@ __device__ __forceinline__ void row_ab(const uint32_t (&p)[6], RowAB& r) {
 
 __device__ __forceinline__ void out_row(const uint32_t (&x)[4], const uint32_t (&y)[4], uint32_t (&o)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = norm255_pair(((x[i] + y[i] + 0x00020002u) >> 2) & 0x00ff00ffu);
+    for (int i = 0; i < 4; ++i) o[i] = quant_norm_pair(x[i] + y[i] + 0x00020002u);
 }
 
 template <bool NHWC>
@@ -183,7 +199,8 @@ struct K16Params {
     int out_w, out_h, reverse, rows_per_cta, src_w;
 };
 
-// Horizontal pattern of an 8-column output group when out_w * Q == 8 * src_w (ratios 8/Q: 8, 4, 8/3, 2, 8/5, 4/3, 8/7, 1):
+// Horizontal pattern of an 8-column output group when out_w * Q == 8 * src_w (ratios 8/Q: 8, 4, 8/3, 2, 8/5, 4/3, 8/7, 1 up or
+// copy; 4/5, 2/3, 8/15 down):
 // every group maps to Q source pixels with the SAME relative indices and weights, so they are compile-time constants and
 // the group's Q + 2 source pixels are fetched as a few aligned 32-bit words (a byte load per tap costs ~4 L1 wavefronts
 // because neighbouring lanes are 3*Q bytes apart; the byte-load version of this kernel was bound by exactly that).
@@ -360,7 +377,7 @@ k1_sixteenths_kernel(const K16Params p) {
                 // low lane: A + B + 2 <= 1023 + (63 << 10) cannot carry into the high lane, and the final mask drops them
                 const uint32_t A = __umulhi(cur[c][j], f0) & 0x03ff03ffu;
                 const uint32_t B = __umulhi(nxt[c][j], f1);
-                o[c][j] = norm255_pair(((A + B + 0x00020002u) >> 2) & 0x00ff00ffu);
+                o[c][j] = quant_norm_pair(A + B + 0x00020002u);
             }
         store_row(y, o);
     }
@@ -390,8 +407,18 @@ int launch_sixteenths(fsd_context* h, const uint8_t* images, int64_t row_pitch, 
     K16Params p;
     p.images = images; p.row_pitch = row_pitch; p.image_pitch = image_pitch; p.entries = entries;
     p.xk = packed_dev; p.yk = packed_dev + out_w; p.out = reinterpret_cast<__half*>(out);
-    p.out_w = out_w; p.out_h = out_h; p.reverse = reverse; p.rows_per_cta = 32; p.src_w = src_w;
+    p.out_w = out_w; p.out_h = out_h; p.reverse = reverse; p.src_w = src_w;
     const int vecs = out_w / 8;
+    // rows per CTA: a CTA re-uses each horizontally filtered source row for the 1-4 output rows that need it, so taller CTAs
+    // save work when up-scaling; but a small launch (the full-image pass: one entry per image) must still fill several
+    // waves of the 148 SMs x ~8 resident CTAs, or the tail wave costs 30 % (1536 CTAs = 1.3 waves at 32 rows)
+    p.rows_per_cta = 32;
+    if (getenv("FSD_K16_ROWS")) p.rows_per_cta = atoi(getenv("FSD_K16_ROWS"));
+    else
+        while (p.rows_per_cta > 8 &&
+               (long long)((vecs + UP2_THREADS - 1) / UP2_THREADS) * ((out_h + p.rows_per_cta - 1) / p.rows_per_cta) * B < 6LL * 148 * 8)
+            p.rows_per_cta >>= 1;
+    if (p.rows_per_cta < 1) p.rows_per_cta = 1;
     dim3 grid((vecs + UP2_THREADS - 1) / UP2_THREADS, (out_h + p.rows_per_cta - 1) / p.rows_per_cta, B);
     // uniform 8-column pattern (out_w * Q == 8 * src_w) -> compile-time taps; anything else -> the table-driven variant
     int q = 0;
@@ -410,6 +437,9 @@ int launch_sixteenths(fsd_context* h, const uint8_t* images, int64_t row_pitch, 
             case 6: K16_GO(6) break;
             case 7: K16_GO(7) break;
             case 8: K16_GO(8) break;
+            case 10: K16_GO(10) break;  // down-scales: 1.25x
+            case 12: K16_GO(12) break;  //              1.5x
+            case 15: K16_GO(15) break;  //              1.875x: 1920x1080 -> 1024x576, the full-image pass of config 1
             default: K16_GO(0) break;
         }
 #undef K16_GO

@@ -1,14 +1,16 @@
 // Kernel 2 — fused YOLO pose-head decode.
 //
-// 2a  fsd_pose_decode:   per anchor sigmoid(cls) > conf gate (warp ballot); only surviving anchors are decoded,
-//                        warp-cooperatively: 32 lanes fetch the 64 DFL logits + 15 key-point values of one
-//                        survivor in one round trip, 16-lane shuffle softmax-expectation, anchor/stride decode,
-//                        xywh -> xyxy exactly in ultralytics' operation order, compaction through one atomic
-//                        per survivor into the entry's candidate list (order fixed later by the anchor index).
+// 2a  fsd_pose_decode:   pass 1: per anchor `cls logit >= gate` (the logit form of sigmoid(cls) > conf, found on the device
+//                        with the same sigmoid) + warp-aggregated compaction: survivors get their row slot, one atomic per
+//                        warp; pass 2: ONE WARP PER SURVIVOR over the whole grid: 32 lanes fetch the 64 DFL logits + 15
+//                        key-point values in one round trip, 16-lane shuffle softmax-expectation, anchor/stride decode,
+//                        xywh -> xyxy exactly in ultralytics' operation order (list order is fixed later by the anchor index).
 // 2b  fsd_finalize_dets: for the rows Kernel 3 stage 1 kept: scale_boxes / scale_coords / clip, int()
 //                        truncation (utils/yolo_wrapper.py:138), sahi clamp, + slice shift, packed per image in
 //                        (entry, rank) order — the order the reference appends ObjectPredictions in.
 // All arithmetic is fp32 with explicitly rounded (non-contracted) operations so results track torch's fp32 ops.
+#include <cstring>
+
 #include "fsd_common.cuh"
 
 namespace fsd {
@@ -38,32 +40,82 @@ template <int LAYOUT> __device__ __forceinline__ size_t idx(int b, int c, int a,
     return LAYOUT == FSD_PLANAR ? ((size_t)b * C + c) * hw + a : ((size_t)b * hw + a) * C + c;
 }
 
-template <typename T, int LAYOUT>
+// ---- Kernel 2a, pass 1: confidence gate + compaction -------------------------------------------------------------------
+// `sigmoid_rn(x) > conf` is monotone in x, so it equals `x >= x_gate` for the smallest float x_gate that passes; the host
+// entry point finds x_gate ON THE DEVICE with the very same sigmoid_rn (k2_find_gate_kernel: bisection over the ordered
+// float bit patterns), which makes the gate one compare per anchor instead of a double-precision exp — and provably the
+// same survivor set.  Survivors get their final row slot here (one atomic per warp and entry); only the anchor index is
+// written.  Pass 2 decodes them with every warp of the grid, so a slice with thousands of survivors no longer serialises
+// them inside the few warps that scanned its anchors.
+__device__ __forceinline__ uint32_t float_order_key(float x) {  // monotone float -> uint32
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void k2_find_gate_kernel(float conf, float* __restrict__ x_gate) {
+    // smallest float (excluding NaN) with sigmoid_rn(x) > conf; +inf when none does (conf >= 1)
+    uint32_t lo = float_order_key(-INFINITY), hi = float_order_key(INFINITY);  // invariant: answer in (lo, hi] or none
+    if (!(sigmoid_rn(INFINITY) > conf)) { *x_gate = INFINITY; return; }
+    if (sigmoid_rn(-INFINITY) > conf) { *x_gate = -INFINITY; return; }
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (sigmoid_rn(float_from_order_key(mid)) > conf) hi = mid; else lo = mid;
+    }
+    *x_gate = float_from_order_key(hi);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(K2_THREADS)
-k2_pose_decode_kernel(const K2Levels L, int B, float conf, float* __restrict__ cand, int cap,
-                      int* __restrict__ count) {
+k2_gate_kernel(const K2Levels L, int B, const float* __restrict__ x_gate_p, float* __restrict__ cand, int cap,
+               int* __restrict__ count) {
     const int A = L.a_begin[3];
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int a = blockIdx.x * K2_THREADS + threadIdx.x;  // global anchor index of this thread
-    int lvl = 0;
-    if (a >= L.a_begin[1]) lvl = 1;
-    if (a >= L.a_begin[2]) lvl = 2;
+    const float x_gate = __ldg(x_gate_p);
     bool pass = false;
-    float score = 0.f;
     if (a < A) {
-        const int al = a - L.a_begin[lvl];
+        int lvl = 0;
+        if (a >= L.a_begin[1]) lvl = 1;
+        if (a >= L.a_begin[2]) lvl = 2;
         const int hw = L.h[lvl] * L.w[lvl];
-        score = sigmoid_rn(ldf<T>(reinterpret_cast<const T*>(L.cls[lvl]), idx<LAYOUT>(b, 0, al, 1, hw)));
-        pass = score > conf;
+        // one class: the class tensor is [B, hw] in either layout
+        pass = ldf<T>(reinterpret_cast<const T*>(L.cls[lvl]), (size_t)b * hw + (a - L.a_begin[lvl])) >= x_gate;
     }
-    unsigned ballot = __ballot_sync(0xffffffffu, pass);
-    while (ballot) {  // warp-cooperative decode of each surviving anchor of this warp
-        const int src = __ffs(ballot) - 1;
-        ballot &= ballot - 1;
-        const int sa = __shfl_sync(0xffffffffu, a, src);
-        const int sl = __shfl_sync(0xffffffffu, lvl, src);
-        const float sscore = __shfl_sync(0xffffffffu, score, src);
+    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+    if (ballot == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count + b, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pass) {
+        const int pos = base + __popc(ballot & ((1u << lane) - 1u));
+        if (pos < cap) cand[((size_t)b * cap + pos) * ROW + 5] = __int_as_float(a);
+    }
+}
+
+// ---- Kernel 2a, pass 2: one warp per survivor, taken from every entry's list by the whole grid -------------------------
+template <typename T, int LAYOUT>
+__global__ void __launch_bounds__(K2_THREADS)
+k2_pose_decode_kernel(const K2Levels L, int B, float* __restrict__ cand, int cap, const int* __restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * K2_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * K2_THREADS) >> 5;
+    // warps walk the concatenation of all lists: survivor t of the grid = entry b, slot t - start(b)
+    int b = 0, start = 0, nb = min(__ldg(count), cap);
+    for (int t = gw;; t += nw) {
+        while (b < B && t >= start + nb) {
+            start += nb;
+            ++b;
+            if (b < B) nb = min(__ldg(count + b), cap);
+        }
+        if (b >= B) break;
+        float* row = cand + ((size_t)b * cap + (t - start)) * ROW;
+        const int sa = __float_as_int(row[5]);
+        int sl = 0;
+        if (sa >= L.a_begin[1]) sl = 1;
+        if (sa >= L.a_begin[2]) sl = 2;
         const int al = sa - L.a_begin[sl];
         const int w = L.w[sl], hw = L.h[sl] * w;
         const float stride = (float)(8 << sl);
@@ -74,6 +126,7 @@ k2_pose_decode_kernel(const K2Levels L, int B, float conf, float* __restrict__ c
         const float v1 = ldf<T>(boxp, idx<LAYOUT>(b, lane + 32, al, 64, hw));
         float kv = 0.f;
         if (lane < 15) kv = ldf<T>(reinterpret_cast<const T*>(L.kpt[sl]), idx<LAYOUT>(b, lane, al, 15, hw));
+        const float sscore = sigmoid_rn(ldf<T>(reinterpret_cast<const T*>(L.cls[sl]), (size_t)b * hw + al));
         // softmax-expectation over 16-lane groups
         float m0 = v0, m1 = v1;
 #pragma unroll
@@ -115,24 +168,16 @@ k2_pose_decode_kernel(const K2Levels L, int B, float conf, float* __restrict__ c
             const float xy = __fmul_rn(__fadd_rn(__fmul_rn(kv, 2.0f), __fsub_rn(anc, 0.5f)), stride);
             kout = comp == 2 ? sigmoid_rn(kv) : xy;
         }
-        int pos = 0;
-        if (lane == 0) pos = atomicAdd(count + b, 1);
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (pos < cap) {
-            float* row = cand + ((size_t)b * cap + pos) * ROW;
-            float val = 0.f;
-            if (lane == 0) val = __fsub_rn(cx, hw2);
-            else if (lane == 1) val = __fsub_rn(cy, hh2);
-            else if (lane == 2) val = __fadd_rn(cx, hw2);
-            else if (lane == 3) val = __fadd_rn(cy, hh2);
-            else if (lane == 4) val = sscore;
-            else if (lane == 5) val = __int_as_float(sa);
-            const float kshift = __shfl_sync(0xffffffffu, kout, (lane + 26) & 31);  // lanes 6..20 <- kout of lanes 0..14
-            if (lane >= 6 && lane < 21) val = kshift;
-            if (lane < ROW) row[lane] = val;
-        } else {
-            __shfl_sync(0xffffffffu, kout, (lane + 26) & 31);  // keep the warp converged on the shuffle
-        }
+        float val = 0.f;
+        if (lane == 0) val = __fsub_rn(cx, hw2);
+        else if (lane == 1) val = __fsub_rn(cy, hh2);
+        else if (lane == 2) val = __fadd_rn(cx, hw2);
+        else if (lane == 3) val = __fadd_rn(cy, hh2);
+        else if (lane == 4) val = sscore;
+        else if (lane == 5) val = __int_as_float(sa);
+        const float kshift = __shfl_sync(0xffffffffu, kout, (lane + 26) & 31);  // lanes 6..20 <- kout of lanes 0..14
+        if (lane >= 6 && lane < 21) val = kshift;
+        if (lane < ROW) row[lane] = val;
     }
 }
 
@@ -280,17 +325,43 @@ extern "C" int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const v
     cudaStream_t stream = (cudaStream_t)stream_;
     FSD_CUDA(cudaSetDevice(h->device));
     FSD_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * B, stream));
-    dim3 grid((a + K2_THREADS - 1) / K2_THREADS, B);
+    // the gate logit for this confidence, found once on the device with the kernel's own sigmoid (cached in the handle)
+    float* x_gate = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        uint32_t bits;
+        memcpy(&bits, &conf, 4);
+        auto it = h->decode_gates.find(bits);
+        if (it == h->decode_gates.end()) {
+            FSD_CUDA(cudaMalloc(&x_gate, sizeof(float)));
+            h->dev_allocs.push_back(x_gate);
+            k2_find_gate_kernel<<<1, 1, 0, stream>>>(conf, x_gate);
+            FSD_CUDA(cudaGetLastError());
+            cudaEvent_t ready;  // other streams may use the cached value: they wait for this event first
+            FSD_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            FSD_CUDA(cudaEventRecord(ready, stream));
+            it = h->decode_gates.emplace(bits, std::make_pair(x_gate, ready)).first;
+        } else {
+            x_gate = it->second.first;
+            FSD_CUDA(cudaStreamWaitEvent(stream, it->second.second, 0));
+        }
+    }
     TimedLaunch timed(h, FSD_KERNEL_DECODE, (int64_t)B * a * 80 * (dtype == FSD_F16 ? 2 : 4), a, stream);
+    dim3 grid((a + K2_THREADS - 1) / K2_THREADS, B);
+    if (dtype == FSD_F16) k2_gate_kernel<__half><<<grid, K2_THREADS, 0, stream>>>(L, B, x_gate, cand, cap_per_entry, count);
+    else k2_gate_kernel<float><<<grid, K2_THREADS, 0, stream>>>(L, B, x_gate, cand, cap_per_entry, count);
+    FSD_CUDA(cudaGetLastError());
+    // pass 2: one warp per survivor over a grid of a few CTAs per SM (the survivor count lives on the device)
+    const int grid2 = h->sm_count * 4;
     if (dtype == FSD_F16) {
-        if (layout == FSD_PLANAR) k2_pose_decode_kernel<__half, FSD_PLANAR><<<grid, K2_THREADS, 0, stream>>>(L, B, conf, cand, cap_per_entry, count);
-        else k2_pose_decode_kernel<__half, FSD_CHANNELS_LAST><<<grid, K2_THREADS, 0, stream>>>(L, B, conf, cand, cap_per_entry, count);
+        if (layout == FSD_PLANAR) k2_pose_decode_kernel<__half, FSD_PLANAR><<<grid2, K2_THREADS, 0, stream>>>(L, B, cand, cap_per_entry, count);
+        else k2_pose_decode_kernel<__half, FSD_CHANNELS_LAST><<<grid2, K2_THREADS, 0, stream>>>(L, B, cand, cap_per_entry, count);
     } else {
-        if (layout == FSD_PLANAR) k2_pose_decode_kernel<float, FSD_PLANAR><<<grid, K2_THREADS, 0, stream>>>(L, B, conf, cand, cap_per_entry, count);
-        else k2_pose_decode_kernel<float, FSD_CHANNELS_LAST><<<grid, K2_THREADS, 0, stream>>>(L, B, conf, cand, cap_per_entry, count);
+        if (layout == FSD_PLANAR) k2_pose_decode_kernel<float, FSD_PLANAR><<<grid2, K2_THREADS, 0, stream>>>(L, B, cand, cap_per_entry, count);
+        else k2_pose_decode_kernel<float, FSD_CHANNELS_LAST><<<grid2, K2_THREADS, 0, stream>>>(L, B, cand, cap_per_entry, count);
     }
     FSD_CUDA(cudaGetLastError());
-    h->launches += 1;
+    h->launches += 2;
     return FSD_OK;
 }
 

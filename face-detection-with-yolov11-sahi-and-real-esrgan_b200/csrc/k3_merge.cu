@@ -46,6 +46,7 @@ struct K3Params {
     uint8_t* workspace; size_t ws_per_segment;
     int P;  // power of two >= seg_cap
     int use_global;
+    int n_lo, n_hi;  // the shared-memory kernel takes the segments with n_lo < n <= n_hi (tiered launches, see fsd_merge)
 };
 
 __device__ __forceinline__ uint32_t score_key_desc(float s) {
@@ -200,21 +201,21 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     __shared__ uint32_t s_kkey[64];
     __shared__ uint32_t s_rem[130];      // removed bits of the whole segment (4096) + slack for the 64-bit window
     __shared__ unsigned long long s_keepmask, s_rembefore, s_remafter;
-    __shared__ int s_kcount, s_ktotal, s_stop;
+    __shared__ int s_kcount, s_ktotal, s_stop, s_flagged;
 
     const int s = blockIdx.x;
     const int tid = threadIdx.x;
     const int off = p.seg_offsets[s];
     int n = p.seg_counts ? p.seg_counts[s] : p.seg_cap;
     n = min(max(n, 0), p.seg_cap);
-    if (n > K3_SMEM_MAX_P) return;  // the cluster launch owns this segment
+    if (n <= p.n_lo || n > p.n_hi) return;  // another tier's launch (or the cluster launch) owns this segment
     if (n == 0) {
         if (tid == 0) p.keep_count[s] = 0;
         return;
     }
     int P = 64;
     while (P < n) P <<= 1;
-    // the launch is sized for the capacity; the segment decides how many warps stay
+    // the launch is sized for the tier's capacity; the segment decides how many warps stay
     const int T = min((int)blockDim.x, P <= 64 ? 64 : (P <= 256 ? 128 : (P <= 1024 ? 256 : 512)));
     if (tid >= T) return;
     const int lane = tid & 31;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
         }
     }
     for (int i = tid; i < 130; i += T) s_rem[i] = 0;
-    if (tid == 0) { s_ktotal = 0; s_stop = 0; s_kcount = 0; }
+    if (tid == 0) { s_ktotal = 0; s_stop = 0; s_kcount = 0; s_flagged = 0; }
     k3_bar(T);
     auto keyhi = [&](int r) -> uint32_t { return mc.tie_rule ? (uint32_t)(keys[r] >> 32) : 0u; };
 
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
             for (int q = kr + 1; q < m && keyhi(q) == kk; ++q) {
                 if (parent[q] == q && suppresses(sbox[q], sbox[kr], scat[q], scat[kr], kk, kk, mc)) {
                     atomicOr(&step[kr], q + 1);
-                    atomicOr(&step[q], K3_HASB);
+                    if (!(atomicOr(&step[q], K3_HASB) & K3_HASB)) atomicAdd(&s_flagged, 1);
                     break;
                 }
             }
@@ -436,62 +437,38 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
             if (!(kscore > cscore)) kcat = scat[cr];
         }
     };
-    if (p.type == FSD_GREEDYNMM) {
+    const int flagged = tie_merge ? s_flagged : 0;  // keeps whose merge list holds an earlier equal-score keep (uniform over the CTA)
+    if (p.type == FSD_GREEDYNMM && flagged == 0) {
         // candidates of a keep in append order = ascending rank: every thread owns one keep, all threads walk the claim array
-        // together (uniform addresses: broadcast reads), a hit folds into the growing union box
+        // together (uniform addresses: broadcast reads), a hit folds into the growing union box — no sort
         for (int i0 = 0; i0 < K; i0 += T) {
             const int i = i0 + tid;
             const int kr = i < K ? keepr[i] : -1;
-            const bool mine = kr >= 0 && !(tie_merge && (step[kr] & K3_HASB));
             double kb[4] = {0, 0, 0, 0};
             float kscore = 0.f;
             int kcat = 0;
-            if (mine) {
+            if (kr >= 0) {
                 const float4 b = sbox[kr];
                 kb[0] = b.x; kb[1] = b.y; kb[2] = b.z; kb[3] = b.w;
                 kscore = p.scores[(size_t)(off + (int)vals[kr]) * p.score_stride];
                 kcat = scat[kr];
             }
             for (int r = keepr[i0] + 1; r < m; ++r)
-                if (parent[r] == kr && r != kr && mine) fold_one(kb, kscore, kcat, r);
-            if (mine) {
-                emit(i, kr, kb, kscore, kcat);
-                if (tie_merge) {  // a later equal-score keep may fold THIS keep's merged box (only that keep reads it)
-                    sbox[kr] = make_float4((float)kb[0], (float)kb[1], (float)kb[2], (float)kb[3]);
-                    scat[kr] = kcat;
-                }
-            }
-        }
-        if (tie_merge) {
-            k3_bar(T);
-            if (tid == 0) {  // keeps with backward claims, in rank order (they are rare: exact score ties between overlapping keeps)
-                for (int i = 0; i < K; ++i) {
-                    const int kr = keepr[i];
-                    if (!(step[kr] & K3_HASB)) continue;
-                    const float4 b = sbox[kr];
-                    double kb[4] = {(double)b.x, (double)b.y, (double)b.z, (double)b.w};
-                    const float kscore = p.scores[(size_t)(off + (int)vals[kr]) * p.score_stride];
-                    int kcat = scat[kr];
-                    for (int r = 0; r < m; ++r) {
-                        const bool fwd = parent[r] == kr && r != kr;
-                        const bool bwd = parent[r] == r && (step[r] & ~K3_HASB) == kr + 1;
-                        if (fwd || bwd) fold_one(kb, kscore, kcat, r);
-                    }
-                    emit(i, kr, kb, kscore, kcat);
-                    sbox[kr] = make_float4((float)kb[0], (float)kb[1], (float)kb[2], (float)kb[3]);
-                    scat[kr] = kcat;
-                }
-            }
+                if (parent[r] == kr && r != kr) fold_one(kb, kscore, kcat, r);
+            if (kr >= 0) emit(i, kr, kb, kscore, kcat);
         }
         return;
     }
-    // ---- NMM replay: key = (keep rank : 15 bits | append sequence : 30 bits | candidate rank : 15 bits), ascending ----
+    // ---- replay through sorted lists: NMM (step-major append order), and GREEDYNMM when the tie rule made a keep claim an
+    // earlier keep (those keeps fold AFTER the keeps they claimed, reading their merged boxes: lists make that O(list)) ----
+    // key = (keep rank : 15 bits | append sequence : 30 bits | candidate rank : 15 bits), ascending
     for (int r = tid; r < P; r += T) {
         uint64_t key = ~0ull;
         if (r < m) {
-            const int pr = parent[r];
+            int pr = parent[r];
+            if (p.type == FSD_GREEDYNMM && pr == r && (step[r] & ~K3_HASB)) pr = (step[r] & ~K3_HASB) - 1;  // claimed keep
             if (pr >= 0 && pr != r) {
-                const uint64_t seq = (uint64_t)step[r] * 32768ull + (uint64_t)(32767 - r);
+                const uint64_t seq = p.type == FSD_NMM ? (uint64_t)step[r] * 32768ull + (uint64_t)(32767 - r) : (uint64_t)r;
                 key = ((uint64_t)pr << 45) | (seq << 15) | (uint64_t)r;
             }
         }
@@ -506,7 +483,7 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
         if (q == 0 || (int)(keys[q - 1] >> 45) != pr) runs[pr] = q;
     }
     k3_bar(T);
-    for (int i = tid; i < K; i += T) {
+    auto fold_list = [&](int i) {
         const int kr = keepr[i];
         const float4 b = sbox[kr];
         double kb[4] = {(double)b.x, (double)b.y, (double)b.z, (double)b.w};
@@ -521,6 +498,18 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
             }
         }
         emit(i, kr, kb, kscore, kcat);
+        if (flagged) {  // a later equal-score keep may fold THIS keep's merged box (only that keep reads it)
+            sbox[kr] = make_float4((float)kb[0], (float)kb[1], (float)kb[2], (float)kb[3]);
+            scat[kr] = kcat;
+        }
+    };
+    for (int i = tid; i < K; i += T)
+        if (!(flagged && (step[keepr[i]] & K3_HASB))) fold_list(i);
+    if (flagged) {
+        k3_bar(T);
+        if (tid == 0)  // the keeps with backward claims, in rank order; every list is walked once: O(m) in total
+            for (int i = 0; i < K; ++i)
+                if (step[keepr[i]] & K3_HASB) fold_list(i);
     }
 }
 
@@ -1183,15 +1172,29 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
         return FSD_OK;
     }
     {
-        const int Psm = p.P < K3_SMEM_MAX_P ? p.P : K3_SMEM_MAX_P;
-        const size_t smem = (size_t)Psm * K3_BYTES_PER_BOX;
-        const int threads = Psm <= 64 ? 64 : (Psm <= 256 ? 128 : (Psm <= 1024 ? 256 : 512));
+        // shared-memory kernel in up to two tiers, so that a launch whose CAPACITY is large does not make every small segment
+        // pay for 196 KB of shared memory (one CTA per SM): tier A takes the segments of at most 1024 boxes (48 KB, several CTAs
+        // per SM), tier B those of 1025..4096; a CTA returns at once when its segment belongs to another launch
         FSD_CUDA(cudaFuncSetAttribute(k3_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_MAX_P * K3_BYTES_PER_BOX));
         p.use_global = 0;
-        TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, stream);
-        k3_merge_kernel<<<S, threads, smem, stream>>>(p);
+        const int PA = p.P < 1024 ? p.P : 1024;
+        p.n_lo = -1; p.n_hi = PA;
+        {
+            TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, stream);
+            k3_merge_kernel<<<S, PA <= 64 ? 64 : (PA <= 256 ? 128 : 256), (size_t)PA * K3_BYTES_PER_BOX, stream>>>(p);
+        }
         FSD_CUDA(cudaGetLastError());
         h->launches += 1;
+        if (p.P > 1024) {
+            const int PB = p.P < K3_SMEM_MAX_P ? p.P : K3_SMEM_MAX_P;
+            p.n_lo = 1024; p.n_hi = PB;
+            {
+                TimedLaunch timed(h, FSD_KERNEL_MERGE, S, -max_segment, stream);
+                k3_merge_kernel<<<S, 512, (size_t)PB * K3_BYTES_PER_BOX, stream>>>(p);
+            }
+            FSD_CUDA(cudaGetLastError());
+            h->launches += 1;
+        }
     }
     if (p.P > K3_SMEM_MAX_P) {
         // segments above 4096 boxes: a cluster of 8 CTAs each (k3_merge_cluster_kernel)

@@ -321,17 +321,28 @@ attach_keypoints_kernel(const float* __restrict__ merged, int merged_stride,
                         const int32_t* __restrict__ m_off, const int32_t* __restrict__ m_cnt,
                         const float* __restrict__ dets, int det_stride,
                         const int32_t* __restrict__ d_off, const int32_t* __restrict__ d_cnt,
-                        int32_t* __restrict__ src_index) {
+                        int32_t* __restrict__ src_index, int smem_boxes) {
+    extern __shared__ float4 s_det[];  // the image's detection boxes, staged once (rows are 96 B apart in HBM: a warp-wide
+                                       // scan straight from global memory touches one sector per lane and per box)
     const int s = blockIdx.x;
     const int mo = m_off[s], mn = m_cnt[s], dof = d_off[s], dn = d_cnt[s];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool staged = dn <= smem_boxes;  // uniform over the CTA
+    if (staged) {
+        for (int j = threadIdx.x; j < dn; j += blockDim.x)
+            s_det[j] = *reinterpret_cast<const float4*>(dets + (size_t)(dof + j) * det_stride);
+        __syncthreads();
+    }
+    auto det_box = [&](int j) -> float4 {
+        return staged ? s_det[j] : *reinterpret_cast<const float4*>(dets + (size_t)(dof + j) * det_stride);
+    };
     for (int i = warp; i < mn; i += nwarps) {
         const float4 mb = *reinterpret_cast<const float4*>(merged + (size_t)(mo + i) * merged_stride);
         const double bx1 = mb.x, by1 = mb.y, bx2 = mb.z, by2 = mb.w;
         int exact = -1, best = -1;
         double best_iou = 0.0;
         for (int j = lane; j < dn; j += 32) {
-            const float4 d = *reinterpret_cast<const float4*>(dets + (size_t)(dof + j) * det_stride);
+            const float4 d = det_box(j);
             if (d.x == mb.x && d.y == mb.y && d.z == mb.z && d.w == mb.w) { exact = j; continue; }
             if (fminf(mb.z, d.z) < fmaxf(mb.x, d.x) || fminf(mb.w, d.w) < fmaxf(mb.y, d.y)) continue;  // IoU 0 never wins
             const double ix1 = fmax(bx1, (double)d.x), iy1 = fmax(by1, (double)d.y);
@@ -341,26 +352,27 @@ attach_keypoints_kernel(const float* __restrict__ merged, int merged_stride,
             const double iou = uni > 0 ? inter / uni : 0.0;
             if (iou > best_iou) { best_iou = iou; best = j; }  // ascending j per lane: keeps the lane's first maximum
         }
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            exact = max(exact, __shfl_xor_sync(0xffffffffu, exact, o));
-            const double oi = __shfl_xor_sync(0xffffffffu, best_iou, o);
-            const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-            if (oi > best_iou || (oi == best_iou && ob >= 0 && (best < 0 || ob < best))) { best_iou = oi; best = ob; }
-        }
+        exact = __reduce_max_sync(0xffffffffu, exact);
         int res = -1;
-        if (exact >= 0) res = exact;
-        else if (best >= 0 && best_iou > 0.5) {
-            // the cache is a dict keyed by the box: the value is the LAST detection inserted with that box
-            const float4 d = *reinterpret_cast<const float4*>(dets + (size_t)(dof + best) * det_stride);
-            int last = best;
-            for (int j = best + 1 + lane; j < dn; j += 32) {
-                const float4 e = *reinterpret_cast<const float4*>(dets + (size_t)(dof + j) * det_stride);
-                if (e.x == d.x && e.y == d.y && e.z == d.z && e.w == d.w) last = j;
-            }
+        if (exact >= 0) {
+            res = exact;
+        } else {
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-            res = last;
+            for (int o = 16; o >= 1; o >>= 1) {
+                const double oi = __shfl_xor_sync(0xffffffffu, best_iou, o);
+                const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+                if (oi > best_iou || (oi == best_iou && ob >= 0 && (best < 0 || ob < best))) { best_iou = oi; best = ob; }
+            }
+            if (best >= 0 && best_iou > 0.5) {
+                // the cache is a dict keyed by the box: the value is the LAST detection inserted with that box
+                const float4 d = det_box(best);
+                int last = best;
+                for (int j = best + 1 + lane; j < dn; j += 32) {
+                    const float4 e = det_box(j);
+                    if (e.x == d.x && e.y == d.y && e.z == d.z && e.w == d.w) last = j;
+                }
+                res = __reduce_max_sync(0xffffffffu, last);
+            }
         }
         if (lane == 0) src_index[mo + i] = res < 0 ? -1 : dof + res;
     }
@@ -471,8 +483,10 @@ extern "C" int fsd_attach_keypoints(fsd_handle_t h, const float* merged, int mer
                   "fsd_attach_keypoints: row strides must be multiples of 4 floats (16-byte rows)");
     if (S == 0) return FSD_OK;
     FSD_CUDA(cudaSetDevice(h->device));
+    const int smem_boxes = 4096;  // 64 KB: images with more per-slice detections scan global memory instead (config 3's 9900)
+    FSD_CUDA(cudaFuncSetAttribute(attach_keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_boxes * 16));
     TimedLaunch timed(h, FSD_KERNEL_ATTACH, S, 0, (cudaStream_t)stream_);
-    attach_keypoints_kernel<<<S, 256, 0, (cudaStream_t)stream_>>>(merged, merged_stride, m_off, m_cnt, dets, det_stride, d_off, d_cnt, src_index);
+    attach_keypoints_kernel<<<S, 256, smem_boxes * 16, (cudaStream_t)stream_>>>(merged, merged_stride, m_off, m_cnt, dets, det_stride, d_off, d_cnt, src_index, smem_boxes);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

@@ -48,7 +48,8 @@ def test_slices_match_oracle(cuda_device, case, dtype):
     assert torch.equal(out.cpu(), ref), f"max diff {(out.cpu().float() - ref.float()).abs().max()}"
 
 
-@pytest.mark.parametrize("shape", [(1080, 1920), (768, 1024), (2160, 3840), (1366, 2048), (2340, 4160), (37, 53)])
+@pytest.mark.parametrize("shape", [(1080, 1920), (768, 1024), (2160, 3840), (1366, 2048), (2340, 4160), (37, 53),
+                                   (640, 1280), (768, 1536), (1080, 1920 + 0)])  # 1.25x / 1.5x / 1.875x down: compile-time tap patterns Q = 10 / 12 / 15
 def test_full_image_pass_matches_oracle(cuda_device, shape):
     """The perform_standard_pred pass: down-scale (r<1), copy (r==1), exact-2x area path, tiny up-scale."""
     import fsd_b200.ops as ops
@@ -63,6 +64,10 @@ def test_full_image_pass_matches_oracle(cuda_device, shape):
                                        dtype=dtype, reverse_channels=reverse)
             ref = _oracle_batch([img], [(0, 0, 0)], W, H, 1024, dtype == torch.float16, reverse)
             assert torch.equal(out.cpu(), ref)
+            if dtype == torch.float16:  # channels-last output (what the engine consumes) through the same path
+                cl = ops.gather_letterbox(pool, torch.tensor([[0, 0, 0]], dtype=torch.int32), W, H, imgsz=1024, dtype=dtype,
+                                          reverse_channels=reverse, channels_last=True)
+                assert torch.equal(cl.cpu().contiguous(), ref)
 
 
 def test_bad_pitch_is_rejected(cuda_device):

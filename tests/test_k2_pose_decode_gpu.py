@@ -164,3 +164,47 @@ def test_stage1_nms_and_finalize_match_oracle(cuda_device, shape):
         assert np.abs(gotb[:, 4].numpy() - d[:, 4].numpy()).max() <= SCORE_TOL
         total += d.shape[0]
     assert total > 10
+
+
+@pytest.mark.parametrize("conf", [0.5, 0.25, 0.01, 0.001, 0.9, 0.999])
+def test_logit_gate_equals_the_sigmoid_gate(cuda_device, conf):
+    """Pass 1 gates on `logit >= x_gate` with x_gate found on the device; that must select exactly the anchors whose
+    kernel-side score sigmoid_rn(logit) exceeds conf — for EVERY fp16 logit and a dense sweep of fp32 logits around the gate."""
+    import fsd_b200.ops as ops
+
+    def survivors_and_scores(cls_vals, c):
+        n = cls_vals.numel()
+        side = int(np.ceil(np.sqrt(n / 1.0)))
+        h = w = side
+        pad = torch.full((h * w - n,), -1e4, dtype=cls_vals.dtype)
+        cls0 = torch.cat([cls_vals, pad]).view(1, 1, h, w)
+        levels = [(torch.zeros((1, 64, h, w), dtype=cls_vals.dtype), cls0, torch.zeros((1, 15, h, w), dtype=cls_vals.dtype))]
+        for _ in range(2):
+            levels.append((torch.zeros((1, 64, 1, 1), dtype=cls_vals.dtype), torch.full((1, 1, 1, 1), -1e4, dtype=cls_vals.dtype),
+                           torch.zeros((1, 15, 1, 1), dtype=cls_vals.dtype)))
+        cand, count = ops.pose_decode(_to_dev(levels, cuda_device, False), c, cap_per_entry=h * w + 2)
+        k = int(count[0])
+        rows = cand[0, :k].cpu()
+        return rows[:, 5].view(torch.int32).long(), rows[:, 4]
+
+    half_all = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.float16)
+    half_all = half_all[torch.isfinite(half_all.float())]
+    logit = float(np.log(conf / (1 - conf)))
+    sweep = torch.tensor(np.nextafter(np.float32(logit), np.float32(np.inf)) + 0, dtype=torch.float32)
+    around = [np.float32(logit)]
+    for _ in range(3000):
+        around.append(np.nextafter(around[-1], np.float32(np.inf)))
+    lo = np.float32(logit)
+    for _ in range(3000):
+        lo = np.nextafter(lo, np.float32(-np.inf))
+        around.append(lo)
+    for vals in (half_all, torch.tensor(np.array(around, dtype=np.float32))):
+        all_idx, all_sc = survivors_and_scores(vals, -1.0)          # conf -1: every anchor passes, scores of all logits
+        score = torch.empty(vals.numel())
+        keep = all_idx < vals.numel()
+        score[all_idx[keep]] = all_sc[keep]
+        got_idx, got_sc = survivors_and_scores(vals, conf)
+        got = set(got_idx[got_idx < vals.numel()].tolist())
+        want = set(torch.nonzero(score > conf).flatten().tolist())
+        assert got == want, (len(got), len(want), sorted(got ^ want)[:5])
+        assert len(want) > 0 and len(want) < vals.numel()
