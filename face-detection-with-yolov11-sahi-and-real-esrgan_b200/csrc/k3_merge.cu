@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     int P = 64;
     while (P < n) P <<= 1;
     // the launch is sized for the tier's capacity; the segment decides how many warps stay
-    const int T = min((int)blockDim.x, P <= 64 ? 64 : (P <= 256 ? 128 : (P <= 1024 ? 256 : 512)));
+    // (the phases are latency-bound — dependent shared-memory reads and min/max chains — so more warps per segment pay off:
+    // profiles/r1_k3_greedynmm_n1024.summary.txt showed 2 warps per scheduler at 19 % issue utilisation)
+    const int T = min((int)blockDim.x, P <= 64 ? 64 : (P <= 128 ? 128 : (P <= 256 ? 256 : 512)));
     if (tid >= T) return;
     const int lane = tid & 31;
 
@@ -341,16 +343,37 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
             }
             if (!stop) {
                 // sweep: every not-yet-removed lower rank against this chunk's new keeps (first match claims it)
+                // Most (keep, rank) pairs are disjoint boxes: four keeps are rejected at a time with independent min/max
+                // chains (instruction-level parallelism on the common path); the exact test runs, in keep order, only for
+                // a group that holds an overlapping keep.  thr <= 0 matches disjoint boxes too: no quick reject then.
+                const bool quick = mc.thr > 0.0;
                 for (int j = c0 + cn + tid; j < m; j += T) {
                     if ((s_rem[j >> 5] >> (j & 31)) & 1u) continue;
                     const float4 bj = sbox[j];
                     const int cj = scat[j];
                     const uint32_t kj = keyhi(j);
-                    for (int k = 0; k < kc; ++k) {
-                        if (suppresses(s_kbox[k], bj, s_kcat[k], cj, s_kkey[k], kj, mc)) {
-                            atomicOr(&s_rem[j >> 5], 1u << (j & 31));
-                            parent[j] = s_klist[k];
-                            break;
+                    bool hit = false;
+                    for (int k0 = 0; k0 < kc && !hit; k0 += 4) {
+                        const int kn = min(4, kc - k0);
+                        unsigned ov = 0xfu;
+                        if (quick) {
+                            ov = 0;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float4 a = s_kbox[min(k0 + u, kc - 1)];
+                                if (fminf(a.z, bj.z) > fmaxf(a.x, bj.x) && fminf(a.w, bj.w) > fmaxf(a.y, bj.y)) ov |= 1u << u;
+                            }
+                        }
+                        if (ov == 0) continue;
+                        for (int u = 0; u < kn; ++u) {
+                            if (!((ov >> u) & 1u)) continue;
+                            const int k = k0 + u;
+                            if (suppresses(s_kbox[k], bj, s_kcat[k], cj, s_kkey[k], kj, mc)) {
+                                atomicOr(&s_rem[j >> 5], 1u << (j & 31));
+                                parent[j] = s_klist[k];
+                                hit = true;
+                                break;
+                            }
                         }
                     }
                 }
@@ -1181,7 +1204,7 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
         p.n_lo = -1; p.n_hi = PA;
         {
             TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, stream);
-            k3_merge_kernel<<<S, PA <= 64 ? 64 : (PA <= 256 ? 128 : 256), (size_t)PA * K3_BYTES_PER_BOX, stream>>>(p);
+            k3_merge_kernel<<<S, PA <= 64 ? 64 : (PA <= 128 ? 128 : (PA <= 256 ? 256 : 512)), (size_t)PA * K3_BYTES_PER_BOX, stream>>>(p);
         }
         FSD_CUDA(cudaGetLastError());
         h->launches += 1;

@@ -378,6 +378,10 @@ attach_keypoints_kernel(const float* __restrict__ merged, int merged_stride,
     }
 }
 
+int launch_crop_tma(fsd_context* h, const uint8_t* bgr, int H, int W, int64_t row_pitch, int pre_h, int pre_w,
+                    const int32_t* table_dev, const int32_t* table_host, int T, void* tiles, int n_images, int64_t image_pitch,
+                    int64_t tiles_image_stride, int64_t units, cudaStream_t stream, bool* taken);  // k4_crop_tma.cu
+
 }  // namespace fsd
 
 using namespace fsd;
@@ -440,6 +444,12 @@ extern "C" int fsd_esrgan_crop(fsd_handle_t h, const uint8_t* bgr, int H, int W,
     FSD_CUDA(cudaSetDevice(h->device));
     int64_t crop_bytes = (int64_t)H * W * 3;  // algorithmic: source once + every tile once
     for (int i = 0; i < T; ++i) crop_bytes += (int64_t)3 * table_host[i * TT + 2] * table_host[i * TT + 3] * (dtype == FSD_F16 ? 2 : 4);
+    if (dtype == FSD_F16) {  // bulk-copy pipeline (TMA boxes in, bulk stores out) when every tile qualifies: k4_crop_tma.cu
+        bool taken = false;
+        const int rc = launch_crop_tma(h, bgr, H, W, row_pitch, pre_h, pre_w, table_dev, table_host, T, tiles, n_images, image_pitch,
+                                       tiles_image_stride, crop_bytes * n_images, (cudaStream_t)stream_, &taken);
+        if (rc != FSD_OK || taken) return rc;
+    }
     TimedLaunch timed(h, FSD_KERNEL_ESRGAN_CROP, crop_bytes * n_images, n_images, (cudaStream_t)stream_);
     if (dtype == FSD_F16) k4_crop_kernel<__half><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>(bgr, H, W, row_pitch, pre_h, pre_w, table_dev, (__half*)tiles, image_pitch, tiles_image_stride);
     else k4_crop_kernel<float><<<grid, K4_THREADS, 0, (cudaStream_t)stream_>>>(bgr, H, W, row_pitch, pre_h, pre_w, table_dev, (float*)tiles, image_pitch, tiles_image_stride);

@@ -189,15 +189,27 @@ def test_logit_gate_equals_the_sigmoid_gate(cuda_device, conf):
 
     half_all = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.float16)
     half_all = half_all[torch.isfinite(half_all.float())]
-    logit = float(np.log(conf / (1 - conf)))
-    sweep = torch.tensor(np.nextafter(np.float32(logit), np.float32(np.inf)) + 0, dtype=torch.float32)
-    around = [np.float32(logit)]
-    for _ in range(3000):
-        around.append(np.nextafter(around[-1], np.float32(np.inf)))
-    lo = np.float32(logit)
-    for _ in range(3000):
-        lo = np.nextafter(lo, np.float32(-np.inf))
-        around.append(lo)
+    # centre of the fp32 sweep: the gate as numpy's float32 arithmetic sees it (bisection over the ordered bit patterns; for
+    # conf 0.5 it is ~3e-8, millions of ulps above 0.0) — the device may land a few ulps away, the sweep covers +-3000
+    def sig32(x):
+        e = np.float32(np.exp(-np.float64(x)))
+        return np.float32(1.0) / (np.float32(1.0) + e)
+
+    def key(x):
+        u = int(np.float32(x).view(np.uint32))
+        return (~u & 0xffffffff) if u & 0x80000000 else (u | 0x80000000)
+
+    def unkey(k):
+        return np.uint32((k & 0x7fffffff) if k & 0x80000000 else (~k & 0xffffffff)).view(np.float32)
+
+    lo_k, hi_k = key(np.float32(-100.0)), key(np.float32(100.0))
+    while hi_k - lo_k > 1:
+        mid = (lo_k + hi_k) // 2
+        if sig32(unkey(mid)) > np.float32(conf):
+            hi_k = mid
+        else:
+            lo_k = mid
+    around = [unkey(k) for k in range(hi_k - 3000, hi_k + 3000)]
     for vals in (half_all, torch.tensor(np.array(around, dtype=np.float32))):
         all_idx, all_sc = survivors_and_scores(vals, -1.0)          # conf -1: every anchor passes, scores of all logits
         score = torch.empty(vals.numel())
