@@ -646,6 +646,28 @@ def run_extras(args, dev, yolo, eng, h, peak, use_graphs):
             nb, t = ss[0][0], sum(t for _, _, t in ss) / len(ss)
             c5[name] = {"achieved": gbs(nb, t), "frac": gbs(nb, t) / peak, "unit": "GB/s", "launch_us": 1e3 * t, "bytes_per_launch": nb,
                         "frames_per_launch": F, "share_of_enhance_stage": t / (ms_enh / 3)}
+    # Kernel 4 alone on a stream of frames (no network): a single 1080p frame is 20 MB (crop) / 75 MB (stitch), i.e. 3-11 us at HBM
+    # speed — launch latency — so the kernels' bandwidth shows at 8 frames per launch (the reference's per-frame call is F = 1)
+    F8 = 8
+    fr8 = torch.stack([frames.view(i % F) for i in range(F8)]).contiguous()
+    table, _ = ops.esrgan_tile_table(1080, 1920, 2, 400, 10, 0)
+    tiles8, tab_dev = ops.esrgan_crop(fr8, table, 2, 0, torch.float16)
+    out8 = ops.esrgan_out_buffer(table, 2, torch.float16, dev, n_images=F8)
+    out8.uniform_(0.0, 1.0)
+    dst8 = ops.esrgan_stitch(out8, table, tab_dev, 2, 1080, 1920)
+    sync()
+    h.timing_enable((K.FSD_KERNEL_ESRGAN_CROP, K.FSD_KERNEL_ESRGAN_STITCH))
+    for _ in range(10):
+        ops.esrgan_crop(fr8, table, 2, 0, torch.float16, tab_dev=tab_dev, tiles=tiles8)
+        ops.esrgan_stitch(out8, table, tab_dev, 2, 1080, 1920, out=dst8)
+    s8 = by_kernel(h.timing_read())
+    h.timing_enable(())
+    for kid, name in ((K.FSD_KERNEL_ESRGAN_CROP, "k4_crop_8_frames"), (K.FSD_KERNEL_ESRGAN_STITCH, "k4_stitch_8_frames")):
+        ss = sorted(t for _, _, t in s8.get(kid, []))
+        if ss:
+            nb, t = s8[kid][0][0], ss[len(ss) // 2]
+            c5[name] = {"achieved": gbs(nb, t), "frac": gbs(nb, t) / peak, "unit": "GB/s", "launch_us": 1e3 * t, "bytes_per_launch": nb,
+                        "frames_per_launch": F8, "launches_timed": len(ss)}
     extra["c5"] = c5
     return extra
 

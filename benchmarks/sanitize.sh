@@ -9,32 +9,38 @@ set -u
 OUT=${1:-gpurun_out}
 mkdir -p "$OUT"
 SAN=${SAN:-/usr/local/cuda/bin/compute-sanitizer}
-TESTS=(
-  "tests/test_k1_gather_letterbox_gpu.py::test_slices_match_oracle"                    # -k below keeps the two small geometries
-  "tests/test_k1_gather_letterbox_gpu.py::test_sixteenths_path_equals_general_kernel_and_oracle"
-  "tests/test_k2_pose_decode_gpu.py::test_decode_matches_oracle"
-  "tests/test_k2_pose_decode_gpu.py::test_stage1_nms_and_finalize_match_oracle"
+TESTS=(  # one small parametrisation of each kernel (both dtypes / layouts where the kernel is templated on them)
+  "tests/test_k1_gather_letterbox_gpu.py::test_slices_match_oracle[dtype0-case4]"     # general TMA kernel, letterbox border, fp16
+  "tests/test_k1_gather_letterbox_gpu.py::test_slices_match_oracle[dtype1-case4]"     # ... fp32
+  "tests/test_k1_gather_letterbox_gpu.py::test_slices_match_oracle[dtype0-case5]"     # copy: sixteenths path
+  "tests/test_k1_gather_letterbox_gpu.py::test_sixteenths_path_equals_general_kernel_and_oracle[True-case4]"
+  "tests/test_k1_gather_letterbox_gpu.py::test_exact_2x_fast_path_equals_general_kernel_and_oracle[True-size0]"
+  "tests/test_k1_gather_letterbox_gpu.py::test_full_image_pass_matches_oracle[shape6]" # down-scale tap pattern Q = 10
+  "tests/test_k2_pose_decode_gpu.py::test_decode_matches_oracle[0.01-True-dtype1]"
+  "tests/test_k2_pose_decode_gpu.py::test_decode_matches_oracle[0.5-False-dtype0]"
+  "tests/test_k2_pose_decode_gpu.py::test_stage1_nms_and_finalize_match_oracle[shape1]"
   "tests/test_k3_merge_gpu.py::test_hand_made_edge_cases"
-  "tests/test_k3_merge_gpu.py::test_stage2_matches_sahi_oracle"
-  "tests/test_k3_merge_gpu.py::test_small_segments_in_a_large_capacity_launch"
+  "tests/test_k3_merge_gpu.py::test_stage2_matches_sahi_oracle[box_lex-0.5-IOS-GREEDYNMM]"
+  "tests/test_k3_merge_gpu.py::test_stage2_matches_sahi_oracle[index-0.5-IOU-NMM]"
+  "tests/test_k3_merge_gpu.py::test_stage2_matches_sahi_oracle[box_lex-0.5-IOU-NMS]"
+  "tests/test_k3_merge_gpu.py::test_small_segments_in_a_large_capacity_launch"        # both tiers + the cluster kernel
   "tests/test_k3_merge_gpu.py::test_null_parent_with_pre_cap"
   "tests/test_k4_esrgan_gpu.py::test_batched_crop_equals_per_frame_and_tma_equals_load_store"
   "tests/test_k4_esrgan_gpu.py::test_pre_pad_reflect"
-  "tests/test_backbone_kernels_gpu.py::test_bias_act_into_concat_slot_with_residual"
-  "tests/test_backbone_kernels_gpu.py::test_stem_conv_matches_torch"
-  "tests/test_backbone_kernels_gpu.py::test_pointwise_conv_matches_torch"
-  "tests/test_backbone_kernels_gpu.py::test_sppf_pool_equals_cascaded_maxpool"
+  "tests/test_k4_esrgan_gpu.py::test_round_half_even_and_clamp"
+  "tests/test_backbone_kernels_gpu.py::test_bias_act_into_concat_slot_with_residual[silu]"
+  "tests/test_backbone_kernels_gpu.py::test_stem_conv_matches_torch[shape2]"
+  "tests/test_backbone_kernels_gpu.py::test_pointwise_conv_matches_torch[silu-kn1]"
+  "tests/test_backbone_kernels_gpu.py::test_sppf_pool_equals_cascaded_maxpool[hw2]"
   "tests/test_widerface_eval.py::test_device_evaluator_reproduces_reference_evaluator_golden"
 )
-# one parametrisation each: small shapes, both dtypes where the kernel is templated on it
-KEXPR="(case4 or case5 or not case) and (not 2500) and (not 5000) and (GREEDYNMM-IOS-0.5-box_lex or not test_stage2_matches) and (shape2 or not test_stem) and (kn1 or not test_pointwise) and (hw2 or not test_sppf)"
 : > "$OUT/sanitize_summary.txt"
 for tool in memcheck racecheck initcheck; do
   log="$OUT/sanitize_${tool}.log"
   extra=""
   [ "$tool" = "initcheck" ] && extra="--track-unused-memory no"
   timeout 1500 "$SAN" --tool "$tool" $extra --error-exitcode 77 --print-limit 30 --launch-timeout 0 \
-      python -m pytest "${TESTS[@]}" -q -m gpu -k "$KEXPR" -p no:cacheprovider > "$log" 2>&1
+      python -m pytest "${TESTS[@]}" -q -m gpu -p no:cacheprovider > "$log" 2>&1
   rc=$?
   {
     echo "== $tool: exit code $rc (77 = sanitizer reported errors; 124 = timeout)"

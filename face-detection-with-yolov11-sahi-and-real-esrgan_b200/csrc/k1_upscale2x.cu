@@ -55,6 +55,17 @@ __device__ __forceinline__ uint32_t quant_norm_pair(uint32_t t) {
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+__device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) {  // hi32(a * b) + c, one IMAD.HI (FMA pipe)
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) {  // lo | hi << 16 as one IMAD (FMA pipe, not the ALU pipe)
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
+
 // A/B words of one source row for one channel: 4 words = output columns (2j..2j+7), two columns per word
 struct RowAB { uint32_t a[4], b[4]; };
 
@@ -63,14 +74,14 @@ __device__ __forceinline__ void row_ab(const uint32_t (&p)[6], RowAB& r) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t s = p[i] + p[i + 1] * 0x00030003u + (p[i + 2] << 16);
-        r.a[i] = ((s * 3u) >> 2) & 0x0fff0fffu;
+        r.a[i] = (((s * 3u) >> 2) & 0x0fff0fffu) + 0x00020002u;  // + the rounding constant of the vertical pass (A <= 765)
         r.b[i] = (s >> 2) & 0x03ff03ffu;
     }
 }
 
 __device__ __forceinline__ void out_row(const uint32_t (&x)[4], const uint32_t (&y)[4], uint32_t (&o)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = quant_norm_pair(x[i] + y[i] + 0x00020002u);
+    for (int i = 0; i < 4; ++i) o[i] = quant_norm_pair(x[i] + y[i]);  // exactly one of x, y is an A word: it carries the + 2
 }
 
 template <bool NHWC>
@@ -304,7 +315,7 @@ k1_sixteenths_kernel(const K16Params p) {
             // plane 0 <- source channel c0, plane 1 <- 1, plane 2 <- c2
             const uint32_t pA = p.reverse ? sv[2] : sv[0], pC = p.reverse ? sv[0] : sv[2];
             if (i & 1) {
-                dst[0][i >> 1] |= pA << 16; dst[1][i >> 1] |= sv[1] << 16; dst[2][i >> 1] |= pC << 16;
+                dst[0][i >> 1] = pack16(dst[0][i >> 1], pA); dst[1][i >> 1] = pack16(dst[1][i >> 1], sv[1]); dst[2][i >> 1] = pack16(dst[2][i >> 1], pC);
             } else {
                 dst[0][i >> 1] = pA; dst[1][i >> 1] = sv[1]; dst[2][i >> 1] = pC;
             }
@@ -375,9 +386,10 @@ k1_sixteenths_kernel(const K16Params p) {
             for (int j = 0; j < 4; ++j) {
                 // A is masked to its 10-bit lanes; B may keep the <= 6 stray bits the shift moved into bits 10..15 of the
                 // low lane: A + B + 2 <= 1023 + (63 << 10) cannot carry into the high lane, and the final mask drops them
-                const uint32_t A = __umulhi(cur[c][j], f0) & 0x03ff03ffu;
-                const uint32_t B = __umulhi(nxt[c][j], f1);
-                o[c][j] = quant_norm_pair(A + B + 0x00020002u);
+                // hi32(x * f) + addend is ONE IMAD.HI (mad.hi): the rounding constant rides on the first product (A <= 1020 per
+                // lane, so + 2 cannot carry out of its 10 bits), the masked A + 2 on the second
+                const uint32_t A2 = mad_hi(cur[c][j], f0, 0x00020002u) & 0x03ff03ffu;
+                o[c][j] = quant_norm_pair(mad_hi(nxt[c][j], f1, A2));
             }
         store_row(y, o);
     }

@@ -199,8 +199,9 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     __shared__ float4 s_kbox[64];
     __shared__ int s_kcat[64];
     __shared__ uint32_t s_kkey[64];
-    __shared__ uint32_t s_rem[130];      // removed bits of the whole segment (4096) + slack for the 64-bit window
+    __shared__ uint32_t s_rem[132];      // removed bits of the whole segment (4096) + slack for the 64-bit windows
     __shared__ unsigned long long s_keepmask, s_rembefore, s_remafter;
+    __shared__ uint32_t s_rem_snapshot[2];
     __shared__ int s_kcount, s_ktotal, s_stop, s_flagged;
 
     const int s = blockIdx.x;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
             p.parent[g] = -1;  // cut by the pre-NMS cap
         }
     }
-    for (int i = tid; i < 130; i += T) s_rem[i] = 0;
+    for (int i = tid; i < 132; i += T) s_rem[i] = 0;
     if (tid == 0) { s_ktotal = 0; s_stop = 0; s_kcount = 0; s_flagged = 0; }
     k3_bar(T);
     auto keyhi = [&](int r) -> uint32_t { return mc.tie_rule ? (uint32_t)(keys[r] >> 32) : 0u; };
@@ -298,7 +299,8 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
                 uint64_t keepmask = 0;
                 const int kt = s_ktotal;
                 int cnt = 0, stop = 0;
-                for (int b = 0; b < cn; ++b) {
+                const uint64_t live = ~remw & (cn == 64 ? ~0ull : ((1ull << cn) - 1ull));
+                for (int b = 0; b < cn && live != 0; ++b) {  // (a chunk whose ranks earlier keeps removed already has nothing to resolve)
                     const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
                     if (!((remw >> b) & 1ull)) {
                         if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
                     s_rem[w0 + 1] = (uint32_t)(remw >> 32);
                     s_keepmask = keepmask; s_rembefore = before; s_remafter = remw;
                     s_kcount = cnt; s_ktotal = kt + cnt; s_stop = stop;
+                    s_rem_snapshot[0] = s_rem[w0 + 2]; s_rem_snapshot[1] = s_rem[w0 + 3];  // next chunk, before this chunk's sweep
                 }
             }
             k3_bar(T);
@@ -377,7 +380,14 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
                         }
                     }
                 }
-                if (c0 + 64 < m) chunk_bits(c0 + 64, s_diag[(c + 1) & 1]);  // off the critical path: same phase as the sweep
+                // next chunk's match bits, off the critical path (same phase as the sweep) — unless the keeps so far have
+                // already removed every rank of it (dense duplicates: most chunks after the first few), which is final
+                if (c0 + 64 < m) {
+                    const int w1 = (c0 + 64) >> 5, cn1 = min(64, m - c0 - 64);
+                    const uint64_t r1 = (uint64_t)s_rem_snapshot[0] | ((uint64_t)s_rem_snapshot[1] << 32);
+                    (void)w1;
+                    if ((~r1 & (cn1 == 64 ? ~0ull : ((1ull << cn1) - 1ull))) != 0) chunk_bits(c0 + 64, s_diag[(c + 1) & 1]);
+                }
             }
             k3_bar(T);
             if (stop) break;
@@ -1000,16 +1010,37 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
         if (ld_cg(&sc->stop)) break;  // uniform over the cluster
         if (tid < kc) { s_kbox[tid] = ld_cg(&sc->kbox[tid]); s_kcat[tid] = ld_cg(&sc->kcat[tid]); s_klist[tid] = ld_cg(&sc->klist[tid]); s_kkey[tid] = ld_cg(&sc->kkey[tid]); }
         __syncthreads();
-        for (int j = c0 + cn + gtid; j < m; j += TT) {
-            if ((ld_cg(rem + (j >> 5)) >> (j & 31)) & 1u) continue;
-            const float4 bj = ld_cg(sbox + j);
-            const int cj = ld_cg(scat + j);
-            const uint32_t kj = keyhi(j);
-            for (int k = 0; k < kc; ++k) {
-                if (suppresses(s_kbox[k], bj, s_kcat[k], cj, s_kkey[k], kj, mc)) {
-                    atomicOr(rem + (j >> 5), 1u << (j & 31));
-                    __stcg(parent + j, s_klist[k]);
-                    break;
+        {
+            const bool quick = mc.thr > 0.0;  // disjoint boxes cannot match a positive threshold: reject four keeps at a time
+            for (int j = c0 + cn + gtid; j < m; j += TT) {
+                if ((ld_cg(rem + (j >> 5)) >> (j & 31)) & 1u) continue;
+                const float4 bj = ld_cg(sbox + j);
+                int cj = 0;
+                uint32_t kj = 0;
+                bool loaded = false, hit = false;
+                for (int k0 = 0; k0 < kc && !hit; k0 += 4) {
+                    const int kn = min(4, kc - k0);
+                    unsigned ov = 0xfu;
+                    if (quick) {
+                        ov = 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 a = s_kbox[min(k0 + u, kc - 1)];
+                            if (fminf(a.z, bj.z) > fmaxf(a.x, bj.x) && fminf(a.w, bj.w) > fmaxf(a.y, bj.y)) ov |= 1u << u;
+                        }
+                    }
+                    if (ov == 0) continue;
+                    if (!loaded) { cj = ld_cg(scat + j); kj = keyhi(j); loaded = true; }  // only ranks that overlap a keep pay for these
+                    for (int u = 0; u < kn; ++u) {
+                        if (!((ov >> u) & 1u)) continue;
+                        const int k = k0 + u;
+                        if (suppresses(s_kbox[k], bj, s_kcat[k], cj, s_kkey[k], kj, mc)) {
+                            atomicOr(rem + (j >> 5), 1u << (j & 31));
+                            __stcg(parent + j, s_klist[k]);
+                            hit = true;
+                            break;
+                        }
+                    }
                 }
             }
         }

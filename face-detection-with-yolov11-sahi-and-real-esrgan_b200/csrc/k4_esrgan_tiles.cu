@@ -327,6 +327,7 @@ attach_keypoints_kernel(const float* __restrict__ merged, int merged_stride,
     const int s = blockIdx.x;
     const int mo = m_off[s], mn = m_cnt[s], dof = d_off[s], dn = d_cnt[s];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if ((int)(blockIdx.y * nwarps) >= mn) return;  // nothing for this CTA (uniform)
     const bool staged = dn <= smem_boxes;  // uniform over the CTA
     if (staged) {
         for (int j = threadIdx.x; j < dn; j += blockDim.x)
@@ -336,7 +337,8 @@ attach_keypoints_kernel(const float* __restrict__ merged, int merged_stride,
     auto det_box = [&](int j) -> float4 {
         return staged ? s_det[j] : *reinterpret_cast<const float4*>(dets + (size_t)(dof + j) * det_stride);
     };
-    for (int i = warp; i < mn; i += nwarps) {
+    // blockIdx.y splits one image's merged boxes over several CTAs (an image with thousands of boxes must not be one CTA's job)
+    for (int i = blockIdx.y * nwarps + warp; i < mn; i += nwarps * gridDim.y) {
         const float4 mb = *reinterpret_cast<const float4*>(merged + (size_t)(mo + i) * merged_stride);
         const double bx1 = mb.x, by1 = mb.y, bx2 = mb.z, by2 = mb.w;
         int exact = -1, best = -1;
@@ -496,7 +498,7 @@ extern "C" int fsd_attach_keypoints(fsd_handle_t h, const float* merged, int mer
     const int smem_boxes = 4096;  // 64 KB: images with more per-slice detections scan global memory instead (config 3's 9900)
     FSD_CUDA(cudaFuncSetAttribute(attach_keypoints_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_boxes * 16));
     TimedLaunch timed(h, FSD_KERNEL_ATTACH, S, 0, (cudaStream_t)stream_);
-    attach_keypoints_kernel<<<S, 256, smem_boxes * 16, (cudaStream_t)stream_>>>(merged, merged_stride, m_off, m_cnt, dets, det_stride, d_off, d_cnt, src_index, smem_boxes);
+    attach_keypoints_kernel<<<dim3(S, 8), 256, smem_boxes * 16, (cudaStream_t)stream_>>>(merged, merged_stride, m_off, m_cnt, dets, det_stride, d_off, d_cnt, src_index, smem_boxes);
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     return FSD_OK;

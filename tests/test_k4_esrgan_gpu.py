@@ -103,10 +103,11 @@ def test_batched_crop_equals_per_frame_and_tma_equals_load_store(cuda_device, mo
         monkeypatch.setenv("FSD_K4_NO_TMA", "1")
         plain, _ = ops.esrgan_crop(frames, table, 2, 0, torch.float16)
         monkeypatch.delenv("FSD_K4_NO_TMA")
-        n = ops.esrgan_tile_elems(table)
         for i in range(3):
-            assert torch.equal(batch[i, :n], singles[i][:n]) and torch.equal(batch[i, :n], plain[i, :n])
-        assert float(batch[:, :n].float().max()) <= 1.0 and float(batch[:, :n].float().min()) >= 0.0
+            for row in table:  # (the 0-7 padding elements between packed tiles are never written: compare tile views)
+                a = ops.tile_view(batch[i], row)
+                assert torch.equal(a, ops.tile_view(singles[i], row)) and torch.equal(a, ops.tile_view(plain[i], row))
+                assert float(a.float().max()) <= 1.0 and float(a.float().min()) >= 0.0
 
 
 @pytest.mark.parametrize("size,tile,scale", [((61, 77), 32, 2), ((130, 203), 64, 4), ((97, 64), 200, 2)])
