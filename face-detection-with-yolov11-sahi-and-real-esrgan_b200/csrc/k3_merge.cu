@@ -874,7 +874,8 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     __shared__ uint32_t s_kkey[64];
     __shared__ int s_klist[64];
     __shared__ unsigned long long s_keepmask, s_rembefore, s_remafter;
-    extern __shared__ __align__(16) uint8_t k3c_smem[];  // sort block: P/8 keys (8 B) + values (4 B)
+    __shared__ int s_kcount, s_ktotal, s_stop;
+    extern __shared__ __align__(16) uint8_t k3c_smem[];  // sort block: P/8 keys (8 B) + values (4 B); then the cache of this CTA's own ranks (24 B each)
 
     const int s = blockIdx.x / K3_CLUSTER;
     const int crank = (int)cluster.block_rank();
@@ -912,7 +913,7 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
         }
         __stcg(keys + i, key); __stcg(vals + i, v);
     }
-    if (gtid == 0) { sc->ktotal = 0; sc->stop = 0; sc->kcount = 0; }
+    if (gtid == 0) sc->pad = 0;
     cluster.sync();
     uint64_t* lk = reinterpret_cast<uint64_t*>(k3c_smem);
     uint32_t* lv = reinterpret_cast<uint32_t*>(k3c_smem + (size_t)(p.P / K3_CLUSTER) * 8);
@@ -934,7 +935,9 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     for (int i = gtid; i < (m + 31) / 32 + 2; i += TT) __stcg(rem + i, 0u);
     cluster.sync();
     auto keyhi = [&](int r) -> uint32_t { return mc.tie_rule ? (uint32_t)(ld_cg(keys + r) >> 32) : 0u; };
-    // CTA 0: stage a chunk's boxes and compute its 64x64 match bits (double buffered: chunk c + 1 while chunk c is swept)
+    // Every CTA stages a chunk's boxes and computes its 64x64 match bits itself (double buffered: chunk c + 1 while chunk c is
+    // swept): the chunk is then RESOLVED REDUNDANTLY by one warp of every CTA — identical inputs, identical keeps — so no
+    // keep list has to travel between CTAs and ONE cluster barrier per chunk is enough (it publishes the removed bits).
     auto stage_chunk = [&](int c0, int buf) {
         const int cn = min(64, m - c0);
         if (tid < cn) { s_cbox[buf][tid] = ld_cg(sbox + c0 + tid); s_ccat[buf][tid] = ld_cg(scat + c0 + tid); s_ckey[buf][tid] = keyhi(c0 + tid); }
@@ -949,75 +952,81 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
         }
         __syncthreads();
     };
-    if (crank == 0) stage_chunk(0, 0);
+    // The ranks a thread sweeps are fixed for the whole scan (rank = gtid + k * 4096): their boxes, categories and score keys
+    // are cached in this CTA's shared memory once (the sort block is free now), so the sweep never goes back to L2 for them.
+    float4* obox = reinterpret_cast<float4*>(k3c_smem);
+    int* ocat = reinterpret_cast<int*>(k3c_smem + (size_t)(p.P / K3_CLUSTER) * 16);
+    uint32_t* okey = reinterpret_cast<uint32_t*>(k3c_smem + (size_t)(p.P / K3_CLUSTER) * 20);
+    uint32_t alive = 0;  // bit k: rank gtid + k * TT is not removed yet and not passed by the scan
+    for (int k = 0; gtid + k * TT < m; ++k) {
+        const int j = gtid + k * TT;
+        obox[k * T + tid] = ld_cg(sbox + j);
+        ocat[k * T + tid] = ld_cg(scat + j);
+        okey[k * T + tid] = keyhi(j);
+        alive |= 1u << k;
+    }
+    if (tid == 0) { s_ktotal = 0; s_stop = 0; s_kcount = 0; }
+    stage_chunk(0, 0);
 
     // ---- 2. greedy scan in chunks of 64 ranks ---------------------------------------------------------------
     for (int c0 = 0, c = 0; c0 < m; c0 += 64, ++c) {
         const int cn = min(64, m - c0);
         const int buf = c & 1;
-        if (crank == 0) {
-            const uint32_t* dg = s_diag[buf];
-            if (tid < 32) {
-                const uint64_t rowA = lane < cn ? ((uint64_t)dg[2 * lane] | ((uint64_t)dg[2 * lane + 1] << 32)) : 0ull;
-                const uint64_t rowB = lane + 32 < cn ? ((uint64_t)dg[2 * lane + 64] | ((uint64_t)dg[2 * lane + 65] << 32)) : 0ull;
-                const int w0 = c0 >> 5;
-                uint64_t remw = (uint64_t)ld_cg(rem + w0) | ((uint64_t)ld_cg(rem + w0 + 1) << 32);
-                const uint64_t before = remw;
-                uint64_t keepmask = 0;
-                const int kt = ld_cg(&sc->ktotal);
-                int cnt = 0, stop = 0;
-                for (int b = 0; b < cn; ++b) {
-                    const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
-                    if (!((remw >> b) & 1ull)) {
-                        if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
-                        keepmask |= 1ull << b;
-                        ++cnt;
-                        remw |= row;
-                    }
-                }
-                for (int pos = lane; pos < 64; pos += 32) {
-                    if ((keepmask >> pos) & 1ull) {
-                        const int idx = __popcll(keepmask & ((1ull << pos) - 1ull));
-                        const int kr = c0 + pos;
-                        sc->klist[idx] = kr; sc->kbox[idx] = s_cbox[buf][pos]; sc->kcat[idx] = s_ccat[buf][pos]; sc->kkey[idx] = s_ckey[buf][pos];
-                        __stcg(keepr + kt + idx, kr);
-                        __stcg(parent + kr, kr);
-                    }
-                }
-                if (lane == 0) {
-                    __stcg(rem + w0, (uint32_t)remw);
-                    __stcg(rem + w0 + 1, (uint32_t)(remw >> 32));
-                    s_keepmask = keepmask; s_rembefore = before; s_remafter = remw;
-                    sc->kcount = cnt; sc->ktotal = kt + cnt; sc->stop = stop;
+        const uint32_t* dg = s_diag[buf];
+        if (tid < 32) {
+            const uint64_t rowA = lane < cn ? ((uint64_t)dg[2 * lane] | ((uint64_t)dg[2 * lane + 1] << 32)) : 0ull;
+            const uint64_t rowB = lane + 32 < cn ? ((uint64_t)dg[2 * lane + 64] | ((uint64_t)dg[2 * lane + 65] << 32)) : 0ull;
+            const int w0 = c0 >> 5;
+            uint64_t remw = (uint64_t)ld_cg(rem + w0) | ((uint64_t)ld_cg(rem + w0 + 1) << 32);
+            const uint64_t before = remw;
+            uint64_t keepmask = 0;
+            const int kt = s_ktotal;
+            int cnt = 0, stop = 0;
+            const uint64_t live = ~remw & (cn == 64 ? ~0ull : ((1ull << cn) - 1ull));
+            for (int b = 0; b < cn && live != 0; ++b) {
+                const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
+                if (!((remw >> b) & 1ull)) {
+                    if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
+                    keepmask |= 1ull << b;
+                    ++cnt;
+                    remw |= row;
                 }
             }
-            __syncthreads();
-            if (tid < cn) {  // parents of the ranks this chunk's own keeps removed: the first keep whose row holds the rank
-                const uint64_t keepmask = s_keepmask;
-                const int q = tid;
-                if (!((s_rembefore >> q) & 1ull) && !((keepmask >> q) & 1ull) && ((s_remafter >> q) & 1ull)) {
-                    uint64_t km = keepmask & ((1ull << q) - 1ull);
-                    while (km) {
-                        const int b = __ffsll((long long)km) - 1;
-                        km &= km - 1;
-                        if ((dg[2 * b + (q >> 5)] >> (q & 31)) & 1u) { __stcg(parent + c0 + q, c0 + b); break; }
-                    }
+            for (int pos = lane; pos < 64; pos += 32) {
+                if ((keepmask >> pos) & 1ull) {
+                    const int idx = __popcll(keepmask & ((1ull << pos) - 1ull));
+                    const int kr = c0 + pos;
+                    s_klist[idx] = kr; s_kbox[idx] = s_cbox[buf][pos]; s_kcat[idx] = s_ccat[buf][pos]; s_kkey[idx] = s_ckey[buf][pos];
+                    if (crank == 0) { __stcg(keepr + kt + idx, kr); __stcg(parent + kr, kr); }
+                }
+            }
+            if (lane == 0) {
+                s_keepmask = keepmask; s_rembefore = before; s_remafter = remw;
+                s_kcount = cnt; s_ktotal = kt + cnt; s_stop = stop;
+            }
+        }
+        __syncthreads();
+        const int kc = s_kcount, stop = s_stop;
+        if (crank == 0 && tid < cn) {  // parents of the ranks this chunk's own keeps removed: the first keep whose row holds the rank
+            const uint64_t keepmask = s_keepmask;
+            const int q = tid;
+            if (!((s_rembefore >> q) & 1ull) && !((keepmask >> q) & 1ull) && ((s_remafter >> q) & 1ull)) {
+                uint64_t km = keepmask & ((1ull << q) - 1ull);
+                while (km) {
+                    const int b = __ffsll((long long)km) - 1;
+                    km &= km - 1;
+                    if ((dg[2 * b + (q >> 5)] >> (q & 31)) & 1u) { __stcg(parent + c0 + q, c0 + b); break; }
                 }
             }
         }
-        cluster.sync();  // the chunk's keeps (scratch) and the updated removed bits are visible to every CTA
-        const int kc = ld_cg(&sc->kcount);
-        if (ld_cg(&sc->stop)) break;  // uniform over the cluster
-        if (tid < kc) { s_kbox[tid] = ld_cg(&sc->kbox[tid]); s_kcat[tid] = ld_cg(&sc->kcat[tid]); s_klist[tid] = ld_cg(&sc->klist[tid]); s_kkey[tid] = ld_cg(&sc->kkey[tid]); }
-        __syncthreads();
-        {
+        if (!stop) {
             const bool quick = mc.thr > 0.0;  // disjoint boxes cannot match a positive threshold: reject four keeps at a time
-            for (int j = c0 + cn + gtid; j < m; j += TT) {
-                if ((ld_cg(rem + (j >> 5)) >> (j & 31)) & 1u) continue;
-                const float4 bj = ld_cg(sbox + j);
-                int cj = 0;
-                uint32_t kj = 0;
-                bool loaded = false, hit = false;
+            for (int k = 0; (alive >> k) != 0; ++k) {
+                if (!((alive >> k) & 1u)) continue;
+                const int j = gtid + k * TT;
+                if (j < c0 + cn) { alive &= ~(1u << k); continue; }  // the scan has passed this rank
+                const float4 bj = obox[k * T + tid];
+                bool hit = false;
                 for (int k0 = 0; k0 < kc && !hit; k0 += 4) {
                     const int kn = min(4, kc - k0);
                     unsigned ov = 0xfu;
@@ -1030,25 +1039,26 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
                         }
                     }
                     if (ov == 0) continue;
-                    if (!loaded) { cj = ld_cg(scat + j); kj = keyhi(j); loaded = true; }  // only ranks that overlap a keep pay for these
                     for (int u = 0; u < kn; ++u) {
                         if (!((ov >> u) & 1u)) continue;
-                        const int k = k0 + u;
-                        if (suppresses(s_kbox[k], bj, s_kcat[k], cj, s_kkey[k], kj, mc)) {
+                        const int kk = k0 + u;
+                        if (suppresses(s_kbox[kk], bj, s_kcat[kk], ocat[k * T + tid], s_kkey[kk], okey[k * T + tid], mc)) {
                             atomicOr(rem + (j >> 5), 1u << (j & 31));
-                            __stcg(parent + j, s_klist[k]);
+                            __stcg(parent + j, s_klist[kk]);
+                            alive &= ~(1u << k);
                             hit = true;
                             break;
                         }
                     }
                 }
             }
+            if (c0 + 64 < m) stage_chunk(c0 + 64, buf ^ 1);  // next chunk's boxes + match bits, off the critical path
         }
-        if (crank == 0 && c0 + 64 < m) stage_chunk(c0 + 64, buf ^ 1);  // next chunk's match bits, off the critical path
-        cluster.sync();  // all claims of this chunk are in place before the next chunk is resolved
+        cluster.sync();  // the removed bits of this chunk's sweep are visible to every CTA's next resolve
+        if (stop) break;
     }
-    cluster.sync();
-    const int K = ld_cg(&sc->ktotal);
+    __syncthreads();
+    const int K = s_ktotal;  // every CTA resolved every chunk: the same count everywhere
     const bool tie_merge = mc.tie_rule && p.type == FSD_GREEDYNMM;
 
     // ---- tie rule: a keep claims the earlier equal-score keeps it matches (see k3_merge_kernel).  Here the claim is written
@@ -1068,7 +1078,7 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
             for (int q = kr + 1; q < m && keyhi(q) == kk; ++q) {
                 if ((ld_cg(runs + q) & K3C_ISKEEP) && suppresses(ld_cg(sbox + q), bk, ld_cg(scat + q), ck, kk, kk, mc)) {
                     __stcg(parent + kr, q);
-                    atomicOr(runs + q, K3_HASB);
+                    if (!(atomicOr(runs + q, K3_HASB) & K3_HASB)) atomicAdd(&sc->pad, 1);  // sc->pad counts the flagged keeps
                     break;
                 }
             }
@@ -1148,13 +1158,28 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
             __stcg(scat + kr, kcat);
         }
     };
-    for (int i = gtid; i < K; i += TT)
-        if (!(ld_cg(runs + ld_cg(keepr + i)) & K3_HASB)) fold_keep(i);
-    if (tie_merge) {
+    const int flagged = tie_merge ? ld_cg(&sc->pad) : 0;  // uniform over the cluster (read after the cluster barriers above)
+    uint32_t* fbits = rem;  // the removed bits are dead after the scan: bitmap of the flagged keeps by KEEP INDEX
+    if (flagged) {
+        for (int i = gtid; i < (K + 31) / 32 + 1; i += TT) __stcg(fbits + i, 0u);
         cluster.sync();
-        if (gtid == 0)  // keeps whose list holds an earlier keep, in rank order (rare: exact score ties between overlapping keeps)
-            for (int i = 0; i < K; ++i)
-                if (ld_cg(runs + ld_cg(keepr + i)) & K3_HASB) fold_keep(i);
+    }
+    for (int i = gtid; i < K; i += TT) {
+        if (flagged && (ld_cg(runs + ld_cg(keepr + i)) & K3_HASB)) atomicOr(fbits + (i >> 5), 1u << (i & 31));
+        else fold_keep(i);
+    }
+    if (flagged) {
+        cluster.sync();
+        if (gtid == 0) {  // keeps whose list holds an earlier keep, in rank order (rare: exact score ties between overlapping keeps)
+            for (int w = 0; w < (K + 31) / 32; ++w) {
+                uint32_t bits = ld_cg(fbits + w);
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    fold_keep(w * 32 + b);
+                }
+            }
+        }
     }
 }
 
@@ -1252,7 +1277,7 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     }
     if (p.P > K3_SMEM_MAX_P) {
         // segments above 4096 boxes: a cluster of 8 CTAs each (k3_merge_cluster_kernel)
-        const size_t csmem = (size_t)(p.P / K3_CLUSTER) * 12;
+        const size_t csmem = (size_t)(p.P / K3_CLUSTER) * 24;  // sort block (12 B / key) and, after it, the own-rank cache (24 B / rank)
         FSD_CUDA(cudaFuncSetAttribute(k3_merge_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         TimedLaunch timed(h, FSD_KERNEL_MERGE, S, -max_segment, stream);
         k3_merge_cluster_kernel<<<S * K3_CLUSTER, 512, csmem, stream>>>(p);

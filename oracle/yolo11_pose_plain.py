@@ -195,18 +195,24 @@ def build_plain_yolo11n_pose(seed: int = 0, state_dict=None) -> PlainYOLO11Pose:
                     fan_in = m.in_channels // m.groups * m.kernel_size[0] * m.kernel_size[1]
                     m.weight.copy_(torch.randn(m.weight.shape, generator=gen) * (1.6 / math.sqrt(fan_in)))
                     m.bias.zero_()
-        # give the raw head outputs trained-detector-like statistics on a seeded noise image (class logits ~ N(-6, 2): a
-        # fraction of a percent of the anchors passes conf 0.5; DFL logits std 1.5; key-point offsets O(1))
+        # give the raw head outputs trained-detector-like statistics (class logits ~ N(-6, 2): a fraction of a percent of the
+        # anchors passes conf 0.5; DFL logits std 1.5; key-point offsets O(1)) on one synthetic WIDER-like image up-scaled 2x
+        # like a SAHI slice — the same recipe and seed as the bench's GPU arm uses for its random-init network, so both arms
+        # see the same detection load (the per-detection Python work of the reference path is a large part of its time)
+        from fsd_b200.synthetic import make_image  # data generator only (numpy): no network code
+
         model.eval()
         with torch.no_grad():
-            sample = torch.nn.functional.avg_pool2d(torch.rand((1, 3, 644, 644), generator=gen), 5, stride=1)
+            img, _ = make_image(10_000, 320, 320, seed=seed)
+            sample = torch.from_numpy(img).permute(2, 0, 1)[None].float() / 255.0
+            sample = torch.nn.functional.interpolate(sample, scale_factor=2.0, mode="bilinear", align_corners=False)
             for lvl, outs in enumerate(model(sample)):
                 for branch, t, mean_to, std_to in ((model.head.cv2, outs[0], 1.0, 1.5), (model.head.cv3, outs[1], -6.0, 2.0),
                                                    (model.head.cv4, outs[2], 0.0, 1.0)):
                     conv = branch[lvl][-1]
-                    scale = std_to / max(float(t.std()), 1e-6)
+                    scale = std_to / max(float(t.float().std()), 1e-6)
                     conv.weight.mul_(scale)
-                    conv.bias.copy_((conv.bias - float(t.mean())) * scale + mean_to)
+                    conv.bias.copy_((conv.bias - float(t.float().mean())) * scale + mean_to)
     for p in model.parameters():
         p.requires_grad_(False)
     return model.eval()

@@ -174,5 +174,5 @@ def test_full_size_properties(cuda_device, cfg):
         rows[:, :4] = torch.from_numpy(bx[lo:hi]).to(cuda_device)
         rows[:, 4] = torch.from_numpy(a.scores[lo:hi]).to(cuda_device)
         res = ops.merge_segments(rows, torch.zeros(1, dtype=torch.int32, device=cuda_device), None, hi - lo, merge_type="NMS",
-                                 metric="IOS", thr=0.5, precision="fp64")
+                                 metric="IOS", thr=0.5, precision="fp64", tie_rule=eng.tie_rule)
         assert int(res["keep_count"][0]) == hi - lo
