@@ -84,8 +84,11 @@ __device__ __forceinline__ void out_row(const uint32_t (&x)[4], const uint32_t (
     for (int i = 0; i < 4; ++i) o[i] = quant_norm_pair(x[i] + y[i]);  // exactly one of x, y is an A word: it carries the + 2
 }
 
-template <bool NHWC>
-__global__ void __launch_bounds__(UP2_THREADS)
+// MB = minimum resident CTAs per SM the register allocation must allow: 5 -> 88-91 registers (30 % occupancy), 6 -> 80, no
+// spills, 7 -> 72 with one 4-byte spill.  The kernel waits on scattered byte loads (top stall: long scoreboard), so more
+// resident warps hide more latency; FSD_K1_MINBLOCKS selects the variant for the measurement (benchmarks/kernels.py k1).
+template <bool NHWC, int MB>
+__global__ void __launch_bounds__(UP2_THREADS, MB)
 k1_upscale2x_kernel(const Up2Params p) {
     const int b = blockIdx.z;
     const int v = blockIdx.x * UP2_THREADS + threadIdx.x;  // 8-column output vector index
@@ -182,8 +185,12 @@ int launch_upscale2x(fsd_context* h, const uint8_t* images, int64_t row_pitch, i
     dim3 grid((vecs + UP2_THREADS - 1) / UP2_THREADS, (src_h + 1 + UP2_ROWS - 1) / UP2_ROWS, B);
     {
         TimedLaunch timed(h, FSD_KERNEL_GATHER, B, src_w, stream);
-        if (nhwc) k1_upscale2x_kernel<true><<<grid, UP2_THREADS, 0, stream>>>(p);
-        else k1_upscale2x_kernel<false><<<grid, UP2_THREADS, 0, stream>>>(p);
+        const int mb = getenv("FSD_K1_MINBLOCKS") ? atoi(getenv("FSD_K1_MINBLOCKS")) : 6;
+#define UP2_GO(MBV)                                                                  \
+        if (nhwc) k1_upscale2x_kernel<true, MBV><<<grid, UP2_THREADS, 0, stream>>>(p); \
+        else k1_upscale2x_kernel<false, MBV><<<grid, UP2_THREADS, 0, stream>>>(p);
+        if (mb <= 5) { UP2_GO(5) } else if (mb == 6) { UP2_GO(6) } else { UP2_GO(7) }
+#undef UP2_GO
     }
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
