@@ -102,16 +102,31 @@ __global__ void __launch_bounds__(K2_THREADS)
 k2_pose_decode_kernel(const K2Levels L, int B, float* __restrict__ cand, int cap, const int* __restrict__ count) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * K2_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * K2_THREADS) >> 5;
-    // warps walk the concatenation of all lists: survivor t of the grid = entry b, slot t - start(b)
-    int b = 0, start = 0, nb = min(__ldg(count), cap);
+    // warps walk the concatenation of all lists: survivor t of the grid = entry b, slot t - start(b).  The entry is found with
+    // lane-parallel loads of 32 counters + a warp scan per step (a serial walk over the counters is a chain of dependent L2
+    // loads: ~50 us for 96 entries, more than the decode itself)
     for (int t = gw;; t += nw) {
-        while (b < B && t >= start + nb) {
-            start += nb;
-            ++b;
-            if (b < B) nb = min(__ldg(count + b), cap);
+        int b = -1, slot = 0, start = 0;
+        for (int base = 0; base < B; base += 32) {
+            const int c = base + lane < B ? min(__ldg(count + base + lane), cap) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            if (t < start + tot) {
+                const unsigned m = __ballot_sync(0xffffffffu, t < start + incl);
+                const int l = __ffs(m) - 1;
+                b = base + l;
+                slot = t - (start + __shfl_sync(0xffffffffu, incl - c, l));
+                break;
+            }
+            start += tot;
         }
-        if (b >= B) break;
-        float* row = cand + ((size_t)b * cap + (t - start)) * ROW;
+        if (b < 0) break;  // t is past the last survivor (uniform over the warp)
+        float* row = cand + ((size_t)b * cap + slot) * ROW;
         const int sa = __float_as_int(row[5]);
         int sl = 0;
         if (sa >= L.a_begin[1]) sl = 1;

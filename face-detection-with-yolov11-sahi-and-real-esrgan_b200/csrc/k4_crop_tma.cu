@@ -72,48 +72,54 @@ k4_crop_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t* __re
         srun[c] = s_out + (size_t)c * out_plane_bytes + (reinterpret_cast<uintptr_t>(grun[c]) & 15);
     }
     mbar_wait(&s_bar, 0);
+    // one warp per tile row, lanes over the row's 8-pixel groups: no division, and everything that depends on the row or on
+    // the tile (word phase of the staged bytes, alignment class of the shared stores) is warp-uniform
     const int vecs = (pw + 7) >> 3;
     const int sh = (off_b & 3) * 8;
-    const bool odd_word = ((off_b >> 2) & 1) != 0;
-    for (int it = tid; it < rows * vecs; it += CR_THREADS) {
-        const int r = it / vecs, g = it - r * vecs, x = g << 3;
-        const int nx = min(8, pw - x);
-        const int bp = off_b + 24 * g;   // first byte of the group inside the staged 1280-byte row
-        const int pi = bp >> 3;          // its 8-byte pair; (bp & 7) == (off_b & 7) for every group
-        uint32_t w[8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int p = min(pi + k, 2 * CR_BOXW / 2 - 1);  // 160 pairs per row: the clamp only touches bytes no pixel uses
-            const uint32_t* src = s_in + (p >= CR_BOXW / 2 ? CR_ROWS * CR_BOXW : 0) + r * CR_BOXW + (p % (CR_BOXW / 2)) * 2;
-            const uint2 v = *reinterpret_cast<const uint2*>(src);
-            w[2 * k] = v.x; w[2 * k + 1] = v.y;
-        }
-        uint32_t s[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const uint32_t lo = odd_word ? w[k + 1] : w[k], hi = odd_word ? w[k + 2] : w[k + 1];
-            s[k] = __funnelshift_r(lo, hi, sh);  // stream word k = bytes 4k .. 4k+3 of the group's 24 (B,G,R per pixel)
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {  // BGR channel c -> plane 2 - c (RGB)
-            uint32_t o[4];
+    const int wo = (off_b >> 2) & 1;  // the group's first byte lies in word `wo` of its 8-byte pair
+    const int lane = tid & 31, r = tid >> 5;
+    if (r < rows) {
+        const uint32_t* in0 = s_in + r * CR_BOXW;
+        for (int g = lane; g < vecs; g += 32) {
+            const int x = g << 3;
+            const int nx = min(8, pw - x);
+            const int pi = (off_b + 24 * g) >> 3;  // first 8-byte pair of the group inside the staged 1280-byte row
+            uint32_t w[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int ia = 6 * k + c, ib = ia + 3;
-                const uint32_t sel = (uint32_t)(ia & 3) | ((uint32_t)(4 * ((ib >> 2) - (ia >> 2)) + (ib & 3)) << 8);
-                o[k] = cr_norm255_pair(__byte_perm(s[ia >> 2], s[ib >> 2], sel) & 0x00ff00ffu);
+                const int p = min(pi + k, CR_BOXW - 1);  // 160 pairs per row: the clamp only touches bytes no pixel uses
+                const uint2 v = *reinterpret_cast<const uint2*>(in0 + (p >= CR_BOXW / 2 ? CR_ROWS * CR_BOXW + (p - CR_BOXW / 2) * 2 : p * 2));
+                w[2 * k] = v.x; w[2 * k + 1] = v.y;
             }
-            uint8_t* q = srun[2 - c] + ((size_t)r * pw + x) * 2;
-            if (nx == 8) {
-                const uint32_t a = smem_u32(q);
-                if ((a & 15) == 0) *reinterpret_cast<uint4*>(q) = make_uint4(o[0], o[1], o[2], o[3]);
-                else if ((a & 7) == 0) { reinterpret_cast<uint2*>(q)[0] = make_uint2(o[0], o[1]); reinterpret_cast<uint2*>(q)[1] = make_uint2(o[2], o[3]); }
-                else {
+            uint32_t s[6];  // stream word k = bytes 4k .. 4k+3 of the group's 24 (B,G,R per pixel)
+            if (wo) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) reinterpret_cast<uint32_t*>(q)[k] = o[k];  // pw even -> always 4-byte aligned
-                }
+                for (int k = 0; k < 6; ++k) s[k] = __funnelshift_r(w[k + 1], w[k + 2], sh);
             } else {
-                for (int e = 0; e < nx; ++e) reinterpret_cast<unsigned short*>(q)[e] = (unsigned short)(o[e >> 1] >> (16 * (e & 1)));
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s[k] = __funnelshift_r(w[k], w[k + 1], sh);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {  // BGR channel c -> plane 2 - c (RGB)
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ia = 6 * k + c, ib = ia + 3;
+                    const uint32_t sel = (uint32_t)(ia & 3) | ((uint32_t)(4 * ((ib >> 2) - (ia >> 2)) + (ib & 3)) << 8);
+                    o[k] = cr_norm255_pair(__byte_perm(s[ia >> 2], s[ib >> 2], sel) & 0x00ff00ffu);
+                }
+                uint8_t* q = srun[2 - c] + ((size_t)r * pw + x) * 2;
+                if (nx == 8) {
+                    const uint32_t a = smem_u32(q);
+                    if ((a & 15) == 0) *reinterpret_cast<uint4*>(q) = make_uint4(o[0], o[1], o[2], o[3]);
+                    else if ((a & 7) == 0) { reinterpret_cast<uint2*>(q)[0] = make_uint2(o[0], o[1]); reinterpret_cast<uint2*>(q)[1] = make_uint2(o[2], o[3]); }
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) reinterpret_cast<uint32_t*>(q)[k] = o[k];  // pw even -> always 4-byte aligned
+                    }
+                } else {
+                    for (int e = 0; e < nx; ++e) reinterpret_cast<unsigned short*>(q)[e] = (unsigned short)(o[e >> 1] >> (16 * (e & 1)));
+                }
             }
         }
     }
