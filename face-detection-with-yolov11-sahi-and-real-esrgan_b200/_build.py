@@ -82,7 +82,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             list(ex.map(run, jobs))
         objs = [str(OBJ_DIR / (s.stem + ".o")) for s in sources()]
         tmp = LIB_PATH.with_suffix(".so.tmp")
-        link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs]
+        link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs, "-ldl"]
         run(link)
         os.replace(tmp, LIB_PATH)
     return LIB_PATH

@@ -56,6 +56,8 @@ SIGNATURES = {
     "fsd_widerface_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "fsd_widerface_pr_curve": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_double, vp, C.c_int, vp, vp,
                                          vp, C.c_int64, vp, vp]),
+    "fsd_jpeg_info": (C.c_int, [vp, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fsd_jpeg_decode": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, C.c_int64, C.c_int, C.c_int, vp]),
     "fsd_attach_keypoints": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]),
 }
 

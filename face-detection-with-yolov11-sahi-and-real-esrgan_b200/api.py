@@ -21,15 +21,25 @@ def get_sliced_prediction_batch(images: Sequence, detection_model, slice_height:
                                 perform_standard_pred: bool = True, postprocess_type: str = "GREEDYNMM",
                                 postprocess_match_metric: str = "IOS", postprocess_match_threshold: float = 0.5,
                                 postprocess_class_agnostic: bool = False, as_objects: bool = True, pool=None):
-    """images: HWC uint8 arrays / CPU tensors (pinned for async H2D) of ONE common size.  Returns a list of
-    PredictionResult (as_objects=True) or the raw engine.DetectionBatch."""
+    """images: HWC uint8 arrays / CPU tensors (pinned for async H2D) of ONE common size — or encoded JPEGs (`bytes`) of one
+    common size, decoded on the device (f4).  Returns a list of PredictionResult (as_objects=True) or the raw
+    engine.DetectionBatch."""
     eng = detection_model.engine()
     eng.truncate = True
-    h, w = images[0].shape[:2]
-    if pool is None or (pool.n, pool.h, pool.w) != (len(images), h, w):
-        pool = ops.ImagePool(len(images), h, w, eng.device)
-    for i, im in enumerate(images):
-        pool.upload(i, im, non_blocking=True)
+    if isinstance(images[0], (bytes, bytearray)):
+        # (f4) encoded JPEGs: decoded on the device by nvJPEG straight into the image pool (RGB, like PIL's convert("RGB")).
+        # Opt-in by passing bytes: the pixels differ from PIL's libjpeg by a few LSB, so this is outside the bit-exact claims.
+        w, h, _ = ops.jpeg_info(bytes(images[0]))
+        if pool is None or (pool.n, pool.h, pool.w) != (len(images), h, w):
+            pool = ops.ImagePool(len(images), h, w, eng.device)
+        for i, im in enumerate(images):
+            pool.upload_jpeg(i, bytes(im))
+    else:
+        h, w = images[0].shape[:2]
+        if pool is None or (pool.n, pool.h, pool.w) != (len(images), h, w):
+            pool = ops.ImagePool(len(images), h, w, eng.device)
+        for i, im in enumerate(images):
+            pool.upload(i, im, non_blocking=True)
     batch = eng.detect(pool, slice_height, slice_width, overlap_height_ratio, overlap_width_ratio,
                        perform_standard_pred, postprocess_type, postprocess_match_metric,
                        postprocess_match_threshold, postprocess_class_agnostic)

@@ -98,6 +98,16 @@ class ImagePool:
             raise ValueError(f"expected uint8 [{self.h},{self.w},3], got {tuple(t.shape)} {t.dtype}")
         self.buf[index, :, : self.w * 3].copy_(t.reshape(self.h, self.w * 3), non_blocking=non_blocking)
 
+    def upload_jpeg(self, index: int, data: bytes, bgr: bool = False):
+        """(f4) decode a JPEG (bytes) with nvJPEG straight into slot `index` — RGB like PIL's convert("RGB"), or BGR like
+        cv2.imread.  Only the compressed bytes cross PCIe.  Pixels differ from PIL's libjpeg by a few LSB: opt-in."""
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        h = get_handle(self.buf.device.index if self.buf.device.index is not None else torch.cuda.current_device())
+        slot = self.buf[index]
+        check(h.lib.fsd_jpeg_decode(h.h, buf, len(data), 1 if bgr else 0, slot.data_ptr(), self.pitch, self.h, self.w,
+                                    _stream_ptr(self.buf.device)), "fsd_jpeg_decode")
+        torch.cuda.current_stream(self.buf.device).synchronize()  # nvJPEG reads the host bytes asynchronously: keep `buf` alive until done
+
     def view(self, index: int) -> torch.Tensor:
         """[H, W, 3] view of slot `index` (strided when the pitch is padded)."""
         return self.buf[index, :, : self.w * 3].unflatten(1, (self.w, 3))
@@ -542,3 +552,12 @@ def attach_keypoints(merged: torch.Tensor, m_off, m_cnt, dets: torch.Tensor, d_o
                                      int(m_off.shape[0]), src.data_ptr(), _stream_ptr(merged.device)),
           "fsd_attach_keypoints")
     return src
+
+
+def jpeg_info(data: bytes):
+    """(width, height, channels) of a JPEG stream, parsed by nvJPEG on the host."""
+    lib = _cabi.load_library()
+    w, hh, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    check(lib.fsd_jpeg_info(buf, len(data), C.byref(w), C.byref(hh), C.byref(c)), "fsd_jpeg_info")
+    return w.value, hh.value, c.value

@@ -26,6 +26,11 @@ def read_image_as_pil(image, exif_fix: bool = True):
     if isinstance(image, str):
         pil = Image.open(image).convert("RGB")
         return ImageOps.exif_transpose(pil) if exif_fix else pil
+    if isinstance(image, (bytes, bytearray)):  # (f4) an encoded image kept behind a result of the nvJPEG batch path: decoded lazily, on request
+        import io
+
+        pil = Image.open(io.BytesIO(image)).convert("RGB")
+        return ImageOps.exif_transpose(pil) if exif_fix else pil
     if isinstance(image, np.ndarray):
         if image.shape[0] < 5:  # upstream treats a leading dim < 5 as CHW
             image = image[:, :, ::-1]

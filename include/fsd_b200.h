@@ -257,6 +257,16 @@ int fsd_widerface_pr_curve(fsd_handle_t h, const double* pred, const int32_t* pr
                            double iou_thresh, const double* thresh, int T, double* pred_recall, double* proposal,
                            void* scratch, int64_t scratch_bytes, double* pr_curve, void* stream);
 
+/* ---- (f4) JPEG ingest — replaces the host-side PIL decode of read_image_as_pil ([EXT sahi.utils.cv], reached from
+ *      docs sahi/predict.py:229 and docs sahi/prediction.py:173) and the temporary-JPEG hand-offs between pipeline stages
+ *      (pipeline_v4_yolo/1_Inference.py:328-330): a baseline JPEG (host bytes) is decoded by nvJPEG on `stream` straight into
+ *      dst [H, row_pitch] (interleaved RGB; bgr != 0: BGR as cv2.imread gives).  libnvjpeg is loaded on first use; without it
+ *      these two entry points fail with FSD_ERR_ARG.  NOT bit-exact with PIL's libjpeg (a few LSB): opt-in, outside the
+ *      bit-exact parity claims. */
+int fsd_jpeg_info(const uint8_t* jpeg, int64_t len, int* width, int* height, int* channels);
+int fsd_jpeg_decode(fsd_handle_t h, const uint8_t* jpeg, int64_t len, int bgr, uint8_t* dst, int64_t row_pitch, int H, int W,
+                    void* stream);
+
 /* ---- (f2) keypoint attach — replaces YOLOv11PoseDetectionModel.attach_keypoints_to_predictions
  *      (utils/yolo_wrapper.py:168-217), batched over S images: for each merged box pick the LAST stage-1
  *      detection of the same image with the identical box, else the detection whose box has the largest IoU
