@@ -348,6 +348,10 @@ extern "C" int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const v
         memcpy(&bits, &conf, 4);
         auto it = h->decode_gates.find(bits);
         if (it == h->decode_gates.end()) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            FSD_CUDA(cudaStreamIsCapturing(stream, &cap));
+            FSD_CHECK_ARG(cap == cudaStreamCaptureStatusNone,
+                          "fsd_pose_decode: first call for conf=%g inside a stream capture (call it once eagerly first)", conf);
             FSD_CUDA(cudaMalloc(&x_gate, sizeof(float)));
             h->dev_allocs.push_back(x_gate);
             k2_find_gate_kernel<<<1, 1, 0, stream>>>(conf, x_gate);
@@ -358,7 +362,11 @@ extern "C" int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const v
             it = h->decode_gates.emplace(bits, std::make_pair(x_gate, ready)).first;
         } else {
             x_gate = it->second.first;
-            FSD_CUDA(cudaStreamWaitEvent(stream, it->second.second, 0));
+            // (a finished event needs no edge — and an edge to uncaptured work would be illegal inside a stream capture)
+            if (cudaEventQuery(it->second.second) != cudaSuccess) {
+                (void)cudaGetLastError();
+                FSD_CUDA(cudaStreamWaitEvent(stream, it->second.second, 0));
+            }
         }
     }
     TimedLaunch timed(h, FSD_KERNEL_DECODE, (int64_t)B * a * 80 * (dtype == FSD_F16 ? 2 : 4), a, stream);

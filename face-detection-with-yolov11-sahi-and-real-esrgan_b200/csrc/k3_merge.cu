@@ -27,7 +27,8 @@
 namespace fsd {
 
 constexpr int K3_SMEM_MAX_P = 4096;   // segments up to this many boxes live entirely in shared memory
-constexpr int K3_BYTES_PER_BOX = 48;
+constexpr int K3_BYTES_PER_BOX = 48;      // shared-memory kernel: box 16 + key 8 + val 4 + parent 4 + step 4 + cat 4 + keep 4 + run 4
+constexpr int K3_WS_BYTES_PER_BOX = 52;   // workspace of the cluster / fallback kernels: the same + the cluster kernel's NMM step array
 constexpr int K3_CLUSTER = 8;          // CTAs (SMs) that share one large segment
 constexpr int K3_SCRATCH_BYTES = 2048;  // per-segment broadcast area of the cluster kernel (after the box arrays)  // keys 8 + vals 4 + box 16 + parent 4 + step 4 + cat 4 + keep 4 + run 4
 
@@ -270,8 +271,13 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
     k3_bar(T);
     auto keyhi = [&](int r) -> uint32_t { return mc.tie_rule ? (uint32_t)(keys[r] >> 32) : 0u; };
 
-    if (p.type != FSD_NMM) {
-        // ---- 2a. greedy scan in chunks of 64 ranks --------------------------------------------------
+    const bool nmm = p.type == FSD_NMM;
+    {
+        // ---- 2. scan in chunks of 64 ranks -----------------------------------------------------------
+        // greedy (NMS / GREEDYNMM): only the chunk's KEEPS act on lower ranks.  NMM (transitive, A.2.4 `nmm`): EVERY visited rank
+        // acts — an unclaimed rank becomes a keep, a claimed one forwards its unclaimed matches to its keep — so the chunk's
+        // "actors" are all its ranks, each carrying the label (keep rank) it stands for; the claim records the visiting rank
+        // (`step`) for the append order of the replay.  Same two-barrier loop, same sweep.
         // match bits of one chunk: 64 threads per row (two warps = the two 32-bit halves), rows spread over the thread groups
         auto chunk_bits = [&](int c0, uint32_t* dg) {
             const int cn = min(64, m - c0);
@@ -300,38 +306,70 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
                 const int kt = s_ktotal;
                 int cnt = 0, stop = 0;
                 const uint64_t live = ~remw & (cn == 64 ? ~0ull : ((1ull << cn) - 1ull));
-                for (int b = 0; b < cn && live != 0; ++b) {  // (a chunk whose ranks earlier keeps removed already has nothing to resolve)
-                    const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
-                    if (!((remw >> b) & 1ull)) {
-                        if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
-                        keepmask |= 1ull << b;
-                        ++cnt;
-                        remw |= row;
+                if (!nmm) {
+                    for (int b = 0; b < cn && live != 0; ++b) {  // (a chunk whose ranks earlier keeps removed already has nothing to resolve)
+                        const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
+                        if (!((remw >> b) & 1ull)) {
+                            if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
+                            keepmask |= 1ull << b;
+                            ++cnt;
+                            remw |= row;
+                        }
                     }
-                }
-                for (int pos = lane; pos < 64; pos += 32) {
-                    if ((keepmask >> pos) & 1ull) {
-                        const int idx = __popcll(keepmask & ((1ull << pos) - 1ull));
-                        const int kr = c0 + pos;
-                        s_klist[idx] = kr;
-                        keepr[kt + idx] = kr;
-                        s_kbox[idx] = sbox[kr];
-                        s_kcat[idx] = scat[kr];
-                        s_kkey[idx] = keyhi(kr);
-                        parent[kr] = kr;
+                    for (int pos = lane; pos < 64; pos += 32) {
+                        if ((keepmask >> pos) & 1ull) {
+                            const int idx = __popcll(keepmask & ((1ull << pos) - 1ull));
+                            const int kr = c0 + pos;
+                            s_klist[idx] = kr;
+                            keepr[kt + idx] = kr;
+                            s_kbox[idx] = sbox[kr];
+                            s_kcat[idx] = scat[kr];
+                            s_kkey[idx] = keyhi(kr);
+                            parent[kr] = kr;
+                        }
+                    }
+                } else {
+                    // NMM: lane l carries the labels of ranks l and l + 32 (their keep, -1 while unclaimed) through the 64 visits
+                    int labA = lane < cn && ((remw >> lane) & 1ull) ? parent[c0 + lane] : -1;
+                    int labB = lane + 32 < cn && ((remw >> (lane + 32)) & 1ull) ? parent[c0 + lane + 32] : -1;
+                    int stA = -1, stB = -1;
+                    for (int b = 0; b < cn; ++b) {
+                        const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
+                        int lb = __shfl_sync(0xffffffffu, b < 32 ? labA : labB, b & 31);
+                        if (!((remw >> b) & 1ull)) {  // unclaimed when visited: a new keep
+                            lb = c0 + b;
+                            keepmask |= 1ull << b;
+                            ++cnt;
+                            remw |= 1ull << b;
+                            if (lane == (b & 31)) { if (b < 32) labA = lb; else labB = lb; }
+                        }
+                        const uint64_t fresh = row & ~remw;  // the unclaimed lower ranks of the chunk that match rank b
+                        remw |= fresh;
+                        if ((fresh >> lane) & 1ull) { labA = lb; stA = c0 + b; }
+                        if ((fresh >> (lane + 32)) & 1ull) { labB = lb; stB = c0 + b; }
+                    }
+                    // every rank of the chunk is an actor of the sweep, standing for its label
+                    if (lane < cn) { parent[c0 + lane] = labA; if (stA >= 0) step[c0 + lane] = stA; }
+                    if (lane + 32 < cn) { parent[c0 + lane + 32] = labB; if (stB >= 0) step[c0 + lane + 32] = stB; }
+                    for (int pos = lane; pos < cn; pos += 32) {
+                        s_klist[pos] = pos < 32 ? labA : labB;
+                        s_kbox[pos] = sbox[c0 + pos];
+                        s_kcat[pos] = scat[c0 + pos];
+                        s_kkey[pos] = 0u;
+                        if ((keepmask >> pos) & 1ull) keepr[kt + __popcll(keepmask & ((1ull << pos) - 1ull))] = c0 + pos;
                     }
                 }
                 if (lane == 0) {
                     s_rem[w0] = (uint32_t)remw;
                     s_rem[w0 + 1] = (uint32_t)(remw >> 32);
                     s_keepmask = keepmask; s_rembefore = before; s_remafter = remw;
-                    s_kcount = cnt; s_ktotal = kt + cnt; s_stop = stop;
+                    s_kcount = nmm ? cn : cnt; s_ktotal = kt + cnt; s_stop = stop;
                     s_rem_snapshot[0] = s_rem[w0 + 2]; s_rem_snapshot[1] = s_rem[w0 + 3];  // next chunk, before this chunk's sweep
                 }
             }
             k3_bar(T);
             const int kc = s_kcount, stop = s_stop;
-            if (tid < cn) {
+            if (tid < cn && !nmm) {
                 // parents of the ranks this chunk's own keeps removed: the FIRST keep whose row holds the rank
                 const uint64_t keepmask = s_keepmask;
                 const int q = tid;
@@ -374,6 +412,7 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
                             if (suppresses(s_kbox[k], bj, s_kcat[k], cj, s_kkey[k], kj, mc)) {
                                 atomicOr(&s_rem[j >> 5], 1u << (j & 31));
                                 parent[j] = s_klist[k];
+                                if (nmm) step[j] = c0 + k;  // the visit that produced the claim
                                 hit = true;
                                 break;
                             }
@@ -386,29 +425,11 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
                     const int w1 = (c0 + 64) >> 5, cn1 = min(64, m - c0 - 64);
                     const uint64_t r1 = (uint64_t)s_rem_snapshot[0] | ((uint64_t)s_rem_snapshot[1] << 32);
                     (void)w1;
-                    if ((~r1 & (cn1 == 64 ? ~0ull : ((1ull << cn1) - 1ull))) != 0) chunk_bits(c0 + 64, s_diag[(c + 1) & 1]);
+                    if (nmm || (~r1 & (cn1 == 64 ? ~0ull : ((1ull << cn1) - 1ull))) != 0) chunk_bits(c0 + 64, s_diag[(c + 1) & 1]);
                 }
             }
             k3_bar(T);
             if (stop) break;
-        }
-    } else {
-        // ---- 2b. NMM: visit every rank; a claimed rank forwards its unclaimed matches to its keep -------
-        for (int i = 0; i < m; ++i) {
-            if (tid == 0 && parent[i] == -1) {
-                parent[i] = i;
-                keepr[s_ktotal] = i;
-                s_ktotal = s_ktotal + 1;
-            }
-            k3_bar(T);
-            const int k = parent[i];
-            const float4 bi = sbox[i];
-            const int ci = scat[i];
-            for (int j = tid; j < m; j += T) {
-                if (j == i || parent[j] != -1) continue;
-                if (match_pair(bi, sbox[j], ci, scat[j], mc)) { parent[j] = k; step[j] = i; }
-            }
-            k3_bar(T);
         }
     }
     k3_bar(T);
@@ -547,8 +568,8 @@ __global__ void __launch_bounds__(512) k3_merge_kernel(const K3Params p) {
 }
 
 // ---- fallback: one CTA per segment with the arrays in the (L2-resident) workspace ---------------------------------------
-// Used for NMM above 4096 boxes (its rank-by-rank walk would pay two cluster barriers per rank) and as the cross-check of
-// the cluster kernel (FSD_K3_SINGLE_CTA=1).  Plain rank order, no tie rule.
+// Round 1's kernel, kept as the cross-check of the cluster kernel (FSD_K3_SINGLE_CTA=1): plain rank order, no tie rule, NMM as
+// a rank-by-rank walk.
 __global__ void __launch_bounds__(512) k3_merge_global_kernel(const K3Params p) {
     __shared__ uint32_t s_diag[128];   // 64 rows x 2 halves of in-chunk match bits
     __shared__ int s_klist[64];
@@ -798,8 +819,8 @@ __global__ void __launch_bounds__(512) k3_merge_global_kernel(const K3Params p) 
 // in the L2-resident workspace, every phase that is parallel over ranks (rank sort, sweep, replay sort, fold) is split
 // over the cluster's 4096 threads with cluster.sync() between dependent steps, and only the 64x64 in-chunk resolve stays
 // on CTA 0, which broadcasts the chunk's keeps through a small scratch area.  Arrays written by one CTA and read by
-// another are read with ld.global.cg (L2), never through a possibly stale L1 line.  NMS and GREEDYNMM only (NMM's
-// rank-by-rank walk would pay two cluster barriers per rank and keeps the single-CTA path).  CTA 0 resolves a chunk with one
+// another are read with ld.global.cg (L2), never through a possibly stale L1 line.  All three merge types (NMM through the
+// same chunked scan with every rank of a chunk acting for its keep).  CTA 0 resolves a chunk with one
 // warp holding the 64x64 match bits in registers, and computes the NEXT chunk's match bits while the cluster sweeps.
 namespace cg = cooperative_groups;
 
@@ -896,7 +917,8 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     int* scat = reinterpret_cast<int*>(base + 36 * PP);
     int* keepr = reinterpret_cast<int*>(base + 40 * PP);
     int* runs = reinterpret_cast<int*>(base + 44 * PP);
-    K3Scratch* sc = reinterpret_cast<K3Scratch*>(base + (size_t)K3_BYTES_PER_BOX * PP);
+    int* stepc = reinterpret_cast<int*>(base + 48 * PP);          // NMM: rank whose visit produced the claim (the `step` slot holds the removed bits here)
+    K3Scratch* sc = reinterpret_cast<K3Scratch*>(base + (size_t)K3_WS_BYTES_PER_BOX * PP);
 
     const MatchCfg mc = match_cfg(p);
     const int lane = tid & 31;
@@ -968,7 +990,8 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     if (tid == 0) { s_ktotal = 0; s_stop = 0; s_kcount = 0; }
     stage_chunk(0, 0);
 
-    // ---- 2. greedy scan in chunks of 64 ranks ---------------------------------------------------------------
+    // ---- 2. scan in chunks of 64 ranks (greedy, or NMM's transitive walk: see k3_merge_kernel) ----------------------------
+    const bool nmm = p.type == FSD_NMM;
     for (int c0 = 0, c = 0; c0 < m; c0 += 64, ++c) {
         const int cn = min(64, m - c0);
         const int buf = c & 1;
@@ -983,31 +1006,62 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
             const int kt = s_ktotal;
             int cnt = 0, stop = 0;
             const uint64_t live = ~remw & (cn == 64 ? ~0ull : ((1ull << cn) - 1ull));
-            for (int b = 0; b < cn && live != 0; ++b) {
-                const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
-                if (!((remw >> b) & 1ull)) {
-                    if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
-                    keepmask |= 1ull << b;
-                    ++cnt;
-                    remw |= row;
+            if (!nmm) {
+                for (int b = 0; b < cn && live != 0; ++b) {
+                    const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
+                    if (!((remw >> b) & 1ull)) {
+                        if (p.max_keep > 0 && kt + cnt >= p.max_keep) { stop = 1; break; }
+                        keepmask |= 1ull << b;
+                        ++cnt;
+                        remw |= row;
+                    }
                 }
-            }
-            for (int pos = lane; pos < 64; pos += 32) {
-                if ((keepmask >> pos) & 1ull) {
-                    const int idx = __popcll(keepmask & ((1ull << pos) - 1ull));
-                    const int kr = c0 + pos;
-                    s_klist[idx] = kr; s_kbox[idx] = s_cbox[buf][pos]; s_kcat[idx] = s_ccat[buf][pos]; s_kkey[idx] = s_ckey[buf][pos];
-                    if (crank == 0) { __stcg(keepr + kt + idx, kr); __stcg(parent + kr, kr); }
+                for (int pos = lane; pos < 64; pos += 32) {
+                    if ((keepmask >> pos) & 1ull) {
+                        const int idx = __popcll(keepmask & ((1ull << pos) - 1ull));
+                        const int kr = c0 + pos;
+                        s_klist[idx] = kr; s_kbox[idx] = s_cbox[buf][pos]; s_kcat[idx] = s_ccat[buf][pos]; s_kkey[idx] = s_ckey[buf][pos];
+                        if (crank == 0) { __stcg(keepr + kt + idx, kr); __stcg(parent + kr, kr); }
+                    }
+                }
+            } else {
+                // NMM (see k3_merge_kernel): every rank of the chunk acts, standing for its label; lane l carries ranks l, l + 32
+                int labA = lane < cn && ((remw >> lane) & 1ull) ? ld_cg(parent + c0 + lane) : -1;
+                int labB = lane + 32 < cn && ((remw >> (lane + 32)) & 1ull) ? ld_cg(parent + c0 + lane + 32) : -1;
+                int stA = -1, stB = -1;
+                for (int b = 0; b < cn; ++b) {
+                    const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? rowA : rowB, b & 31);
+                    int lb = __shfl_sync(0xffffffffu, b < 32 ? labA : labB, b & 31);
+                    if (!((remw >> b) & 1ull)) {
+                        lb = c0 + b;
+                        keepmask |= 1ull << b;
+                        ++cnt;
+                        remw |= 1ull << b;
+                        if (lane == (b & 31)) { if (b < 32) labA = lb; else labB = lb; }
+                    }
+                    const uint64_t fresh = row & ~remw;
+                    remw |= fresh;
+                    if ((fresh >> lane) & 1ull) { labA = lb; stA = c0 + b; }
+                    if ((fresh >> (lane + 32)) & 1ull) { labB = lb; stB = c0 + b; }
+                }
+                if (crank == 0) {
+                    if (lane < cn) { __stcg(parent + c0 + lane, labA); if (stA >= 0) __stcg(stepc + c0 + lane, stA); }
+                    if (lane + 32 < cn) { __stcg(parent + c0 + lane + 32, labB); if (stB >= 0) __stcg(stepc + c0 + lane + 32, stB); }
+                }
+                for (int pos = lane; pos < cn; pos += 32) {
+                    s_klist[pos] = pos < 32 ? labA : labB;
+                    s_kbox[pos] = s_cbox[buf][pos]; s_kcat[pos] = s_ccat[buf][pos]; s_kkey[pos] = 0u;
+                    if (crank == 0 && ((keepmask >> pos) & 1ull)) __stcg(keepr + kt + __popcll(keepmask & ((1ull << pos) - 1ull)), c0 + pos);
                 }
             }
             if (lane == 0) {
                 s_keepmask = keepmask; s_rembefore = before; s_remafter = remw;
-                s_kcount = cnt; s_ktotal = kt + cnt; s_stop = stop;
+                s_kcount = nmm ? cn : cnt; s_ktotal = kt + cnt; s_stop = stop;
             }
         }
         __syncthreads();
         const int kc = s_kcount, stop = s_stop;
-        if (crank == 0 && tid < cn) {  // parents of the ranks this chunk's own keeps removed: the first keep whose row holds the rank
+        if (crank == 0 && tid < cn && !nmm) {  // parents of the ranks this chunk's own keeps removed: the first keep whose row holds the rank
             const uint64_t keepmask = s_keepmask;
             const int q = tid;
             if (!((s_rembefore >> q) & 1ull) && !((keepmask >> q) & 1ull) && ((s_remafter >> q) & 1ull)) {
@@ -1045,6 +1099,7 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
                         if (suppresses(s_kbox[kk], bj, s_kcat[kk], ocat[k * T + tid], s_kkey[kk], okey[k * T + tid], mc)) {
                             atomicOr(rem + (j >> 5), 1u << (j & 31));
                             __stcg(parent + j, s_klist[kk]);
+                            if (nmm) __stcg(stepc + j, c0 + kk);  // the visit that produced the claim
                             alive &= ~(1u << k);
                             hit = true;
                             break;
@@ -1113,7 +1168,10 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
         uint64_t key = ~0ull;
         if (r < m) {
             const int pr = ld_cg(parent + r);
-            if (pr >= 0 && pr != r) key = ((uint64_t)pr << 45) | ((uint64_t)r << 15) | (uint64_t)r;
+            if (pr >= 0 && pr != r) {
+                const uint64_t seq = nmm ? (uint64_t)ld_cg(stepc + r) * 32768ull + (uint64_t)(32767 - r) : (uint64_t)r;
+                key = ((uint64_t)pr << 45) | (seq << 15) | (uint64_t)r;
+            }
         }
         __stcg(keys + r, key);
     }
@@ -1196,7 +1254,7 @@ using namespace fsd;
 extern "C" int64_t fsd_merge_workspace_bytes(int64_t N, int S, int max_segment) {
     (void)N;
     if (max_segment <= K3_SMEM_MAX_P) return 256;  // unused, but keep the pointer non-null for callers
-    return (int64_t)S * ((int64_t)pow2_at_least(max_segment) * K3_BYTES_PER_BOX + K3_SCRATCH_BYTES) + 256;
+    return (int64_t)S * ((int64_t)pow2_at_least(max_segment) * K3_WS_BYTES_PER_BOX + K3_SCRATCH_BYTES) + 256;
 }
 
 extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, const float* scores, int score_stride,
@@ -1231,7 +1289,7 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     p.P = pow2_at_least(max_segment);
     p.use_global = p.P > K3_SMEM_MAX_P;
     p.workspace = reinterpret_cast<uint8_t*>(workspace);
-    p.ws_per_segment = (size_t)p.P * K3_BYTES_PER_BOX + K3_SCRATCH_BYTES;
+    p.ws_per_segment = (size_t)p.P * K3_WS_BYTES_PER_BOX + K3_SCRATCH_BYTES;
     if (p.use_global) {
         FSD_CHECK_ARG(workspace && workspace_bytes >= fsd_merge_workspace_bytes(0, S, max_segment),
                       "fsd_merge: workspace too small (%lld bytes needed)", (long long)fsd_merge_workspace_bytes(0, S, max_segment));
@@ -1242,8 +1300,8 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     const bool force_single = getenv("FSD_K3_SINGLE_CTA") != nullptr;
     // the path is chosen per segment ON THE DEVICE from its actual count: both kernels are launched over all S segments when
     // the capacity allows large ones, and each returns at once for the segments that belong to the other
-    if (p.use_global && (type == FSD_NMM || force_single)) {
-        // NMM above 4096 boxes / cross-check mode: one CTA per segment over the workspace (takes EVERY segment of the launch)
+    if (p.use_global && force_single) {
+        // cross-check mode (FSD_K3_SINGLE_CTA=1): one CTA per segment over the workspace (takes EVERY segment of the launch)
         TimedLaunch timed(h, FSD_KERNEL_MERGE, S, max_segment, stream);
         k3_merge_global_kernel<<<S, 512, 0, stream>>>(p);
         FSD_CUDA(cudaGetLastError());
