@@ -223,8 +223,32 @@ def bench_k5():
            lambda: ops.upsample2x_concat(a, b))
 
 
+def bench_k10():
+    """1x1 convolutions of the backbone (96 network inputs of 1024^2): tcgen05 kernel vs the mma.sync kernel vs cuDNN + epilogue."""
+    cl = lambda *shape: torch.randn(shape, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    torch.backends.cudnn.benchmark = True
+    for name, k, n, hw in (("b2.cv1 32->32 256^2", 32, 32, 256), ("b2.cv2 48->64 256^2", 48, 64, 256), ("head.cv3 64->64 128^2", 64, 64, 128),
+                           ("b4.cv2 96->128 128^2", 96, 128, 128), ("h16.cv1 256->64 128^2", 256, 64, 128), ("b6.cv1 128->128 64^2", 128, 128, 64),
+                           ("b6.cv2 192->128 64^2", 192, 128, 64), ("h13.cv1 384->128 64^2", 384, 128, 64), ("b8.cv1 256->256 32^2 (library only)", 256, 256, 32),
+                           ("psa 128->256 32^2", 128, 256, 32)):
+        x = cl(96, k, hw, hw)
+        w = (torch.randn((n, k, 1, 1), device=dev) / k ** 0.5).half().contiguous(memory_format=torch.channels_last)
+        bias = torch.randn((n,), device=dev).half()
+        out = cl(96, n, hw, hw)
+        nbytes = (x.numel() + out.numel()) * 2
+        if ops.pointwise_tc_supported(k, n):
+            os.environ.pop("FSD_K7_NO_TC", None)
+            report(f"K10 tcgen05 pointwise conv + bias + SiLU {name}", nbytes, lambda: ops.pointwise_conv(x, w, bias, "silu", out=out))
+        os.environ["FSD_K7_NO_TC"] = "1"
+        if ops.pointwise_conv_supported(k, n):
+            report(f"   K7 mma.sync kernel {name}", nbytes, lambda: ops.pointwise_conv(x, w, bias, "silu", out=out))
+        os.environ.pop("FSD_K7_NO_TC", None)
+        report(f"   cuDNN conv + fsd_bias_act {name}", nbytes, lambda: ops.bias_act(torch.nn.functional.conv2d(x, w), bias, "silu", out=out))
+        del x, out
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4), ("k5", bench_k5)):
+    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4), ("k5", bench_k5), ("k10", bench_k10)):
         if which in ("all", name):
             fn()

@@ -61,11 +61,13 @@ class Conv(nn.Module):
             if (c.kernel_size == (1, 1) and c.stride == (1, 1) and c.groups == 1 and USE_POINTWISE_KERNEL and up2 is None
                     and x.stride(1) == 1 and x.shape[2] * x.shape[3] >= 1024):
                 # low-intensity 1x1 layers: one kernel does GEMM + bias + activation (+ residual) into the slot
-                from ..ops import pointwise_conv, pointwise_conv_supported
+                from ..ops import pointwise_conv, pointwise_conv_supported, pointwise_tc_enabled, pointwise_tc_supported
 
-                # measured (profiles/r1_kernels_k7.jsonl): it beats cuDNN + epilogue for K, N <= 64 (0.55 vs 0.34 of peak
-                # at 32->32); for N = 128 its SiLU epilogue is issue/MUFU-bound and the library pair is faster
-                if pointwise_conv_supported(c.in_channels, c.out_channels) and c.in_channels <= 64 and c.out_channels <= 64:
+                # tensor-core kernel (tcgen05, k10_pointwise_tc.cu): every shape it takes.  The mma.sync kernel (FSD_K7_NO_TC=1) only
+                # beats cuDNN + epilogue for K, N <= 64 (profiles/r1_kernels_k7.jsonl: 0.55 vs 0.34 of peak at 32->32; for N = 128
+                # its SiLU epilogue is issue/MUFU-bound and the library pair is faster)
+                tc = pointwise_tc_enabled() and pointwise_tc_supported(c.in_channels, c.out_channels)
+                if pointwise_conv_supported(c.in_channels, c.out_channels) and (tc or (c.in_channels <= 64 and c.out_channels <= 64)):
                     return pointwise_conv(x, c.weight, c.bias, act, out=out, residual=residual, out2=out2)
             y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
             if y.is_contiguous(memory_format=torch.channels_last):

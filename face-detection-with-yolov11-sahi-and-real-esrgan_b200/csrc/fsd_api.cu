@@ -60,7 +60,6 @@ int fsd_destroy(fsd_handle_t h) {
     for (auto& kv : h->resize_tables)
         if (kv.second.dev) cudaFree(kv.second.dev);
     for (void* d : h->dev_allocs) cudaFree(d);
-    for (auto& kv : h->decode_gates) cudaEventDestroy(kv.second.second);
     for (auto& t : h->timing_samples) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     delete h;

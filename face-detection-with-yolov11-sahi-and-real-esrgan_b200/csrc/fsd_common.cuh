@@ -56,8 +56,8 @@ struct fsd_context {
     std::map<std::tuple<uintptr_t, int, int, int64_t, int64_t, int, int>, CUtensorMap> tensor_maps;
     std::map<std::tuple<int, int, int, int>, std::shared_ptr<void>> k1_plans;  // Kernel 1 geometry plans
     std::vector<void*> dev_allocs;  // device buffers owned by the handle (freed in fsd_destroy)
-    // Kernel 2a: confidence (float bits) -> (device pointer to the gate logit, event recorded after it was computed)
-    std::map<uint32_t, std::pair<float*, cudaEvent_t>> decode_gates;
+    // Kernel 2a: confidence (float bits) -> device pointer to the gate logit (computed and synchronised on first use)
+    std::map<uint32_t, float*> decode_gates;
     void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
     // optional device timing (fsd_kernel_timing_enable): CUDA events recorded on the launching stream right around
     // each kernel launch, inside the library, so no host-side preparation falls between the two records

@@ -1,0 +1,337 @@
+// Kernel 10: 1x1 convolution (+ bias + activation [+ residual] -> concat slot [+ second destination]) on the 5th-generation
+// tensor cores: TMA-fed, tcgen05.mma with the accumulator in tensor memory, warp-specialised and persistent.
+//
+// Same contract as Kernel 7 (fsd_pointwise_conv, include/fsd_b200.h) — it is reached through that entry point — for the ultralytics
+// Conv(c1, c2, 1, 1) layers of the YOLO11 graph (C3k2.cv1/cv2, C3k.cv1-3, SPPF.cv1/cv2, C2PSA, head cv3; run from
+// utils/yolo_wrapper.py:72).  A 1x1 convolution over channels-last activations is the GEMM
+//     D[P pixels, N] = X[P, K] * W[N, K]^T            (both operands K-major in memory)
+// with P in the millions and K, N <= 512 / 256: 2..8 flop per byte, i.e. bound by HBM, not by the tensor cores.  What the
+// tensor-core path buys is everything around the math: no per-thread fragment loads, no register accumulators, one thread
+// issuing the MMAs while TMA streams the activations and four warps drain finished tiles.
+//
+//   warp 0   : TMA producer.  The weights (<= 96 KB) are loaded once per CTA; activation tiles of 128 pixels stream through a ring
+//              of KS-channel slabs (KS = 64 / 32 / 16 channels = one 128 / 64 / 32-byte swizzle span; UTMALDG.2D).
+//   warp 1   : allocates tensor memory (2 accumulators x N fp32 columns) and issues tcgen05.mma M=128, N, K=16 per slab step (UTCHMMA);
+//              tcgen05.commit releases ring slots and hands accumulators to the epilogue.
+//   warps 2-5: epilogue.  tcgen05.ld (LDTM) 32 lanes x 16 columns, + bias, activation, fp16, staged through shared memory so that the
+//              global stores (and the residual loads) are row-contiguous 16-byte vectors, exactly as in Kernel 7.
+// The accumulator is double buffered, so the epilogue of tile t overlaps the loads and MMAs of tile t+1.
+#include "fsd_common.cuh"
+
+namespace fsd {
+
+constexpr int K10_THREADS = 192;
+constexpr int K10_TILE = 128;          // pixels per tile = MMA M
+constexpr int K10_STAGE_PITCH = 72;    // halves per staged output row (64 columns + 16 bytes: conflict-free 16-byte accesses)
+constexpr int K10_MAX_STAGES = 16;
+
+struct K10Params {
+    const __half* bias;
+    __half* out;
+    const __half* res;
+    __half* out2;
+    long long P;
+    int K, N, KS, n_slabs, stages, n_tiles, tmem_cols;
+    int out_stride, res_stride, out2_stride, out2_c0;
+    float slope;
+    uint32_t b_bytes, b_region, slab_bytes, sbo_bytes, layout_type;  // b_region = b_bytes rounded up to 1024
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void k10_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol error traps after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void k10_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void k10_tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_alloc(uint32_t* smem_result, uint32_t cols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t cols) {  // the allocating warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {  // 32 lanes x 16 fp32 columns: lane = row
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major operand in a TMA-swizzled slab (rows of KS halves = one swizzle span, 8-row groups
+// `sbo` bytes apart); layout: 2 = 128-byte swizzle, 4 = 64-byte, 6 = 32-byte (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major; CuTe writes 1)
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;        // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                       // descriptor version
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+template <int ACT>
+__device__ __forceinline__ float k10_act(float v, float slope) {
+    if (ACT == 1) return fast_silu(v);
+    if (ACT == 2) return v > 0.f ? v : v * slope;
+    return v;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(K10_THREADS, 1)
+k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const K10Params p) {
+    extern __shared__ uint8_t k10_raw[];
+    __shared__ uint64_t full_bar[K10_MAX_STAGES], empty_bar[K10_MAX_STAGES], b_bar, acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_bias[256];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // dynamic smem (1024-byte aligned for the 128-byte swizzle atoms): [weights | activation ring | 4 x epilogue staging]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(k10_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_b = smem;
+    uint8_t* smem_a = smem + p.b_region;
+    __half* stage_base = reinterpret_cast<__half*>(smem_a + (size_t)p.stages * p.slab_bytes);
+
+    for (int i = threadIdx.x; i < p.N; i += K10_THREADS) s_bias[i] = __half2float(__ldg(p.bias + i));
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&b_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tc_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(&b_bar, p.b_bytes);
+            for (int s = 0; s < p.n_slabs; ++s)
+                k10_tma_load_2d(smem_b + (size_t)s * p.N * p.KS * 2, &map_w, &b_bar, s * p.KS, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int s = 0; s < p.n_slabs; ++s) {
+                    k10_mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], p.slab_bytes);
+                    k10_tma_load_2d(smem_a + (size_t)stage * p.slab_bytes, &map_x, &full_bar[stage], s * p.KS, tile * K10_TILE);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(K10_TILE >> 4) << 24);
+            const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b);
+            k10_mbar_wait(&b_bar, 0);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                k10_mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
+                for (int s = 0; s < p.n_slabs; ++s) {
+                    k10_mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = a0 + (uint32_t)stage * p.slab_bytes;
+                    const uint32_t b_addr = b0 + (uint32_t)s * (uint32_t)(p.N * p.KS * 2);
+                    for (int k = 0; k < p.KS; k += 16) {
+                        tc_mma_f16(d_tmem, tc_smem_desc(a_addr + 2 * k, p.sbo_bytes, p.layout_type),
+                                   tc_smem_desc(b_addr + 2 * k, p.sbo_bytes, p.layout_type), idesc, (s | k) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);  // the slab may be overwritten once these MMAs have read it
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ================= epilogue warps (TMEM lane quarter = warp % 4) =================
+        const int q = warp & 3;
+        __half* stg = stage_base + (size_t)(warp - 2) * 32 * K10_STAGE_PITCH;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            k10_mbar_wait(&acc_full[acc], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.N);
+            const long long pix0 = (long long)tile * K10_TILE + q * 32;
+            for (int c0 = 0; c0 < p.N; c0 += 64) {
+                const int cw = p.N - c0 < 64 ? p.N - c0 : 64;  // 16, 32, 48 or 64 columns
+                uint32_t v[4][16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (16 * j < cw) tc_ld16(t_row + (uint32_t)(c0 + 16 * j), v[j]);
+                tc_wait_ld();
+                if (c0 + 64 >= p.N) {  // last read of this accumulator: hand it back to the MMA warp before the stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) k10_mbar_arrive(&acc_empty[acc]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (16 * j < cw) {
+                        uint32_t h[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float f0 = k10_act<ACT>(__uint_as_float(v[j][2 * e]) + s_bias[c0 + 16 * j + 2 * e], p.slope);
+                            const float f1 = k10_act<ACT>(__uint_as_float(v[j][2 * e + 1]) + s_bias[c0 + 16 * j + 2 * e + 1], p.slope);
+                            const __half2 o = __floats2half2_rn(f0, f1);
+                            h[e] = *reinterpret_cast<const uint32_t*>(&o);
+                        }
+                        uint4* d = reinterpret_cast<uint4*>(stg + (size_t)lane * K10_STAGE_PITCH + 16 * j);
+                        d[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                        d[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                    }
+                }
+                __syncwarp();
+                // row-contiguous 16-byte stores (+ residual, + second destination)
+                const int nch = cw >> 3;
+                for (int i = lane; i < 32 * nch; i += 32) {
+                    const int r = i / nch, c = i - r * nch;
+                    const long long pix = pix0 + r;
+                    if (pix >= p.P) continue;
+                    uint4 o = *reinterpret_cast<const uint4*>(stg + (size_t)r * K10_STAGE_PITCH + c * 8);
+                    const int col = c0 + c * 8;
+                    if (p.res) {
+                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)pix * p.res_stride + col));
+                        __half2* ho = reinterpret_cast<__half2*>(&o);
+                        const __half2* hr = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) ho[e] = __hadd2(ho[e], hr[e]);
+                    }
+                    *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_stride + col) = o;
+                    if (p.out2 && col >= p.out2_c0) *reinterpret_cast<uint4*>(p.out2 + (size_t)pix * p.out2_stride + (col - p.out2_c0)) = o;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tc_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// Shapes the tensor-core path takes; everything else stays on Kernel 7 / the library convolution.
+bool k10_supported(int K, int N) {
+    return K % 16 == 0 && K >= 16 && K <= 512 && N % 16 == 0 && N >= 16 && N <= 256 && (size_t)K * N * 2 <= 96 * 1024;
+}
+
+static bool k10_encode(fsd_context* h, CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                       uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return ((encode_fn)h->encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// -> FSD_OK with *taken = true when the launch was made; *taken = false leaves the call to Kernel 7
+int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const void* w, const void* bias, void* out, int64_t out_stride,
+                        const void* res, int64_t res_stride, void* out2, int64_t out2_stride, int out2_c0, int64_t P, int K, int N,
+                        int act, float slope, cudaStream_t stream, bool* taken) {
+    *taken = false;
+    if (!k10_supported(K, N) || !h->encode_tiled || P >= (1LL << 31) - K10_TILE) return FSD_OK;
+    K10Params p;
+    p.bias = (const __half*)bias; p.out = (__half*)out; p.res = (const __half*)res; p.out2 = (__half*)out2;
+    p.P = P; p.K = K; p.N = N;
+    p.KS = K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : 16);
+    p.n_slabs = K / p.KS;
+    p.out_stride = (int)out_stride; p.res_stride = (int)res_stride; p.out2_stride = (int)out2_stride; p.out2_c0 = out2_c0;
+    p.slope = slope;
+    p.b_bytes = (uint32_t)K * N * 2;
+    p.b_region = (p.b_bytes + 1023u) & ~1023u;
+    p.slab_bytes = (uint32_t)K10_TILE * p.KS * 2;
+    p.sbo_bytes = 8u * p.KS * 2;
+    p.layout_type = p.KS == 64 ? 2u : (p.KS == 32 ? 4u : 6u);
+    const CUtensorMapSwizzle swz = p.KS == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.KS == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    p.n_tiles = (int)((P + K10_TILE - 1) / K10_TILE);
+    int cols = 32;
+    while (cols < 2 * N) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t staging = (size_t)4 * 32 * K10_STAGE_PITCH * sizeof(__half);
+    const size_t budget = 200 * 1024;
+    int stages = (int)((budget - p.b_region - staging) / p.slab_bytes);
+    if (stages > K10_MAX_STAGES) stages = K10_MAX_STAGES;
+    if (stages < 2) return FSD_OK;
+    p.stages = stages;
+    const size_t smem = 1024 + p.b_region + (size_t)stages * p.slab_bytes + staging;
+
+    CUtensorMap mx, mw;
+    if (!k10_encode(h, &mx, x, (uint64_t)K, (uint64_t)P, (uint64_t)x_stride * 2, (uint32_t)p.KS, K10_TILE, swz)) return FSD_OK;
+    if (!k10_encode(h, &mw, w, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)p.KS, (uint32_t)N, swz)) return FSD_OK;
+
+    const int grid = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
+#define K10_GO(ACT)                                                                                                     \
+    {                                                                                                                   \
+        auto kern = k10_pointwise_tc_kernel<ACT>;                                                                       \
+        FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        kern<<<grid, K10_THREADS, smem, stream>>>(mx, mw, p);                                                           \
+    }
+    {
+        TimedLaunch timed(h, FSD_KERNEL_POINTWISE, (int64_t)P * (K + N + (res ? N : 0) + (out2 ? N - out2_c0 : 0)) * 2, N, stream);
+        if (act == 0) K10_GO(0) else if (act == 1) K10_GO(1) else K10_GO(2)
+    }
+#undef K10_GO
+    FSD_CUDA(cudaGetLastError());
+    h->launches += 1;
+    *taken = true;
+    return FSD_OK;
+}
+
+}  // namespace fsd

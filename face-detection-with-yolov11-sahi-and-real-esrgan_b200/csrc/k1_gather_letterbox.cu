@@ -416,6 +416,8 @@ int launch_upscale2x(fsd_context* h, const uint8_t* images, int64_t row_pitch, i
                      int B, int src_w, int src_h, int reverse, int nhwc, void* out, cudaStream_t stream);  // k1_upscale2x.cu
 bool pack_sixteenths_tables(const std::vector<int32_t>& xt, const std::vector<int32_t>& yt, int src_w, int src_h, int out_w,
                             int out_h, std::vector<int32_t>& packed);
+int launch_copy_convert(fsd_context* h, const uint8_t* images, int64_t row_pitch, int64_t image_pitch, const int32_t* entries, int B,
+                        int w, int hgt, int reverse, int nhwc, void* out, cudaStream_t stream);
 int launch_sixteenths(fsd_context* h, const uint8_t* images, int64_t row_pitch, int64_t image_pitch, const int32_t* entries,
                       int B, int src_w, const int32_t* packed_dev, int out_w, int out_h, int reverse, int nhwc, void* out,
                       cudaStream_t stream);
@@ -464,6 +466,15 @@ extern "C" int fsd_gather_letterbox(fsd_handle_t h, const uint8_t* images, int n
         if (n_images == 1) image_pitch = row_pitch * H;
         return launch_upscale2x(h, images, row_pitch, image_pitch, entries, B, src_w, src_h, p.reverse,
                                 out_layout == FSD_CHANNELS_LAST, out, stream);
+    }
+
+    // the source box already has the network-input size: pure copy-convert (k1_copy_convert.cu); FSD_K1_NO_COPY=1 sends it down
+    // the sixteenths path instead (identity taps), which the parity tests use to cover both
+    if (mode == K1_MODE_LINEAR && dtype == FSD_F16 && p.new_w == src_w && p.new_h == src_h && p.pad_left == 0 && p.pad_top == 0 &&
+        p.out_w == p.new_w && p.out_h == p.new_h && !getenv("FSD_K1_GENERIC") && !getenv("FSD_K1_NO_COPY")) {
+        if (n_images == 1) image_pitch = row_pitch * H;
+        return launch_copy_convert(h, images, row_pitch, image_pitch, entries, B, src_w, src_h, p.reverse,
+                                   out_layout == FSD_CHANNELS_LAST, out, stream);
     }
 
     std::vector<int32_t> xt, yt;

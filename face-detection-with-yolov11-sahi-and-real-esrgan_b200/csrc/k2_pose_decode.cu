@@ -356,17 +356,11 @@ extern "C" int fsd_pose_decode(fsd_handle_t h, const void* const box[3], const v
             h->dev_allocs.push_back(x_gate);
             k2_find_gate_kernel<<<1, 1, 0, stream>>>(conf, x_gate);
             FSD_CUDA(cudaGetLastError());
-            cudaEvent_t ready;  // other streams may use the cached value: they wait for this event first
-            FSD_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-            FSD_CUDA(cudaEventRecord(ready, stream));
-            it = h->decode_gates.emplace(bits, std::make_pair(x_gate, ready)).first;
+            // once per confidence value and handle: finished before anyone (any stream, any later capture) can use the cached value
+            FSD_CUDA(cudaStreamSynchronize(stream));
+            h->decode_gates.emplace(bits, x_gate);
         } else {
-            x_gate = it->second.first;
-            // (a finished event needs no edge — and an edge to uncaptured work would be illegal inside a stream capture)
-            if (cudaEventQuery(it->second.second) != cudaSuccess) {
-                (void)cudaGetLastError();
-                FSD_CUDA(cudaStreamWaitEvent(stream, it->second.second, 0));
-            }
+            x_gate = it->second;
         }
     }
     TimedLaunch timed(h, FSD_KERNEL_DECODE, (int64_t)B * a * 80 * (dtype == FSD_F16 ? 2 : 4), a, stream);

@@ -191,6 +191,13 @@ static int k7_launch(fsd_context* h, const K7Params& p, cudaStream_t s) {
 
 }  // namespace fsd
 
+namespace fsd {
+bool k10_supported(int K, int N);
+int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const void* w, const void* bias, void* out, int64_t out_stride,
+                        const void* res, int64_t res_stride, void* out2, int64_t out2_stride, int out2_c0, int64_t P, int K, int N,
+                        int act, float slope, cudaStream_t stream, bool* taken);
+}  // namespace fsd
+
 using namespace fsd;
 
 extern "C" int fsd_pointwise_conv(fsd_handle_t h, const void* x, int64_t x_pixel_stride, const void* weight, const void* bias,
@@ -200,9 +207,11 @@ extern "C" int fsd_pointwise_conv(fsd_handle_t h, const void* x, int64_t x_pixel
     FSD_CHECK_ARG(h && x && weight && bias && out, "fsd_pointwise_conv: null argument");
     FSD_CHECK_ARG(dtype == FSD_F16, "fsd_pointwise_conv: only fp16 is implemented");
     FSD_CHECK_ARG(n_pixels >= 0 && act >= 0 && act <= 2, "fsd_pointwise_conv: bad sizes / activation");
-    FSD_CHECK_ARG(in_channels >= 16 && in_channels % 16 == 0 && in_channels <= 128, "fsd_pointwise_conv: in_channels must be a multiple of 16 in [16, 128]");
-    FSD_CHECK_ARG(out_channels == 16 || out_channels == 32 || out_channels == 64 || out_channels == 128,
-                  "fsd_pointwise_conv: out_channels must be 16, 32, 64 or 128 (got %d)", out_channels);
+    const bool k7_shape = in_channels >= 16 && in_channels % 16 == 0 && in_channels <= 128 &&
+                          (out_channels == 16 || out_channels == 32 || out_channels == 64 || out_channels == 128);
+    FSD_CHECK_ARG(k7_shape || k10_supported(in_channels, out_channels),
+                  "fsd_pointwise_conv: unsupported shape %d -> %d (channels must be multiples of 16; see fsd_pointwise_conv_supported)",
+                  in_channels, out_channels);
     FSD_CHECK_ARG(x_pixel_stride >= in_channels && x_pixel_stride % 8 == 0, "fsd_pointwise_conv: bad input stride");
     FSD_CHECK_ARG(out_pixel_stride >= out_channels && out_pixel_stride % 8 == 0, "fsd_pointwise_conv: bad output stride");
     FSD_CHECK_ARG(!residual || (residual_pixel_stride >= out_channels && residual_pixel_stride % 8 == 0), "fsd_pointwise_conv: bad residual stride");
@@ -214,13 +223,25 @@ extern "C" int fsd_pointwise_conv(fsd_handle_t h, const void* x, int64_t x_pixel
         return FSD_ERR_ALIGN;
     }
     if (n_pixels == 0) return FSD_OK;
+    cudaStream_t s = (cudaStream_t)stream_;
+    FSD_CUDA(cudaSetDevice(h->device));
+    // tensor-core path (k10_pointwise_tc.cu: TMA + tcgen05.mma + tensor memory) for every shape it takes; FSD_K7_NO_TC=1 keeps the
+    // mma.sync kernel below (the parity tests run both)
+    if (k10_supported(in_channels, out_channels) && !getenv("FSD_K7_NO_TC")) {
+        bool taken = false;
+        const int rc = launch_pointwise_tc(h, x, x_pixel_stride, weight, bias, out, out_pixel_stride, residual, residual_pixel_stride, out2,
+                                           out2_pixel_stride, out2_first_channel, n_pixels, in_channels, out_channels, act, slope, s, &taken);
+        if (rc != FSD_OK || taken) return rc;
+    }
+    if (!k7_shape) {
+        set_error("fsd_pointwise_conv: %d -> %d needs the tensor-core path, which is unavailable here", in_channels, out_channels);
+        return FSD_ERR_ARG;
+    }
     K7Params p;
     p.x = (const __half*)x; p.w = (const __half*)weight; p.bias = (const __half*)bias; p.out = (__half*)out;
     p.res = (const __half*)residual; p.out2 = (__half*)out2; p.P = n_pixels; p.K = in_channels;
     p.x_stride = (int)x_pixel_stride; p.out_stride = (int)out_pixel_stride; p.res_stride = (int)residual_pixel_stride;
     p.out2_stride = (int)out2_pixel_stride; p.out2_c0 = out2_first_channel; p.act = act; p.slope = slope;
-    cudaStream_t s = (cudaStream_t)stream_;
-    FSD_CUDA(cudaSetDevice(h->device));
     switch (out_channels) {
         case 16: return k7_launch<16>(h, p, s);
         case 32: return k7_launch<32>(h, p, s);

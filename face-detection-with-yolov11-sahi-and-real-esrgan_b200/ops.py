@@ -5,6 +5,8 @@ path is done by the hand-written sm_100a kernels in csrc/.  All functions raise 
 """
 from __future__ import annotations
 
+import os
+
 import contextlib
 import ctypes as C
 import warnings
@@ -357,8 +359,20 @@ def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: to
     return out
 
 
+def pointwise_tc_enabled() -> bool:
+    """The tensor-core 1x1 kernel (csrc/k10_pointwise_tc.cu) is on unless FSD_K7_NO_TC is set."""
+    return not os.environ.get("FSD_K7_NO_TC")
+
+
+def pointwise_tc_supported(k: int, n: int) -> bool:
+    """Shapes the tcgen05 path of fsd_pointwise_conv takes: channels in multiples of 16, weights <= 96 KB (resident in smem)."""
+    return k % 16 == 0 and 16 <= k <= 512 and n % 16 == 0 and 16 <= n <= 256 and k * n * 2 <= 96 * 1024
+
+
 def pointwise_conv_supported(k: int, n: int) -> bool:
-    """Layer shapes Kernel 7 takes (the rest stays on the library convolution + fsd_bias_act)."""
+    """Layer shapes fsd_pointwise_conv takes (the rest stays on the library convolution + fsd_bias_act)."""
+    if pointwise_tc_enabled() and pointwise_tc_supported(k, n):
+        return True
     return k % 16 == 0 and 16 <= k <= 128 and n in (16, 32, 64, 128)
 
 

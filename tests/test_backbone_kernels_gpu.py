@@ -129,11 +129,14 @@ def test_stem_conv_matches_torch(cuda_device, shape):
 
 @pytest.mark.parametrize("kn", [(32, 32), (48, 64), (64, 64), (96, 128), (112, 32), (64, 16), (16, 128), (128, 128)])
 @pytest.mark.parametrize("act", ["silu", "none"])
-def test_pointwise_conv_matches_torch(cuda_device, kn, act):
+@pytest.mark.parametrize("tensor_cores", [True, False])
+def test_pointwise_conv_matches_torch(cuda_device, kn, act, tensor_cores, monkeypatch):
     """(a5) fsd_pointwise_conv == act(conv2d 1x1 + bias) (+ residual) computed in fp32 on the same fp16 inputs, written into
     a concat slot with the trailing channels copied to a second destination; ragged pixel count (not a multiple of 32)."""
     import fsd_b200.ops as ops
 
+    if not tensor_cores:
+        monkeypatch.setenv("FSD_K7_NO_TC", "1")  # the mma.sync kernel (Kernel 7); default: tcgen05 (Kernel 10)
     K, N = kn
     g = torch.Generator().manual_seed(K * 1000 + N)
     cl = lambda t: t.half().to(cuda_device).contiguous(memory_format=torch.channels_last)  # noqa: E731
@@ -157,7 +160,45 @@ def test_pointwise_conv_matches_torch(cuda_device, kn, act):
     assert plain.is_contiguous(memory_format=torch.channels_last)
     err = (plain.float() - y).abs()
     assert float((err - 1e-3 * y.abs()).max()) <= 1e-3, float(err.max())
-    assert not ops.pointwise_conv_supported(256, 64) and not ops.pointwise_conv_supported(24, 64)
+    assert not ops.pointwise_conv_supported(512, 256) and not ops.pointwise_conv_supported(24, 64)
+    assert ops.pointwise_conv_supported(256, 64) == tensor_cores
+
+
+@pytest.mark.parametrize("kn", [(16, 16), (32, 48), (64, 256), (96, 64), (192, 128), (256, 64), (384, 128), (128, 256), (320, 144), (512, 80)])
+@pytest.mark.parametrize("act", ["silu", "none", "lrelu"])
+def test_tensor_core_pointwise_conv_wide_shapes(cuda_device, kn, act):
+    """(a5) the tcgen05 path of fsd_pointwise_conv on the shapes Kernel 7 cannot take (K up to 512, N up to 256, every slab width
+    64 / 32 / 16 and multi-chunk epilogues): fp32 reference on the same fp16 inputs; many tiles per CTA (ring wrap, both accumulators),
+    a ragged last tile, slot input/output, residual and second destination."""
+    import fsd_b200.ops as ops
+
+    K, N = kn
+    g = torch.Generator().manual_seed(K * 7 + N)
+    cl = lambda t: t.half().to(cuda_device).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    B, H, W = 5, 131, 127  # 83185 pixels = 650 tiles (4-5 per CTA), last tile ragged
+    xbuf = cl(torch.randn((B, K + 8, H, W), generator=g))
+    x = xbuf[:, 8:]
+    w = (torch.randn((N, K, 1, 1), generator=g) / K ** 0.5).half().to(cuda_device)
+    bias = torch.randn((N,), generator=g).half().to(cuda_device)
+    res = cl(torch.randn((B, N, H, W), generator=g))
+    f = {"silu": torch.nn.functional.silu, "none": lambda t: t, "lrelu": lambda t: torch.nn.functional.leaky_relu(t, 0.2)}[act]
+    y = f(torch.nn.functional.conv2d(x.float(), w.float(), bias.float()))
+    want = y.half() + res
+    buf = torch.full((B, N + 24, H, W), float("nan"), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    tail = torch.empty((B, 16, H, W), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+    out = ops.pointwise_conv(x, w, bias, act, out=buf[:, 8:8 + N], residual=res, out2=tail)
+    assert torch.isnan(buf[:, :8]).all() and torch.isnan(buf[:, 8 + N:]).all()
+    err = (out.float() - want.float()).abs()
+    assert float((err - 3e-3 * want.float().abs()).max()) <= 3e-3, float(err.max())
+    assert torch.equal(tail, out[:, N - 16:])
+    plain = ops.pointwise_conv(x, w, bias, act)
+    err = (plain.float() - y).abs()
+    assert float((err - 2e-3 * y.abs()).max()) <= 2e-3, float(err.max())
+    # tiny problem: fewer tiles than SMs, one ragged tile
+    xs = cl(torch.randn((1, K, 3, 5), generator=g))
+    ys = f(torch.nn.functional.conv2d(xs.float(), w.float(), bias.float()))
+    err = (ops.pointwise_conv(xs, w, bias, act).float() - ys).abs()
+    assert float((err - 2e-3 * ys.abs()).max()) <= 2e-3, float(err.max())
 
 
 def test_space_to_depth_stem_equals_plain_layers(cuda_device):

@@ -71,7 +71,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert b"sizes must be" in lib.fsd_last_error()
     buf = (ctypes.c_int32 * 4)()
     assert lib.fsd_slice_plan(100, 100, 40, 40, 0.2, 0.2, buf, 1, ctypes.byref(n)) == -4 and n.value == 9
-    assert lib.fsd_merge_workspace_bytes(100, 2, 5000) == 2 * (8192 * 48 + 2048) + 256  # box arrays + the cluster kernel's scratch
+    assert lib.fsd_merge_workspace_bytes(100, 2, 5000) == 2 * (8192 * 52 + 2048) + 256  # box arrays (+ NMM step array) + the cluster kernel's scratch
     tab = (ctypes.c_int32 * 12)()
     assert lib.fsd_esrgan_tile_table(3, 3, 2, 2, 10, 5, tab, 1, ctypes.byref(n), None) == -1  # reflect pad >= size
 

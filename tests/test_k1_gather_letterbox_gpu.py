@@ -154,6 +154,34 @@ def test_sixteenths_path_equals_general_kernel_and_oracle(cuda_device, case, cha
     assert torch.equal(general, fast)
 
 
+@pytest.mark.parametrize("case", [(768, 1024, 1024, 32), (96, 128, 128, 32), (64, 72, 72, 8), (32, 40, 40, 8), (16, 16, 16, 16)])
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("reverse", [True, False])
+def test_copy_convert_path_equals_sixteenths_path_and_oracle(cuda_device, case, channels_last, reverse, monkeypatch):
+    """Scale 1 (the box already has the network-input size): k1_copy_convert_kernel — aligned 16-pixel groups, unaligned x0
+    (byte-load path) and a ragged 8-pixel row end — equals cv2 (oracle) and the sixteenths kernel with identity taps bit for bit."""
+    import fsd_b200.ops as ops
+
+    sh, sw, imgsz, stride = case
+    H, W = sh + 19, sw + 37
+    rng = np.random.default_rng(sh * 11 + sw)
+    images = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(2)]
+    images[0][:2, :3] = [[[0, 255, 1], [254, 128, 127], [2, 3, 253]]] * 2
+    entries = [(0, 0, 0), (1, 16, 19), (0, 5, 2), (1, 32, 0), (0, 37, 7)]
+    pool = ops.ImagePool.from_numpy(images, cuda_device)
+    ent = torch.tensor(entries, dtype=torch.int32)
+    kw = dict(imgsz=imgsz, stride=stride, reverse_channels=reverse, dtype=torch.float16, channels_last=channels_last)
+    fast = ops.gather_letterbox(pool, ent, sw, sh, **kw)
+    assert fast.shape == (5, 3, sh, sw)
+    if reverse and stride == 32:
+        assert torch.equal(fast.cpu(), _oracle_batch(images, entries, sw, sh, imgsz, True, True))
+    want = torch.stack([torch.from_numpy(np.ascontiguousarray(images[i][y:y + sh, x:x + sw, ::-1] if reverse else images[i][y:y + sh, x:x + sw]))
+                        for i, x, y in entries]).permute(0, 3, 1, 2).float().div(255.0).half()
+    assert torch.equal(fast.cpu(), want)
+    monkeypatch.setenv("FSD_K1_NO_COPY", "1")
+    assert torch.equal(ops.gather_letterbox(pool, ent, sw, sh, **kw), fast)
+
+
 def test_in_library_kernel_timing(cuda_device):
     """fsd_kernel_timing_*: one sample per instrumented launch, tagged (kernel id, entries, src_w), positive device time;
     kernels outside the mask are not sampled and re-enabling clears the list."""
