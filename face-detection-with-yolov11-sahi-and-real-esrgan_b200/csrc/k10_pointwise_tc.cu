@@ -22,7 +22,8 @@ namespace fsd {
 
 constexpr int K10_THREADS = 192;
 constexpr int K10_TILE = 128;          // pixels per tile = MMA M
-constexpr int K10_STAGE_PITCH = 72;    // halves per staged output row (64 columns + 16 bytes: conflict-free 16-byte accesses)
+constexpr int K10_CHUNK = 32;          // accumulator columns per epilogue step
+constexpr int K10_STAGE_PITCH = 40;    // halves per staged output row (32 columns + 16 bytes: conflict-free 16-byte accesses)
 constexpr int K10_MAX_STAGES = 16;
 
 struct K10Params {
@@ -108,15 +109,25 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t sbo_by
     return d;
 }
 
+// SiLU with ONE MUFU op: v * sigmoid(v) = h + h * tanh(h), h = v / 2 (tanh.approx: 2^-11 relative on tanh, i.e. <= 2.4e-4 * |v|
+// absolute on the result — the size of an fp16 rounding step of the activations; opt-in with FSD_K10_SILU=tanh)
+__device__ __forceinline__ float tanh_silu(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
 template <int ACT>
 __device__ __forceinline__ float k10_act(float v, float slope) {
+    if (ACT == 3) return tanh_silu(v);
     if (ACT == 1) return fast_silu(v);
     if (ACT == 2) return v > 0.f ? v : v * slope;
     return v;
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(K10_THREADS, 1)
+__global__ void __launch_bounds__(K10_THREADS, 4)
 k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const K10Params p) {
     extern __shared__ uint8_t k10_raw[];
     __shared__ uint64_t full_bar[K10_MAX_STAGES], empty_bar[K10_MAX_STAGES], b_bar, acc_full[2], acc_empty[2];
@@ -202,20 +213,20 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.N);
             const long long pix0 = (long long)tile * K10_TILE + q * 32;
-            for (int c0 = 0; c0 < p.N; c0 += 64) {
-                const int cw = p.N - c0 < 64 ? p.N - c0 : 64;  // 16, 32, 48 or 64 columns
-                uint32_t v[4][16];
+            for (int c0 = 0; c0 < p.N; c0 += K10_CHUNK) {
+                const int cw = p.N - c0 < K10_CHUNK ? p.N - c0 : K10_CHUNK;  // 16 or 32 columns
+                uint32_t v[K10_CHUNK / 16][16];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < K10_CHUNK / 16; ++j)
                     if (16 * j < cw) tc_ld16(t_row + (uint32_t)(c0 + 16 * j), v[j]);
                 tc_wait_ld();
-                if (c0 + 64 >= p.N) {  // last read of this accumulator: hand it back to the MMA warp before the stores
+                if (c0 + K10_CHUNK >= p.N) {  // last read of this accumulator: hand it back to the MMA warp before the stores
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) k10_mbar_arrive(&acc_empty[acc]);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < K10_CHUNK / 16; ++j) {
                     if (16 * j < cw) {
                         uint32_t h[8];
 #pragma unroll
@@ -304,19 +315,33 @@ int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const v
     int cols = 32;
     while (cols < 2 * N) cols <<= 1;
     p.tmem_cols = cols;
+    // CTAs per SM: one CTA's four epilogue warps cannot hide their own tensor-memory / shared-memory / store latencies (one tile per
+    // ~2800 cycles measured with a single CTA per SM at K = N = 32, against 700 at the HBM roofline), so small shapes run up to four
+    // CTAs per SM — bounded by tensor memory (512 columns per SM) and by a ring of at least two slabs per CTA
     const size_t staging = (size_t)4 * 32 * K10_STAGE_PITCH * sizeof(__half);
-    const size_t budget = 200 * 1024;
-    int stages = (int)((budget - p.b_region - staging) / p.slab_bytes);
-    if (stages > K10_MAX_STAGES) stages = K10_MAX_STAGES;
+    int ctas = 512 / p.tmem_cols < 4 ? 512 / p.tmem_cols : 4;
+    if (getenv("FSD_K10_CTAS")) ctas = atoi(getenv("FSD_K10_CTAS")) < ctas ? atoi(getenv("FSD_K10_CTAS")) : ctas;
+    if (ctas < 1) ctas = 1;
+    int stages = 0;
+    size_t smem = 0;
+    for (; ctas >= 1; --ctas) {
+        const size_t budget = (size_t)216 * 1024 / ctas - 3 * 1024;  // static shared memory + the driver's 1 KB per CTA
+        const size_t fixed = 1024 + p.b_region + staging;
+        if (budget < fixed + 2 * (size_t)p.slab_bytes) continue;
+        stages = (int)((budget - fixed) / p.slab_bytes);
+        if (stages > K10_MAX_STAGES) stages = K10_MAX_STAGES;
+        // (pad the request so that no more CTAs than tensor memory allows ever share an SM)
+        smem = budget;
+        break;
+    }
     if (stages < 2) return FSD_OK;
     p.stages = stages;
-    const size_t smem = 1024 + p.b_region + (size_t)stages * p.slab_bytes + staging;
 
     CUtensorMap mx, mw;
     if (!k10_encode(h, &mx, x, (uint64_t)K, (uint64_t)P, (uint64_t)x_stride * 2, (uint32_t)p.KS, K10_TILE, swz)) return FSD_OK;
     if (!k10_encode(h, &mw, w, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)p.KS, (uint32_t)N, swz)) return FSD_OK;
 
-    const int grid = p.n_tiles < h->sm_count ? p.n_tiles : h->sm_count;
+    const int grid = p.n_tiles < h->sm_count * ctas ? p.n_tiles : h->sm_count * ctas;
 #define K10_GO(ACT)                                                                                                     \
     {                                                                                                                   \
         auto kern = k10_pointwise_tc_kernel<ACT>;                                                                       \
@@ -325,7 +350,8 @@ int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const v
     }
     {
         TimedLaunch timed(h, FSD_KERNEL_POINTWISE, (int64_t)P * (K + N + (res ? N : 0) + (out2 ? N - out2_c0 : 0)) * 2, N, stream);
-        if (act == 0) K10_GO(0) else if (act == 1) K10_GO(1) else K10_GO(2)
+        const char* silu = getenv("FSD_K10_SILU");
+        if (act == 0) K10_GO(0) else if (act == 1 && silu && !strcmp(silu, "tanh")) K10_GO(3) else if (act == 1) K10_GO(1) else K10_GO(2)
     }
 #undef K10_GO
     FSD_CUDA(cudaGetLastError());

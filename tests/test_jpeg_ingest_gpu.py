@@ -1,6 +1,8 @@
 """(f4) nvJPEG ingest: a JPEG decoded on the device into the image pool, against PIL's host decode (what the reference's
-read_image_as_pil does).  NOT bit-exact by nature — different IDCT / chroma up-sampling implementations — so the bar is a
-tolerance: identical size and channel order, mean absolute difference < 1 LSB, 4:4:4 streams within 3 LSB everywhere."""
+read_image_as_pil does).  NOT bit-exact by nature.  Measured on B200 (benchmarks/jpeg_probe.py, gpurun_out -> DESIGN §3): 4:4:4 streams
+and smooth content differ by 0.5 LSB on average, at most 4 (IDCT rounding); 4:2:0 streams of per-channel NOISE differ by ~5 LSB on
+average in the chroma-heavy channels because nvJPEG replicates chroma samples where libjpeg interpolates them ("fancy up-sampling") —
+both decoders are then equally far from the uncompressed original.  The bars below state exactly that."""
 import io
 
 import numpy as np
@@ -17,14 +19,20 @@ def _jpeg(img, quality, subsampling):
     return buf.getvalue()
 
 
+def _smooth(h, w):
+    yy, xx = np.mgrid[0:h, 0:w]
+    return np.stack([xx * 255 // w, yy * 255 // h, (xx + yy) * 255 // (h + w)], -1).astype(np.uint8)
+
+
 @pytest.mark.parametrize("size", [(768, 1024), (301, 517)])
 @pytest.mark.parametrize("subsampling", [0, 2])  # 4:4:4 and 4:2:0
-def test_device_decode_tracks_pil(cuda_device, size, subsampling):
+@pytest.mark.parametrize("content", ["noise", "smooth"])
+def test_device_decode_tracks_pil(cuda_device, size, subsampling, content):
     import fsd_b200.ops as ops
     from fsd_b200.synthetic import make_image
 
     H, W = size
-    img, _ = make_image(3, H, W)
+    img = make_image(3, H, W)[0] if content == "noise" else _smooth(H, W)
     data = _jpeg(img, 92, subsampling)
     assert ops.jpeg_info(data) == (W, H, 3)
     want = np.asarray(Image.open(io.BytesIO(data)).convert("RGB")).astype(np.int32)
@@ -32,9 +40,13 @@ def test_device_decode_tracks_pil(cuda_device, size, subsampling):
     pool.upload_jpeg(1, data)
     got = pool.view(1).cpu().numpy().astype(np.int32)
     d = np.abs(got - want)
-    assert got.shape == want.shape and d.mean() < 1.0, d.mean()
-    if subsampling == 0:
-        assert d.max() <= 3, d.max()
+    assert got.shape == want.shape
+    if subsampling == 0 or content == "smooth":
+        assert d.mean() < 1.0 and d.max() <= 6, (d.mean(), d.max())
+    else:  # chroma noise at 4:2:0: the decoders interpolate chroma differently; neither is closer to the source image
+        assert d.mean() < 8.0, d.mean()
+        assert np.abs(got - img).mean() <= np.abs(want - img).mean() + 1.5
+        assert np.abs(got[..., ::-1] - want).mean() > 2 * d.mean()  # (and the channel order is right)
     pool.upload_jpeg(0, data, bgr=True)
     assert np.array_equal(pool.view(0).cpu().numpy()[..., ::-1], pool.view(1).cpu().numpy())
     with pytest.raises(Exception):
