@@ -239,7 +239,7 @@ def bench_k10():
         if ops.pointwise_tc_supported(k, n):
             os.environ.pop("FSD_K7_NO_TC", None)
             report(f"K10 tcgen05 pointwise conv + bias + SiLU {name}", nbytes, lambda: ops.pointwise_conv(x, w, bias, "silu", out=out))
-            for key, val in (("FSD_K10_SILU", "tanh"), ("FSD_K10_CTAS", "2"), ("FSD_K10_CTAS", "1")):
+            for key, val in (("FSD_K10_SILU", "tanh"), ("FSD_K10_CTAS", "4"), ("FSD_K10_CTAS", "2"), ("FSD_K10_CTAS", "1")):
                 os.environ[key] = val
                 report(f"   K10 with {key}={val} {name}", nbytes, lambda: ops.pointwise_conv(x, w, bias, "silu", out=out))
                 os.environ.pop(key)

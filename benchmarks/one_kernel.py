@@ -43,6 +43,14 @@ elif which == "k1_c1":  # C1 slices 640^2 -> 1024^2: the sixteenths path
     out = torch.empty((ent.shape[0], 3, 1024, 1024), dtype=torch.float16, device=dev, memory_format=torch.channels_last)
     for _ in range(iters):
         ops.gather_letterbox(pool, ent, 640, 640, 1024, 32, True, torch.float16, out=out)
+elif which in ("k10", "k10_wide"):  # 1x1 convolution on tcgen05: 32->32 at 256^2 (epilogue-heavy) / 96->128 at 128^2
+    k, n, hw = (32, 32, 256) if which == "k10" else (96, 128, 128)
+    x = torch.randn((96, k, hw, hw), device=dev).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((n, k, 1, 1), device=dev) / k ** 0.5).half()
+    b = torch.randn((n,), device=dev).half()
+    out = torch.empty((96, n, hw, hw), device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    for _ in range(iters):
+        ops.pointwise_conv(x, w, b, "silu", out=out)
 elif which == "k7":
     x = torch.randn((96, 48, 256, 256), device=dev).half().contiguous(memory_format=torch.channels_last)
     w = (torch.randn((64, 48, 1, 1), device=dev) / 7).half()

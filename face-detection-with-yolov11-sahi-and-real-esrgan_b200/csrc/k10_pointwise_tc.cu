@@ -20,10 +20,11 @@
 
 namespace fsd {
 
-constexpr int K10_THREADS = 192;
+constexpr int K10_EPI_WARPS = 8;        // two warps per tensor-memory lane quarter, alternating 16-column steps
+constexpr int K10_THREADS = 64 + 32 * K10_EPI_WARPS;
 constexpr int K10_TILE = 128;          // pixels per tile = MMA M
-constexpr int K10_CHUNK = 32;          // accumulator columns per epilogue step
-constexpr int K10_STAGE_PITCH = 40;    // halves per staged output row (32 columns + 16 bytes: conflict-free 16-byte accesses)
+constexpr int K10_CHUNK = 16;          // accumulator columns per epilogue step (one tcgen05.ld.32x32b.x16)
+constexpr int K10_STAGE_PITCH = 24;    // halves per staged output row (16 columns + 16 bytes: conflict-free 16-byte accesses)
 constexpr int K10_MAX_STAGES = 16;
 
 struct K10Params {
@@ -126,13 +127,13 @@ __device__ __forceinline__ float k10_act(float v, float slope) {
     return v;
 }
 
-template <int ACT>
-__global__ void __launch_bounds__(K10_THREADS, 4)
+template <int ACT, int MINB>
+__global__ void __launch_bounds__(K10_THREADS, MINB)
 k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const K10Params p) {
     extern __shared__ uint8_t k10_raw[];
     __shared__ uint64_t full_bar[K10_MAX_STAGES], empty_bar[K10_MAX_STAGES], b_bar, acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float s_bias[256];
+    __shared__ __align__(16) float s_bias[256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // dynamic smem (1024-byte aligned for the 128-byte swizzle atoms): [weights | activation ring | 4 x epilogue staging]
@@ -147,7 +148,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         tma_prefetch_desc(&map_w);
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&b_bar, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], p.N >= 2 * K10_CHUNK ? K10_EPI_WARPS : 4); }
         fence_barrier_init();
     }
     if (warp == 1) tc_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
@@ -203,64 +204,63 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             }
         }
     } else {
-        // ================= epilogue warps (TMEM lane quarter = warp % 4) =================
-        const int q = warp & 3;
+        // ================= epilogue warps (TMEM lane quarter = warp % 4; warps 2-5 take the even 16-column steps, 6-9 the odd) ====
+        const int q = warp & 3, half = (warp - 2) >> 2;
         __half* stg = stage_base + (size_t)(warp - 2) * 32 * K10_STAGE_PITCH;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            k10_mbar_wait(&acc_full[acc], (it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.N);
-            const long long pix0 = (long long)tile * K10_TILE + q * 32;
-            for (int c0 = 0; c0 < p.N; c0 += K10_CHUNK) {
-                const int cw = p.N - c0 < K10_CHUNK ? p.N - c0 : K10_CHUNK;  // 16 or 32 columns
-                uint32_t v[K10_CHUNK / 16][16];
+        if (half * K10_CHUNK < p.N) {  // (N = 16: the second set has no step)
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                k10_mbar_wait(&acc_full[acc], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.N);
+                const long long pix0 = (long long)tile * K10_TILE + q * 32;
+                for (int c0 = half * K10_CHUNK; c0 < p.N; c0 += 2 * K10_CHUNK) {
+                    uint32_t v[16];
+                    tc_ld16(t_row + (uint32_t)c0, v);
+                    tc_wait_ld();
+                    if (c0 + 2 * K10_CHUNK >= p.N) {  // this warp's last read of the accumulator: hand it back before the stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) k10_mbar_arrive(&acc_empty[acc]);
+                    }
+                    uint32_t h[8];
 #pragma unroll
-                for (int j = 0; j < K10_CHUNK / 16; ++j)
-                    if (16 * j < cw) tc_ld16(t_row + (uint32_t)(c0 + 16 * j), v[j]);
-                tc_wait_ld();
-                if (c0 + K10_CHUNK >= p.N) {  // last read of this accumulator: hand it back to the MMA warp before the stores
-                    tc_fence_before();
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * e4]);
+                        const __half2 o0 = __floats2half2_rn(k10_act<ACT>(__uint_as_float(v[4 * e4]) + bb.x, p.slope),
+                                                             k10_act<ACT>(__uint_as_float(v[4 * e4 + 1]) + bb.y, p.slope));
+                        const __half2 o1 = __floats2half2_rn(k10_act<ACT>(__uint_as_float(v[4 * e4 + 2]) + bb.z, p.slope),
+                                                             k10_act<ACT>(__uint_as_float(v[4 * e4 + 3]) + bb.w, p.slope));
+                        h[2 * e4] = *reinterpret_cast<const uint32_t*>(&o0);
+                        h[2 * e4 + 1] = *reinterpret_cast<const uint32_t*>(&o1);
+                    }
+                    uint4* d = reinterpret_cast<uint4*>(stg + (size_t)lane * K10_STAGE_PITCH);
+                    d[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                    d[1] = make_uint4(h[4], h[5], h[6], h[7]);
                     __syncwarp();
-                    if (lane == 0) k10_mbar_arrive(&acc_empty[acc]);
-                }
+                    // row-contiguous stores: two 16-byte pieces per row (+ residual, + second destination)
 #pragma unroll
-                for (int j = 0; j < K10_CHUNK / 16; ++j) {
-                    if (16 * j < cw) {
-                        uint32_t h[8];
+                    for (int i2 = 0; i2 < 2; ++i2) {
+                        const int i = lane + 32 * i2;
+                        const int r = i >> 1, c = i & 1;
+                        const long long pix = pix0 + r;
+                        if (pix < p.P) {
+                            uint4 o = *reinterpret_cast<const uint4*>(stg + (size_t)r * K10_STAGE_PITCH + c * 8);
+                            const int col = c0 + c * 8;
+                            if (p.res) {
+                                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)pix * p.res_stride + col));
+                                __half2* ho = reinterpret_cast<__half2*>(&o);
+                                const __half2* hr = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float f0 = k10_act<ACT>(__uint_as_float(v[j][2 * e]) + s_bias[c0 + 16 * j + 2 * e], p.slope);
-                            const float f1 = k10_act<ACT>(__uint_as_float(v[j][2 * e + 1]) + s_bias[c0 + 16 * j + 2 * e + 1], p.slope);
-                            const __half2 o = __floats2half2_rn(f0, f1);
-                            h[e] = *reinterpret_cast<const uint32_t*>(&o);
+                                for (int e = 0; e < 4; ++e) ho[e] = __hadd2(ho[e], hr[e]);
+                            }
+                            *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_stride + col) = o;
+                            if (p.out2 && col >= p.out2_c0) *reinterpret_cast<uint4*>(p.out2 + (size_t)pix * p.out2_stride + (col - p.out2_c0)) = o;
                         }
-                        uint4* d = reinterpret_cast<uint4*>(stg + (size_t)lane * K10_STAGE_PITCH + 16 * j);
-                        d[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                        d[1] = make_uint4(h[4], h[5], h[6], h[7]);
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
-                // row-contiguous 16-byte stores (+ residual, + second destination)
-                const int nch = cw >> 3;
-                for (int i = lane; i < 32 * nch; i += 32) {
-                    const int r = i / nch, c = i - r * nch;
-                    const long long pix = pix0 + r;
-                    if (pix >= p.P) continue;
-                    uint4 o = *reinterpret_cast<const uint4*>(stg + (size_t)r * K10_STAGE_PITCH + c * 8);
-                    const int col = c0 + c * 8;
-                    if (p.res) {
-                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res + (size_t)pix * p.res_stride + col));
-                        __half2* ho = reinterpret_cast<__half2*>(&o);
-                        const __half2* hr = reinterpret_cast<const __half2*>(&rr);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) ho[e] = __hadd2(ho[e], hr[e]);
-                    }
-                    *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_stride + col) = o;
-                    if (p.out2 && col >= p.out2_c0) *reinterpret_cast<uint4*>(p.out2 + (size_t)pix * p.out2_stride + (col - p.out2_c0)) = o;
-                }
-                __syncwarp();
             }
         }
     }
@@ -316,11 +316,12 @@ int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const v
     while (cols < 2 * N) cols <<= 1;
     p.tmem_cols = cols;
     // CTAs per SM: one CTA's four epilogue warps cannot hide their own tensor-memory / shared-memory / store latencies (one tile per
-    // ~2800 cycles measured with a single CTA per SM at K = N = 32, against 700 at the HBM roofline), so small shapes run up to four
+    // ~2800 cycles measured with a single CTA per SM at K = N = 32, against 700 at the HBM roofline), so small shapes run three (optionally four)
     // CTAs per SM — bounded by tensor memory (512 columns per SM) and by a ring of at least two slabs per CTA
-    const size_t staging = (size_t)4 * 32 * K10_STAGE_PITCH * sizeof(__half);
-    int ctas = 512 / p.tmem_cols < 4 ? 512 / p.tmem_cols : 4;
-    if (getenv("FSD_K10_CTAS")) ctas = atoi(getenv("FSD_K10_CTAS")) < ctas ? atoi(getenv("FSD_K10_CTAS")) : ctas;
+    const size_t staging = (size_t)K10_EPI_WARPS * 32 * K10_STAGE_PITCH * sizeof(__half);
+    int want = getenv("FSD_K10_CTAS") ? atoi(getenv("FSD_K10_CTAS")) : 3;  // 4 selects the 48-register build of the kernel
+    if (want > 4) want = 4;
+    int ctas = 512 / p.tmem_cols < want ? 512 / p.tmem_cols : want;
     if (ctas < 1) ctas = 1;
     int stages = 0;
     size_t smem = 0;
@@ -344,7 +345,7 @@ int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const v
     const int grid = p.n_tiles < h->sm_count * ctas ? p.n_tiles : h->sm_count * ctas;
 #define K10_GO(ACT)                                                                                                     \
     {                                                                                                                   \
-        auto kern = k10_pointwise_tc_kernel<ACT>;                                                                       \
+        auto kern = ctas >= 4 ? k10_pointwise_tc_kernel<ACT, 4> : k10_pointwise_tc_kernel<ACT, 3>;                      \
         FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
         kern<<<grid, K10_THREADS, smem, stream>>>(mx, mw, p);                                                           \
     }
