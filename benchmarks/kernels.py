@@ -252,8 +252,30 @@ def bench_k10():
         del x, out
 
 
+def bench_conv3():
+    """dense 3x3 stride-1 convolutions of the backbone (96 network inputs of 1024^2): fsd_conv3x3 (tcgen05 implicit GEMM) vs cuDNN + epilogue."""
+    cl = lambda *shape: torch.randn(shape, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    torch.backends.cudnn.benchmark = True
+    for name, k, n, hw in (("b2.m 16->8 256^2", 16, 8, 256), ("b4.m 32->16 128^2", 32, 16, 128), ("b4.m 16->32 128^2", 16, 32, 128),
+                           ("head.cv2 64->64 128^2", 64, 64, 128), ("head.cv4 64->16 128^2", 64, 16, 128), ("c3k 32->32 64^2", 32, 32, 64),
+                           ("b6 32->64 64^2", 32, 64, 64), ("b6 64->32 64^2", 64, 32, 64), ("head 64->64 64^2", 64, 64, 64),
+                           ("head.cv4 128->16 64^2", 128, 16, 64), ("c3k 64->64 32^2", 64, 64, 32), ("head.cv4 256->16 32^2", 256, 16, 32)):
+        x = cl(96, k, hw, hw)
+        w = (torch.randn((n, k, 3, 3), device=dev) / (3 * k ** 0.5)).half().contiguous(memory_format=torch.channels_last)
+        taps = ops.conv3x3_tap_major(w)
+        bias = torch.randn((n,), device=dev).half()
+        out = cl(96, n, hw, hw)
+        nbytes = (x.numel() + out.numel()) * 2
+        report(f"K10 tcgen05 conv3x3 + bias + SiLU {name}", nbytes, lambda: ops.conv3x3(x, taps, bias, "silu", out=out))
+        os.environ["FSD_K10_SILU"] = "tanh"
+        report(f"   with FSD_K10_SILU=tanh {name}", nbytes, lambda: ops.conv3x3(x, taps, bias, "silu", out=out))
+        os.environ.pop("FSD_K10_SILU")
+        report(f"   cuDNN conv + fsd_bias_act {name}", nbytes, lambda: ops.bias_act(torch.nn.functional.conv2d(x, w, None, 1, 1), bias, "silu", out=out))
+        del x, out
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4), ("k5", bench_k5), ("k10", bench_k10)):
+    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4), ("k5", bench_k5), ("k10", bench_k10), ("conv3", bench_conv3)):
         if which in ("all", name):
             fn()

@@ -61,14 +61,25 @@ class Conv(nn.Module):
             if (c.kernel_size == (1, 1) and c.stride == (1, 1) and c.groups == 1 and USE_POINTWISE_KERNEL and up2 is None
                     and x.stride(1) == 1 and x.shape[2] * x.shape[3] >= 1024):
                 # low-intensity 1x1 layers: one kernel does GEMM + bias + activation (+ residual) into the slot
-                from ..ops import pointwise_conv, pointwise_conv_supported, pointwise_tc_enabled, pointwise_tc_supported
+                from ..ops import pointwise_conv, pointwise_conv_supported, pointwise_tc_enabled, pointwise_tc_preferred
 
                 # tensor-core kernel (tcgen05, k10_pointwise_tc.cu): every shape it takes.  The mma.sync kernel (FSD_K7_NO_TC=1) only
                 # beats cuDNN + epilogue for K, N <= 64 (profiles/r1_kernels_k7.jsonl: 0.55 vs 0.34 of peak at 32->32; for N = 128
                 # its SiLU epilogue is issue/MUFU-bound and the library pair is faster)
-                tc = pointwise_tc_enabled() and pointwise_tc_supported(c.in_channels, c.out_channels)
+                tc = pointwise_tc_enabled() and pointwise_tc_preferred(c.in_channels, c.out_channels)
                 if pointwise_conv_supported(c.in_channels, c.out_channels) and (tc or (c.in_channels <= 64 and c.out_channels <= 64)):
                     return pointwise_conv(x, c.weight, c.bias, act, out=out, residual=residual, out2=out2)
+            if (c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and c.dilation == (1, 1) and c.groups == 1
+                    and out2 is None and up2 is None and x.stride(1) == 1 and x.shape[2] * x.shape[3] >= 256):
+                # dense 3x3 layers: implicit GEMM on the tensor cores with the epilogue fused (fsd_conv3x3)
+                from ..ops import conv3x3, conv3x3_supported, conv3x3_tap_major, conv3x3_tc_enabled
+
+                if conv3x3_tc_enabled() and conv3x3_supported(c.in_channels, c.out_channels):
+                    cached = getattr(self, "_w_taps", None)  # (weight version, tap-major copy)
+                    if cached is None or cached[0] != (c.weight._version, c.weight.data_ptr()):
+                        cached = ((c.weight._version, c.weight.data_ptr()), conv3x3_tap_major(c.weight))
+                        self._w_taps = cached
+                    return conv3x3(x, cached[1], c.bias, act, out=out, residual=residual)
             y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
             if y.is_contiguous(memory_format=torch.channels_last):
                 from ..ops import bias_act

@@ -16,6 +16,13 @@
 //   warps 2-5: epilogue.  tcgen05.ld (LDTM) 32 lanes x 16 columns, + bias, activation, fp16, staged through shared memory so that the
 //              global stores (and the residual loads) are row-contiguous 16-byte vectors, exactly as in Kernel 7.
 // The accumulator is double buffered, so the epilogue of tile t overlaps the loads and MMAs of tile t+1.
+//
+// The same kernel is the 3x3 convolution (stride 1, pad 1; fsd_conv3x3, ultralytics Conv(c1, c2, 3, 1) inside Bottleneck / C3k / the head
+// branches) as an implicit GEMM: a tile is a 16 x 8 pixel patch of one image, and each of the nine taps is ONE 4-D TMA box
+// [KS channels, 16, 8, 1] at the patch origin shifted by (kx - 1, ky - 1) — TMA's out-of-bounds zero fill is the padding — landing in
+// the very same K-major swizzled slab layout as the 1x1 case.  The MMA loop runs over 9 x (C / KS) slabs against the tap-major weights
+// [3][3][N][C] resident in shared memory; the epilogue maps accumulator rows back to (y, x).  The nine boxes of a tile overlap, so the
+// input is fetched from HBM once and from L2 nine times.
 #include "fsd_common.cuh"
 
 namespace fsd {
@@ -37,6 +44,8 @@ struct K10Params {
     int out_stride, res_stride, out2_stride, out2_c0;
     float slope;
     uint32_t b_bytes, b_region, slab_bytes, sbo_bytes, layout_type;  // b_region = b_bytes rounded up to 1024
+    int taps, total_slabs, n_valid;           // 1 or 9 taps; total_slabs = taps * n_slabs; columns actually stored
+    int H, W, tiles_x, tiles_per_image;       // 3x3 only: image size and the 16 x 8 patch grid
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------------
@@ -65,6 +74,13 @@ __device__ __forceinline__ void k10_tma_load_2d(void* smem_dst, const CUtensorMa
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void k10_tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c, int x, int y, int n) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(x), "r"(y), "r"(n)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -127,7 +143,7 @@ __device__ __forceinline__ float k10_act(float v, float slope) {
     return v;
 }
 
-template <int ACT, int MINB>
+template <int ACT, int MINB, bool CONV3>
 __global__ void __launch_bounds__(K10_THREADS, MINB)
 k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const K10Params p) {
     extern __shared__ uint8_t k10_raw[];
@@ -161,15 +177,32 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         // ================= TMA producer =================
         if (lane == 0) {
             mbar_expect_tx(&b_bar, p.b_bytes);
-            for (int s = 0; s < p.n_slabs; ++s)
-                k10_tma_load_2d(smem_b + (size_t)s * p.N * p.KS * 2, &map_w, &b_bar, s * p.KS, 0);
+            for (int s = 0; s < p.total_slabs; ++s) {
+                uint8_t* dst = smem_b + (size_t)s * p.N * p.KS * 2;
+                if (CONV3) tma_load_3d(dst, &map_w, &b_bar, (s % p.n_slabs) * p.KS, 0, s / p.n_slabs);
+                else k10_tma_load_2d(dst, &map_w, &b_bar, s * p.KS, 0);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int s = 0; s < p.n_slabs; ++s) {
+                int n = 0, ty = 0, tx = 0;
+                if (CONV3) {
+                    n = tile / p.tiles_per_image;
+                    const int rem = tile - n * p.tiles_per_image;
+                    ty = rem / p.tiles_x;
+                    tx = rem - ty * p.tiles_x;
+                }
+                for (int s = 0; s < p.total_slabs; ++s) {
                     k10_mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], p.slab_bytes);
-                    k10_tma_load_2d(smem_a + (size_t)stage * p.slab_bytes, &map_x, &full_bar[stage], s * p.KS, tile * K10_TILE);
+                    uint8_t* dst = smem_a + (size_t)stage * p.slab_bytes;
+                    if (CONV3) {
+                        const int tap = s / p.n_slabs, cs = s - tap * p.n_slabs;
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        k10_tma_load_4d(dst, &map_x, &full_bar[stage], cs * p.KS, tx * 16 + kx - 1, ty * 8 + ky - 1, n);
+                    } else {
+                        k10_tma_load_2d(dst, &map_x, &full_bar[stage], s * p.KS, tile * K10_TILE);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -188,7 +221,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 k10_mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
-                for (int s = 0; s < p.n_slabs; ++s) {
+                for (int s = 0; s < p.total_slabs; ++s) {
                     k10_mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = a0 + (uint32_t)stage * p.slab_bytes;
@@ -214,7 +247,16 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 k10_mbar_wait(&acc_full[acc], (it >> 1) & 1);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.N);
+                // accumulator row m = 32 q + r  ->  pixel: 1x1: tile * 128 + m;  3x3: (y0 + m / 16, x0 + m % 16) of image n
                 const long long pix0 = (long long)tile * K10_TILE + q * 32;
+                int img = 0, y0 = 0, x0 = 0;
+                if (CONV3) {
+                    img = tile / p.tiles_per_image;
+                    const int rem = tile - img * p.tiles_per_image;
+                    const int ty = rem / p.tiles_x;
+                    y0 = ty * 8 + 2 * q;
+                    x0 = (rem - ty * p.tiles_x) * 16;
+                }
                 for (int c0 = half * K10_CHUNK; c0 < p.N; c0 += 2 * K10_CHUNK) {
                     uint32_t v[16];
                     tc_ld16(t_row + (uint32_t)c0, v);
@@ -244,8 +286,15 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     for (int i2 = 0; i2 < 2; ++i2) {
                         const int i = lane + 32 * i2;
                         const int r = i >> 1, c = i & 1;
-                        const long long pix = pix0 + r;
-                        if (pix < p.P) {
+                        long long pix = pix0 + r;
+                        bool ok = pix < p.P;
+                        if (CONV3) {
+                            const int y = y0 + (r >> 4), x = x0 + (r & 15);
+                            ok = y < p.H && x < p.W;
+                            pix = ((long long)img * p.H + y) * p.W + x;
+                        }
+                        const int col_first = c0 + c * 8;
+                        if (ok && col_first < p.n_valid) {
                             uint4 o = *reinterpret_cast<const uint4*>(stg + (size_t)r * K10_STAGE_PITCH + c * 8);
                             const int col = c0 + c * 8;
                             if (p.res) {
@@ -277,47 +326,66 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 bool k10_supported(int K, int N) {
     return K % 16 == 0 && K >= 16 && K <= 512 && N % 16 == 0 && N >= 16 && N <= 256 && (size_t)K * N * 2 <= 96 * 1024;
 }
-
-static bool k10_encode(fsd_context* h, CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
-                       uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
-    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {row_stride_bytes};
-    cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    return ((encode_fn)h->encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+// 3x3: N = 8 runs as a 16-column MMA whose upper half is never stored (the tap-major weights come zero-padded to 16 rows)
+bool k10_conv3_supported(int K, int N) {
+    const int n_mma = N == 8 ? 16 : N;
+    return K % 16 == 0 && K >= 16 && K <= 256 && (N == 8 || (N % 16 == 0 && N >= 16 && N <= 256)) && (size_t)9 * K * n_mma * 2 <= 96 * 1024;
 }
 
-// -> FSD_OK with *taken = true when the launch was made; *taken = false leaves the call to Kernel 7
-int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const void* w, const void* bias, void* out, int64_t out_stride,
-                        const void* res, int64_t res_stride, void* out2, int64_t out2_stride, int out2_c0, int64_t P, int K, int N,
-                        int act, float slope, cudaStream_t stream, bool* taken) {
+typedef CUresult (*k10_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp16 tensor map of `rank` dimensions (dims / box innermost first; strides in bytes for dimensions 1..rank-1)
+static bool k10_encode(fsd_context* h, CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                       const uint32_t* box, CUtensorMapSwizzle swz) {
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bx[4], estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
+    return ((k10_encode_fn)h->encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Shared launcher.  taps = 1: x is [P, K] with row stride x_stride (elements), w is [N, K].  taps = 9: x is n_img channels-last images
+// of H x W pixels (pixel stride x_stride), w is tap-major [3][3][n_mma][K]; P = n_img * H * W.
+// -> FSD_OK with *taken = true when the launch was made; *taken = false: shape / resources not supported here
+static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride, int n_img, int H, int W, const void* w, const void* bias,
+                      void* out, int64_t out_stride, const void* res, int64_t res_stride, void* out2, int64_t out2_stride, int out2_c0,
+                      int64_t P, int K, int N, int act, float slope, cudaStream_t stream, bool* taken) {
     *taken = false;
-    if (!k10_supported(K, N) || !h->encode_tiled || P >= (1LL << 31) - K10_TILE) return FSD_OK;
+    const int n_mma = (taps == 9 && N == 8) ? 16 : N;
+    if (!h->encode_tiled || P >= (1LL << 31) - K10_TILE) return FSD_OK;
     K10Params p;
     p.bias = (const __half*)bias; p.out = (__half*)out; p.res = (const __half*)res; p.out2 = (__half*)out2;
-    p.P = P; p.K = K; p.N = N;
+    p.P = P; p.K = K; p.N = n_mma; p.n_valid = N;
     p.KS = K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : 16);
     p.n_slabs = K / p.KS;
+    p.taps = taps; p.total_slabs = taps * p.n_slabs;
     p.out_stride = (int)out_stride; p.res_stride = (int)res_stride; p.out2_stride = (int)out2_stride; p.out2_c0 = out2_c0;
     p.slope = slope;
-    p.b_bytes = (uint32_t)K * N * 2;
+    p.b_bytes = (uint32_t)taps * K * n_mma * 2;
     p.b_region = (p.b_bytes + 1023u) & ~1023u;
     p.slab_bytes = (uint32_t)K10_TILE * p.KS * 2;
     p.sbo_bytes = 8u * p.KS * 2;
     p.layout_type = p.KS == 64 ? 2u : (p.KS == 32 ? 4u : 6u);
     const CUtensorMapSwizzle swz = p.KS == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.KS == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    p.n_tiles = (int)((P + K10_TILE - 1) / K10_TILE);
+    p.H = H; p.W = W; p.tiles_x = 1; p.tiles_per_image = 1;
+    if (taps == 9) {
+        p.tiles_x = (W + 15) / 16;
+        p.tiles_per_image = p.tiles_x * ((H + 7) / 8);
+        if ((int64_t)p.tiles_per_image * n_img >= (1LL << 31)) return FSD_OK;
+        p.n_tiles = p.tiles_per_image * n_img;
+    } else {
+        p.n_tiles = (int)((P + K10_TILE - 1) / K10_TILE);
+    }
     int cols = 32;
-    while (cols < 2 * N) cols <<= 1;
+    while (cols < 2 * n_mma) cols <<= 1;
     p.tmem_cols = cols;
-    // CTAs per SM: one CTA's four epilogue warps cannot hide their own tensor-memory / shared-memory / store latencies (one tile per
-    // ~2800 cycles measured with a single CTA per SM at K = N = 32, against 700 at the HBM roofline), so small shapes run three (optionally four)
-    // CTAs per SM — bounded by tensor memory (512 columns per SM) and by a ring of at least two slabs per CTA
+    // CTAs per SM: one CTA's epilogue warps cannot hide their own tensor-memory / shared-memory / store latencies (one tile per
+    // ~2800 cycles measured with a single CTA of four epilogue warps per SM at K = N = 32, against 700 at the HBM roofline), so small
+    // shapes run three (optionally four) CTAs per SM — bounded by tensor memory (512 columns per SM) and by a ring of >= 2 slabs per CTA
     const size_t staging = (size_t)K10_EPI_WARPS * 32 * K10_STAGE_PITCH * sizeof(__half);
     int want = getenv("FSD_K10_CTAS") ? atoi(getenv("FSD_K10_CTAS")) : 3;  // 4 selects the 48-register build of the kernel
     if (want > 4) want = 4;
@@ -331,34 +399,96 @@ int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const v
         if (budget < fixed + 2 * (size_t)p.slab_bytes) continue;
         stages = (int)((budget - fixed) / p.slab_bytes);
         if (stages > K10_MAX_STAGES) stages = K10_MAX_STAGES;
-        // (pad the request so that no more CTAs than tensor memory allows ever share an SM)
-        smem = budget;
+        smem = budget;  // (the padded request also keeps more CTAs than tensor memory allows from sharing an SM)
         break;
     }
     if (stages < 2) return FSD_OK;
     p.stages = stages;
 
     CUtensorMap mx, mw;
-    if (!k10_encode(h, &mx, x, (uint64_t)K, (uint64_t)P, (uint64_t)x_stride * 2, (uint32_t)p.KS, K10_TILE, swz)) return FSD_OK;
-    if (!k10_encode(h, &mw, w, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)p.KS, (uint32_t)N, swz)) return FSD_OK;
+    if (taps == 9) {
+        const uint64_t xd[4] = {(uint64_t)K, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+        const uint64_t xs[3] = {(uint64_t)x_stride * 2, (uint64_t)W * x_stride * 2, (uint64_t)H * W * x_stride * 2};
+        const uint32_t xb[4] = {(uint32_t)p.KS, 16, 8, 1};
+        if (!k10_encode(h, &mx, x, 4, xd, xs, xb, swz)) return FSD_OK;
+        const uint64_t wd[3] = {(uint64_t)K, (uint64_t)n_mma, 9};
+        const uint64_t ws[2] = {(uint64_t)K * 2, (uint64_t)n_mma * K * 2};
+        const uint32_t wb[3] = {(uint32_t)p.KS, (uint32_t)n_mma, 1};
+        if (!k10_encode(h, &mw, w, 3, wd, ws, wb, swz)) return FSD_OK;
+    } else {
+        const uint64_t xd[2] = {(uint64_t)K, (uint64_t)P};
+        const uint64_t xs[1] = {(uint64_t)x_stride * 2};
+        const uint32_t xb[2] = {(uint32_t)p.KS, K10_TILE};
+        if (!k10_encode(h, &mx, x, 2, xd, xs, xb, swz)) return FSD_OK;
+        const uint64_t wd[2] = {(uint64_t)K, (uint64_t)N};
+        const uint64_t ws[1] = {(uint64_t)K * 2};
+        const uint32_t wb[2] = {(uint32_t)p.KS, (uint32_t)N};
+        if (!k10_encode(h, &mw, w, 2, wd, ws, wb, swz)) return FSD_OK;
+    }
 
     const int grid = p.n_tiles < h->sm_count * ctas ? p.n_tiles : h->sm_count * ctas;
-#define K10_GO(ACT)                                                                                                     \
+#define K10_GO2(ACT, C3)                                                                                                \
     {                                                                                                                   \
-        auto kern = ctas >= 4 ? k10_pointwise_tc_kernel<ACT, 4> : k10_pointwise_tc_kernel<ACT, 3>;                      \
+        auto kern = ctas >= 4 ? k10_pointwise_tc_kernel<ACT, 4, C3> : k10_pointwise_tc_kernel<ACT, 3, C3>;              \
         FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
         kern<<<grid, K10_THREADS, smem, stream>>>(mx, mw, p);                                                           \
     }
+#define K10_GO(ACT) { if (taps == 9) K10_GO2(ACT, true) else K10_GO2(ACT, false) }
     {
-        TimedLaunch timed(h, FSD_KERNEL_POINTWISE, (int64_t)P * (K + N + (res ? N : 0) + (out2 ? N - out2_c0 : 0)) * 2, N, stream);
+        // algorithmic bytes: input + output (+ residual, + second destination) once
+        TimedLaunch timed(h, taps == 9 ? FSD_KERNEL_CONV3X3 : FSD_KERNEL_POINTWISE,
+                          (int64_t)P * (K + N + (res ? N : 0) + (out2 ? N - out2_c0 : 0)) * 2, N, stream);
         const char* silu = getenv("FSD_K10_SILU");
         if (act == 0) K10_GO(0) else if (act == 1 && silu && !strcmp(silu, "tanh")) K10_GO(3) else if (act == 1) K10_GO(1) else K10_GO(2)
     }
 #undef K10_GO
+#undef K10_GO2
     FSD_CUDA(cudaGetLastError());
     h->launches += 1;
     *taken = true;
     return FSD_OK;
 }
 
+int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const void* w, const void* bias, void* out, int64_t out_stride,
+                        const void* res, int64_t res_stride, void* out2, int64_t out2_stride, int out2_c0, int64_t P, int K, int N,
+                        int act, float slope, cudaStream_t stream, bool* taken) {
+    *taken = false;
+    if (!k10_supported(K, N)) return FSD_OK;
+    return k10_launch(h, 1, x, x_stride, 1, 1, 1, w, bias, out, out_stride, res, res_stride, out2, out2_stride, out2_c0, P, K, N, act, slope,
+                      stream, taken);
+}
+
 }  // namespace fsd
+
+using namespace fsd;
+
+extern "C" int fsd_conv3x3_supported(int in_channels, int out_channels) { return k10_conv3_supported(in_channels, out_channels) ? 1 : 0; }
+
+extern "C" int fsd_conv3x3(fsd_handle_t h, const void* x, int64_t x_pixel_stride, int n_images, int H, int W, const void* weight_taps,
+                           const void* bias, void* out, int64_t out_pixel_stride, const void* residual, int64_t residual_pixel_stride,
+                           int in_channels, int out_channels, int act, float slope, int dtype, void* stream_) {
+    FSD_CHECK_ARG(h && x && weight_taps && bias && out, "fsd_conv3x3: null argument");
+    FSD_CHECK_ARG(dtype == FSD_F16, "fsd_conv3x3: only fp16 is implemented");
+    FSD_CHECK_ARG(n_images >= 0 && H > 0 && W > 0 && act >= 0 && act <= 2, "fsd_conv3x3: bad sizes / activation");
+    FSD_CHECK_ARG(k10_conv3_supported(in_channels, out_channels), "fsd_conv3x3: unsupported shape %d -> %d (see fsd_conv3x3_supported)",
+                  in_channels, out_channels);
+    FSD_CHECK_ARG(x_pixel_stride >= in_channels && x_pixel_stride % 8 == 0, "fsd_conv3x3: bad input stride");
+    FSD_CHECK_ARG(out_pixel_stride >= out_channels && out_pixel_stride % 8 == 0, "fsd_conv3x3: bad output stride");
+    FSD_CHECK_ARG(!residual || (residual_pixel_stride >= out_channels && residual_pixel_stride % 8 == 0), "fsd_conv3x3: bad residual stride");
+    if (((uintptr_t)x & 15) || ((uintptr_t)weight_taps & 15) || ((uintptr_t)out & 15) || ((uintptr_t)residual & 15)) {
+        set_error("fsd_conv3x3: pointers must be 16-byte aligned");
+        return FSD_ERR_ALIGN;
+    }
+    if (n_images == 0) return FSD_OK;
+    FSD_CUDA(cudaSetDevice(h->device));
+    bool taken = false;
+    const int rc = k10_launch(h, 9, x, x_pixel_stride, n_images, H, W, weight_taps, bias, out, out_pixel_stride, residual, residual_pixel_stride,
+                              nullptr, 0, 0, (int64_t)n_images * H * W, in_channels, out_channels, act, slope, (cudaStream_t)stream_, &taken);
+    if (rc != FSD_OK) return rc;
+    if (!taken) {
+        set_error("fsd_conv3x3: the tensor-core path could not be set up for %d -> %d at %dx%d (tensor map / shared memory)", in_channels,
+                  out_channels, H, W);
+        return FSD_ERR_CAPACITY;
+    }
+    return FSD_OK;
+}

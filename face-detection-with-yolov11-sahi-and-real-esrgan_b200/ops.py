@@ -369,6 +369,12 @@ def pointwise_tc_supported(k: int, n: int) -> bool:
     return k % 16 == 0 and 16 <= k <= 512 and n % 16 == 0 and 16 <= n <= 256 and k * n * 2 <= 96 * 1024
 
 
+def pointwise_tc_preferred(k: int, n: int) -> bool:
+    """Where the tcgen05 kernel beats both alternatives (profiles/r2_kernels_k10.jsonl): everything it takes except N > 128 (one CTA
+    per SM for lack of tensor-memory columns; cuDNN + epilogue is a little faster there)."""
+    return pointwise_tc_supported(k, n) and n <= 128
+
+
 def pointwise_conv_supported(k: int, n: int) -> bool:
     """Layer shapes fsd_pointwise_conv takes (the rest stays on the library convolution + fsd_bias_act)."""
     if pointwise_tc_enabled() and pointwise_tc_supported(k, n):
@@ -402,6 +408,48 @@ def pointwise_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, ac
                                    out2.data_ptr() if out2 is not None else None, s2, n - c2 if out2 is not None else 0,
                                    b * hh * ww, k, n, _ACT[act], float(slope), _TORCH_DTYPE[x.dtype], _stream_ptr(x.device)),
           "fsd_pointwise_conv")
+    return out
+
+
+def conv3x3_tc_enabled() -> bool:
+    """The tensor-core 3x3 convolution (fsd_conv3x3) is on unless FSD_NO_CONV3_TC is set."""
+    return not os.environ.get("FSD_NO_CONV3_TC")
+
+
+def conv3x3_supported(k: int, n: int) -> bool:
+    """Shapes fsd_conv3x3 takes (stride 1, pad 1, dense): asks the library, which owns the rule."""
+    return bool(_cabi.load_library().fsd_conv3x3_supported(int(k), int(n)))
+
+
+def conv3x3_tap_major(weight: torch.Tensor) -> torch.Tensor:
+    """[N, K, 3, 3] convolution weight -> the tap-major [3, 3, n, K] fp16 matrix fsd_conv3x3 reads (n = 16 with zero rows 8..15 when N = 8)."""
+    n, k = int(weight.shape[0]), int(weight.shape[1])
+    w = weight.detach().permute(2, 3, 0, 1).contiguous()
+    if n == 8:
+        w = torch.cat([w, torch.zeros_like(w)], dim=2).contiguous()
+    return w
+
+
+def conv3x3(x: torch.Tensor, weight_taps: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: float = 0.2,
+            out: torch.Tensor | None = None, residual: torch.Tensor | None = None) -> torch.Tensor:
+    """(a5) act(conv3x3(x, stride 1, pad 1) + bias) (+ residual) in one tensor-core kernel.  x [B,K,H,W] and out [B,N,H,W] (default: a
+    new dense tensor) / residual may be channel slots of channels-last fp16 buffers; weight_taps from conv3x3_tap_major()."""
+    _require_cuda(x, "x")
+    b, k, hh, ww = x.shape
+    n = int(bias.shape[0])
+    if x.dtype != torch.float16 or weight_taps.dtype != torch.float16:
+        raise ValueError("conv3x3 needs fp16 tensors")
+    if tuple(weight_taps.shape) != (3, 3, 16 if n == 8 else n, k) or not weight_taps.is_contiguous():
+        raise ValueError("conv3x3: weight_taps must be the contiguous tap-major matrix of conv3x3_tap_major()")
+    sx = _slot_stride(x, b, k, hh, ww, "x")
+    if out is None:
+        out = torch.empty((b, n, hh, ww), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    so = _slot_stride(out, b, n, hh, ww, "out")
+    sr = _slot_stride(residual, b, n, hh, ww, "residual") if residual is not None else 0
+    h = _handle_for(x)
+    check(h.lib.fsd_conv3x3(h.h, x.data_ptr(), sx, b, hh, ww, weight_taps.data_ptr(), bias.data_ptr(), out.data_ptr(), so,
+                            residual.data_ptr() if residual is not None else None, sr, k, n, _ACT[act], float(slope),
+                            _TORCH_DTYPE[x.dtype], _stream_ptr(x.device)), "fsd_conv3x3")
     return out
 
 

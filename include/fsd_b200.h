@@ -56,13 +56,13 @@ int64_t fsd_launch_count(fsd_handle_t h);
  *   FSD_KERNEL_DECODE         units = bytes of the head tensors (80 values per anchor), tag = anchors per entry
  *   FSD_KERNEL_MERGE          units = segments, tag = max_segment
  *   FSD_KERNEL_ESRGAN_CROP / _STITCH   units = algorithmic bytes, tag = images of the launch
- *   FSD_KERNEL_BIAS_ACT / _STEM / _POINTWISE / _SPPF   units = bytes the launch moves, tag = channels
+ *   FSD_KERNEL_BIAS_ACT / _STEM / _POINTWISE / _SPPF / _CONV3X3   units = bytes the launch moves, tag = channels
  *   FSD_KERNEL_FINALIZE / _ATTACH / _PACK   units = entries / images
  * Launches captured into a CUDA graph cannot be bracketed (bench.py times the backbone's kernels in an eager step).
  * (the reference has no counterpart; its timing is wall-clock around model.predict, utils/yolo_wrapper.py:67-80) */
 enum { FSD_KERNEL_GATHER = 1, FSD_KERNEL_DECODE = 2, FSD_KERNEL_MERGE = 3, FSD_KERNEL_ESRGAN_CROP = 4, FSD_KERNEL_BIAS_ACT = 5,
        FSD_KERNEL_STEM = 6, FSD_KERNEL_POINTWISE = 7, FSD_KERNEL_FINALIZE = 8, FSD_KERNEL_ATTACH = 9, FSD_KERNEL_PACK = 10,
-       FSD_KERNEL_ESRGAN_STITCH = 11, FSD_KERNEL_SPPF = 12 };
+       FSD_KERNEL_ESRGAN_STITCH = 11, FSD_KERNEL_SPPF = 12, FSD_KERNEL_CONV3X3 = 13 };
 int fsd_kernel_timing_enable(fsd_handle_t h, unsigned kernel_mask /* OR of (1u << FSD_KERNEL_*); 0 = off */);
 int fsd_kernel_timing_read(fsd_handle_t h, double* samples /* [cap,4] or NULL */, int cap, int* n);
 
@@ -207,6 +207,19 @@ int fsd_pointwise_conv(fsd_handle_t h, const void* x, int64_t x_pixel_stride, co
                        void* out, int64_t out_pixel_stride, const void* residual, int64_t residual_pixel_stride,
                        void* out2, int64_t out2_pixel_stride, int out2_first_channel, int64_t n_pixels,
                        int in_channels, int out_channels, int act, float slope, int dtype, void* stream);
+
+/* ---- (a5) 3x3 convolution, stride 1, pad 1, + bias + activation (+ residual) -> channel slot, on the tensor cores
+ *      (csrc/k10_pointwise_tc.cu: implicit GEMM, nine shifted 4-D TMA boxes per 16x8-pixel tile, tcgen05.mma into tensor memory).
+ *      x: n_images channels-last images [H, W, in_channels] fp16, x_pixel_stride elements between pixels (a channel slot of a wider
+ *      buffer is fine); weight_taps: TAP-MAJOR [3][3][n][in_channels] fp16 with n = out_channels (16 when out_channels == 8: rows
+ *      8..15 zero); out / residual as in fsd_pointwise_conv.  fsd_conv3x3_supported: in_channels % 16 == 0 (<= 256), out_channels 8
+ *      or a multiple of 16 (<= 256), 9 * in * n * 2 bytes <= 96 KB (the weights stay resident in shared memory).  Replaces cuDNN
+ *      convolution + fsd_bias_act for ultralytics Conv(c1, c2, 3, 1) (Bottleneck.cv1/cv2, C3k, head cv2/cv3/cv4 branches; run from
+ *      utils/yolo_wrapper.py:72).  fp32 accumulation; results agree with the library path to fp16 rounding. */
+int fsd_conv3x3_supported(int in_channels, int out_channels);
+int fsd_conv3x3(fsd_handle_t h, const void* x, int64_t x_pixel_stride, int n_images, int H, int W, const void* weight_taps,
+                const void* bias, void* out, int64_t out_pixel_stride, const void* residual, int64_t residual_pixel_stride,
+                int in_channels, int out_channels, int act, float slope, int dtype, void* stream);
 
 /* ---- (a5) YOLO neck: out = concat(nearest_upsample_2x(a), b) along channels, channels-last, in ONE pass.
  *      a [N,ah,aw,ca], b [N,2ah,2aw,cb], out [N,2ah,2aw,ca+cb]; replaces torch's upsample kernel + concat kernel. */

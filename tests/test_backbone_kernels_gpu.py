@@ -201,6 +201,59 @@ def test_tensor_core_pointwise_conv_wide_shapes(cuda_device, kn, act):
     assert float((err - 2e-3 * ys.abs()).max()) <= 2e-3, float(err.max())
 
 
+@pytest.mark.parametrize("kn", [(16, 8), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64), (64, 32), (64, 64), (64, 16), (128, 16), (256, 16),
+                                (48, 48), (96, 32)])
+@pytest.mark.parametrize("act", ["silu", "none"])
+def test_tensor_core_conv3x3_matches_torch(cuda_device, kn, act):
+    """(a5) fsd_conv3x3 (implicit GEMM on tcgen05: nine shifted TMA boxes per 16x8 tile, zero fill = padding) == act(conv2d 3x3 pad 1 +
+    bias) (+ residual) in fp32 on the same fp16 inputs: ragged image sizes (partial tiles in both directions, an image smaller than a
+    tile), several images, slot input / output, every slab width."""
+    import fsd_b200.ops as ops
+
+    K, N = kn
+    assert ops.conv3x3_supported(K, N) and not ops.conv3x3_supported(24, 16) and not ops.conv3x3_supported(128, 128)
+    g = torch.Generator().manual_seed(K * 31 + N)
+    cl = lambda t: t.half().to(cuda_device).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    f = torch.nn.functional.silu if act == "silu" else (lambda t: t)
+    w = (torch.randn((N, K, 3, 3), generator=g) / (3 * K ** 0.5)).half().to(cuda_device)
+    bias = torch.randn((N,), generator=g).half().to(cuda_device)
+    taps = ops.conv3x3_tap_major(w)
+    for B, H, W in ((3, 37, 29), (2, 64, 80), (1, 5, 7), (5, 131, 127)):
+        xbuf = cl(torch.randn((B, K + 8, H, W), generator=g))
+        x = xbuf[:, 8:]
+        res = cl(torch.randn((B, N, H, W), generator=g))
+        y = f(torch.nn.functional.conv2d(x.float(), w.float(), bias.float(), padding=1))
+        want = y.half() + res
+        buf = torch.full((B, N + 16, H, W), float("nan"), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+        out = ops.conv3x3(x, taps, bias, act, out=buf[:, 8:8 + N], residual=res)
+        assert torch.isnan(buf[:, :8]).all() and torch.isnan(buf[:, 8 + N:]).all()
+        err = (out.float() - want.float()).abs()
+        assert float((err - 3e-3 * want.float().abs()).max()) <= 3e-3, (B, H, W, float(err.max()))
+        plain = ops.conv3x3(x, taps, bias, act)
+        assert plain.is_contiguous(memory_format=torch.channels_last)
+        err = (plain.float() - y).abs()
+        assert float((err - 2e-3 * y.abs()).max()) <= 2e-3, (B, H, W, float(err.max()))
+
+
+def test_backbone_tensor_core_layers_equal_library_layers(cuda_device, monkeypatch):
+    """The YOLO11n-pose graph with the tcgen05 1x1 / 3x3 kernels vs the same weights on cuDNN + fsd_bias_act (+ the mma.sync 1x1 kernel):
+    per-level relative error of the raw head tensors stays at fp16 accumulation noise."""
+    from fsd_b200.backbones import yolo11_pose as yp
+
+    g = torch.Generator().manual_seed(11)
+    model = yp.build_yolo11n_pose().half().to(cuda_device).to(memory_format=torch.channels_last)
+    x = torch.rand((2, 3, 256, 320), generator=g).half().to(cuda_device).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        got = model(x)
+        monkeypatch.setenv("FSD_K7_NO_TC", "1")
+        monkeypatch.setenv("FSD_NO_CONV3_TC", "1")
+        want = model(x)
+    for lv_got, lv_want in zip(got, want):
+        for a, b in zip(lv_got, lv_want):
+            rel = float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-6))
+            assert rel < 2e-2, rel
+
+
 def test_space_to_depth_stem_equals_plain_layers(cuda_device):
     """(a5) layers 0+1 through the space-to-depth stem (fsd_stem_conv(space_to_depth) + 2x2 convolution) vs the plain
     pair (fsd_stem_conv + cuDNN 3x3 stride-2 convolution): same products and sums, so the results agree to fp16 rounding of
