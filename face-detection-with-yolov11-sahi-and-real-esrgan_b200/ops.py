@@ -412,8 +412,10 @@ def pointwise_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, ac
 
 
 def conv3x3_tc_enabled() -> bool:
-    """The tensor-core 3x3 convolution (fsd_conv3x3) is on unless FSD_NO_CONV3_TC is set."""
-    return not os.environ.get("FSD_NO_CONV3_TC")
+    """The tensor-core 3x3 convolution (fsd_conv3x3) is opt-in (FSD_CONV3_TC=1): correct, but with one TMA box per tap it is bound by
+    the TMA unit's request rate (9 x 128 box rows per tile) and loses to cuDNN's small-channel kernels + fsd_bias_act on every
+    backbone shape (profiles/r2_kernels_conv3.jsonl)."""
+    return bool(os.environ.get("FSD_CONV3_TC"))
 
 
 def conv3x3_supported(k: int, n: int) -> bool:
