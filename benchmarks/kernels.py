@@ -239,7 +239,7 @@ def bench_k10():
         if ops.pointwise_tc_supported(k, n):
             os.environ.pop("FSD_K7_NO_TC", None)
             report(f"K10 tcgen05 pointwise conv + bias + SiLU {name}", nbytes, lambda: ops.pointwise_conv(x, w, bias, "silu", out=out))
-            for key, val in (("FSD_K10_SILU", "tanh"), ("FSD_K10_CTAS", "4"), ("FSD_K10_CTAS", "2"), ("FSD_K10_CTAS", "1")):
+            for key, val in (("FSD_SILU", "tanh"), ("FSD_K10_CTAS", "4"), ("FSD_K10_CTAS", "2"), ("FSD_K10_CTAS", "1")):
                 os.environ[key] = val
                 report(f"   K10 with {key}={val} {name}", nbytes, lambda: ops.pointwise_conv(x, w, bias, "silu", out=out))
                 os.environ.pop(key)
@@ -267,9 +267,9 @@ def bench_conv3():
         out = cl(96, n, hw, hw)
         nbytes = (x.numel() + out.numel()) * 2
         report(f"K10 tcgen05 conv3x3 + bias + SiLU {name}", nbytes, lambda: ops.conv3x3(x, taps, bias, "silu", out=out))
-        os.environ["FSD_K10_SILU"] = "tanh"
-        report(f"   with FSD_K10_SILU=tanh {name}", nbytes, lambda: ops.conv3x3(x, taps, bias, "silu", out=out))
-        os.environ.pop("FSD_K10_SILU")
+        os.environ["FSD_SILU"] = "tanh"
+        report(f"   with FSD_SILU=tanh {name}", nbytes, lambda: ops.conv3x3(x, taps, bias, "silu", out=out))
+        os.environ.pop("FSD_SILU")
         report(f"   cuDNN conv + fsd_bias_act {name}", nbytes, lambda: ops.bias_act(torch.nn.functional.conv2d(x, w, None, 1, 1), bias, "silu", out=out))
         del x, out
 

@@ -45,7 +45,8 @@ struct K10Params {
     float slope;
     uint32_t b_bytes, b_region, slab_bytes, sbo_bytes, layout_type;  // b_region = b_bytes rounded up to 1024
     int taps, total_slabs, n_valid;           // 1 or 9 taps; total_slabs = taps * n_slabs; columns actually stored
-    int H, W, tiles_x, tiles_per_image;       // 3x3 only: image size and the 16 x 8 patch grid
+    int H, W, tiles_x, tiles_per_image;       // 3x3 only: image size and the patch grid (16 x 8, halo mode: 8 x 16)
+    int a_per_tile, baseoff_mode;             // ring slots one tile consumes; halo mode: how the descriptor's base offset is set
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------------
@@ -117,22 +118,14 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // shared-memory matrix descriptor, K-major operand in a TMA-swizzled slab (rows of KS halves = one swizzle span, 8-row groups
 // `sbo` bytes apart); layout: 2 = 128-byte swizzle, 4 = 64-byte, 6 = 32-byte (cute::UMMA::SmemDescriptor, version 1 = sm_100)
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout, uint32_t base_offset = 0) {
     uint64_t d = (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(base_offset & 7u) << 49;      // phase of the start address inside the swizzle pattern (0 when pattern-aligned)
     d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major; CuTe writes 1)
     d |= (uint64_t)(sbo_bytes >> 4) << 32;        // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                       // descriptor version
     d |= (uint64_t)layout << 61;
     return d;
-}
-
-// SiLU with ONE MUFU op: v * sigmoid(v) = h + h * tanh(h), h = v / 2 (tanh.approx: 2^-11 relative on tanh, i.e. <= 2.4e-4 * |v|
-// absolute on the result — the size of an fp16 rounding step of the activations; opt-in with FSD_K10_SILU=tanh)
-__device__ __forceinline__ float tanh_silu(float v) {
-    const float h = 0.5f * v;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
 }
 
 template <int ACT>
@@ -143,9 +136,11 @@ __device__ __forceinline__ float k10_act(float v, float slope) {
     return v;
 }
 
-template <int ACT, int MINB, bool CONV3>
+// MODE 0: 1x1 (flat pixel tiles); 1: 3x3, one TMA box per tap; 2: 3x3, ONE halo box per tile, the taps are shifted descriptors
+template <int ACT, int MINB, int MODE>
 __global__ void __launch_bounds__(K10_THREADS, MINB)
 k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const K10Params p) {
+    constexpr bool CONV3 = MODE != 0;
     extern __shared__ uint8_t k10_raw[];
     __shared__ uint64_t full_bar[K10_MAX_STAGES], empty_bar[K10_MAX_STAGES], b_bar, acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
@@ -192,11 +187,13 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     ty = rem / p.tiles_x;
                     tx = rem - ty * p.tiles_x;
                 }
-                for (int s = 0; s < p.total_slabs; ++s) {
+                for (int s = 0; s < p.a_per_tile; ++s) {
                     k10_mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], p.slab_bytes);
                     uint8_t* dst = smem_a + (size_t)stage * p.slab_bytes;
-                    if (CONV3) {
+                    if (MODE == 2) {  // the whole 18 x 16 pixel halo patch (rows y0-1.., columns x0-1..x0+14) of the 16 x 8 output tile
+                        k10_tma_load_4d(dst, &map_x, &full_bar[stage], 0, tx * 8 - 1, ty * 16 - 1, n);
+                    } else if (MODE == 1) {
                         const int tap = s / p.n_slabs, cs = s - tap * p.n_slabs;
                         const int ky = tap / 3, kx = tap - 3 * ky;
                         k10_tma_load_4d(dst, &map_x, &full_bar[stage], cs * p.KS, tx * 16 + kx - 1, ty * 8 + ky - 1, n);
@@ -221,17 +218,36 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 k10_mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
-                for (int s = 0; s < p.total_slabs; ++s) {
+                if (MODE == 2) {
+                    // nine taps = nine descriptors into the one halo patch: pixel (yy, xx) sits at (yy * 16 + xx) * row bytes, so tap
+                    // (ky, kx) starts (ky * 16 + kx) rows in and the 8-pixel row groups are 16 rows apart
                     k10_mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = a0 + (uint32_t)stage * p.slab_bytes;
-                    const uint32_t b_addr = b0 + (uint32_t)s * (uint32_t)(p.N * p.KS * 2);
-                    for (int k = 0; k < p.KS; k += 16) {
-                        tc_mma_f16(d_tmem, tc_smem_desc(a_addr + 2 * k, p.sbo_bytes, p.layout_type),
-                                   tc_smem_desc(b_addr + 2 * k, p.sbo_bytes, p.layout_type), idesc, (s | k) ? 1u : 0u);
+                    const uint32_t a_base = a0 + (uint32_t)stage * p.slab_bytes, row_bytes = (uint32_t)p.KS * 2;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * 16 + tap % 3) * row_bytes;
+                        const uint32_t boff = p.baseoff_mode == 1 ? (a_addr >> 7) & 7u : 0u;
+                        const uint32_t b_addr = b0 + (uint32_t)tap * (uint32_t)(p.N * p.KS * 2);
+                        for (int k = 0; k < p.KS; k += 16) {
+                            tc_mma_f16(d_tmem, tc_smem_desc(a_addr + 2 * k, 16u * row_bytes, p.layout_type, boff),
+                                       tc_smem_desc(b_addr + 2 * k, p.sbo_bytes, p.layout_type), idesc, (tap | k) ? 1u : 0u);
+                        }
                     }
-                    tc_commit(&empty_bar[stage]);  // the slab may be overwritten once these MMAs have read it
+                    tc_commit(&empty_bar[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                } else {
+                    for (int s = 0; s < p.total_slabs; ++s) {
+                        k10_mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = a0 + (uint32_t)stage * p.slab_bytes;
+                        const uint32_t b_addr = b0 + (uint32_t)s * (uint32_t)(p.N * p.KS * 2);
+                        for (int k = 0; k < p.KS; k += 16) {
+                            tc_mma_f16(d_tmem, tc_smem_desc(a_addr + 2 * k, p.sbo_bytes, p.layout_type),
+                                       tc_smem_desc(b_addr + 2 * k, p.sbo_bytes, p.layout_type), idesc, (s | k) ? 1u : 0u);
+                        }
+                        tc_commit(&empty_bar[stage]);  // the slab may be overwritten once these MMAs have read it
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
                 }
                 tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
             }
@@ -254,8 +270,8 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     img = tile / p.tiles_per_image;
                     const int rem = tile - img * p.tiles_per_image;
                     const int ty = rem / p.tiles_x;
-                    y0 = ty * 8 + 2 * q;
-                    x0 = (rem - ty * p.tiles_x) * 16;
+                    y0 = MODE == 2 ? ty * 16 + 4 * q : ty * 8 + 2 * q;
+                    x0 = (rem - ty * p.tiles_x) * (MODE == 2 ? 8 : 16);
                 }
                 for (int c0 = half * K10_CHUNK; c0 < p.N; c0 += 2 * K10_CHUNK) {
                     uint32_t v[16];
@@ -289,7 +305,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                         long long pix = pix0 + r;
                         bool ok = pix < p.P;
                         if (CONV3) {
-                            const int y = y0 + (r >> 4), x = x0 + (r & 15);
+                            const int y = MODE == 2 ? y0 + (r >> 3) : y0 + (r >> 4), x = MODE == 2 ? x0 + (r & 7) : x0 + (r & 15);
                             ok = y < p.H && x < p.W;
                             pix = ((long long)img * p.H + y) * p.W + x;
                         }
@@ -372,9 +388,14 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     p.layout_type = p.KS == 64 ? 2u : (p.KS == 32 ? 4u : 6u);
     const CUtensorMapSwizzle swz = p.KS == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.KS == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     p.H = H; p.W = W; p.tiles_x = 1; p.tiles_per_image = 1;
+    // 3x3 with one channel slab: ONE halo box per tile (FSD_C3_HALO=0 keeps one box per tap); FSD_C3_BASEOFF picks the descriptor rule
+    const bool halo = taps == 9 && p.n_slabs == 1 && !(getenv("FSD_C3_HALO") && atoi(getenv("FSD_C3_HALO")) == 0);
+    p.baseoff_mode = getenv("FSD_C3_BASEOFF") ? atoi(getenv("FSD_C3_BASEOFF")) : 1;
+    p.a_per_tile = halo ? 1 : p.total_slabs;
+    if (halo) p.slab_bytes = 18u * 16u * (uint32_t)p.KS * 2;
     if (taps == 9) {
-        p.tiles_x = (W + 15) / 16;
-        p.tiles_per_image = p.tiles_x * ((H + 7) / 8);
+        p.tiles_x = halo ? (W + 7) / 8 : (W + 15) / 16;
+        p.tiles_per_image = p.tiles_x * (halo ? (H + 15) / 16 : (H + 7) / 8);
         if ((int64_t)p.tiles_per_image * n_img >= (1LL << 31)) return FSD_OK;
         p.n_tiles = p.tiles_per_image * n_img;
     } else {
@@ -409,7 +430,7 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     if (taps == 9) {
         const uint64_t xd[4] = {(uint64_t)K, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
         const uint64_t xs[3] = {(uint64_t)x_stride * 2, (uint64_t)W * x_stride * 2, (uint64_t)H * W * x_stride * 2};
-        const uint32_t xb[4] = {(uint32_t)p.KS, 16, 8, 1};
+        const uint32_t xb[4] = {(uint32_t)p.KS, 16, halo ? 18u : 8u, 1};
         if (!k10_encode(h, &mx, x, 4, xd, xs, xb, swz)) return FSD_OK;
         const uint64_t wd[3] = {(uint64_t)K, (uint64_t)n_mma, 9};
         const uint64_t ws[2] = {(uint64_t)K * 2, (uint64_t)n_mma * K * 2};
@@ -433,13 +454,12 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
         FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
         kern<<<grid, K10_THREADS, smem, stream>>>(mx, mw, p);                                                           \
     }
-#define K10_GO(ACT) { if (taps == 9) K10_GO2(ACT, true) else K10_GO2(ACT, false) }
+#define K10_GO(ACT) { if (halo) K10_GO2(ACT, 2) else if (taps == 9) K10_GO2(ACT, 1) else K10_GO2(ACT, 0) }
     {
         // algorithmic bytes: input + output (+ residual, + second destination) once
         TimedLaunch timed(h, taps == 9 ? FSD_KERNEL_CONV3X3 : FSD_KERNEL_POINTWISE,
                           (int64_t)P * (K + N + (res ? N : 0) + (out2 ? N - out2_c0 : 0)) * 2, N, stream);
-        const char* silu = getenv("FSD_K10_SILU");
-        if (act == 0) K10_GO(0) else if (act == 1 && silu && !strcmp(silu, "tanh")) K10_GO(3) else if (act == 1) K10_GO(1) else K10_GO(2)
+        if (act == 0) K10_GO(0) else if (act == 1 && silu_tanh_mode()) K10_GO(3) else if (act == 1) K10_GO(1) else K10_GO(2)
     }
 #undef K10_GO
 #undef K10_GO2

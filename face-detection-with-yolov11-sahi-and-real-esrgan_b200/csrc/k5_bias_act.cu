@@ -12,6 +12,7 @@ namespace fsd {
 constexpr int K5_THREADS = 256;
 
 template <int ACT> __device__ __forceinline__ float activate(float v, float slope) {
+    if (ACT == 3) return tanh_silu(v);  // SiLU, one-MUFU form (FSD_SILU=tanh)
     if (ACT == 1) return fast_silu(v);  // SiLU
     if (ACT == 2) return v > 0.f ? v : v * slope;           // LeakyReLU
     return v;
@@ -203,6 +204,7 @@ extern "C" int fsd_bias_act_inplace(fsd_handle_t h, void* x, const void* bias, i
     FSD_CUDA(cudaSetDevice(h->device));
 #define LAUNCH(K, T) \
     if (act == 0) K<0><<<grid, K5_THREADS, 0, s>>>((T*)x, (const T*)bias, n_vec, c_vec, slope); \
+    else if (act == 1 && silu_tanh_mode()) K<3><<<grid, K5_THREADS, 0, s>>>((T*)x, (const T*)bias, n_vec, c_vec, slope); \
     else if (act == 1) K<1><<<grid, K5_THREADS, 0, s>>>((T*)x, (const T*)bias, n_vec, c_vec, slope); \
     else K<2><<<grid, K5_THREADS, 0, s>>>((T*)x, (const T*)bias, n_vec, c_vec, slope);
     TimedLaunch timed(h, FSD_KERNEL_BIAS_ACT, (int64_t)n_vec * 32, channels, s);  // read + write once
@@ -251,6 +253,7 @@ extern "C" int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, voi
         const int64_t bytes = (int64_t)n_pixels * 2 * ((residual ? 3 : 2) * channels + (out2 ? channels - out2_first_channel : 0) + (up2x ? 4 * channels : 0));
         TimedLaunch timed(h, FSD_KERNEL_BIAS_ACT, bytes, channels, s);
         if (act == 0) k5_bias_act_general_half_kernel<0><<<grid, K5_THREADS, 0, s>>>(a);
+        else if (act == 1 && silu_tanh_mode()) k5_bias_act_general_half_kernel<3><<<grid, K5_THREADS, 0, s>>>(a);
         else if (act == 1) k5_bias_act_general_half_kernel<1><<<grid, K5_THREADS, 0, s>>>(a);
         else k5_bias_act_general_half_kernel<2><<<grid, K5_THREADS, 0, s>>>(a);
     }
