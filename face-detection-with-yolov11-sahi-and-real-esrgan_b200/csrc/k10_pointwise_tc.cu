@@ -390,7 +390,9 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     p.H = H; p.W = W; p.tiles_x = 1; p.tiles_per_image = 1;
     // 3x3 with one channel slab: ONE halo box per tile (FSD_C3_HALO=0 keeps one box per tap); FSD_C3_BASEOFF picks the descriptor rule
     const bool halo = taps == 9 && p.n_slabs == 1 && !(getenv("FSD_C3_HALO") && atoi(getenv("FSD_C3_HALO")) == 0);
-    p.baseoff_mode = getenv("FSD_C3_BASEOFF") ? atoi(getenv("FSD_C3_BASEOFF")) : 1;
+    // measured (gpurun_out/r2_c3halo_*.log): the swizzle phase follows the ABSOLUTE shared-memory address, so a descriptor that starts
+    // s pixel rows into a swizzle pattern needs base offset 0; writing (start >> 7) & 7 there breaks K = 32 and 64 (FSD_C3_BASEOFF=1 shows it)
+    p.baseoff_mode = getenv("FSD_C3_BASEOFF") ? atoi(getenv("FSD_C3_BASEOFF")) : 0;
     p.a_per_tile = halo ? 1 : p.total_slabs;
     if (halo) p.slab_bytes = 18u * 16u * (uint32_t)p.KS * 2;
     if (taps == 9) {
