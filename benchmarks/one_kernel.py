@@ -51,6 +51,15 @@ elif which in ("k10", "k10_wide"):  # 1x1 convolution on tcgen05: 32->32 at 256^
     out = torch.empty((96, n, hw, hw), device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
     for _ in range(iters):
         ops.pointwise_conv(x, w, b, "silu", out=out)
+elif which in ("conv3", "conv3_small"):  # 3x3 convolution on tcgen05 (halo mode): 64->64 at 128^2 / 16->8 at 256^2
+    k, n, hw = (64, 64, 128) if which == "conv3" else (16, 8, 256)
+    x = torch.randn((96, k, hw, hw), device=dev).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((n, k, 3, 3), device=dev) / (3 * k ** 0.5)).half()
+    taps = ops.conv3x3_tap_major(w)
+    b = torch.randn((n,), device=dev).half()
+    out = torch.empty((96, n, hw, hw), device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    for _ in range(iters):
+        ops.conv3x3(x, taps, b, "silu", out=out)
 elif which == "k7":
     x = torch.randn((96, 48, 256, 256), device=dev).half().contiguous(memory_format=torch.channels_last)
     w = (torch.randn((64, 48, 1, 1), device=dev) / 7).half()
