@@ -58,37 +58,60 @@ struct K5GenArgs {
     uint4* up; int up_stride; int H, W;  // optional nearest-2x up-sampled destination ([N, 2H, 2W] pixels, own stride)
 };
 
+// one 8-channel vector: bias + activation (+ residual) -> out slot (+ second destination, + 2x up-sampled copies)
 template <int ACT>
-__global__ void __launch_bounds__(K5_THREADS) k5_bias_act_general_half_kernel(const K5GenArgs a) {
-    for (unsigned i = blockIdx.x * K5_THREADS + threadIdx.x; i < a.n_vec; i += gridDim.x * K5_THREADS) {
+__device__ __forceinline__ void k5_apply(const K5GenArgs& a, unsigned pix, int c, uint4 v, uint4 r) {
+    const uint4 b = __ldg(a.bias + c);
+    __half2* hv = reinterpret_cast<__half2*>(&v);
+    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+    const __half2* hr = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(hv[k]);
+        const float2 g = __half22float2(hb[k]);
+        __half2 o = __floats2half2_rn(activate<ACT>(f.x + g.x, a.slope), activate<ACT>(f.y + g.y, a.slope));
+        // the residual is added in fp16 after the activation is rounded, exactly as torch's `x + act(conv)` does
+        if (a.res) o = __hadd2(o, hr[k]);
+        hv[k] = o;
+    }
+    a.out[(size_t)pix * a.out_stride + c] = v;
+    if (a.out2 && c >= a.out2_c0) a.out2[(size_t)pix * a.out2_stride + (c - a.out2_c0)] = v;
+    if (a.up) {  // FPN: the next stage concatenates the nearest-2x up-sampled map — store the four copies here
+        const unsigned hw = (unsigned)(a.H * a.W);
+        const unsigned n = pix / hw, rem = pix - n * hw;
+        const unsigned y = rem / (unsigned)a.W, x = rem - y * (unsigned)a.W;
+        uint4* d = a.up + (((size_t)n * 2 * a.H + 2 * y) * 2 * a.W + 2 * x) * a.up_stride + c;
+        const size_t row = (size_t)2 * a.W * a.up_stride;
+        d[0] = v; d[a.up_stride] = v; d[row] = v; d[row + a.up_stride] = v;
+    }
+}
+
+// Two independent vectors per thread and trip: with one 16-byte load in flight per thread a fully occupied SM holds 32 KB in flight,
+// short of the ~46 KB that 23 B/clk/SM x ~2000 cycles of loaded-HBM latency ask for (top stall: long scoreboard, r1_k5_bias_act.summary)
+template <int ACT>
+__global__ void __launch_bounds__(K5_THREADS, 2048 / K5_THREADS * 3 / 4) k5_bias_act_general_half_kernel(const K5GenArgs a) {
+    const unsigned stride = gridDim.x * K5_THREADS;
+    unsigned i = blockIdx.x * K5_THREADS + threadIdx.x;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (; i + stride < a.n_vec; i += 2 * stride) {  // (the host keeps n_vec below 2^32 - 2^28: no wrap)
+        const unsigned j = i + stride;
+        const unsigned pix0 = i / (unsigned)a.c_vec, pix1 = j / (unsigned)a.c_vec;
+        const int c0 = (int)(i - pix0 * (unsigned)a.c_vec), c1 = (int)(j - pix1 * (unsigned)a.c_vec);
+        const uint4 v0 = __ldcs(a.x + i), v1 = __ldcs(a.x + j);
+        uint4 r0 = zero, r1 = zero;
+        if (a.res) {
+            r0 = __ldg(a.res + (size_t)pix0 * a.res_stride + c0);
+            r1 = __ldg(a.res + (size_t)pix1 * a.res_stride + c1);
+        }
+        k5_apply<ACT>(a, pix0, c0, v0, r0);
+        k5_apply<ACT>(a, pix1, c1, v1, r1);
+    }
+    for (; i < a.n_vec; i += stride) {
         const unsigned pix = i / (unsigned)a.c_vec;
         const int c = (int)(i - pix * (unsigned)a.c_vec);
-        uint4 v = __ldcs(a.x + i);
-        const uint4 b = __ldg(a.bias + c);
-        uint4 r = make_uint4(0, 0, 0, 0);
-        if (a.res) r = __ldg(a.res + (size_t)pix * a.res_stride + c);
-        __half2* hv = reinterpret_cast<__half2*>(&v);
-        const __half2* hb = reinterpret_cast<const __half2*>(&b);
-        const __half2* hr = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = __half22float2(hv[k]);
-            const float2 g = __half22float2(hb[k]);
-            __half2 o = __floats2half2_rn(activate<ACT>(f.x + g.x, a.slope), activate<ACT>(f.y + g.y, a.slope));
-            // the residual is added in fp16 after the activation is rounded, exactly as torch's `x + act(conv)` does
-            if (a.res) o = __hadd2(o, hr[k]);
-            hv[k] = o;
-        }
-        a.out[(size_t)pix * a.out_stride + c] = v;
-        if (a.out2 && c >= a.out2_c0) a.out2[(size_t)pix * a.out2_stride + (c - a.out2_c0)] = v;
-        if (a.up) {  // FPN: the next stage concatenates the nearest-2x up-sampled map — store the four copies here
-            const unsigned hw = (unsigned)(a.H * a.W);
-            const unsigned n = pix / hw, rem = pix - n * hw;
-            const unsigned y = rem / (unsigned)a.W, x = rem - y * (unsigned)a.W;
-            uint4* d = a.up + (((size_t)n * 2 * a.H + 2 * y) * 2 * a.W + 2 * x) * a.up_stride + c;
-            const size_t row = (size_t)2 * a.W * a.up_stride;
-            d[0] = v; d[a.up_stride] = v; d[row] = v; d[row + a.up_stride] = v;
-        }
+        const uint4 v = __ldcs(a.x + i);
+        const uint4 r = a.res ? __ldg(a.res + (size_t)pix * a.res_stride + c) : zero;
+        k5_apply<ACT>(a, pix, c, v, r);
     }
 }
 
@@ -237,7 +260,7 @@ extern "C" int fsd_bias_act(fsd_handle_t h, const void* x, const void* bias, voi
     }
     if (n_pixels == 0) return FSD_OK;
     const size_t n_vec = (size_t)n_pixels * channels / 8;
-    FSD_CHECK_ARG(n_vec < 0xffffffffull, "fsd_bias_act: tensor too large for one launch (%zu vectors)", n_vec);
+    FSD_CHECK_ARG(n_vec < 0xf0000000ull, "fsd_bias_act: tensor too large for one launch (%zu vectors)", n_vec);
     K5GenArgs a;
     a.x = (const uint4*)x; a.bias = (const uint4*)bias; a.out = (uint4*)out; a.res = (const uint4*)residual; a.out2 = (uint4*)out2;
     a.n_vec = (unsigned)n_vec; a.c_vec = channels / 8; a.out_stride = (int)(out_pixel_stride / 8);
