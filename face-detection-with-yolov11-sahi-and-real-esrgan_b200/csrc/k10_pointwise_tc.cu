@@ -102,6 +102,28 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with the two 64-bit descriptors given as (lo, hi) halves: the issue loop below only ever adds to the low words
+__device__ __forceinline__ void tc_mma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// KSTEPS MMAs of K = 16 over one K-major slab pair; descriptor low words advance by 32 bytes (2 x 16-byte units) per step.
+// The issuing thread is the serial resource of this kernel (one lane issues every MMA of the CTA): with the descriptors rebuilt
+// from scratch the compiler spent ~37 instructions and ~190 cycles per MMA (profiles/r2_conv3_tc: 36 MMAs = 6900 of the 7000
+// cycles per tile), so everything that does not change is hoisted and the steps are unrolled.
+template <int KSTEPS>
+__device__ __forceinline__ void tc_issue_slab(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              bool clears) {
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) tc_mma_f16_lohi(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (clears && k == 0) ? 0u : 1u);
+}
 // arrives on the mbarrier when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -209,7 +231,16 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N >> 3, M >> 4
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(K10_TILE >> 4) << 24);
-            const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b);
+            // shared-memory descriptors (cute::UMMA::SmemDescriptor, K-major): low word = address >> 4 | LBO (1, unused) << 16, high word =
+            // SBO >> 4 | version 1 << 14 | swizzle mode << 29; base offset 0 — the swizzle phase follows the absolute address (measured)
+            const uint32_t a_lo_base = ((smem_u32(smem_a) & 0x3ffffu) >> 4) | (1u << 16);
+            const uint32_t b_lo_base = ((smem_u32(smem_b) & 0x3ffffu) >> 4) | (1u << 16);
+            const uint32_t hi_common = (1u << 14) | (p.layout_type << 29);
+            const uint32_t a_hi = (p.sbo_bytes >> 4) | hi_common, b_hi = a_hi;
+            const uint32_t row16 = (uint32_t)p.KS * 2 >> 4;                  // one pixel row of a slab in 16-byte units
+            const uint32_t a_hi_halo = (16u * row16) | hi_common;              // halo patch: 8-row groups are 16 pixel rows apart
+            const uint32_t slab16 = p.slab_bytes >> 4, bslab16 = (uint32_t)(p.N * p.KS * 2) >> 4;
+            const int ksteps = p.KS >> 4;
             k10_mbar_wait(&b_bar, 0);
             int stage = 0, it = 0;
             uint32_t phase = 0;
@@ -223,28 +254,26 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     // (ky, kx) starts (ky * 16 + kx) rows in and the 8-pixel row groups are 16 rows apart
                     k10_mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_base = a0 + (uint32_t)stage * p.slab_bytes, row_bytes = (uint32_t)p.KS * 2;
+                    const uint32_t a_lo0 = a_lo_base + (uint32_t)stage * slab16;
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * 16 + tap % 3) * row_bytes;
-                        const uint32_t boff = p.baseoff_mode == 1 ? (a_addr >> 7) & 7u : 0u;
-                        const uint32_t b_addr = b0 + (uint32_t)tap * (uint32_t)(p.N * p.KS * 2);
-                        for (int k = 0; k < p.KS; k += 16) {
-                            tc_mma_f16(d_tmem, tc_smem_desc(a_addr + 2 * k, 16u * row_bytes, p.layout_type, boff),
-                                       tc_smem_desc(b_addr + 2 * k, p.sbo_bytes, p.layout_type), idesc, (tap | k) ? 1u : 0u);
-                        }
+                        const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * 16 + tap % 3) * row16;
+                        const uint32_t b_lo = b_lo_base + (uint32_t)tap * bslab16;
+                        if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
+                        else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
+                        else tc_issue_slab<1>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
                     }
                     tc_commit(&empty_bar[stage]);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 } else {
-                    for (int s = 0; s < p.total_slabs; ++s) {
+                    uint32_t b_lo = b_lo_base;
+                    for (int s = 0; s < p.total_slabs; ++s, b_lo += bslab16) {
                         k10_mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_addr = a0 + (uint32_t)stage * p.slab_bytes;
-                        const uint32_t b_addr = b0 + (uint32_t)s * (uint32_t)(p.N * p.KS * 2);
-                        for (int k = 0; k < p.KS; k += 16) {
-                            tc_mma_f16(d_tmem, tc_smem_desc(a_addr + 2 * k, p.sbo_bytes, p.layout_type),
-                                       tc_smem_desc(b_addr + 2 * k, p.sbo_bytes, p.layout_type), idesc, (s | k) ? 1u : 0u);
-                        }
+                        const uint32_t a_lo = a_lo_base + (uint32_t)stage * slab16;
+                        if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
+                        else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
+                        else tc_issue_slab<1>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
                         tc_commit(&empty_bar[stage]);  // the slab may be overwritten once these MMAs have read it
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
