@@ -259,7 +259,8 @@ def bench_conv3():
     for name, k, n, hw in (("b2.m 16->8 256^2", 16, 8, 256), ("b4.m 32->16 128^2", 32, 16, 128), ("b4.m 16->32 128^2", 16, 32, 128),
                            ("head.cv2 64->64 128^2", 64, 64, 128), ("head.cv4 64->16 128^2", 64, 16, 128), ("c3k 32->32 64^2", 32, 32, 64),
                            ("b6 32->64 64^2", 32, 64, 64), ("b6 64->32 64^2", 64, 32, 64), ("head 64->64 64^2", 64, 64, 64),
-                           ("head.cv4 128->16 64^2", 128, 16, 64), ("c3k 64->64 32^2", 64, 64, 32), ("head.cv4 256->16 32^2", 256, 16, 32)):
+                           ("head.cv4 128->16 64^2", 128, 16, 64), ("c3k 64->64 32^2", 64, 64, 32), ("head.cv4 256->16 32^2", 256, 16, 32),
+                           ("head.cv4 16->16 128^2", 16, 16, 128), ("head.cv4 16->16 64^2", 16, 16, 64)):
         x = cl(96, k, hw, hw)
         w = (torch.randn((n, k, 3, 3), device=dev) / (3 * k ** 0.5)).half().contiguous(memory_format=torch.channels_last)
         taps = ops.conv3x3_tap_major(w)
@@ -267,9 +268,9 @@ def bench_conv3():
         out = cl(96, n, hw, hw)
         nbytes = (x.numel() + out.numel()) * 2
         report(f"K10 tcgen05 conv3x3 + bias + SiLU {name}", nbytes, lambda: ops.conv3x3(x, taps, bias, "silu", out=out))
-        os.environ["FSD_SILU"] = "tanh"
-        report(f"   with FSD_SILU=tanh {name}", nbytes, lambda: ops.conv3x3(x, taps, bias, "silu", out=out))
-        os.environ.pop("FSD_SILU")
+        os.environ["FSD_K10_EW"] = "8"
+        report(f"   with 8 epilogue warps {name}", nbytes, lambda: ops.conv3x3(x, taps, bias, "silu", out=out))
+        os.environ.pop("FSD_K10_EW")
         report(f"   cuDNN conv + fsd_bias_act {name}", nbytes, lambda: ops.bias_act(torch.nn.functional.conv2d(x, w, None, 1, 1), bias, "silu", out=out))
         del x, out
 

@@ -27,8 +27,10 @@
 
 namespace fsd {
 
-constexpr int K10_EPI_WARPS = 8;        // two warps per tensor-memory lane quarter, alternating 16-column steps
-constexpr int K10_THREADS = 64 + 32 * K10_EPI_WARPS;
+// epilogue warps per CTA: EW / 4 warps per tensor-memory lane quarter, interleaving 16-column steps.  8 when several CTAs share an SM;
+// 16 when the resident weights leave room for only one CTA (its epilogue must then hide its own latencies: SiLU alone is 16 N cycles
+// of MUFU per tile and SM)
+constexpr int K10_EPI_WARPS_MAX = 16;
 constexpr int K10_TILE = 128;          // pixels per tile = MMA M
 constexpr int K10_CHUNK = 16;          // accumulator columns per epilogue step (one tcgen05.ld.32x32b.x16)
 constexpr int K10_STAGE_PITCH = 24;    // halves per staged output row (16 columns + 16 bytes: conflict-free 16-byte accesses)
@@ -159,8 +161,8 @@ __device__ __forceinline__ float k10_act(float v, float slope) {
 }
 
 // MODE 0: 1x1 (flat pixel tiles); 1: 3x3, one TMA box per tap; 2: 3x3, ONE halo box per tile, the taps are shifted descriptors
-template <int ACT, int MINB, int MODE>
-__global__ void __launch_bounds__(K10_THREADS, MINB)
+template <int ACT, int MINB, int MODE, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, MINB)
 k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const K10Params p) {
     constexpr bool CONV3 = MODE != 0;
     extern __shared__ uint8_t k10_raw[];
@@ -175,13 +177,14 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     uint8_t* smem_a = smem + p.b_region;
     __half* stage_base = reinterpret_cast<__half*>(smem_a + (size_t)p.stages * p.slab_bytes);
 
+    constexpr int K10_THREADS = 64 + 32 * EW, SETS = EW / 4;
     for (int i = threadIdx.x; i < p.N; i += K10_THREADS) s_bias[i] = __half2float(__ldg(p.bias + i));
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_w);
         for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&b_bar, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], p.N >= 2 * K10_CHUNK ? K10_EPI_WARPS : 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * (p.N / K10_CHUNK < SETS ? p.N / K10_CHUNK : SETS)); }
         fence_barrier_init();
     }
     if (warp == 1) tc_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
@@ -282,10 +285,10 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             }
         }
     } else {
-        // ================= epilogue warps (TMEM lane quarter = warp % 4; warps 2-5 take the even 16-column steps, 6-9 the odd) ====
+        // ================= epilogue warps (TMEM lane quarter = warp % 4; warp set (warp - 2) / 4 takes every SETS-th 16-column step) ====
         const int q = warp & 3, half = (warp - 2) >> 2;
         __half* stg = stage_base + (size_t)(warp - 2) * 32 * K10_STAGE_PITCH;
-        if (half * K10_CHUNK < p.N) {  // (N = 16: the second set has no step)
+        if (half * K10_CHUNK < p.N) {  // (a set beyond N / 16 has no step)
             int it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
@@ -302,11 +305,11 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     y0 = MODE == 2 ? ty * 16 + 4 * q : ty * 8 + 2 * q;
                     x0 = (rem - ty * p.tiles_x) * (MODE == 2 ? 8 : 16);
                 }
-                for (int c0 = half * K10_CHUNK; c0 < p.N; c0 += 2 * K10_CHUNK) {
+                for (int c0 = half * K10_CHUNK; c0 < p.N; c0 += SETS * K10_CHUNK) {
                     uint32_t v[16];
                     tc_ld16(t_row + (uint32_t)c0, v);
                     tc_wait_ld();
-                    if (c0 + 2 * K10_CHUNK >= p.N) {  // this warp's last read of the accumulator: hand it back before the stores
+                    if (c0 + SETS * K10_CHUNK >= p.N) {  // this warp's last read of the accumulator: hand it back before the stores
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) k10_mbar_arrive(&acc_empty[acc]);
@@ -438,7 +441,7 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     // CTAs per SM: one CTA's epilogue warps cannot hide their own tensor-memory / shared-memory / store latencies (one tile per
     // ~2800 cycles measured with a single CTA of four epilogue warps per SM at K = N = 32, against 700 at the HBM roofline), so small
     // shapes run three (optionally four) CTAs per SM — bounded by tensor memory (512 columns per SM) and by a ring of >= 2 slabs per CTA
-    const size_t staging = (size_t)K10_EPI_WARPS * 32 * K10_STAGE_PITCH * sizeof(__half);
+    const size_t staging = (size_t)K10_EPI_WARPS_MAX * 32 * K10_STAGE_PITCH * sizeof(__half);  // (sized for 16 warps; 8 use half)
     int want = getenv("FSD_K10_CTAS") ? atoi(getenv("FSD_K10_CTAS")) : 3;  // 4 selects the 48-register build of the kernel
     if (want > 4) want = 4;
     int ctas = 512 / p.tmem_cols < want ? 512 / p.tmem_cols : want;
@@ -479,11 +482,13 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     }
 
     const int grid = p.n_tiles < h->sm_count * ctas ? p.n_tiles : h->sm_count * ctas;
+    const bool wide_epilogue = ctas == 1 && n_mma >= 64 && !(getenv("FSD_K10_EW") && atoi(getenv("FSD_K10_EW")) == 8);
 #define K10_GO2(ACT, C3)                                                                                                \
     {                                                                                                                   \
-        auto kern = ctas >= 4 ? k10_pointwise_tc_kernel<ACT, 4, C3> : k10_pointwise_tc_kernel<ACT, 3, C3>;              \
+        auto kern = wide_epilogue ? k10_pointwise_tc_kernel<ACT, 1, C3, 16>                                            \
+                                  : (ctas >= 4 ? k10_pointwise_tc_kernel<ACT, 4, C3, 8> : k10_pointwise_tc_kernel<ACT, 3, C3, 8>); \
         FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
-        kern<<<grid, K10_THREADS, smem, stream>>>(mx, mw, p);                                                           \
+        kern<<<grid, wide_epilogue ? 64 + 32 * 16 : 64 + 32 * 8, smem, stream>>>(mx, mw, p);                            \
     }
 #define K10_GO(ACT) { if (halo) K10_GO2(ACT, 2) else if (taps == 9) K10_GO2(ACT, 1) else K10_GO2(ACT, 0) }
     {
