@@ -231,7 +231,9 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp walks the loop (uniform control flow lets the compiler keep the descriptors in uniform registers) and ONE
+        // elected lane issues the MMAs and commits of a tile.
+        {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, both K-major, N >> 3, M >> 4
             const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(K10_TILE >> 4) << 24);
             // shared-memory descriptors (cute::UMMA::SmemDescriptor, K-major): low word = address >> 4 | LBO (1, unused) << 16, high word =
@@ -257,31 +259,38 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     // (ky, kx) starts (ky * 16 + kx) rows in and the 8-pixel row groups are 16 rows apart
                     k10_mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_lo0 = a_lo_base + (uint32_t)stage * slab16;
+                    if (elect_one_sync()) {
+                        const uint32_t a_lo0 = a_lo_base + (uint32_t)stage * slab16;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * 16 + tap % 3) * row16;
-                        const uint32_t b_lo = b_lo_base + (uint32_t)tap * bslab16;
-                        if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
-                        else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
-                        else tc_issue_slab<1>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * 16 + tap % 3) * row16;
+                            const uint32_t b_lo = b_lo_base + (uint32_t)tap * bslab16;
+                            if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
+                            else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
+                            else tc_issue_slab<1>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
+                        }
+                        tc_commit(&empty_bar[stage]);
+                        tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
                     }
-                    tc_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 } else {
                     uint32_t b_lo = b_lo_base;
                     for (int s = 0; s < p.total_slabs; ++s, b_lo += bslab16) {
                         k10_mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t a_lo = a_lo_base + (uint32_t)stage * slab16;
-                        if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
-                        else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
-                        else tc_issue_slab<1>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
-                        tc_commit(&empty_bar[stage]);  // the slab may be overwritten once these MMAs have read it
+                        if (elect_one_sync()) {
+                            const uint32_t a_lo = a_lo_base + (uint32_t)stage * slab16;
+                            if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
+                            else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
+                            else tc_issue_slab<1>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
+                            tc_commit(&empty_bar[stage]);  // the slab may be overwritten once these MMAs have read it
+                            if (s + 1 == p.total_slabs) tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+                        }
+                        __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
                 }
-                tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
             }
         }
     } else {
@@ -441,21 +450,36 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     // CTAs per SM: one CTA's epilogue warps cannot hide their own tensor-memory / shared-memory / store latencies (one tile per
     // ~2800 cycles measured with a single CTA of four epilogue warps per SM at K = N = 32, against 700 at the HBM roofline), so small
     // shapes run three (optionally four) CTAs per SM — bounded by tensor memory (512 columns per SM) and by a ring of >= 2 slabs per CTA
-    const size_t staging = (size_t)K10_EPI_WARPS_MAX * 32 * K10_STAGE_PITCH * sizeof(__half);  // (sized for 16 warps; 8 use half)
+    // CTAs per SM: one CTA's epilogue warps cannot hide their own tensor-memory / shared-memory / store latencies (one tile per ~2800
+    // cycles with a single CTA of four epilogue warps per SM at K = N = 32, against 700 at the HBM roofline), so small shapes run three
+    // (optionally four) CTAs per SM — bounded by tensor memory (512 columns per SM) and by a ring of >= 2 slabs per CTA; a shape whose
+    // resident weights leave room for one CTA only gets sixteen epilogue warps instead of eight
     int want = getenv("FSD_K10_CTAS") ? atoi(getenv("FSD_K10_CTAS")) : 3;  // 4 selects the 48-register build of the kernel
     if (want > 4) want = 4;
-    int ctas = 512 / p.tmem_cols < want ? 512 / p.tmem_cols : want;
-    if (ctas < 1) ctas = 1;
-    int stages = 0;
+    int ctas = 1, stages = 0;
     size_t smem = 0;
-    for (; ctas >= 1; --ctas) {
-        const size_t budget = (size_t)216 * 1024 / ctas - 3 * 1024;  // static shared memory + the driver's 1 KB per CTA
-        const size_t fixed = 1024 + p.b_region + staging;
-        if (budget < fixed + 2 * (size_t)p.slab_bytes) continue;
-        stages = (int)((budget - fixed) / p.slab_bytes);
-        if (stages > K10_MAX_STAGES) stages = K10_MAX_STAGES;
-        smem = budget;  // (the padded request also keeps more CTAs than tensor memory allows from sharing an SM)
-        break;
+    bool wide_epilogue = false;
+    auto plan = [&](int epi_warps, int first_ctas) {
+        const size_t staging = (size_t)epi_warps * 32 * K10_STAGE_PITCH * sizeof(__half);
+        for (ctas = first_ctas; ctas >= 1; --ctas) {
+            const size_t budget = (size_t)216 * 1024 / ctas - 3 * 1024;  // static shared memory + the driver's 1 KB per CTA
+            const size_t fixed = 1024 + p.b_region + staging;
+            if (budget < fixed + 2 * (size_t)p.slab_bytes) continue;
+            stages = (int)((budget - fixed) / p.slab_bytes);
+            if (stages > K10_MAX_STAGES) stages = K10_MAX_STAGES;
+            smem = budget;  // (the padded request also keeps more CTAs than tensor memory allows from sharing an SM)
+            return true;
+        }
+        stages = 0;
+        return false;
+    };
+    const int tmem_ctas = 512 / p.tmem_cols < want ? 512 / p.tmem_cols : want;
+    if (!plan(8, tmem_ctas < 1 ? 1 : tmem_ctas)) return FSD_OK;
+    if (ctas == 1 && n_mma >= 64 && !(getenv("FSD_K10_EW") && atoi(getenv("FSD_K10_EW")) == 8)) {
+        const int s8 = stages;
+        const size_t m8 = smem;
+        if (plan(16, 1)) wide_epilogue = true;
+        else { stages = s8; smem = m8; ctas = 1; }
     }
     if (stages < 2) return FSD_OK;
     p.stages = stages;
@@ -482,7 +506,6 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     }
 
     const int grid = p.n_tiles < h->sm_count * ctas ? p.n_tiles : h->sm_count * ctas;
-    const bool wide_epilogue = ctas == 1 && n_mma >= 64 && !(getenv("FSD_K10_EW") && atoi(getenv("FSD_K10_EW")) == 8);
 #define K10_GO2(ACT, C3)                                                                                                \
     {                                                                                                                   \
         auto kern = wide_epilogue ? k10_pointwise_tc_kernel<ACT, 1, C3, 16>                                            \
