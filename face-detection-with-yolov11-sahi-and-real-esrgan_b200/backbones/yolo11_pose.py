@@ -72,9 +72,9 @@ class Conv(nn.Module):
             if (c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and c.dilation == (1, 1) and c.groups == 1
                     and out2 is None and up2 is None and x.stride(1) == 1 and x.shape[2] * x.shape[3] >= 256):
                 # dense 3x3 layers: implicit GEMM on the tensor cores with the epilogue fused (fsd_conv3x3)
-                from ..ops import conv3x3, conv3x3_supported, conv3x3_tap_major, conv3x3_tc_enabled
+                from ..ops import conv3x3, conv3x3_preferred, conv3x3_tap_major, conv3x3_tc_enabled
 
-                if conv3x3_tc_enabled() and conv3x3_supported(c.in_channels, c.out_channels):
+                if conv3x3_tc_enabled() and conv3x3_preferred(c.in_channels, c.out_channels):
                     cached = getattr(self, "_w_taps", None)  # (weight version, tap-major copy)
                     if cached is None or cached[0] != (c.weight._version, c.weight.data_ptr()):
                         cached = ((c.weight._version, c.weight.data_ptr()), conv3x3_tap_major(c.weight))

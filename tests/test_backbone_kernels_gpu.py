@@ -244,10 +244,9 @@ def test_backbone_tensor_core_layers_equal_library_layers(cuda_device, monkeypat
     model = yp.build_yolo11n_pose().half().to(cuda_device).to(memory_format=torch.channels_last)
     x = torch.rand((2, 3, 256, 320), generator=g).half().to(cuda_device).contiguous(memory_format=torch.channels_last)
     with torch.no_grad():
-        monkeypatch.setenv("FSD_CONV3_TC", "1")
         got = model(x)
-        monkeypatch.delenv("FSD_CONV3_TC")
         monkeypatch.setenv("FSD_K7_NO_TC", "1")
+        monkeypatch.setenv("FSD_NO_CONV3_TC", "1")
         want = model(x)
     for lv_got, lv_want in zip(got, want):
         for a, b in zip(lv_got, lv_want):
