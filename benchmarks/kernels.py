@@ -275,8 +275,26 @@ def bench_conv3():
         del x, out
 
 
+def bench_dw():
+    """depth-wise 3x3 layers of the head (96 network inputs of 1024^2): fsd_dwconv3x3 vs cuDNN grouped convolution + epilogue."""
+    cl = lambda *shape: torch.randn(shape, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    torch.backends.cudnn.benchmark = True
+    for name, c, hw in (("head.cv3 dw 64ch 128^2", 64, 128), ("head.cv3 dw 128ch 64^2", 128, 64), ("head.cv3 dw 64ch 64^2", 64, 64),
+                        ("head.cv3 dw 256ch 32^2", 256, 32), ("head.cv3 dw 64ch 32^2", 64, 32)):
+        x = cl(96, c, hw, hw)
+        w = (torch.randn((c, 1, 3, 3), device=dev) / 3).half()
+        taps = ops.dwconv3x3_tap_major(w)
+        bias = torch.randn((c,), device=dev).half()
+        out = cl(96, c, hw, hw)
+        nbytes = (x.numel() + out.numel()) * 2
+        report(f"K11 dwconv3x3 + bias + SiLU {name}", nbytes, lambda: ops.dwconv3x3(x, taps, bias, "silu", out=out))
+        report(f"   cuDNN grouped conv + fsd_bias_act {name}", nbytes,
+               lambda: ops.bias_act(torch.nn.functional.conv2d(x, w, None, 1, 1, 1, c), bias, "silu", out=out))
+        del x, out
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4), ("k5", bench_k5), ("k10", bench_k10), ("conv3", bench_conv3)):
+    for name, fn in (("ref", bench_ref), ("k1", bench_k1), ("k2", bench_k2), ("k3", bench_k3), ("k4", bench_k4), ("k5", bench_k5), ("k10", bench_k10), ("conv3", bench_conv3), ("dw", bench_dw)):
         if which in ("all", name):
             fn()

@@ -47,6 +47,9 @@ SIGNATURES = {
     "fsd_conv3x3_supported": (C.c_int, [C.c_int, C.c_int]),
     "fsd_conv3x3": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int,
                               C.c_int, C.c_float, C.c_int, vp]),
+    "fsd_conv2x2_supported": (C.c_int, [C.c_int, C.c_int]),
+    "fsd_conv2x2": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
+    "fsd_dwconv3x3": (C.c_int, [vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
     "fsd_sppf_pool": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fsd_upsample2x_concat": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "fsd_esrgan_tile_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int,
@@ -71,7 +74,7 @@ FSD_KERNEL_GATHER, FSD_KERNEL_DECODE, FSD_KERNEL_MERGE, FSD_KERNEL_ESRGAN_CROP, 
 FSD_KERNEL_STEM, FSD_KERNEL_POINTWISE, FSD_KERNEL_FINALIZE, FSD_KERNEL_ATTACH, FSD_KERNEL_PACK = 6, 7, 8, 9, 10
 FSD_KERNEL_ESRGAN_STITCH, FSD_KERNEL_SPPF = 11, 12
 KERNEL_NAMES = {1: "k1_gather", 2: "k2a_decode", 3: "k3_merge", 4: "k4_crop", 5: "k5_bias_act", 6: "k6_stem", 7: "k7_pointwise",
-                8: "k2b_finalize", 9: "attach_keypoints", 10: "pack", 11: "k4_stitch", 12: "k5_sppf", 13: "k10_conv3x3"}
+                8: "k2b_finalize", 9: "attach_keypoints", 10: "pack", 11: "k4_stitch", 12: "k5_sppf", 13: "k10_conv3x3", 14: "k11_dwconv3x3"}
 FSD_PLANAR, FSD_CHANNELS_LAST = 0, 1
 
 _lib = None

@@ -80,6 +80,17 @@ class Conv(nn.Module):
                         cached = ((c.weight._version, c.weight.data_ptr()), conv3x3_tap_major(c.weight))
                         self._w_taps = cached
                     return conv3x3(x, cached[1], c.bias, act, out=out, residual=residual)
+            if (c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and c.dilation == (1, 1)
+                    and c.groups == c.in_channels == c.out_channels and residual is None and out2 is None and up2 is None
+                    and x.stride(1) == 1 and not os.environ.get("FSD_NO_DWCONV")):
+                # depth-wise 3x3 layers: one stencil kernel with the epilogue fused (fsd_dwconv3x3)
+                from ..ops import dwconv3x3, dwconv3x3_tap_major
+
+                cached = getattr(self, "_w_taps", None)
+                if cached is None or cached[0] != (c.weight._version, c.weight.data_ptr()):
+                    cached = ((c.weight._version, c.weight.data_ptr()), dwconv3x3_tap_major(c.weight))
+                    self._w_taps = cached
+                return dwconv3x3(x, cached[1], c.bias, act, out=out)
             y = F.conv2d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
             if y.is_contiguous(memory_format=torch.channels_last):
                 from ..ops import bias_act
@@ -358,9 +369,13 @@ class YOLO11Pose(nn.Module):
                     for kx in range(3):
                         b, dx = tap[kx]
                         w2[:, (dy * 2 + dx) * 16:(dy * 2 + dx + 1) * 16, a, b] = w1[:, :, ky, kx]
-                cached = (key, w0, w2.contiguous(memory_format=torch.channels_last))
+                cached = (key, w0, w2.contiguous(memory_format=torch.channels_last), w2.permute(2, 3, 0, 1).contiguous())
                 self._stem_weights = cached
             s = stem_conv(x, cached[1], c0.bias, space_to_depth=True)
+            from ..ops import conv2x2, conv2x2_supported, conv3x3_tc_enabled
+
+            if conv3x3_tc_enabled() and conv2x2_supported(64, c1.out_channels):
+                return conv2x2(s, cached[3], c1.bias, "silu")  # tensor-core implicit GEMM with the epilogue fused
             y = F.conv2d(s, cached[2], None, 1, 0)
             if y.is_contiguous(memory_format=torch.channels_last):
                 return bias_act(y, c1.bias, "silu")

@@ -48,7 +48,8 @@ struct K10Params {
     uint32_t b_bytes, b_region, slab_bytes, sbo_bytes, layout_type;  // b_region = b_bytes rounded up to 1024
     int taps, total_slabs, n_valid;           // 1 or 9 taps; total_slabs = taps * n_slabs; columns actually stored
     int H, W, tiles_x, tiles_per_image;       // 3x3 only: image size and the patch grid (16 x 8, halo mode: 8 x 16)
-    int a_per_tile, baseoff_mode;             // ring slots one tile consumes; halo mode: how the descriptor's base offset is set
+    int a_per_tile, baseoff_mode;             // ring slots one tile consumes; (base offset rule: measurement knob, unused)
+    int kh, kw, pad;                          // filter taps and padding: 3, 3, 1 or (halo mode only) 2, 2, 0
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------------
@@ -217,11 +218,11 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     mbar_expect_tx(&full_bar[stage], p.slab_bytes);
                     uint8_t* dst = smem_a + (size_t)stage * p.slab_bytes;
                     if (MODE == 2) {  // the whole 18 x 16 pixel halo patch (rows y0-1.., columns x0-1..x0+14) of the 16 x 8 output tile
-                        k10_tma_load_4d(dst, &map_x, &full_bar[stage], 0, tx * 8 - 1, ty * 16 - 1, n);
+                        k10_tma_load_4d(dst, &map_x, &full_bar[stage], 0, tx * 8 - p.pad, ty * 16 - p.pad, n);
                     } else if (MODE == 1) {
                         const int tap = s / p.n_slabs, cs = s - tap * p.n_slabs;
                         const int ky = tap / 3, kx = tap - 3 * ky;
-                        k10_tma_load_4d(dst, &map_x, &full_bar[stage], cs * p.KS, tx * 16 + kx - 1, ty * 8 + ky - 1, n);
+                        k10_tma_load_4d(dst, &map_x, &full_bar[stage], cs * p.KS, tx * 16 + kx - p.pad, ty * 8 + ky - p.pad, n);
                     } else {
                         k10_tma_load_2d(dst, &map_x, &full_bar[stage], s * p.KS, tile * K10_TILE);
                     }
@@ -262,12 +263,17 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     if (elect_one_sync()) {
                         const uint32_t a_lo0 = a_lo_base + (uint32_t)stage * slab16;
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)((tap / 3) * 16 + tap % 3) * row16;
-                            const uint32_t b_lo = b_lo_base + (uint32_t)tap * bslab16;
-                            if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
-                            else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
-                            else tc_issue_slab<1>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, tap == 0);
+                        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                if (ky >= p.kh || kx >= p.kw) continue;  // (2 x 2 filters use four of the nine unrolled slots)
+                                const uint32_t a_lo = a_lo0 + (uint32_t)(ky * 16 + kx) * row16;
+                                const uint32_t b_lo = b_lo_base + (uint32_t)(ky * p.kw + kx) * bslab16;
+                                const bool first = ky == 0 && kx == 0;
+                                if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, first);
+                                else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, first);
+                                else tc_issue_slab<1>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, first);
+                            }
                         }
                         tc_commit(&empty_bar[stage]);
                         tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
@@ -389,6 +395,11 @@ bool k10_conv3_supported(int K, int N) {
     return K % 16 == 0 && K >= 16 && K <= 256 && (N == 8 || (N % 16 == 0 && N >= 16 && N <= 256)) && (size_t)9 * K * n_mma * 2 <= 96 * 1024;
 }
 
+// 2 x 2, no padding (layer 1 of the backbone on the space-to-depth stem output): one channel slab only (halo mode)
+bool k10_conv2_supported(int K, int N) {
+    return (K == 16 || K == 32 || K == 64) && N % 16 == 0 && N >= 16 && N <= 256 && (size_t)4 * K * N * 2 <= 96 * 1024;
+}
+
 typedef CUresult (*k10_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -408,11 +419,12 @@ static bool k10_encode(fsd_context* h, CUtensorMap* m, const void* base, int ran
 // Shared launcher.  taps = 1: x is [P, K] with row stride x_stride (elements), w is [N, K].  taps = 9: x is n_img channels-last images
 // of H x W pixels (pixel stride x_stride), w is tap-major [3][3][n_mma][K]; P = n_img * H * W.
 // -> FSD_OK with *taken = true when the launch was made; *taken = false: shape / resources not supported here
-static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride, int n_img, int H, int W, const void* w, const void* bias,
+static int k10_launch(fsd_context* h, int taps, int kh, int pad, const void* x, int64_t x_stride, int n_img, int Hin, int Win, const void* w, const void* bias,
                       void* out, int64_t out_stride, const void* res, int64_t res_stride, void* out2, int64_t out2_stride, int out2_c0,
                       int64_t P, int K, int N, int act, float slope, cudaStream_t stream, bool* taken) {
     *taken = false;
-    const int n_mma = (taps == 9 && N == 8) ? 16 : N;
+    const int n_mma = (taps > 1 && N == 8) ? 16 : N;
+    const int H = Hin - kh + 1 + 2 * pad, W = Win - kh + 1 + 2 * pad;  // output size (taps = 1: unused)
     if (!h->encode_tiled || P >= (1LL << 31) - K10_TILE) return FSD_OK;
     K10Params p;
     p.bias = (const __half*)bias; p.out = (__half*)out; p.res = (const __half*)res; p.out2 = (__half*)out2;
@@ -420,6 +432,7 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     p.KS = K % 64 == 0 ? 64 : (K % 32 == 0 ? 32 : 16);
     p.n_slabs = K / p.KS;
     p.taps = taps; p.total_slabs = taps * p.n_slabs;
+    p.kh = kh; p.kw = kh; p.pad = pad;
     p.out_stride = (int)out_stride; p.res_stride = (int)res_stride; p.out2_stride = (int)out2_stride; p.out2_c0 = out2_c0;
     p.slope = slope;
     p.b_bytes = (uint32_t)taps * K * n_mma * 2;
@@ -430,13 +443,15 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     const CUtensorMapSwizzle swz = p.KS == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.KS == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     p.H = H; p.W = W; p.tiles_x = 1; p.tiles_per_image = 1;
     // 3x3 with one channel slab: ONE halo box per tile (FSD_C3_HALO=0 keeps one box per tap); FSD_C3_BASEOFF picks the descriptor rule
-    const bool halo = taps == 9 && p.n_slabs == 1 && !(getenv("FSD_C3_HALO") && atoi(getenv("FSD_C3_HALO")) == 0);
+    const bool halo = taps > 1 && p.n_slabs == 1 && (taps != 9 || !(getenv("FSD_C3_HALO") && atoi(getenv("FSD_C3_HALO")) == 0));
+    if (taps > 1 && taps != 9 && !halo) return FSD_OK;  // (2 x 2 filters only exist in halo mode)
+    const uint32_t halo_rows = 16u + (uint32_t)kh - 1u;
     // measured (gpurun_out/r2_c3halo_*.log): the swizzle phase follows the ABSOLUTE shared-memory address, so a descriptor that starts
     // s pixel rows into a swizzle pattern needs base offset 0; writing (start >> 7) & 7 there breaks K = 32 and 64 (FSD_C3_BASEOFF=1 shows it)
     p.baseoff_mode = getenv("FSD_C3_BASEOFF") ? atoi(getenv("FSD_C3_BASEOFF")) : 0;
     p.a_per_tile = halo ? 1 : p.total_slabs;
-    if (halo) p.slab_bytes = 18u * 16u * (uint32_t)p.KS * 2;
-    if (taps == 9) {
+    if (halo) p.slab_bytes = halo_rows * 16u * (uint32_t)p.KS * 2;
+    if (taps > 1) {
         p.tiles_x = halo ? (W + 7) / 8 : (W + 15) / 16;
         p.tiles_per_image = p.tiles_x * (halo ? (H + 15) / 16 : (H + 7) / 8);
         if ((int64_t)p.tiles_per_image * n_img >= (1LL << 31)) return FSD_OK;
@@ -485,12 +500,12 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
     p.stages = stages;
 
     CUtensorMap mx, mw;
-    if (taps == 9) {
-        const uint64_t xd[4] = {(uint64_t)K, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
-        const uint64_t xs[3] = {(uint64_t)x_stride * 2, (uint64_t)W * x_stride * 2, (uint64_t)H * W * x_stride * 2};
-        const uint32_t xb[4] = {(uint32_t)p.KS, 16, halo ? 18u : 8u, 1};
+    if (taps > 1) {
+        const uint64_t xd[4] = {(uint64_t)K, (uint64_t)Win, (uint64_t)Hin, (uint64_t)n_img};
+        const uint64_t xs[3] = {(uint64_t)x_stride * 2, (uint64_t)Win * x_stride * 2, (uint64_t)Hin * Win * x_stride * 2};
+        const uint32_t xb[4] = {(uint32_t)p.KS, 16, halo ? halo_rows : 8u, 1};
         if (!k10_encode(h, &mx, x, 4, xd, xs, xb, swz)) return FSD_OK;
-        const uint64_t wd[3] = {(uint64_t)K, (uint64_t)n_mma, 9};
+        const uint64_t wd[3] = {(uint64_t)K, (uint64_t)n_mma, (uint64_t)taps};
         const uint64_t ws[2] = {(uint64_t)K * 2, (uint64_t)n_mma * K * 2};
         const uint32_t wb[3] = {(uint32_t)p.KS, (uint32_t)n_mma, 1};
         if (!k10_encode(h, &mw, w, 3, wd, ws, wb, swz)) return FSD_OK;
@@ -513,11 +528,11 @@ static int k10_launch(fsd_context* h, int taps, const void* x, int64_t x_stride,
         FSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
         kern<<<grid, wide_epilogue ? 64 + 32 * 16 : 64 + 32 * 8, smem, stream>>>(mx, mw, p);                            \
     }
-#define K10_GO(ACT) { if (halo) K10_GO2(ACT, 2) else if (taps == 9) K10_GO2(ACT, 1) else K10_GO2(ACT, 0) }
+#define K10_GO(ACT) { if (halo) K10_GO2(ACT, 2) else if (taps > 1) K10_GO2(ACT, 1) else K10_GO2(ACT, 0) }
     {
         // algorithmic bytes: input + output (+ residual, + second destination) once
-        TimedLaunch timed(h, taps == 9 ? FSD_KERNEL_CONV3X3 : FSD_KERNEL_POINTWISE,
-                          (int64_t)P * (K + N + (res ? N : 0) + (out2 ? N - out2_c0 : 0)) * 2, N, stream);
+        TimedLaunch timed(h, taps > 1 ? FSD_KERNEL_CONV3X3 : FSD_KERNEL_POINTWISE,
+                          ((int64_t)(taps > 1 ? (int64_t)n_img * Hin * Win : P) * K + (int64_t)P * (N + (res ? N : 0) + (out2 ? N - out2_c0 : 0))) * 2, N, stream);
         if (act == 0) K10_GO(0) else if (act == 1 && silu_tanh_mode()) K10_GO(3) else if (act == 1) K10_GO(1) else K10_GO(2)
     }
 #undef K10_GO
@@ -533,7 +548,7 @@ int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const v
                         int act, float slope, cudaStream_t stream, bool* taken) {
     *taken = false;
     if (!k10_supported(K, N)) return FSD_OK;
-    return k10_launch(h, 1, x, x_stride, 1, 1, 1, w, bias, out, out_stride, res, res_stride, out2, out2_stride, out2_c0, P, K, N, act, slope,
+    return k10_launch(h, 1, 1, 0, x, x_stride, 1, 1, 1, w, bias, out, out_stride, res, res_stride, out2, out2_stride, out2_c0, P, K, N, act, slope,
                       stream, taken);
 }
 
@@ -561,12 +576,41 @@ extern "C" int fsd_conv3x3(fsd_handle_t h, const void* x, int64_t x_pixel_stride
     if (n_images == 0) return FSD_OK;
     FSD_CUDA(cudaSetDevice(h->device));
     bool taken = false;
-    const int rc = k10_launch(h, 9, x, x_pixel_stride, n_images, H, W, weight_taps, bias, out, out_pixel_stride, residual, residual_pixel_stride,
+    const int rc = k10_launch(h, 9, 3, 1, x, x_pixel_stride, n_images, H, W, weight_taps, bias, out, out_pixel_stride, residual, residual_pixel_stride,
                               nullptr, 0, 0, (int64_t)n_images * H * W, in_channels, out_channels, act, slope, (cudaStream_t)stream_, &taken);
     if (rc != FSD_OK) return rc;
     if (!taken) {
         set_error("fsd_conv3x3: the tensor-core path could not be set up for %d -> %d at %dx%d (tensor map / shared memory)", in_channels,
                   out_channels, H, W);
+        return FSD_ERR_CAPACITY;
+    }
+    return FSD_OK;
+}
+
+extern "C" int fsd_conv2x2_supported(int in_channels, int out_channels) { return k10_conv2_supported(in_channels, out_channels) ? 1 : 0; }
+
+extern "C" int fsd_conv2x2(fsd_handle_t h, const void* x, int64_t x_pixel_stride, int n_images, int H, int W, const void* weight_taps,
+                           const void* bias, void* out, int64_t out_pixel_stride, int in_channels, int out_channels, int act, float slope,
+                           int dtype, void* stream_) {
+    FSD_CHECK_ARG(h && x && weight_taps && bias && out, "fsd_conv2x2: null argument");
+    FSD_CHECK_ARG(dtype == FSD_F16, "fsd_conv2x2: only fp16 is implemented");
+    FSD_CHECK_ARG(n_images >= 0 && H > 1 && W > 1 && act >= 0 && act <= 2, "fsd_conv2x2: bad sizes / activation");
+    FSD_CHECK_ARG(k10_conv2_supported(in_channels, out_channels), "fsd_conv2x2: unsupported shape %d -> %d (see fsd_conv2x2_supported)",
+                  in_channels, out_channels);
+    FSD_CHECK_ARG(x_pixel_stride >= in_channels && x_pixel_stride % 8 == 0, "fsd_conv2x2: bad input stride");
+    FSD_CHECK_ARG(out_pixel_stride >= out_channels && out_pixel_stride % 8 == 0, "fsd_conv2x2: bad output stride");
+    if (((uintptr_t)x & 15) || ((uintptr_t)weight_taps & 15) || ((uintptr_t)out & 15)) {
+        set_error("fsd_conv2x2: pointers must be 16-byte aligned");
+        return FSD_ERR_ALIGN;
+    }
+    if (n_images == 0) return FSD_OK;
+    FSD_CUDA(cudaSetDevice(h->device));
+    bool taken = false;
+    const int rc = k10_launch(h, 4, 2, 0, x, x_pixel_stride, n_images, H, W, weight_taps, bias, out, out_pixel_stride, nullptr, 0, nullptr, 0, 0,
+                              (int64_t)n_images * (H - 1) * (W - 1), in_channels, out_channels, act, slope, (cudaStream_t)stream_, &taken);
+    if (rc != FSD_OK) return rc;
+    if (!taken) {
+        set_error("fsd_conv2x2: the tensor-core path could not be set up for %d -> %d at %dx%d", in_channels, out_channels, H, W);
         return FSD_ERR_CAPACITY;
     }
     return FSD_OK;

@@ -459,6 +459,52 @@ def conv3x3(x: torch.Tensor, weight_taps: torch.Tensor, bias: torch.Tensor, act:
     return out
 
 
+def conv2x2_supported(k: int, n: int) -> bool:
+    return bool(_cabi.load_library().fsd_conv2x2_supported(int(k), int(n)))
+
+
+def conv2x2(x: torch.Tensor, weight_taps: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: float = 0.2,
+            out: torch.Tensor | None = None) -> torch.Tensor:
+    """(a5) act(conv2x2(x, stride 1, no padding) + bias) on the tensor cores: x [B,K,H,W] -> [B,N,H-1,W-1]; weight_taps is the
+    contiguous tap-major [2, 2, N, K] fp16 matrix (`w.permute(2, 3, 0, 1).contiguous()`)."""
+    _require_cuda(x, "x")
+    b, k, hh, ww = x.shape
+    n = int(bias.shape[0])
+    if x.dtype != torch.float16 or tuple(weight_taps.shape) != (2, 2, n, k) or not weight_taps.is_contiguous() or weight_taps.dtype != torch.float16:
+        raise ValueError("conv2x2 needs fp16 tensors and a contiguous tap-major [2, 2, N, K] weight")
+    sx = _slot_stride(x, b, k, hh, ww, "x")
+    if out is None:
+        out = torch.empty((b, n, hh - 1, ww - 1), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    so = _slot_stride(out, b, n, hh - 1, ww - 1, "out")
+    h = _handle_for(x)
+    check(h.lib.fsd_conv2x2(h.h, x.data_ptr(), sx, b, hh, ww, weight_taps.data_ptr(), bias.data_ptr(), out.data_ptr(), so, k, n,
+                            _ACT[act], float(slope), _TORCH_DTYPE[x.dtype], _stream_ptr(x.device)), "fsd_conv2x2")
+    return out
+
+
+def dwconv3x3_tap_major(weight: torch.Tensor) -> torch.Tensor:
+    """[C, 1, 3, 3] depth-wise weight -> the tap-major [9, C] fp16 matrix fsd_dwconv3x3 reads."""
+    c = int(weight.shape[0])
+    return weight.detach().reshape(c, 9).t().contiguous()
+
+
+def dwconv3x3(x: torch.Tensor, weight_taps: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: float = 0.2,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """(a5) act(depthwise_conv3x3(x, stride 1, pad 1) + bias) in one kernel; x / out may be channel slots of channels-last fp16 buffers."""
+    _require_cuda(x, "x")
+    b, c, hh, ww = x.shape
+    if x.dtype != torch.float16 or weight_taps.dtype != torch.float16 or tuple(weight_taps.shape) != (9, c) or not weight_taps.is_contiguous():
+        raise ValueError("dwconv3x3 needs fp16 tensors and the contiguous [9, C] matrix of dwconv3x3_tap_major()")
+    sx = _slot_stride(x, b, c, hh, ww, "x")
+    if out is None:
+        out = torch.empty((b, c, hh, ww), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    so = _slot_stride(out, b, c, hh, ww, "out")
+    h = _handle_for(x)
+    check(h.lib.fsd_dwconv3x3(h.h, x.data_ptr(), sx, b, hh, ww, weight_taps.data_ptr(), bias.data_ptr(), out.data_ptr(), so, c,
+                              _ACT[act], float(slope), _TORCH_DTYPE[x.dtype], _stream_ptr(x.device)), "fsd_dwconv3x3")
+    return out
+
+
 def sppf_pool_(buf: torch.Tensor) -> torch.Tensor:
     """(a5) fills channel slots 1..3 of the dense channels-last [N,4c,H,W] fp16 buffer with the cascaded 5x5 max pools of
     slot 0 (ultralytics SPPF), one launch."""

@@ -56,13 +56,13 @@ int64_t fsd_launch_count(fsd_handle_t h);
  *   FSD_KERNEL_DECODE         units = bytes of the head tensors (80 values per anchor), tag = anchors per entry
  *   FSD_KERNEL_MERGE          units = segments, tag = max_segment
  *   FSD_KERNEL_ESRGAN_CROP / _STITCH   units = algorithmic bytes, tag = images of the launch
- *   FSD_KERNEL_BIAS_ACT / _STEM / _POINTWISE / _SPPF / _CONV3X3   units = bytes the launch moves, tag = channels
+ *   FSD_KERNEL_BIAS_ACT / _STEM / _POINTWISE / _SPPF / _CONV3X3 / _DWCONV   units = bytes the launch moves, tag = channels
  *   FSD_KERNEL_FINALIZE / _ATTACH / _PACK   units = entries / images
  * Launches captured into a CUDA graph cannot be bracketed (bench.py times the backbone's kernels in an eager step).
  * (the reference has no counterpart; its timing is wall-clock around model.predict, utils/yolo_wrapper.py:67-80) */
 enum { FSD_KERNEL_GATHER = 1, FSD_KERNEL_DECODE = 2, FSD_KERNEL_MERGE = 3, FSD_KERNEL_ESRGAN_CROP = 4, FSD_KERNEL_BIAS_ACT = 5,
        FSD_KERNEL_STEM = 6, FSD_KERNEL_POINTWISE = 7, FSD_KERNEL_FINALIZE = 8, FSD_KERNEL_ATTACH = 9, FSD_KERNEL_PACK = 10,
-       FSD_KERNEL_ESRGAN_STITCH = 11, FSD_KERNEL_SPPF = 12, FSD_KERNEL_CONV3X3 = 13 };
+       FSD_KERNEL_ESRGAN_STITCH = 11, FSD_KERNEL_SPPF = 12, FSD_KERNEL_CONV3X3 = 13, FSD_KERNEL_DWCONV = 14 };
 int fsd_kernel_timing_enable(fsd_handle_t h, unsigned kernel_mask /* OR of (1u << FSD_KERNEL_*); 0 = off */);
 int fsd_kernel_timing_read(fsd_handle_t h, double* samples /* [cap,4] or NULL */, int cap, int* n);
 
@@ -220,6 +220,22 @@ int fsd_conv3x3_supported(int in_channels, int out_channels);
 int fsd_conv3x3(fsd_handle_t h, const void* x, int64_t x_pixel_stride, int n_images, int H, int W, const void* weight_taps,
                 const void* bias, void* out, int64_t out_pixel_stride, const void* residual, int64_t residual_pixel_stride,
                 int in_channels, int out_channels, int act, float slope, int dtype, void* stream);
+
+/* ---- (a5) 2x2 convolution, stride 1, no padding, + bias + activation on the same tensor-core pipeline (halo mode): layer 1 of
+ *      yolo11-pose (Conv(16, 32, 3, 2)) evaluated on the space-to-depth output of fsd_stem_conv, where it is algebraically a 2x2
+ *      stride-1 convolution over 64 channels.  x: [n, H, W, in_channels]; out: [n, H-1, W-1, out_channels]; weight_taps TAP-MAJOR
+ *      [2][2][out_channels][in_channels].  in_channels 16 / 32 / 64, out_channels a multiple of 16. */
+int fsd_conv2x2_supported(int in_channels, int out_channels);
+int fsd_conv2x2(fsd_handle_t h, const void* x, int64_t x_pixel_stride, int n_images, int H, int W, const void* weight_taps,
+                const void* bias, void* out, int64_t out_pixel_stride, int in_channels, int out_channels, int act, float slope,
+                int dtype, void* stream);
+
+/* ---- (a5) depth-wise 3x3 convolution, stride 1, pad 1, + bias + activation -> channel slot (csrc/k11_dwconv3x3.cu).
+ *      x: n_images channels-last images [H, W, channels] fp16; weight_taps: TAP-MAJOR [9][channels] fp16 (tap = 3 ky + kx).
+ *      Replaces cuDNN's grouped convolution + fsd_bias_act for ultralytics DWConv(c, c, 3) (head cv3 branches) and C2PSA's positional
+ *      convolution (run from utils/yolo_wrapper.py:72).  fp32 accumulation in tap order. */
+int fsd_dwconv3x3(fsd_handle_t h, const void* x, int64_t x_pixel_stride, int n_images, int H, int W, const void* weight_taps,
+                  const void* bias, void* out, int64_t out_pixel_stride, int channels, int act, float slope, int dtype, void* stream);
 
 /* ---- (a5) YOLO neck: out = concat(nearest_upsample_2x(a), b) along channels, channels-last, in ONE pass.
  *      a [N,ah,aw,ca], b [N,2ah,2aw,cb], out [N,2ah,2aw,ca+cb]; replaces torch's upsample kernel + concat kernel. */

@@ -235,6 +235,50 @@ def test_tensor_core_conv3x3_matches_torch(cuda_device, kn, act):
         assert float((err - 2e-3 * y.abs()).max()) <= 2e-3, (B, H, W, float(err.max()))
 
 
+@pytest.mark.parametrize("kn", [(64, 32), (16, 16), (32, 64), (64, 128)])
+def test_tensor_core_conv2x2_matches_torch(cuda_device, kn):
+    """(a5) fsd_conv2x2 (layer 1 on the space-to-depth stem output) == silu(conv2d 2x2, no padding + bias) in fp32 on the same inputs."""
+    import fsd_b200.ops as ops
+
+    K, N = kn
+    g = torch.Generator().manual_seed(K + N)
+    cl = lambda t: t.half().to(cuda_device).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    w = (torch.randn((N, K, 2, 2), generator=g) / (2 * K ** 0.5)).half().to(cuda_device)
+    bias = torch.randn((N,), generator=g).half().to(cuda_device)
+    taps = w.permute(2, 3, 0, 1).contiguous()
+    for B, H, W in ((3, 38, 30), (2, 65, 81), (1, 2, 2), (4, 129, 129)):
+        x = cl(torch.randn((B, K, H, W), generator=g))
+        y = torch.nn.functional.silu(torch.nn.functional.conv2d(x.float(), w.float(), bias.float()))
+        out = ops.conv2x2(x, taps, bias, "silu")
+        assert out.shape == (B, N, H - 1, W - 1) and out.is_contiguous(memory_format=torch.channels_last)
+        err = (out.float() - y).abs()
+        assert float((err - 2e-3 * y.abs()).max()) <= 2e-3, (B, H, W, float(err.max()))
+
+
+@pytest.mark.parametrize("c", [8, 64, 128, 256])
+@pytest.mark.parametrize("act", ["silu", "none"])
+def test_depthwise_conv3x3_matches_torch(cuda_device, c, act):
+    """(a5) fsd_dwconv3x3 == act(conv2d(groups = C, 3x3, pad 1) + bias) in fp32 on the same fp16 inputs; slot input / output, borders."""
+    import fsd_b200.ops as ops
+
+    g = torch.Generator().manual_seed(c)
+    cl = lambda t: t.half().to(cuda_device).contiguous(memory_format=torch.channels_last)  # noqa: E731
+    f = torch.nn.functional.silu if act == "silu" else (lambda t: t)
+    w = (torch.randn((c, 1, 3, 3), generator=g) / 3).half().to(cuda_device)
+    bias = torch.randn((c,), generator=g).half().to(cuda_device)
+    taps = ops.dwconv3x3_tap_major(w)
+    for B, H, W in ((3, 37, 29), (1, 1, 1), (2, 64, 80), (1, 3, 130)):
+        xbuf = cl(torch.randn((B, c + 8, H, W), generator=g))
+        x = xbuf[:, 8:]
+        y = f(torch.nn.functional.conv2d(x.float(), w.float(), bias.float(), padding=1, groups=c))
+        buf = torch.full((B, c + 16, H, W), float("nan"), dtype=torch.float16, device=cuda_device).contiguous(memory_format=torch.channels_last)
+        out = ops.dwconv3x3(x, taps, bias, act, out=buf[:, 8:8 + c])
+        assert torch.isnan(buf[:, :8]).all() and torch.isnan(buf[:, 8 + c:]).all()
+        err = (out.float() - y).abs()
+        assert float((err - 1e-3 * y.abs()).max()) <= 1e-3, (B, H, W, float(err.max()))
+        assert torch.equal(ops.dwconv3x3(x, taps, bias, act), out)
+
+
 def test_backbone_tensor_core_layers_equal_library_layers(cuda_device, monkeypatch):
     """The YOLO11n-pose graph with the tcgen05 1x1 / 3x3 kernels vs the same weights on cuDNN + fsd_bias_act (+ the mma.sync 1x1 kernel):
     per-level relative error of the raw head tensors stays at fp16 accumulation noise."""
@@ -247,6 +291,7 @@ def test_backbone_tensor_core_layers_equal_library_layers(cuda_device, monkeypat
         got = model(x)
         monkeypatch.setenv("FSD_K7_NO_TC", "1")
         monkeypatch.setenv("FSD_NO_CONV3_TC", "1")
+        monkeypatch.setenv("FSD_NO_DWCONV", "1")
         want = model(x)
     for lv_got, lv_want in zip(got, want):
         for a, b in zip(lv_got, lv_want):
