@@ -19,7 +19,7 @@ struct K11Params {
     const __half* w;     // tap-major [9][C]
     const __half* bias;  // [C]
     uint4* out;
-    long long n_vec;     // pixels * C / 8
+    int rows;            // n_images * H
     int H, W, C, cv;     // cv = C / 8
     int x_stride, out_stride;  // pixel strides in 16-byte vectors
     float slope;
@@ -32,6 +32,8 @@ __device__ __forceinline__ float k11_act(float v, float slope) {
     return v;
 }
 
+// A CTA stages the weights once and walks image rows (row = image * H + y); its threads walk the row's (pixel, channel-vector) pairs.
+// All index arithmetic is 32-bit (the first version's three 64-bit divisions per thread cost more than the convolution).
 template <int ACT>
 __global__ void __launch_bounds__(K11_THREADS) k11_dwconv3x3_kernel(const K11Params p) {
     extern __shared__ float k11_smem[];  // [9][C] weights, then [C] bias
@@ -40,43 +42,45 @@ __global__ void __launch_bounds__(K11_THREADS) k11_dwconv3x3_kernel(const K11Par
     for (int i = threadIdx.x; i < 9 * p.C; i += K11_THREADS) ws[i] = __half2float(__ldg(p.w + i));
     for (int i = threadIdx.x; i < p.C; i += K11_THREADS) bs[i] = __half2float(__ldg(p.bias + i));
     __syncthreads();
-    const long long stride = (long long)gridDim.x * K11_THREADS;
-    for (long long i = (long long)blockIdx.x * K11_THREADS + threadIdx.x; i < p.n_vec; i += stride) {
-        const long long pix = i / p.cv;
-        const int c = (int)(i - pix * p.cv);
-        const int x = (int)(pix % p.W);
-        const long long row = pix / p.W;  // n * H + y
-        const int y = (int)(row % p.H);
-        float acc[8];
+    const int row_vecs = p.W * p.cv;
+    for (int r = blockIdx.x; r < p.rows; r += gridDim.x) {
+        const int y = r % p.H;
+        const bool has_up = y > 0, has_down = y + 1 < p.H;
+        const uint4* xrow = p.x + (size_t)r * p.W * p.x_stride;
+        uint4* orow = p.out + (size_t)r * p.W * p.out_stride;
+        for (int t = threadIdx.x; t < row_vecs; t += K11_THREADS) {
+            const int x = t / p.cv, c = t - x * p.cv;
+            float acc[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int yy = y + ky - 1;
+            for (int ky = 0; ky < 3; ++ky) {
+                if ((ky == 0 && !has_up) || (ky == 2 && !has_down)) continue;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int xx = x + kx - 1;
-                if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
-                const uint4 v = __ldg(p.x + (pix + (long long)(ky - 1) * p.W + (kx - 1)) * p.x_stride + c);
-                const float4 w0 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * p.C + 8 * c);
-                const float4 w1 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * p.C + 8 * c + 4);
-                const __half2* hv = reinterpret_cast<const __half2*>(&v);
-                const float2 f0 = __half22float2(hv[0]), f1 = __half22float2(hv[1]), f2 = __half22float2(hv[2]), f3 = __half22float2(hv[3]);
-                acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
-                acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
-                acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
-                acc[6] = fmaf(f3.x, w1.z, acc[6]); acc[7] = fmaf(f3.y, w1.w, acc[7]);
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = x + kx - 1;
+                    if (xx < 0 || xx >= p.W) continue;
+                    const uint4 v = __ldg(xrow + ((ky - 1) * p.W + xx) * p.x_stride + c);
+                    const float4 w0 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * p.C + 8 * c);
+                    const float4 w1 = *reinterpret_cast<const float4*>(ws + (ky * 3 + kx) * p.C + 8 * c + 4);
+                    const __half2* hv = reinterpret_cast<const __half2*>(&v);
+                    const float2 f0 = __half22float2(hv[0]), f1 = __half22float2(hv[1]), f2 = __half22float2(hv[2]), f3 = __half22float2(hv[3]);
+                    acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
+                    acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
+                    acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
+                    acc[6] = fmaf(f3.x, w1.z, acc[6]); acc[7] = fmaf(f3.y, w1.w, acc[7]);
+                }
             }
+            const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * c), b1 = *reinterpret_cast<const float4*>(bs + 8 * c + 4);
+            const __half2 o0 = __floats2half2_rn(k11_act<ACT>(acc[0] + b0.x, p.slope), k11_act<ACT>(acc[1] + b0.y, p.slope));
+            const __half2 o1 = __floats2half2_rn(k11_act<ACT>(acc[2] + b0.z, p.slope), k11_act<ACT>(acc[3] + b0.w, p.slope));
+            const __half2 o2 = __floats2half2_rn(k11_act<ACT>(acc[4] + b1.x, p.slope), k11_act<ACT>(acc[5] + b1.y, p.slope));
+            const __half2 o3 = __floats2half2_rn(k11_act<ACT>(acc[6] + b1.z, p.slope), k11_act<ACT>(acc[7] + b1.w, p.slope));
+            uint4 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&o0); o.y = *reinterpret_cast<const uint32_t*>(&o1);
+            o.z = *reinterpret_cast<const uint32_t*>(&o2); o.w = *reinterpret_cast<const uint32_t*>(&o3);
+            orow[x * p.out_stride + c] = o;
         }
-        const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * c), b1 = *reinterpret_cast<const float4*>(bs + 8 * c + 4);
-        const __half2 o0 = __floats2half2_rn(k11_act<ACT>(acc[0] + b0.x, p.slope), k11_act<ACT>(acc[1] + b0.y, p.slope));
-        const __half2 o1 = __floats2half2_rn(k11_act<ACT>(acc[2] + b0.z, p.slope), k11_act<ACT>(acc[3] + b0.w, p.slope));
-        const __half2 o2 = __floats2half2_rn(k11_act<ACT>(acc[4] + b1.x, p.slope), k11_act<ACT>(acc[5] + b1.y, p.slope));
-        const __half2 o3 = __floats2half2_rn(k11_act<ACT>(acc[6] + b1.z, p.slope), k11_act<ACT>(acc[7] + b1.w, p.slope));
-        uint4 o;
-        o.x = *reinterpret_cast<const uint32_t*>(&o0); o.y = *reinterpret_cast<const uint32_t*>(&o1);
-        o.z = *reinterpret_cast<const uint32_t*>(&o2); o.w = *reinterpret_cast<const uint32_t*>(&o3);
-        p.out[pix * p.out_stride + c] = o;
     }
 }
 
@@ -101,11 +105,12 @@ extern "C" int fsd_dwconv3x3(fsd_handle_t h, const void* x, int64_t x_pixel_stri
     K11Params p;
     p.x = (const uint4*)x; p.w = (const __half*)weight_taps; p.bias = (const __half*)bias; p.out = (uint4*)out;
     p.H = H; p.W = W; p.C = channels; p.cv = channels / 8;
-    p.n_vec = (long long)n_images * H * W * p.cv;
+    FSD_CHECK_ARG((int64_t)n_images * H < (1LL << 31) && (int64_t)W * (x_pixel_stride > out_pixel_stride ? x_pixel_stride : out_pixel_stride) < (1LL << 31),
+                  "fsd_dwconv3x3: tensor too large for one launch");
+    p.rows = n_images * H;
     p.x_stride = (int)(x_pixel_stride / 8); p.out_stride = (int)(out_pixel_stride / 8); p.slope = slope;
     const size_t smem = (size_t)10 * channels * sizeof(float);
-    const long long want = (p.n_vec + K11_THREADS - 1) / K11_THREADS;
-    const int grid = (int)(want < (long long)h->sm_count * 16 ? want : (long long)h->sm_count * 16);
+    const int grid = p.rows < h->sm_count * 8 ? p.rows : h->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
     cudaStream_t s = (cudaStream_t)stream_;
     FSD_CUDA(cudaSetDevice(h->device));
     {
