@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(K11_THREADS) k11_dwconv3x3_kernel(const K11Par
     const int pairs = (p.W + 1) >> 1;
     const int row_items = pairs * p.cv;
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int r = blockIdx.x; r < p.rows; r += gridDim.x) {
+    // a CTA owns a band of consecutive rows, so two of the three input rows of every output row are already in this SM's L1
+    const int band = (p.rows + gridDim.x - 1) / gridDim.x;
+    const int r_end = min(p.rows, ((int)blockIdx.x + 1) * band);
+    for (int r = blockIdx.x * band; r < r_end; ++r) {
         const int y = r % p.H;
         const uint4* xrow = p.x + (size_t)r * p.W * p.x_stride;
         uint4* orow = p.out + (size_t)r * p.W * p.out_stride;
@@ -133,7 +136,8 @@ extern "C" int fsd_dwconv3x3(fsd_handle_t h, const void* x, int64_t x_pixel_stri
     p.rows = n_images * H;
     p.x_stride = (int)(x_pixel_stride / 8); p.out_stride = (int)(out_pixel_stride / 8); p.slope = slope;
     const size_t smem = (size_t)9 * channels * 2 + (size_t)channels * sizeof(float);
-    const int grid = p.rows < h->sm_count * 8 ? p.rows : h->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
+    int grid = h->sm_count * 3;  // 3 resident CTAs of 256 threads per SM (78 registers), each walking a band of rows
+    if (p.rows < grid * 4) grid = (p.rows + 3) / 4;
     cudaStream_t s = (cudaStream_t)stream_;
     FSD_CUDA(cudaSetDevice(h->device));
     {
