@@ -257,7 +257,7 @@ def main():
     # steps).  One eager step with the backbone's own kernels timed by the library comes first: launches inside a replayed
     # graph cannot be bracketed individually.
     use_graphs = not args.no_graphs
-    backbone_ids = (K.FSD_KERNEL_BIAS_ACT, K.FSD_KERNEL_STEM, K.FSD_KERNEL_POINTWISE, K.FSD_KERNEL_SPPF)
+    backbone_ids = (K.FSD_KERNEL_BIAS_ACT, K.FSD_KERNEL_STEM, K.FSD_KERNEL_POINTWISE, K.FSD_KERNEL_SPPF, K.FSD_KERNEL_CONV3X3, K.FSD_KERNEL_DWCONV)
     path_ids = (K.FSD_KERNEL_GATHER, K.FSD_KERNEL_DECODE, K.FSD_KERNEL_MERGE, K.FSD_KERNEL_FINALIZE, K.FSD_KERNEL_ATTACH, K.FSD_KERNEL_PACK)
     step_resident(0)  # cold eager step: cuDNN algorithm search, module loads
     step_resident(1)
@@ -384,7 +384,9 @@ def main():
                            "ms_per_step": tms / args.steps, "share_of_step": tms / args.steps / step_ms})
     ours_backbone_ms = 0.0
     for kid, label in ((K.FSD_KERNEL_BIAS_ACT, "k5_bias_act kernels via fsd_bias_act (conv epilogue: bias + SiLU [+ residual] -> concat slot)"),
-                       (K.FSD_KERNEL_STEM, "k6_stem_conv_kernel via fsd_stem_conv"), (K.FSD_KERNEL_POINTWISE, "k7_pointwise_conv_kernel via fsd_pointwise_conv"),
+                       (K.FSD_KERNEL_STEM, "k6_stem_conv_kernel via fsd_stem_conv"), (K.FSD_KERNEL_POINTWISE, "k10_pointwise_tc_kernel (tcgen05 1x1 convolution + epilogue) via fsd_pointwise_conv"),
+                       (K.FSD_KERNEL_CONV3X3, "k10_pointwise_tc_kernel (tcgen05 implicit-GEMM 3x3 / 2x2 convolution + epilogue) via fsd_conv3x3 / fsd_conv2x2"),
+                       (K.FSD_KERNEL_DWCONV, "k11_dwconv3x3_kernel via fsd_dwconv3x3"),
                        (K.FSD_KERNEL_SPPF, "k5_sppf_pool_kernel via fsd_sppf_pool")):
         ss = eager.get(kid, [])
         if ss:

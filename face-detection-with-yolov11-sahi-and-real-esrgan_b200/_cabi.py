@@ -72,7 +72,7 @@ FSD_NMS, FSD_GREEDYNMM, FSD_NMM = 0, 1, 2
 FSD_IOU, FSD_IOS = 0, 1
 FSD_KERNEL_GATHER, FSD_KERNEL_DECODE, FSD_KERNEL_MERGE, FSD_KERNEL_ESRGAN_CROP, FSD_KERNEL_BIAS_ACT = 1, 2, 3, 4, 5
 FSD_KERNEL_STEM, FSD_KERNEL_POINTWISE, FSD_KERNEL_FINALIZE, FSD_KERNEL_ATTACH, FSD_KERNEL_PACK = 6, 7, 8, 9, 10
-FSD_KERNEL_ESRGAN_STITCH, FSD_KERNEL_SPPF = 11, 12
+FSD_KERNEL_ESRGAN_STITCH, FSD_KERNEL_SPPF, FSD_KERNEL_CONV3X3, FSD_KERNEL_DWCONV = 11, 12, 13, 14
 KERNEL_NAMES = {1: "k1_gather", 2: "k2a_decode", 3: "k3_merge", 4: "k4_crop", 5: "k5_bias_act", 6: "k6_stem", 7: "k7_pointwise",
                 8: "k2b_finalize", 9: "attach_keypoints", 10: "pack", 11: "k4_stitch", 12: "k5_sppf", 13: "k10_conv3x3", 14: "k11_dwconv3x3"}
 FSD_PLANAR, FSD_CHANNELS_LAST = 0, 1
