@@ -330,8 +330,10 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                         if (lane == 0) k10_mbar_arrive(&acc_empty[acc]);
                     }
                     uint32_t h[8];
+                    const bool upper = c0 + 8 < p.n_valid;  // (N = 8 runs as a 16-column MMA: columns 8..15 are padding, skip their math)
 #pragma unroll
                     for (int e4 = 0; e4 < 4; ++e4) {
+                        if (e4 >= 2 && !upper) { h[2 * e4] = 0u; h[2 * e4 + 1] = 0u; continue; }
                         const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * e4]);
                         const __half2 o0 = __floats2half2_rn(k10_act<ACT>(__uint_as_float(v[4 * e4]) + bb.x, p.slope),
                                                              k10_act<ACT>(__uint_as_float(v[4 * e4 + 1]) + bb.y, p.slope));
