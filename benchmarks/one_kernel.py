@@ -60,6 +60,16 @@ elif which in ("conv3", "conv3_small"):  # 3x3 convolution on tcgen05 (halo mode
     out = torch.empty((96, n, hw, hw), device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
     for _ in range(iters):
         ops.conv3x3(x, taps, b, "silu", out=out)
+elif which == "conv2":  # layer 1 on the space-to-depth stem output: 2x2 convolution, 64 -> 32, 257 x 257 -> 256 x 256
+    x = torch.randn((32, 64, 257, 257), device=dev).half().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((32, 64, 2, 2), device=dev) / 16).half()
+    taps = w.permute(2, 3, 0, 1).contiguous()
+    b = torch.randn((32,), device=dev).half()
+    for _ in range(iters):
+        out = ops.conv2x2(x, taps, b, "silu")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.silu(torch.nn.functional.conv2d(x.float(), w.float(), b.float()))
+    print("conv2 max abs diff", float((out.float() - ref).abs().max()))
 elif which == "k7":
     x = torch.randn((96, 48, 256, 256), device=dev).half().contiguous(memory_format=torch.channels_last)
     w = (torch.randn((64, 48, 1, 1), device=dev) / 7).half()
