@@ -220,8 +220,8 @@ class SlicedFaceDetector:
         for kind, shape in shapes:
             x = self._network_input(kind, shape)
             if x is None:
-                x = torch.zeros(shape, dtype=self.dtype, device=self.device,
-                                memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+                x = torch.zeros(shape, dtype=self.dtype, device=self.device).contiguous(
+                    memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
             bufs.append(x)
 
         def once():
