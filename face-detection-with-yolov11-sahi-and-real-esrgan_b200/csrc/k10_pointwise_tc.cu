@@ -56,21 +56,29 @@ struct K10Params {
 __device__ __forceinline__ void k10_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: a protocol error traps after ~2 s instead of hanging the GPU
-__device__ __forceinline__ void k10_mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a protocol error traps after ~2 s instead of hanging the GPU.  try_wait carries a suspend-time hint, so a waiting
+// thread mostly sleeps in hardware instead of spinning through issue slots that the epilogue warps need (the waits were 28 % of all
+// instructions in profiles/r2_conv3_small_tc.summary.txt); `backoff_ns` adds a sleep between polls for waits that are not latency
+// critical (the producer's free-slot wait).
+__device__ __forceinline__ void k10_mbar_wait(uint64_t* bar, uint32_t parity, unsigned backoff_ns = 0) {
     const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    for (;;) {
+    long long t0 = 0;
+    for (unsigned polls = 1;; ++polls) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(20000u)
             : "memory");
         if (done) return;
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (backoff_ns) __nanosleep(backoff_ns);
+        if ((polls & 0xfffu) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();
+        }
     }
 }
 __device__ __forceinline__ void k10_tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
@@ -214,7 +222,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     tx = rem - ty * p.tiles_x;
                 }
                 for (int s = 0; s < p.a_per_tile; ++s) {
-                    k10_mbar_wait(&empty_bar[stage], phase ^ 1);
+                    k10_mbar_wait(&empty_bar[stage], phase ^ 1, 64);
                     mbar_expect_tx(&full_bar[stage], p.slab_bytes);
                     uint8_t* dst = smem_a + (size_t)stage * p.slab_bytes;
                     if (MODE == 2) {  // the whole 18 x 16 pixel halo patch (rows y0-1.., columns x0-1..x0+14) of the 16 x 8 output tile
