@@ -134,7 +134,10 @@ def bench_k3():
     from test_k3_merge_gpu import sahi_like_boxes
 
     rng = np.random.default_rng(0)
-    for n_target, S in ((256, 148), (1024, 148), (4096, 32), (9900, 8)):
+    sizes = ((256, 148), (1024, 148), (4096, 32), (9900, 8))
+    if os.environ.get("FSD_K3_BENCH_SIZES"):  # e.g. "2048x4,4096x4,4096x32"
+        sizes = tuple(tuple(int(v) for v in t.split("x")) for t in os.environ["FSD_K3_BENCH_SIZES"].split(","))
+    for n_target, S in sizes:
         seg = sahi_like_boxes(rng, max(2, n_target // 3), dup=(1, 5), size=(10, 60), canvas=(3840, 2160))
         while len(seg) < n_target:
             seg = np.concatenate([seg, sahi_like_boxes(rng, 50, dup=(1, 5), size=(10, 60), canvas=(3840, 2160))])

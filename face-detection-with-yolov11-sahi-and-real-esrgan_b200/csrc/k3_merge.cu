@@ -48,6 +48,7 @@ struct K3Params {
     int P;  // power of two >= seg_cap
     int use_global;
     int n_lo, n_hi;  // the shared-memory kernel takes the segments with n_lo < n <= n_hi (tiered launches, see fsd_merge)
+    int cluster_min; // segments with more boxes than this go to the cluster kernel (<= K3_SMEM_MAX_P)
 };
 
 __device__ __forceinline__ uint32_t score_key_desc(float s) {
@@ -904,7 +905,7 @@ __global__ void __cluster_dims__(K3_CLUSTER, 1, 1) __launch_bounds__(512) k3_mer
     const int off = p.seg_offsets[s];
     int n = p.seg_counts ? p.seg_counts[s] : p.seg_cap;
     n = min(max(n, 0), p.seg_cap);
-    if (n <= K3_SMEM_MAX_P) return;  // uniform over the cluster: the shared-memory launch owns this segment
+    if (n <= p.cluster_min) return;  // uniform over the cluster: the shared-memory launch owns this segment
     int P = 64;
     while (P < n) P <<= 1;
     uint8_t* base = p.workspace + (size_t)s * p.ws_per_segment;
@@ -1251,9 +1252,17 @@ static int pow2_at_least(int n) {
 
 using namespace fsd;
 
+// Segments above this many boxes take the 8-CTA cluster kernel.  Default 4096 = the shared-memory kernel's capacity; FSD_K3_CLUSTER_MIN
+// (1024 / 2048) moves the hand-over down for measurements.
+static int k3_cluster_min() {
+    const char* v = getenv("FSD_K3_CLUSTER_MIN");
+    const int t = v ? atoi(v) : K3_SMEM_MAX_P;
+    return t <= 1024 ? 1024 : (t <= 2048 ? 2048 : K3_SMEM_MAX_P);
+}
+
 extern "C" int64_t fsd_merge_workspace_bytes(int64_t N, int S, int max_segment) {
     (void)N;
-    if (max_segment <= K3_SMEM_MAX_P) return 256;  // unused, but keep the pointer non-null for callers
+    if (max_segment <= k3_cluster_min()) return 256;  // unused, but keep the pointer non-null for callers
     return (int64_t)S * ((int64_t)pow2_at_least(max_segment) * K3_WS_BYTES_PER_BOX + K3_SCRATCH_BYTES) + 256;
 }
 
@@ -1287,7 +1296,8 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
     p.keep = keep; p.keep_count = keep_count; p.parent = parent; p.merged_boxes = merged_boxes;
     p.merged_scores = merged_scores; p.merged_cats = merged_cats;
     p.P = pow2_at_least(max_segment);
-    p.use_global = p.P > K3_SMEM_MAX_P;
+    p.cluster_min = k3_cluster_min();
+    p.use_global = p.P > p.cluster_min;
     p.workspace = reinterpret_cast<uint8_t*>(workspace);
     p.ws_per_segment = (size_t)p.P * K3_WS_BYTES_PER_BOX + K3_SCRATCH_BYTES;
     if (p.use_global) {
@@ -1322,8 +1332,8 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
         }
         FSD_CUDA(cudaGetLastError());
         h->launches += 1;
-        if (p.P > 1024) {
-            const int PB = p.P < K3_SMEM_MAX_P ? p.P : K3_SMEM_MAX_P;
+        if (p.P > 1024 && p.cluster_min > 1024) {
+            const int PB = p.P < p.cluster_min ? p.P : p.cluster_min;
             p.n_lo = 1024; p.n_hi = PB;
             {
                 TimedLaunch timed(h, FSD_KERNEL_MERGE, S, -max_segment, stream);
@@ -1333,8 +1343,8 @@ extern "C" int fsd_merge(fsd_handle_t h, const float* boxes, int box_stride, con
             h->launches += 1;
         }
     }
-    if (p.P > K3_SMEM_MAX_P) {
-        // segments above 4096 boxes: a cluster of 8 CTAs each (k3_merge_cluster_kernel)
+    if (p.P > p.cluster_min) {
+        // segments above the hand-over size (4096 boxes by default): a cluster of 8 CTAs each (k3_merge_cluster_kernel)
         const size_t csmem = (size_t)(p.P / K3_CLUSTER) * 24;  // sort block (12 B / key) and, after it, the own-rank cache (24 B / rank)
         FSD_CUDA(cudaFuncSetAttribute(k3_merge_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
         TimedLaunch timed(h, FSD_KERNEL_MERGE, S, -max_segment, stream);
