@@ -125,6 +125,27 @@ class Bottleneck(nn.Module):
         self.add = shortcut and c1 == c2
 
     def forward(self, x, out=None):
+        c1, c2 = self.cv1.conv, self.cv2.conv
+        if (c1.out_channels == 8 and x.is_cuda and x.dtype == torch.float16 and not torch.is_grad_enabled() and x.stride(1) == 1
+                and c1.kernel_size == (3, 3) and c2.kernel_size == (3, 3) and c1.stride == (1, 1) and c2.stride == (1, 1)
+                and c1.groups == 1 and c2.groups == 1 and isinstance(self.cv1.act, nn.SiLU) and isinstance(self.cv2.act, nn.SiLU)
+                and not os.environ.get("FSD_NO_CONV3_TC")):
+            # An 8-channel hidden tensor (yolo11n: C3k2 of layer 2) is below the tensor-core kernel's K = 16: carry it as 16 channels
+            # whose upper half is exactly zero (zero weight rows and bias -> SiLU(0) = 0) and give cv2 zero weight columns there —
+            # the same sums, both convolutions on fsd_conv3x3 instead of cuDNN + epilogue for cv2.
+            from ..ops import conv3x3, conv3x3_supported, conv3x3_tap_major
+
+            if conv3x3_supported(c1.in_channels, 16) and conv3x3_supported(16, c2.out_channels) and c1.in_channels <= 64:
+                key = (c1.weight._version, c1.weight.data_ptr(), c2.weight._version, c2.weight.data_ptr())
+                cached = getattr(self, "_padded", None)
+                if cached is None or cached[0] != key:
+                    w1 = torch.cat([c1.weight.detach(), torch.zeros_like(c1.weight)], dim=0)           # [16, K, 3, 3]
+                    b1 = torch.cat([c1.bias.detach(), torch.zeros_like(c1.bias)], dim=0)
+                    w2 = torch.cat([c2.weight.detach(), torch.zeros_like(c2.weight)], dim=1)           # [N, 16, 3, 3]
+                    cached = (key, conv3x3_tap_major(w1), b1.contiguous(), conv3x3_tap_major(w2))
+                    self._padded = cached
+                hidden = conv3x3(x, cached[1], cached[2], "silu")
+                return conv3x3(hidden, cached[3], c2.bias, "silu", out=out, residual=x if self.add else None)
         return self.cv2(self.cv1(x), out=out, residual=x if self.add else None)
 
 

@@ -1253,11 +1253,11 @@ static int pow2_at_least(int n) {
 using namespace fsd;
 
 // Segments above this many boxes take the 8-CTA cluster kernel.  Default 4096 = the shared-memory kernel's capacity; FSD_K3_CLUSTER_MIN
-// (1024 / 2048) moves the hand-over down for measurements.
+// = 2048 moves the hand-over down for measurements (smaller values are not supported by the cluster kernel).
 static int k3_cluster_min() {
     const char* v = getenv("FSD_K3_CLUSTER_MIN");
     const int t = v ? atoi(v) : K3_SMEM_MAX_P;
-    return t <= 1024 ? 1024 : (t <= 2048 ? 2048 : K3_SMEM_MAX_P);
+    return t <= 2048 ? 2048 : K3_SMEM_MAX_P;
 }
 
 extern "C" int64_t fsd_merge_workspace_bytes(int64_t N, int S, int max_segment) {
