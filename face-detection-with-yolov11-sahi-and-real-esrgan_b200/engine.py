@@ -75,6 +75,8 @@ class SlicedFaceDetector:
         self.device = torch.device(device)
         self.dtype = torch.float16 if half else torch.float32
         self.imgsz, self.conf, self.stride, self.iou, self.max_det = imgsz, conf, stride, iou, max_det
+        if os.environ.get("FSD_CHUNK_ENTRIES"):  # (measurement knob: network inputs per backbone call)
+            chunk_entries = max(1, int(os.environ["FSD_CHUNK_ENTRIES"]))
         self.cap, self.reverse, self.chunk, self.truncate = cap_per_entry, reverse_channels, chunk_entries, truncate
         self.channels_last = channels_last
         # a private copy: Module.half() / .float() convert in place, and one YOLO front end may own an fp16 and an fp32 engine
