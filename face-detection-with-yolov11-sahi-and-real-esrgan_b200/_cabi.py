@@ -42,6 +42,7 @@ SIGNATURES = {
     "fsd_bias_act": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, vp, C.c_int64, C.c_int, C.c_int,
                                C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
     "fsd_stem_conv": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "fsd_pointwise_conv_supported": (C.c_int, [C.c_int, C.c_int]),
     "fsd_pointwise_conv": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int,
                                      C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp]),
     "fsd_conv3x3_supported": (C.c_int, [C.c_int, C.c_int]),

@@ -200,6 +200,14 @@ int launch_pointwise_tc(fsd_context* h, const void* x, int64_t x_stride, const v
 
 using namespace fsd;
 
+// 0: not supported; 1: the mma.sync kernel only (K <= 128, N in 16/32/64/128); 2: the tcgen05 kernel takes it (it is preferred when both do)
+extern "C" int fsd_pointwise_conv_supported(int in_channels, int out_channels) {
+    if (k10_supported(in_channels, out_channels)) return 2;
+    const bool k7_shape = in_channels >= 16 && in_channels % 16 == 0 && in_channels <= 128 &&
+                          (out_channels == 16 || out_channels == 32 || out_channels == 64 || out_channels == 128);
+    return k7_shape ? 1 : 0;
+}
+
 extern "C" int fsd_pointwise_conv(fsd_handle_t h, const void* x, int64_t x_pixel_stride, const void* weight, const void* bias,
                                   void* out, int64_t out_pixel_stride, const void* residual, int64_t residual_pixel_stride,
                                   void* out2, int64_t out2_pixel_stride, int out2_first_channel, int64_t n_pixels,

@@ -366,7 +366,7 @@ def pointwise_tc_enabled() -> bool:
 
 def pointwise_tc_supported(k: int, n: int) -> bool:
     """Shapes the tcgen05 path of fsd_pointwise_conv takes: channels in multiples of 16, weights <= 96 KB (resident in smem)."""
-    return k % 16 == 0 and 16 <= k <= 512 and n % 16 == 0 and 16 <= n <= 256 and k * n * 2 <= 96 * 1024
+    return int(_cabi.load_library().fsd_pointwise_conv_supported(int(k), int(n))) == 2  # (the library owns the rule)
 
 
 def pointwise_tc_preferred(k: int, n: int) -> bool:
@@ -377,9 +377,8 @@ def pointwise_tc_preferred(k: int, n: int) -> bool:
 
 def pointwise_conv_supported(k: int, n: int) -> bool:
     """Layer shapes fsd_pointwise_conv takes (the rest stays on the library convolution + fsd_bias_act)."""
-    if pointwise_tc_enabled() and pointwise_tc_supported(k, n):
-        return True
-    return k % 16 == 0 and 16 <= k <= 128 and n in (16, 32, 64, 128)
+    level = int(_cabi.load_library().fsd_pointwise_conv_supported(int(k), int(n)))
+    return level == 2 if pointwise_tc_enabled() and level == 2 else (k % 16 == 0 and 16 <= k <= 128 and n in (16, 32, 64, 128))
 
 
 def pointwise_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, act: str = "silu", slope: float = 0.2,

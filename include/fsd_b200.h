@@ -203,6 +203,9 @@ int fsd_stem_conv(fsd_handle_t h, const void* x, int E, int H, int W, const void
  *      with their own pixel strides (elements), exactly as in fsd_bias_act.  K % 16 == 0, K <= 128, N in {16,32,64,128}
  *      (the weight matrix and two staging tiles per warp live in shared memory).  Replaces cuDNN convolution + epilogue pass for
  *      ultralytics Conv(c1, c2, 1, 1) layers (C3k2.cv1/cv2, C3k.cv1-3, head cv3; run from utils/yolo_wrapper.py:72). */
+/* 0: shape not supported; 1: the mma.sync kernel only; 2: the tcgen05 kernel takes it (channels in multiples of 16, K <= 512, N <= 256,
+ * K * N * 2 bytes <= 96 KB) */
+int fsd_pointwise_conv_supported(int in_channels, int out_channels);
 int fsd_pointwise_conv(fsd_handle_t h, const void* x, int64_t x_pixel_stride, const void* weight, const void* bias,
                        void* out, int64_t out_pixel_stride, const void* residual, int64_t residual_pixel_stride,
                        void* out2, int64_t out2_pixel_stride, int out2_first_channel, int64_t n_pixels,

@@ -126,3 +126,28 @@ def test_get_sliced_prediction_argument_errors():
 
     with pytest.raises(ValueError, match="postprocess_type should be one of"):
         get_sliced_prediction(np.zeros((8, 8, 3), np.uint8), None, 4, 4, postprocess_type="FOO")
+
+
+def test_convolution_shape_rules_and_tap_major_layouts():
+    """The library owns the shape rules of the tensor-core convolutions (no GPU needed); the tap-major weight helpers are pure layout."""
+    import torch
+
+    import fsd_b200._cabi as cabi
+    import fsd_b200.ops as ops
+
+    lib = cabi.load_library()
+    assert lib.fsd_pointwise_conv_supported(64, 64) == 2 and lib.fsd_pointwise_conv_supported(384, 128) == 2
+    assert lib.fsd_pointwise_conv_supported(512, 256) == 0 and lib.fsd_pointwise_conv_supported(24, 64) == 0  # 256 KB of weights; K % 16
+    assert lib.fsd_pointwise_conv_supported(128, 256) == 2 and lib.fsd_pointwise_conv_supported(256, 256) == 0
+    assert lib.fsd_conv3x3_supported(64, 64) == 1 and lib.fsd_conv3x3_supported(16, 8) == 1 and lib.fsd_conv3x3_supported(8, 16) == 0
+    assert lib.fsd_conv3x3_supported(128, 128) == 0 and lib.fsd_conv3x3_supported(256, 16) == 1
+    assert lib.fsd_conv2x2_supported(64, 32) == 1 and lib.fsd_conv2x2_supported(128, 32) == 0
+    assert ops.conv3x3_preferred(64, 64) and not ops.conv3x3_preferred(128, 16)
+    w = torch.arange(2 * 16 * 9, dtype=torch.float16).reshape(2, 16, 3, 3)
+    t = ops.conv3x3_tap_major(torch.cat([w] * 8))  # N = 16
+    assert t.shape == (3, 3, 16, 16) and torch.equal(t[1, 2, 0], w[0, :, 1, 2])
+    t8 = ops.conv3x3_tap_major(torch.cat([w] * 4))  # N = 8 -> zero-padded to 16 rows
+    assert t8.shape == (3, 3, 16, 16) and float(t8[:, :, 8:].abs().max()) == 0 and torch.equal(t8[0, 0, 1], w[1, :, 0, 0])
+    dw = torch.arange(24 * 9, dtype=torch.float16).reshape(24, 1, 3, 3)
+    td = ops.dwconv3x3_tap_major(dw)
+    assert td.shape == (9, 24) and torch.equal(td[5], dw[:, 0, 1, 2])
