@@ -50,17 +50,19 @@ struct K10Params {
     int H, W, tiles_x, tiles_per_image;       // 3x3 only: image size and the patch grid (16 x 8, halo mode: 8 x 16)
     int a_per_tile, baseoff_mode;             // ring slots one tile consumes; (base offset rule: measurement knob, unused)
     int kh, kw, pad;                          // filter taps and padding: 3, 3, 1 or (halo mode only) 2, 2, 0
+    long long watchdog_cycles;                // > 0: a wait longer than this traps (debugging aid, FSD_K10_WATCHDOG_S); 0: wait for ever
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void k10_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a protocol error traps after ~2 s instead of hanging the GPU.  try_wait carries a suspend-time hint, so a waiting
+// mbarrier wait.  With FSD_K10_WATCHDOG_S=<seconds> a wait that long traps instead of hanging the GPU (bring-up aid; off by default: a
+// kernel frozen by a profiler or by time-slicing with another context must not be killed for it).  try_wait carries a suspend-time hint, so a waiting
 // thread mostly sleeps in hardware instead of spinning through issue slots that the epilogue warps need (the waits were 28 % of all
 // instructions in profiles/r2_conv3_small_tc.summary.txt); `backoff_ns` adds a sleep between polls for waits that are not latency
 // critical (the producer's free-slot wait).
-__device__ __forceinline__ void k10_mbar_wait(uint64_t* bar, uint32_t parity, unsigned backoff_ns = 0) {
+__device__ __forceinline__ void k10_mbar_wait(uint64_t* bar, uint32_t parity, long long watchdog_cycles, unsigned backoff_ns = 0) {
     const uint32_t addr = smem_u32(bar);
     long long t0 = 0;
     for (unsigned polls = 1;; ++polls) {
@@ -74,10 +76,10 @@ __device__ __forceinline__ void k10_mbar_wait(uint64_t* bar, uint32_t parity, un
             : "memory");
         if (done) return;
         if (backoff_ns) __nanosleep(backoff_ns);
-        if ((polls & 0xfffu) == 0) {
+        if (watchdog_cycles > 0 && (polls & 0xfffu) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();
+            else if (now - t0 > watchdog_cycles) __trap();
         }
     }
 }
@@ -222,7 +224,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                     tx = rem - ty * p.tiles_x;
                 }
                 for (int s = 0; s < p.a_per_tile; ++s) {
-                    k10_mbar_wait(&empty_bar[stage], phase ^ 1, 64);
+                    k10_mbar_wait(&empty_bar[stage], phase ^ 1, p.watchdog_cycles, 64);
                     mbar_expect_tx(&full_bar[stage], p.slab_bytes);
                     uint8_t* dst = smem_a + (size_t)stage * p.slab_bytes;
                     if (MODE == 2) {  // the whole 18 x 16 pixel halo patch (rows y0-1.., columns x0-1..x0+14) of the 16 x 8 output tile
@@ -255,18 +257,18 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             const uint32_t a_hi_halo = (16u * row16) | hi_common;              // halo patch: 8-row groups are 16 pixel rows apart
             const uint32_t slab16 = p.slab_bytes >> 4, bslab16 = (uint32_t)(p.N * p.KS * 2) >> 4;
             const int ksteps = p.KS >> 4;
-            k10_mbar_wait(&b_bar, 0);
+            k10_mbar_wait(&b_bar, 0, p.watchdog_cycles);
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
-                k10_mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+                k10_mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1, p.watchdog_cycles);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
                 if (MODE == 2) {
                     // nine taps = nine descriptors into the one halo patch: pixel (yy, xx) sits at (yy * 16 + xx) * row bytes, so tap
                     // (ky, kx) starts (ky * 16 + kx) rows in and the 8-pixel row groups are 16 rows apart
-                    k10_mbar_wait(&full_bar[stage], phase);
+                    k10_mbar_wait(&full_bar[stage], phase, p.watchdog_cycles);
                     tc_fence_after();
                     if (elect_one_sync()) {
                         const uint32_t a_lo0 = a_lo_base + (uint32_t)stage * slab16;
@@ -291,7 +293,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 } else {
                     uint32_t b_lo = b_lo_base;
                     for (int s = 0; s < p.total_slabs; ++s, b_lo += bslab16) {
-                        k10_mbar_wait(&full_bar[stage], phase);
+                        k10_mbar_wait(&full_bar[stage], phase, p.watchdog_cycles);
                         tc_fence_after();
                         if (elect_one_sync()) {
                             const uint32_t a_lo = a_lo_base + (uint32_t)stage * slab16;
@@ -315,7 +317,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             int it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
-                k10_mbar_wait(&acc_full[acc], (it >> 1) & 1);
+                k10_mbar_wait(&acc_full[acc], (it >> 1) & 1, p.watchdog_cycles);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.N);
                 // accumulator row m = 32 q + r  ->  pixel: 1x1: tile * 128 + m;  3x3: (y0 + m / 16, x0 + m % 16) of image n
@@ -443,6 +445,7 @@ static int k10_launch(fsd_context* h, int taps, int kh, int pad, const void* x, 
     p.n_slabs = K / p.KS;
     p.taps = taps; p.total_slabs = taps * p.n_slabs;
     p.kh = kh; p.kw = kh; p.pad = pad;
+    p.watchdog_cycles = getenv("FSD_K10_WATCHDOG_S") ? (long long)(atof(getenv("FSD_K10_WATCHDOG_S")) * 2.0e9) : 0;
     p.out_stride = (int)out_stride; p.res_stride = (int)res_stride; p.out2_stride = (int)out2_stride; p.out2_c0 = out2_c0;
     p.slope = slope;
     p.b_bytes = (uint32_t)taps * K * n_mma * 2;
