@@ -50,6 +50,8 @@ struct K10Params {
     int H, W, tiles_x, tiles_per_image;       // 3x3 only: image size and the patch grid (16 x 8, halo mode: 8 x 16)
     int a_per_tile, baseoff_mode;             // ring slots one tile consumes; (base offset rule: measurement knob, unused)
     int kh, kw, pad;                          // filter taps and padding: 3, 3, 1 or (halo mode only) 2, 2, 0
+    uint32_t tx_bytes;                        // bytes one TMA box delivers into a ring slot (<= slab_bytes, the slot pitch)
+    int halo_w;                               // halo mode: pixel columns of the patch (8 + kw - 1, or 16 with FSD_C3_HALO_W16=1)
     long long watchdog_cycles;                // > 0: a wait longer than this traps (debugging aid, FSD_K10_WATCHDOG_S); 0: wait for ever
 };
 
@@ -225,7 +227,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 }
                 for (int s = 0; s < p.a_per_tile; ++s) {
                     k10_mbar_wait(&empty_bar[stage], phase ^ 1, p.watchdog_cycles, 64);
-                    mbar_expect_tx(&full_bar[stage], p.slab_bytes);
+                    mbar_expect_tx(&full_bar[stage], p.tx_bytes);
                     uint8_t* dst = smem_a + (size_t)stage * p.slab_bytes;
                     if (MODE == 2) {  // the whole 18 x 16 pixel halo patch (rows y0-1.., columns x0-1..x0+14) of the 16 x 8 output tile
                         k10_tma_load_4d(dst, &map_x, &full_bar[stage], 0, tx * 8 - p.pad, ty * 16 - p.pad, n);
@@ -254,7 +256,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             const uint32_t hi_common = (1u << 14) | (p.layout_type << 29);
             const uint32_t a_hi = (p.sbo_bytes >> 4) | hi_common, b_hi = a_hi;
             const uint32_t row16 = (uint32_t)p.KS * 2 >> 4;                  // one pixel row of a slab in 16-byte units
-            const uint32_t a_hi_halo = (16u * row16) | hi_common;              // halo patch: 8-row groups are 16 pixel rows apart
+            const uint32_t a_hi_halo = ((uint32_t)p.halo_w * row16) | hi_common;  // halo patch: 8-row groups are halo_w pixel rows apart
             const uint32_t slab16 = p.slab_bytes >> 4, bslab16 = (uint32_t)(p.N * p.KS * 2) >> 4;
             const int ksteps = p.KS >> 4;
             k10_mbar_wait(&b_bar, 0, p.watchdog_cycles);
@@ -267,7 +269,8 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.N);
                 if (MODE == 2) {
                     // nine taps = nine descriptors into the one halo patch: pixel (yy, xx) sits at (yy * 16 + xx) * row bytes, so tap
-                    // (ky, kx) starts (ky * 16 + kx) rows in and the 8-pixel row groups are 16 rows apart
+                    // (ky, kx) starts (ky * halo_w + kx) rows in and the 8-pixel row groups are halo_w rows apart (halo_w = 10 for 3 x 3: the
+                    // group stride need not be a multiple of the 1024-byte swizzle pattern, because the phase follows the absolute address)
                     k10_mbar_wait(&full_bar[stage], phase, p.watchdog_cycles);
                     tc_fence_after();
                     if (elect_one_sync()) {
@@ -277,7 +280,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
                                 if (ky >= p.kh || kx >= p.kw) continue;  // (2 x 2 filters use four of the nine unrolled slots)
-                                const uint32_t a_lo = a_lo0 + (uint32_t)(ky * 16 + kx) * row16;
+                                const uint32_t a_lo = a_lo0 + (uint32_t)(ky * p.halo_w + kx) * row16;
                                 const uint32_t b_lo = b_lo_base + (uint32_t)(ky * p.kw + kx) * bslab16;
                                 const bool first = ky == 0 && kx == 0;
                                 if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, first);
@@ -463,7 +466,12 @@ static int k10_launch(fsd_context* h, int taps, int kh, int pad, const void* x, 
     // s pixel rows into a swizzle pattern needs base offset 0; writing (start >> 7) & 7 there breaks K = 32 and 64 (FSD_C3_BASEOFF=1 shows it)
     p.baseoff_mode = getenv("FSD_C3_BASEOFF") ? atoi(getenv("FSD_C3_BASEOFF")) : 0;
     p.a_per_tile = halo ? 1 : p.total_slabs;
-    if (halo) p.slab_bytes = halo_rows * 16u * (uint32_t)p.KS * 2;
+    p.halo_w = getenv("FSD_C3_HALO_W16") ? 16 : 8 + kh - 1;
+    p.tx_bytes = p.slab_bytes;
+    if (halo) {
+        p.tx_bytes = halo_rows * (uint32_t)p.halo_w * (uint32_t)p.KS * 2;
+        p.slab_bytes = (p.tx_bytes + 1023u) & ~1023u;  // (stage bases stay pattern-aligned)
+    }
     if (taps > 1) {
         p.tiles_x = halo ? (W + 7) / 8 : (W + 15) / 16;
         p.tiles_per_image = p.tiles_x * (halo ? (H + 15) / 16 : (H + 7) / 8);
@@ -516,7 +524,7 @@ static int k10_launch(fsd_context* h, int taps, int kh, int pad, const void* x, 
     if (taps > 1) {
         const uint64_t xd[4] = {(uint64_t)K, (uint64_t)Win, (uint64_t)Hin, (uint64_t)n_img};
         const uint64_t xs[3] = {(uint64_t)x_stride * 2, (uint64_t)Win * x_stride * 2, (uint64_t)Hin * Win * x_stride * 2};
-        const uint32_t xb[4] = {(uint32_t)p.KS, 16, halo ? halo_rows : 8u, 1};
+        const uint32_t xb[4] = {(uint32_t)p.KS, halo ? (uint32_t)p.halo_w : 16u, halo ? halo_rows : 8u, 1};
         if (!k10_encode(h, &mx, x, 4, xd, xs, xb, swz)) return FSD_OK;
         const uint64_t wd[3] = {(uint64_t)K, (uint64_t)n_mma, (uint64_t)taps};
         const uint64_t ws[2] = {(uint64_t)K * 2, (uint64_t)n_mma * K * 2};
