@@ -50,6 +50,7 @@ struct K10Params {
     int H, W, tiles_x, tiles_per_image;       // 3x3 only: image size and the patch grid (16 x 8, halo mode: 8 x 16)
     int a_per_tile, baseoff_mode;             // ring slots one tile consumes; (base offset rule: measurement knob, unused)
     int kh, kw, pad;                          // filter taps and padding: 3, 3, 1 or (halo mode only) 2, 2, 0
+    int bias_in_mma;                          // 1: the bias enters through one extra K = 16 MMA step (ones column x bias row), 0: added in the epilogue
     uint32_t tx_bytes;                        // bytes one TMA box delivers into a ring slot (<= slab_bytes, the slot pitch)
     int halo_w;                               // halo mode: pixel columns of the patch (8 + kw - 1, or 16 with FSD_C3_HALO_W16=1)
     long long watchdog_cycles;                // > 0: a wait longer than this traps (debugging aid, FSD_K10_WATCHDOG_S); 0: wait for ever
@@ -191,7 +192,23 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     __half* stage_base = reinterpret_cast<__half*>(smem_a + (size_t)p.stages * p.slab_bytes);
 
     constexpr int K10_THREADS = 64 + 32 * EW, SETS = EW / 4;
-    for (int i = threadIdx.x; i < p.N; i += K10_THREADS) s_bias[i] = __half2float(__ldg(p.bias + i));
+    for (int i = threadIdx.x; i < p.N; i += K10_THREADS) s_bias[i] = i < p.n_valid ? __half2float(__ldg(p.bias + i)) : 0.f;
+    // Bias through the tensor cores: one extra K = 16 step whose A operand is a constant [128 x 16] tile with ones in column 0 and whose
+    // B operand is [N x 16] with the bias in column 0 — the accumulator then already holds conv + bias and the epilogue saves one FADD per
+    // element (it is bound by its instruction count).  Both tiles use the un-swizzled K-major canonical layout: 8-row x 16-byte core
+    // matrices of 128 contiguous bytes, M/N-direction stride (SBO) 128 bytes, K-direction stride (LBO) = rows x 16 bytes.
+    uint8_t* ones_tile = reinterpret_cast<uint8_t*>(stage_base + (size_t)EW * 32 * K10_STAGE_PITCH);
+    uint8_t* bias_tile = ones_tile + 4096;
+    if (p.bias_in_mma) {
+        for (int i = threadIdx.x; i < 256 + 2 * p.N; i += K10_THREADS) {  // 16-byte pieces: 256 of the ones tile, 2 N of the bias tile
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (i < 128) v.x = 0x3c00u;                                              // row i (k-chunk 0): column 0 = 1.0
+            else if (i >= 256 && i < 256 + p.N && i - 256 < p.n_valid) v.x = (uint32_t)__half_as_ushort(__ldg(p.bias + (i - 256)));
+            if (i < 256) reinterpret_cast<uint4*>(ones_tile)[i] = v;
+            else reinterpret_cast<uint4*>(bias_tile)[i - 256] = v;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_w);
@@ -259,6 +276,9 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             const uint32_t a_hi_halo = ((uint32_t)p.halo_w * row16) | hi_common;  // halo patch: 8-row groups are halo_w pixel rows apart
             const uint32_t slab16 = p.slab_bytes >> 4, bslab16 = (uint32_t)(p.N * p.KS * 2) >> 4;
             const int ksteps = p.KS >> 4;
+            // un-swizzled descriptors of the bias step: LBO (K direction) = rows x 16 bytes, SBO (M/N direction) = 128 bytes, layout 0
+            const uint32_t ones_lo = ((smem_u32(ones_tile) & 0x3ffffu) >> 4) | ((2048u >> 4) << 16), ones_hi = (128u >> 4) | (1u << 14);
+            const uint32_t biasd_lo = ((smem_u32(bias_tile) & 0x3ffffu) >> 4) | (((uint32_t)p.N * 16u >> 4) << 16), biasd_hi = ones_hi;
             k10_mbar_wait(&b_bar, 0, p.watchdog_cycles);
             int stage = 0, it = 0;
             uint32_t phase = 0;
@@ -289,6 +309,7 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                             }
                         }
                         tc_commit(&empty_bar[stage]);
+                        if (p.bias_in_mma) tc_mma_f16_lohi(d_tmem, ones_lo, ones_hi, biasd_lo, biasd_hi, idesc, 1u);
                         tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
                     }
                     __syncwarp();
@@ -304,7 +325,10 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                             else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
                             else tc_issue_slab<1>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, s == 0);
                             tc_commit(&empty_bar[stage]);  // the slab may be overwritten once these MMAs have read it
-                            if (s + 1 == p.total_slabs) tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+                            if (s + 1 == p.total_slabs) {
+                                if (p.bias_in_mma) tc_mma_f16_lohi(d_tmem, ones_lo, ones_hi, biasd_lo, biasd_hi, idesc, 1u);
+                                tc_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+                            }
                         }
                         __syncwarp();
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -347,7 +371,8 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 #pragma unroll
                     for (int e4 = 0; e4 < 4; ++e4) {
                         if (e4 >= 2 && !upper) { h[2 * e4] = 0u; h[2 * e4 + 1] = 0u; continue; }
-                        const float4 bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * e4]);
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!p.bias_in_mma) bb = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * e4]);
                         const __half2 o0 = __floats2half2_rn(k10_act<ACT>(__uint_as_float(v[4 * e4]) + bb.x, p.slope),
                                                              k10_act<ACT>(__uint_as_float(v[4 * e4 + 1]) + bb.y, p.slope));
                         const __half2 o1 = __floats2half2_rn(k10_act<ACT>(__uint_as_float(v[4 * e4 + 2]) + bb.z, p.slope),
@@ -448,6 +473,7 @@ static int k10_launch(fsd_context* h, int taps, int kh, int pad, const void* x, 
     p.n_slabs = K / p.KS;
     p.taps = taps; p.total_slabs = taps * p.n_slabs;
     p.kh = kh; p.kw = kh; p.pad = pad;
+    p.bias_in_mma = getenv("FSD_K10_BIAS_EPI") ? 0 : 1;
     p.watchdog_cycles = getenv("FSD_K10_WATCHDOG_S") ? (long long)(atof(getenv("FSD_K10_WATCHDOG_S")) * 2.0e9) : 0;
     p.out_stride = (int)out_stride; p.res_stride = (int)res_stride; p.out2_stride = (int)out2_stride; p.out2_c0 = out2_c0;
     p.slope = slope;
@@ -496,7 +522,7 @@ static int k10_launch(fsd_context* h, int taps, int kh, int pad, const void* x, 
     size_t smem = 0;
     bool wide_epilogue = false;
     auto plan = [&](int epi_warps, int first_ctas) {
-        const size_t staging = (size_t)epi_warps * 32 * K10_STAGE_PITCH * sizeof(__half);
+        const size_t staging = (size_t)epi_warps * 32 * K10_STAGE_PITCH * sizeof(__half) + 4096 + (size_t)n_mma * 32;  // + the bias step's tiles
         for (ctas = first_ctas; ctas >= 1; --ctas) {
             const size_t budget = (size_t)216 * 1024 / ctas - 3 * 1024;  // static shared memory + the driver's 1 KB per CTA
             const size_t fixed = 1024 + p.b_region + staging;
