@@ -48,7 +48,7 @@ struct K10Params {
     uint32_t b_bytes, b_region, slab_bytes, sbo_bytes, layout_type;  // b_region = b_bytes rounded up to 1024
     int taps, total_slabs, n_valid;           // 1 or 9 taps; total_slabs = taps * n_slabs; columns actually stored
     int H, W, tiles_x, tiles_per_image;       // 3x3 only: image size and the patch grid (16 x 8, halo mode: 8 x 16)
-    int a_per_tile, baseoff_mode;             // ring slots one tile consumes; (base offset rule: measurement knob, unused)
+    int a_per_tile, baseoff_mode;             // ring slots one tile consumes; base-offset rule of the halo descriptors (measurement knob)
     int kh, kw, pad;                          // filter taps and padding: 3, 3, 1 or (halo mode only) 2, 2, 0
     int bias_in_mma;                          // 1: the bias enters through one extra K = 16 MMA step (ones column x bias row), 0: added in the epilogue
     uint32_t tx_bytes;                        // bytes one TMA box delivers into a ring slot (<= slab_bytes, the slot pitch)
@@ -303,9 +303,12 @@ k10_pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                                 const uint32_t a_lo = a_lo0 + (uint32_t)(ky * p.halo_w + kx) * row16;
                                 const uint32_t b_lo = b_lo_base + (uint32_t)(ky * p.kw + kx) * bslab16;
                                 const bool first = ky == 0 && kx == 0;
-                                if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, first);
-                                else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, first);
-                                else tc_issue_slab<1>(d_tmem, a_lo, a_hi_halo, b_lo, b_hi, idesc, first);
+                                // (measurement knob FSD_C3_BASEOFF=1: write the start address's pattern phase into the base-offset field,
+                                // bits 49-51 — this is what BREAKS the results; the default leaves it 0)
+                                const uint32_t a_hi_tap = p.baseoff_mode == 1 ? a_hi_halo | (((a_lo >> 3) & 7u) << 17) : a_hi_halo;
+                                if (ksteps == 4) tc_issue_slab<4>(d_tmem, a_lo, a_hi_tap, b_lo, b_hi, idesc, first);
+                                else if (ksteps == 2) tc_issue_slab<2>(d_tmem, a_lo, a_hi_tap, b_lo, b_hi, idesc, first);
+                                else tc_issue_slab<1>(d_tmem, a_lo, a_hi_tap, b_lo, b_hi, idesc, first);
                             }
                         }
                         tc_commit(&empty_bar[stage]);
