@@ -151,3 +151,16 @@ def test_convolution_shape_rules_and_tap_major_layouts():
     dw = torch.arange(24 * 9, dtype=torch.float16).reshape(24, 1, 3, 3)
     td = ops.dwconv3x3_tap_major(dw)
     assert td.shape == (9, 24) and torch.equal(td[5], dw[:, 0, 1, 2])
+
+
+def test_new_convolution_entry_points_validate_arguments_without_a_gpu():
+    """fsd_conv3x3 / fsd_conv2x2 / fsd_dwconv3x3 reject bad arguments before touching the device (status -1 and a message)."""
+    import fsd_b200._cabi as cabi
+
+    lib = cabi.load_library()
+    assert lib.fsd_conv3x3(None, None, 0, 1, 8, 8, None, None, None, 0, None, 0, 16, 16, 1, 0.0, cabi.FSD_F16, None) == -1
+    assert b"fsd_conv3x3" in lib.fsd_last_error()
+    assert lib.fsd_conv2x2(None, None, 0, 1, 8, 8, None, None, None, 0, 64, 32, 1, 0.0, cabi.FSD_F16, None) == -1
+    assert b"fsd_conv2x2" in lib.fsd_last_error()
+    assert lib.fsd_dwconv3x3(None, None, 0, 1, 8, 8, None, None, None, 0, 64, 1, 0.0, cabi.FSD_F16, None) == -1
+    assert b"fsd_dwconv3x3" in lib.fsd_last_error()
